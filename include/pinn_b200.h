@@ -1,0 +1,114 @@
+/*
+ * pinn_b200.h -- C ABI of the fused PDE-residual + parameter-gradient path (libpinn_b200.so).
+ *
+ * One call evaluates, for a tanh MLP u(x) and a block of collocation points, the PDE residual
+ * r_k(x) of one PINNacle problem, the mean-square loss per residual term and (optionally) the
+ * gradient of seeded combinations of those losses w.r.t. all network parameters.
+ *
+ * Reference interfaces this boundary replaces (paths relative to the PINNacle tree):
+ *   - deepxde/model.py:258-279      outputs_losses(): net(x), data.losses(), stack
+ *   - deepxde/nn/pytorch/fnn.py:35-48        FNN.forward
+ *   - deepxde/gradients.py:160-181,258-283   dde.grad.jacobian / dde.grad.hessian
+ *   - src/pde/<problem>.py          the pde(x, u) residual closures (one "kind" each, see enum)
+ *   - deepxde/data/pde.py:147-152 + deepxde/losses.py:16-23   mean of squared residual rows
+ *   - deepxde/model.py:306-315      closure(): sum(losses).backward() -> p.grad
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers (fp32 unless stated), caller-owned; the library allocates
+ *     nothing and keeps no state between calls.  `stream` is a cudaStream_t passed as void*.
+ *   - `params` is the flat parameter vector in torch.nn.Linear / net.parameters() order:
+ *     W0[H,d], b0[H], W1[H,H], b1[H], ..., W_L[m,H], b_L[m]   (row-major, y = x W^T + b).
+ *   - `x` is [n_rows, d] row-major, `aux` is [n_rows, n_aux] row-major or NULL when n_aux == 0.
+ *   - Losses are returned as  loss_k = inv_n_global * sum_rows r_k^2 , i.e. this rank's share of
+ *     the global mean; summing the outputs of all ranks (one all-reduce) gives the global value.
+ *   - Every function returns 0 on success, non-zero on error; pinn_last_error() describes the
+ *     last error of the calling thread.  Unsupported descriptors are errors -- there is no
+ *     fallback path.
+ */
+#ifndef PINN_B200_H_
+#define PINN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PINN_MAX_DIM 6
+#define PINN_MAX_CONSTS 24
+#define PINN_MAX_AUXSEL 8
+#define PINN_MAX_PDE 3
+#define PINN_MAX_AUX 4
+#define PINN_MAX_SEEDS 4
+
+/* Residual kinds.  Taylor coefficients: u_j = du/dx_j, u_jj = d2u/dx_j^2. */
+enum pinn_kind {
+  /* r = cu*[aux]*u + sum_j c1_j u_j + sum_j c2_j*[aux]*u_jj + [aux]   (poisson.py:54-58,111-120,179-193,
+   * 253-258,288-296; heat.py:34-41,88-93,147-152,265-275; wave.py:22-26,85-89,144-149; helmholtz.py:19-27)
+   * consts[0]=cu, consts[1+j]=c1_j, consts[7+j]=c2_j; aux_sel[0]=source column, aux_sel[1]=multiplier of
+   * the cu term, aux_sel[2+j]=multiplier of the c2_j term (-1 = none). */
+  PINN_KIND_LINEAR = 0,
+  PINN_KIND_BURGERS1D = 1,     /* burgers.py:21-25   u_t + u u_x - c0 u_xx                      */
+  PINN_KIND_BURGERS2D = 2,     /* burgers.py:66-80   2 outputs, 2 residuals, c0 = nu            */
+  PINN_KIND_NS2D = 3,          /* ns.py:141-160      (u,v,p): momentum x/y + continuity, c0 = nu */
+  PINN_KIND_NS2D_UNSTEADY = 4, /* ns.py:330-352      + u_t, v_t, aux[aux_sel[0]] added to mom-y  */
+  PINN_KIND_HEAT_NLSRC = 5,    /* heat.py:214-222    u_t - c0 lap u - c1 sin(c2 u^2) aux          */
+  PINN_KIND_GRAYSCOTT = 6,     /* chaotic.py:21-31   c0,c1 = eps; c2 = b; c3 = d                  */
+  PINN_KIND_KS = 7             /* chaotic.py:77-83   u_t + c0 u u_x + c1 u_xx + c2 u_xxxx         */
+};
+
+typedef struct pinn_kind_desc {
+  int32_t kind;                    /* enum pinn_kind */
+  int32_t d;                       /* input dimension  (1..PINN_MAX_DIM) */
+  int32_t m;                       /* output dimension (1..3) */
+  int32_t H;                       /* hidden width */
+  int32_t L;                       /* number of hidden tanh layers (>= 2) */
+  int32_t n_pde;                   /* residual terms (1..PINN_MAX_PDE) */
+  int32_t n_aux;                   /* per-point aux columns (0..PINN_MAX_AUX) */
+  int32_t order[PINN_MAX_DIM];     /* highest pure derivative carried per input direction */
+  int32_t aux_sel[PINN_MAX_AUXSEL];
+  float consts[PINN_MAX_CONSTS];
+} pinn_kind_desc;
+
+/* Number of fp32 parameters P of the network the descriptor names. */
+int64_t pinn_param_count(const pinn_kind_desc* desc);
+
+/* 0 if this build has kernels for the descriptor (jet signature, m, H, kind), else non-zero. */
+int pinn_supported(const pinn_kind_desc* desc);
+
+/* Bytes of device scratch the two calls below need for up to n_seeds reverse passes. */
+size_t pinn_workspace_bytes(const pinn_kind_desc* desc, int n_seeds);
+
+/* Forward only: loss_out[k] = inv_n_global * sum_rows r_k^2, k < n_pde.
+ * resid_out (nullable): [n_rows, n_pde] residual matrix.  Replaces model.py:258-279 for
+ * `_test()` / `predict(operator=pde)` style evaluations (model.py:476-499, 857-871). */
+int pinn_fwd(const pinn_kind_desc* desc, const float* params, const float* x, const float* aux,
+             int64_t n_rows, double inv_n_global, float* loss_out, float* resid_out,
+             void* workspace, size_t workspace_bytes, void* stream);
+
+/* Forward + hand-derived reverse.  seeds: device [n_seeds, n_pde] (grad_output over the loss terms
+ * for each reverse pass, 1 <= n_seeds <= PINN_MAX_SEEDS).  out: device [n_seeds*P + n_pde]:
+ *   out[s*P + i]      = d( sum_k seeds[s][k] * loss_k ) / d params[i]      (written, not accumulated)
+ *   out[n_seeds*P+k]  = loss_k
+ * so that a single all-reduce(SUM) of `out` yields global gradients and losses
+ * (replaces model.py:306-315 and the per-term backward passes of src/optimizer/lr_adaptor.py:33-62,
+ * multiadam.py:247-261). */
+int pinn_fwd_bwd(const pinn_kind_desc* desc, const float* params, const float* x, const float* aux,
+                 int64_t n_rows, double inv_n_global, const float* seeds, int n_seeds, float* out,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernel launches the last pinn_fwd / pinn_fwd_bwd call of this thread enqueued. */
+int pinn_last_launch_count(void);
+
+/* FP32 FFMA micro-benchmark used for the compute roofline denominator: runs `iters` dependent-free
+ * FFMA per thread on every SM and returns achieved TFLOP/s (negative on error). Synchronous. */
+double pinn_ffma_peak_tflops(int iters);
+
+const char* pinn_last_error(void);
+const char* pinn_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINN_B200_H_ */

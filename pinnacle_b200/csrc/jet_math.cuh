@@ -1,0 +1,413 @@
+// jet_math.cuh -- per-(point, neuron) Taylor-jet arithmetic and per-point PDE residuals.
+//
+// Everything here is a pure function of registers, usable from device code and (for the host
+// harness under tests/host_harness, which checks the hand-derived adjoints against autograd
+// without a GPU) from plain C++.
+//
+// Jet layout of one neuron: channel 0 is the value; then, for every input direction j in
+// order, the Taylor coefficients c_k = (1/k!) d^k/ds^k f(x + s e_j), k = 1..K_j.
+// (replaces the repeated reverse passes of deepxde/gradients.py:47-52,222-228.)
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/pinn_b200.h"
+
+#if defined(__CUDACC__)
+#define PINN_HD __host__ __device__ __forceinline__
+#else
+#define PINN_HD inline
+#endif
+
+namespace pinn {
+
+// ---------------------------------------------------------------------------------------------
+// compile-time jet signature
+// ---------------------------------------------------------------------------------------------
+template <int N>
+struct IC {
+  static constexpr int value = N;
+  PINN_HD constexpr operator int() const { return N; }
+};
+
+template <int I, int N, class F>
+PINN_HD void static_for_impl(F&& f) {
+  if constexpr (I < N) {
+    f(IC<I>{});
+    static_for_impl<I + 1, N>(f);
+  }
+}
+template <int N, class F>
+PINN_HD void static_for(F&& f) {
+  static_for_impl<0, N>(f);
+}
+
+template <int... KS>
+struct JetSig {
+  static constexpr int D = sizeof...(KS);
+  static constexpr int C = 1 + (0 + ... + KS);
+  PINN_HD static constexpr int order(int j) {
+    constexpr int o[sizeof...(KS)] = {KS...};
+    return o[j];
+  }
+  // channel of the first-order coefficient of direction j
+  PINN_HD static constexpr int base(int j) {
+    int b = 1;
+    for (int i = 0; i < j; ++i) b += order(i);
+    return b;
+  }
+  PINN_HD static constexpr int chan(int j, int k) { return base(j) + k - 1; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// tanh on jets.  With t = tanh(z), w = 1 - t^2 as power series in s:
+//   t_k = (1/k) sum_{i=1..k} i z_i w_{k-i},   w_k = - sum_{i=0..k} t_i t_{k-i}
+// One transcendental per neuron (t_0).
+// ---------------------------------------------------------------------------------------------
+template <int K>
+PINN_HD void tanh_series(const float (&zz)[K + 1], float t0, float w0, float (&t)[K + 1], float (&w)[K + 1]) {
+  t[0] = t0;
+  w[0] = w0;
+#pragma unroll
+  for (int k = 1; k <= K; ++k) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 1; i <= k; ++i) s = fmaf((float)i * zz[i], w[k - i], s);
+    t[k] = s * (1.0f / (float)k);
+    float ww = 0.f;
+#pragma unroll
+    for (int i = 0; i <= k; ++i) ww = fmaf(t[i], t[k - i], ww);
+    w[k] = -ww;
+  }
+}
+
+template <class SIG>
+PINN_HD void tanh_jet_fwd(const float (&z)[SIG::C], float (&a)[SIG::C]) {
+  const float t0 = tanhf(z[0]);
+  const float w0 = fmaf(-t0, t0, 1.0f);
+  a[0] = t0;
+  static_for<SIG::D>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    constexpr int K = SIG::order(j);
+    constexpr int b = SIG::base(j);
+    if constexpr (K >= 1) {
+      float zz[K + 1], t[K + 1], w[K + 1];
+      zz[0] = 0.f;
+#pragma unroll
+      for (int k = 1; k <= K; ++k) zz[k] = z[b + k - 1];
+      tanh_series<K>(zz, t0, w0, t, w);
+#pragma unroll
+      for (int k = 1; k <= K; ++k) a[b + k - 1] = t[k];
+    }
+  });
+}
+
+// Adjoint of tanh_jet_fwd: given z and abar = dLoss/da, returns zbar = dLoss/dz.
+template <class SIG>
+PINN_HD void tanh_jet_bwd(const float (&z)[SIG::C], const float (&abar)[SIG::C], float (&zbar)[SIG::C]) {
+  const float t0 = tanhf(z[0]);
+  const float w0 = fmaf(-t0, t0, 1.0f);
+  float t0bar = abar[0];
+  float w0bar = 0.f;
+  static_for<SIG::D>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    constexpr int K = SIG::order(j);
+    constexpr int b = SIG::base(j);
+    if constexpr (K >= 1) {
+      float zz[K + 1], t[K + 1], w[K + 1];
+      zz[0] = 0.f;
+#pragma unroll
+      for (int k = 1; k <= K; ++k) zz[k] = z[b + k - 1];
+      tanh_series<K>(zz, t0, w0, t, w);
+      float tb[K + 1], wb[K + 1], zb[K + 1];
+#pragma unroll
+      for (int k = 0; k <= K; ++k) {
+        tb[k] = (k >= 1) ? abar[b + k - 1] : 0.f;
+        wb[k] = 0.f;
+        zb[k] = 0.f;
+      }
+#pragma unroll
+      for (int k = K; k >= 1; --k) {
+        // t_k = (1/k) sum_i i z_i w_{k-i}
+        const float g = tb[k] * (1.0f / (float)k);
+#pragma unroll
+        for (int i = 1; i <= k; ++i) {
+          zb[i] = fmaf((float)i * w[k - i], g, zb[i]);
+          wb[k - i] = fmaf((float)i * zz[i], g, wb[k - i]);
+        }
+        // w_{k-1} = - sum_i t_i t_{k-1-i}   (k-1 >= 1; w_0 is handled once, below)
+        if (k - 1 >= 1) {
+          const float h = -2.0f * wb[k - 1];
+#pragma unroll
+          for (int i = 0; i <= k - 1; ++i) tb[i] = fmaf(t[k - 1 - i], h, tb[i]);
+        }
+      }
+      t0bar += tb[0];
+      w0bar += wb[0];
+#pragma unroll
+      for (int k = 1; k <= K; ++k) zbar[b + k - 1] = zb[k];
+    }
+  });
+  t0bar = fmaf(-2.0f * t0, w0bar, t0bar);   // w_0 = 1 - t_0^2
+  zbar[0] = w0 * t0bar;                     // t_0 = tanh(z_0)
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-point residuals and their adjoints
+// U[o][c]: Taylor-jet of network output o.  Derivatives: u_j = U[.][chan(j,1)],
+// u_jj = 2 U[.][chan(j,2)], u_jjjj = 24 U[.][chan(j,4)].
+// ---------------------------------------------------------------------------------------------
+struct KindParams {
+  int kind;
+  int aux_sel[PINN_MAX_AUXSEL];
+  float c[PINN_MAX_CONSTS];
+};
+
+enum : int { LIN_CU = 0, LIN_C1 = 1, LIN_C2 = 1 + PINN_MAX_DIM, LIN_SEL_SRC = 0, LIN_SEL_CU = 1, LIN_SEL_C2 = 2 };
+
+PINN_HD float aux_or_one(const float* aux, int sel) { return sel >= 0 ? aux[sel] : 1.0f; }
+
+template <class SIG, int M>
+struct Residual {
+  static constexpr int C = SIG::C;
+  static constexpr int D = SIG::D;
+
+  // true when (SIG, M) can host the kind
+  PINN_HD static constexpr bool sig22() { return D >= 2 && SIG::order(0) >= 2 && SIG::order(1) >= 2; }
+
+  PINN_HD static bool valid(int kind) {
+    switch (kind) {
+      case PINN_KIND_LINEAR: return M == 1;
+      case PINN_KIND_BURGERS1D: return M == 1 && D == 2 && SIG::order(0) >= 2 && SIG::order(1) >= 1;
+      case PINN_KIND_BURGERS2D: return M == 2 && D == 3 && sig22() && SIG::order(D - 1) >= 1;
+      case PINN_KIND_NS2D: return M == 3 && D == 2 && sig22();
+      case PINN_KIND_NS2D_UNSTEADY: return M == 3 && D == 3 && sig22() && SIG::order(D - 1) >= 1;
+      case PINN_KIND_HEAT_NLSRC: return M == 1 && D == 3 && sig22() && SIG::order(D - 1) >= 1;
+      case PINN_KIND_GRAYSCOTT: return M == 2 && D == 3 && sig22() && SIG::order(D - 1) >= 1;
+      case PINN_KIND_KS: return M == 1 && D == 2 && SIG::order(0) >= 4 && SIG::order(1) >= 1;
+      default: return false;
+    }
+  }
+
+  // r[k], k < n_pde
+  PINN_HD static void eval(const KindParams& kp, const float* aux, const float (&U)[M][C], float (&r)[PINN_MAX_PDE]) {
+    r[0] = r[1] = r[2] = 0.f;
+    const float* c = kp.c;
+    switch (kp.kind) {
+      case PINN_KIND_LINEAR: {
+        if constexpr (M == 1) {
+          float acc = 0.f;
+          static_for<D>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            if constexpr (SIG::order(j) >= 2) {
+              const float c2 = c[LIN_C2 + j];
+              if (c2 != 0.f) acc = fmaf(2.0f * c2 * aux_or_one(aux, kp.aux_sel[LIN_SEL_C2 + j]), U[0][SIG::chan(j, 2)], acc);
+            }
+          });
+          static_for<D>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            if constexpr (SIG::order(j) >= 1) acc = fmaf(c[LIN_C1 + j], U[0][SIG::chan(j, 1)], acc);
+          });
+          acc = fmaf(c[LIN_CU] * aux_or_one(aux, kp.aux_sel[LIN_SEL_CU]), U[0][0], acc);
+          if (kp.aux_sel[LIN_SEL_SRC] >= 0) acc += aux[kp.aux_sel[LIN_SEL_SRC]];
+          r[0] = acc;
+        }
+      } break;
+      case PINN_KIND_BURGERS1D: {
+        if constexpr (M == 1 && D == 2) {
+          if constexpr (SIG::order(0) >= 2 && SIG::order(1) >= 1) {
+            const float u = U[0][0], ux = U[0][SIG::chan(0, 1)], uxx = 2.0f * U[0][SIG::chan(0, 2)], ut = U[0][SIG::chan(1, 1)];
+            r[0] = ut + u * ux - c[0] * uxx;
+          }
+        }
+      } break;
+      case PINN_KIND_BURGERS2D: {
+        if constexpr (M == 2 && D == 3) {
+          if constexpr (sig22() && SIG::order(2) >= 1) {
+            constexpr int X1 = SIG::chan(0, 1), X2 = SIG::chan(0, 2), Y1 = SIG::chan(1, 1), Y2 = SIG::chan(1, 2), T1 = SIG::chan(2, 1);
+            const float u1 = U[0][0], u2 = U[1][0];
+            r[0] = U[0][T1] + u1 * U[0][X1] + u2 * U[0][Y1] - c[0] * (2.0f * U[0][X2] + 2.0f * U[0][Y2]);
+            r[1] = U[1][T1] + u1 * U[1][X1] + u2 * U[1][Y1] - c[0] * (2.0f * U[1][X2] + 2.0f * U[1][Y2]);
+          }
+        }
+      } break;
+      case PINN_KIND_NS2D:
+      case PINN_KIND_NS2D_UNSTEADY: {
+        if constexpr (M == 3 && (D == 2 || D == 3)) {
+          if constexpr (sig22()) {
+            constexpr int X1 = SIG::chan(0, 1), X2 = SIG::chan(0, 2), Y1 = SIG::chan(1, 1), Y2 = SIG::chan(1, 2);
+            const float u = U[0][0], v = U[1][0];
+            float mx = u * U[0][X1] + v * U[0][Y1] + U[2][X1] - c[0] * (2.0f * U[0][X2] + 2.0f * U[0][Y2]);
+            float my = u * U[1][X1] + v * U[1][Y1] + U[2][Y1] - c[0] * (2.0f * U[1][X2] + 2.0f * U[1][Y2]);
+            if constexpr (D == 3) {
+              if constexpr (SIG::order(2) >= 1) {
+                if (kp.kind == PINN_KIND_NS2D_UNSTEADY) {
+                  constexpr int T1 = SIG::chan(2, 1);
+                  mx += U[0][T1];
+                  my += U[1][T1] + aux[kp.aux_sel[0]];
+                }
+              }
+            }
+            r[0] = mx;
+            r[1] = my;
+            r[2] = U[0][X1] + U[1][Y1];
+          }
+        }
+      } break;
+      case PINN_KIND_HEAT_NLSRC: {
+        if constexpr (M == 1 && D == 3) {
+          if constexpr (sig22() && SIG::order(2) >= 1) {
+            const float u = U[0][0];
+            const float lap = 2.0f * U[0][SIG::chan(0, 2)] + 2.0f * U[0][SIG::chan(1, 2)];
+            r[0] = U[0][SIG::chan(2, 1)] - c[0] * lap - c[1] * sinf(c[2] * u * u) * aux[kp.aux_sel[0]];
+          }
+        }
+      } break;
+      case PINN_KIND_GRAYSCOTT: {
+        if constexpr (M == 2 && D == 3) {
+          if constexpr (sig22() && SIG::order(2) >= 1) {
+            constexpr int X2 = SIG::chan(0, 2), Y2 = SIG::chan(1, 2), T1 = SIG::chan(2, 1);
+            const float u = U[0][0], v = U[1][0];
+            const float lapu = 2.0f * U[0][X2] + 2.0f * U[0][Y2], lapv = 2.0f * U[1][X2] + 2.0f * U[1][Y2];
+            r[0] = U[0][T1] - (c[0] * lapu + c[2] * (1.0f - u) - u * v * v);
+            r[1] = U[1][T1] - (c[1] * lapv - c[3] * v + u * v * v);
+          }
+        }
+      } break;
+      case PINN_KIND_KS: {
+        if constexpr (M == 1 && D == 2) {
+          if constexpr (SIG::order(0) >= 4 && SIG::order(1) >= 1) {
+            const float u = U[0][0], ux = U[0][SIG::chan(0, 1)];
+            r[0] = U[0][SIG::chan(1, 1)] + c[0] * u * ux + c[1] * 2.0f * U[0][SIG::chan(0, 2)] + c[2] * 24.0f * U[0][SIG::chan(0, 4)];
+          }
+        }
+      } break;
+      default: break;
+    }
+  }
+
+  // Ubar = sum_k rbar[k] * d r_k / dU
+  PINN_HD static void adjoint(const KindParams& kp, const float* aux, const float (&U)[M][C], const float (&rb)[PINN_MAX_PDE],
+                              float (&Ub)[M][C]) {
+#pragma unroll
+    for (int o = 0; o < M; ++o)
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) Ub[o][ch] = 0.f;
+    const float* c = kp.c;
+    switch (kp.kind) {
+      case PINN_KIND_LINEAR: {
+        if constexpr (M == 1) {
+          const float g = rb[0];
+          static_for<D>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            if constexpr (SIG::order(j) >= 2) {
+              const float c2 = c[LIN_C2 + j];
+              if (c2 != 0.f) Ub[0][SIG::chan(j, 2)] = 2.0f * c2 * aux_or_one(aux, kp.aux_sel[LIN_SEL_C2 + j]) * g;
+            }
+            if constexpr (SIG::order(j) >= 1) Ub[0][SIG::chan(j, 1)] = c[LIN_C1 + j] * g;
+          });
+          Ub[0][0] = c[LIN_CU] * aux_or_one(aux, kp.aux_sel[LIN_SEL_CU]) * g;
+        }
+      } break;
+      case PINN_KIND_BURGERS1D: {
+        if constexpr (M == 1 && D == 2) {
+          if constexpr (SIG::order(0) >= 2 && SIG::order(1) >= 1) {
+            const float g = rb[0];
+            Ub[0][0] = g * U[0][SIG::chan(0, 1)];
+            Ub[0][SIG::chan(0, 1)] = g * U[0][0];
+            Ub[0][SIG::chan(0, 2)] = -2.0f * c[0] * g;
+            Ub[0][SIG::chan(1, 1)] = g;
+          }
+        }
+      } break;
+      case PINN_KIND_BURGERS2D: {
+        if constexpr (M == 2 && D == 3) {
+          if constexpr (sig22() && SIG::order(2) >= 1) {
+            constexpr int X1 = SIG::chan(0, 1), X2 = SIG::chan(0, 2), Y1 = SIG::chan(1, 1), Y2 = SIG::chan(1, 2), T1 = SIG::chan(2, 1);
+            const float u1 = U[0][0], u2 = U[1][0];
+            Ub[0][0] = rb[0] * U[0][X1] + rb[1] * U[1][X1];
+            Ub[1][0] = rb[0] * U[0][Y1] + rb[1] * U[1][Y1];
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+              Ub[o][X1] = rb[o] * u1;
+              Ub[o][Y1] = rb[o] * u2;
+              Ub[o][X2] = -2.0f * c[0] * rb[o];
+              Ub[o][Y2] = -2.0f * c[0] * rb[o];
+              Ub[o][T1] = rb[o];
+            }
+          }
+        }
+      } break;
+      case PINN_KIND_NS2D:
+      case PINN_KIND_NS2D_UNSTEADY: {
+        if constexpr (M == 3 && (D == 2 || D == 3)) {
+          if constexpr (sig22()) {
+            constexpr int X1 = SIG::chan(0, 1), X2 = SIG::chan(0, 2), Y1 = SIG::chan(1, 1), Y2 = SIG::chan(1, 2);
+            const float u = U[0][0], v = U[1][0];
+            const float gx = rb[0], gy = rb[1], gc = rb[2];
+            Ub[0][0] = gx * U[0][X1] + gy * U[1][X1];
+            Ub[1][0] = gx * U[0][Y1] + gy * U[1][Y1];
+            Ub[0][X1] = gx * u + gc;
+            Ub[0][Y1] = gx * v;
+            Ub[1][X1] = gy * u;
+            Ub[1][Y1] = gy * v + gc;
+            Ub[2][X1] = gx;
+            Ub[2][Y1] = gy;
+            Ub[0][X2] = Ub[0][Y2] = -2.0f * c[0] * gx;
+            Ub[1][X2] = Ub[1][Y2] = -2.0f * c[0] * gy;
+            if constexpr (D == 3) {
+              if constexpr (SIG::order(2) >= 1) {
+                if (kp.kind == PINN_KIND_NS2D_UNSTEADY) {
+                  constexpr int T1 = SIG::chan(2, 1);
+                  Ub[0][T1] = gx;
+                  Ub[1][T1] = gy;
+                }
+              }
+            }
+          }
+        }
+      } break;
+      case PINN_KIND_HEAT_NLSRC: {
+        if constexpr (M == 1 && D == 3) {
+          if constexpr (sig22() && SIG::order(2) >= 1) {
+            const float u = U[0][0], g = rb[0];
+            Ub[0][0] = -c[1] * cosf(c[2] * u * u) * 2.0f * c[2] * u * aux[kp.aux_sel[0]] * g;
+            Ub[0][SIG::chan(0, 2)] = -2.0f * c[0] * g;
+            Ub[0][SIG::chan(1, 2)] = -2.0f * c[0] * g;
+            Ub[0][SIG::chan(2, 1)] = g;
+          }
+        }
+      } break;
+      case PINN_KIND_GRAYSCOTT: {
+        if constexpr (M == 2 && D == 3) {
+          if constexpr (sig22() && SIG::order(2) >= 1) {
+            constexpr int X2 = SIG::chan(0, 2), Y2 = SIG::chan(1, 2), T1 = SIG::chan(2, 1);
+            const float u = U[0][0], v = U[1][0];
+            Ub[0][0] = rb[0] * (c[2] + v * v) - rb[1] * v * v;
+            Ub[1][0] = rb[0] * 2.0f * u * v + rb[1] * (c[3] - 2.0f * u * v);
+            Ub[0][T1] = rb[0];
+            Ub[1][T1] = rb[1];
+            Ub[0][X2] = Ub[0][Y2] = -2.0f * c[0] * rb[0];
+            Ub[1][X2] = Ub[1][Y2] = -2.0f * c[1] * rb[1];
+          }
+        }
+      } break;
+      case PINN_KIND_KS: {
+        if constexpr (M == 1 && D == 2) {
+          if constexpr (SIG::order(0) >= 4 && SIG::order(1) >= 1) {
+            const float g = rb[0];
+            Ub[0][0] = c[0] * U[0][SIG::chan(0, 1)] * g;
+            Ub[0][SIG::chan(0, 1)] = c[0] * U[0][0] * g;
+            Ub[0][SIG::chan(0, 2)] = 2.0f * c[1] * g;
+            Ub[0][SIG::chan(0, 4)] = 24.0f * c[2] * g;
+            Ub[0][SIG::chan(1, 1)] = g;
+          }
+        }
+      } break;
+      default: break;
+    }
+  }
+};
+
+}  // namespace pinn

@@ -1,0 +1,266 @@
+// pinn_api.cu -- C ABI (include/pinn_b200.h): descriptor validation, workspace carve-up, launches.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "pinn_configs.h"
+#include "pinn_dispatch.h"
+#include "pinn_helpers.cuh"
+
+namespace pinn {
+
+#define PINN_DECL(ID, ...) template <> const ConfigInfo* get_config<ID>();
+PINN_FOR_EACH_CONFIG(PINN_DECL)
+#undef PINN_DECL
+
+static const ConfigInfo* const* all_configs() {
+  static const ConfigInfo* table[PINN_NUM_CONFIGS] = {
+#define PINN_ENTRY(ID, ...) get_config<ID>(),
+      PINN_FOR_EACH_CONFIG(PINN_ENTRY)
+#undef PINN_ENTRY
+  };
+  return table;
+}
+
+static thread_local std::string g_err;
+static thread_local int g_launches = 0;
+
+static int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+
+static const ConfigInfo* find_config(const pinn_kind_desc* d, std::string* why) {
+  if (d == nullptr) { *why = "null descriptor"; return nullptr; }
+  if (d->d < 1 || d->d > PINN_MAX_DIM) { *why = "input dimension out of range"; return nullptr; }
+  if (d->L < 2 || d->L > kMaxLayers) { *why = "L (hidden tanh layers) must be in 2.." + std::to_string(kMaxLayers); return nullptr; }
+  if (d->n_pde < 1 || d->n_pde > PINN_MAX_PDE) { *why = "n_pde out of range"; return nullptr; }
+  if (d->n_aux < 0 || d->n_aux > PINN_MAX_AUX) { *why = "n_aux out of range"; return nullptr; }
+  for (int i = 0; i < PINN_MAX_AUXSEL; ++i)
+    if (d->aux_sel[i] >= d->n_aux) { *why = "aux selector beyond n_aux"; return nullptr; }
+  const ConfigInfo* const* tab = all_configs();
+  for (int i = 0; i < PINN_NUM_CONFIGS; ++i) {
+    const ConfigInfo* c = tab[i];
+    if (c == nullptr || c->H != d->H || c->m != d->m || c->d != d->d) continue;
+    bool same = true;
+    for (int j = 0; j < d->d; ++j) same = same && (c->order[j] == d->order[j]);
+    if (!same) continue;
+    if (!c->valid_kind(d->kind)) continue;
+    return c;
+  }
+  char buf[256];
+  snprintf(buf, sizeof buf, "no kernel instantiated for kind=%d d=%d m=%d H=%d order=(%d,%d,%d,%d,%d,%d)", d->kind, d->d, d->m, d->H,
+           d->order[0], d->order[1], d->order[2], d->order[3], d->order[4], d->order[5]);
+  *why = buf;
+  return nullptr;
+}
+
+static long long param_count(const pinn_kind_desc* d) {
+  return (long long)d->d * d->H + d->H + (long long)(d->L - 1) * ((long long)d->H * d->H + d->H) + (long long)d->H * d->m + d->m;
+}
+
+struct DeviceInfo {
+  int sms = 0;
+  bool ok = false;
+  std::string err;
+};
+
+static const DeviceInfo& device_info() {
+  static thread_local DeviceInfo di;
+  static thread_local int cached_dev = -1;
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    di.ok = false;
+    di.err = std::string("cudaGetDevice: ") + cudaGetErrorString(e);
+    return di;
+  }
+  if (dev != cached_dev || !di.ok) {
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) {
+      di.ok = false;
+      di.err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+      return di;
+    }
+    if (prop.major != 10) {
+      di.ok = false;
+      di.err = "libpinn_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+      return di;
+    }
+    di.sms = prop.multiProcessorCount;
+    di.ok = true;
+    cached_dev = dev;
+  }
+  return di;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+  size_t off_wpack, off_stash, off_gpart, off_lpart, total;
+};
+
+static Workspace carve(const pinn_kind_desc* d, const ConfigInfo* c, int grid, int n_seeds) {
+  Workspace w;
+  size_t o = 0;
+  w.off_wpack = o;
+  o = align_up(o + (size_t)2 * (d->L - 1) * d->H * d->H * sizeof(float), 256);
+  w.off_stash = o;
+  o = align_up(o + (size_t)grid * d->L * c->E4 * c->NT * 16, 256);
+  w.off_gpart = o;
+  o = align_up(o + (size_t)grid * (n_seeds > 0 ? n_seeds : 0) * param_count(d) * sizeof(float), 256);
+  w.off_lpart = o;
+  o = align_up(o + (size_t)grid * PINN_MAX_PDE * sizeof(double), 256);
+  w.total = o;
+  return w;
+}
+
+static int run(const pinn_kind_desc* desc, const float* params, const float* x, const float* aux, int64_t n_rows, double inv_n,
+               const float* seeds, int n_seeds, float* grad_out, float* loss_out, float* resid_out, void* workspace,
+               size_t workspace_bytes, void* stream_v) {
+  g_launches = 0;
+  std::string why;
+  const ConfigInfo* c = find_config(desc, &why);
+  if (c == nullptr) return fail(why);
+  const bool bwd = n_seeds > 0;
+  if (bwd && n_seeds > PINN_MAX_SEEDS) return fail("n_seeds exceeds PINN_MAX_SEEDS");
+  if (params == nullptr || loss_out == nullptr || workspace == nullptr) return fail("null pointer argument");
+  if (n_rows < 0) return fail("negative n_rows");
+  if (n_rows > 0 && x == nullptr) return fail("x is null");
+  if (desc->n_aux > 0 && n_rows > 0 && aux == nullptr) return fail("descriptor needs aux columns but aux is null");
+  if (bwd && (seeds == nullptr || grad_out == nullptr)) return fail("null seeds/out");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail("workspace must be 256-byte aligned");
+  const DeviceInfo& di = device_info();
+  if (!di.ok) return fail(di.err);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  const int max_grid = di.sms;
+  const Workspace ws = carve(desc, c, max_grid, n_seeds);
+  if (workspace_bytes < ws.total) return fail("workspace too small: need " + std::to_string(ws.total) + " bytes");
+
+  static thread_local bool prepared[PINN_NUM_CONFIGS] = {};
+  if (!prepared[c->id]) {
+    cudaError_t e = c->prepare();
+    if (e != cudaSuccess) return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    prepared[c->id] = true;
+  }
+
+  const long long P = param_count(desc);
+  const long long ntiles = (n_rows + c->T - 1) / c->T;
+  int grid = (int)(ntiles < max_grid ? ntiles : max_grid);
+  char* wsb = static_cast<char*>(workspace);
+  float* wpack = reinterpret_cast<float*>(wsb + ws.off_wpack);
+  float* gpart = reinterpret_cast<float*>(wsb + ws.off_gpart);
+  double* lpart = reinterpret_cast<double*>(wsb + ws.off_lpart);
+
+  if (grid > 0) {
+    const int total = (desc->L - 1) * desc->H * desc->H;
+    pinn_pack_weights<<<(total + 255) / 256, 256, 0, st>>>(params, wpack, desc->H, desc->d, desc->L);
+    ++g_launches;
+
+    LaunchParams lp{};
+    lp.kp.kind = desc->kind;
+    for (int i = 0; i < PINN_MAX_AUXSEL; ++i) lp.kp.aux_sel[i] = desc->aux_sel[i];
+    for (int i = 0; i < PINN_MAX_CONSTS; ++i) lp.kp.c[i] = desc->consts[i];
+    lp.L = desc->L;
+    lp.n_aux = desc->n_aux;
+    lp.n_pde = desc->n_pde;
+    lp.n_seeds = n_seeds;
+    lp.n_rows = n_rows;
+    lp.P = P;
+    lp.inv_n = (float)inv_n;
+    lp.params = params;
+    lp.wpack = wpack;
+    lp.x = x;
+    lp.aux = aux;
+    lp.seeds = seeds;
+    lp.stash = reinterpret_cast<float*>(wsb + ws.off_stash);
+    lp.gpart = gpart;
+    lp.lpart = lpart;
+    lp.resid_out = resid_out;
+    cudaError_t e = c->launch(lp, bwd, grid, st);
+    if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
+    ++g_launches;
+  }
+  const long long SP = (long long)n_seeds * P;
+  const long long work = SP > 0 ? SP : 1;
+  pinn_reduce_partials<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(gpart, lpart, grid, SP, desc->n_pde, inv_n, grad_out, loss_out);
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(std::string("reduce launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace pinn
+
+using namespace pinn;
+
+extern "C" {
+
+int64_t pinn_param_count(const pinn_kind_desc* desc) { return desc ? param_count(desc) : -1; }
+
+int pinn_supported(const pinn_kind_desc* desc) {
+  std::string why;
+  if (find_config(desc, &why) == nullptr) return fail(why);
+  return 0;
+}
+
+size_t pinn_workspace_bytes(const pinn_kind_desc* desc, int n_seeds) {
+  std::string why;
+  const ConfigInfo* c = find_config(desc, &why);
+  if (c == nullptr) { fail(why); return 0; }
+  if (n_seeds < 0 || n_seeds > PINN_MAX_SEEDS) { fail("n_seeds out of range"); return 0; }
+  const DeviceInfo& di = device_info();
+  if (!di.ok) { fail(di.err); return 0; }
+  return carve(desc, c, di.sms, n_seeds).total;
+}
+
+int pinn_fwd(const pinn_kind_desc* desc, const float* params, const float* x, const float* aux, int64_t n_rows, double inv_n_global,
+             float* loss_out, float* resid_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return run(desc, params, x, aux, n_rows, inv_n_global, nullptr, 0, nullptr, loss_out, resid_out, workspace, workspace_bytes, stream);
+}
+
+int pinn_fwd_bwd(const pinn_kind_desc* desc, const float* params, const float* x, const float* aux, int64_t n_rows, double inv_n_global,
+                 const float* seeds, int n_seeds, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n_seeds < 1) return fail("n_seeds must be >= 1");
+  if (desc == nullptr || out == nullptr) return fail("null pointer argument");
+  const long long P = param_count(desc);
+  return run(desc, params, x, aux, n_rows, inv_n_global, seeds, n_seeds, out, out + (size_t)n_seeds * P, nullptr, workspace,
+             workspace_bytes, stream);
+}
+
+int pinn_last_launch_count(void) { return g_launches; }
+
+double pinn_ffma_peak_tflops(int iters) {
+  const DeviceInfo& di = device_info();
+  if (!di.ok) { fail(di.err); return -1.0; }
+  float* out = nullptr;
+  if (cudaMalloc(&out, 4) != cudaSuccess) { fail("cudaMalloc"); return -1.0; }
+  const int blocks = di.sms * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  pinn_ffma_probe<<<blocks, threads>>>(out, 16);
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0);
+  pinn_ffma_probe<<<blocks, threads>>>(out, iters);
+  cudaEventRecord(e1);
+  cudaError_t e = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (e != cudaSuccess || ms <= 0.f) { fail(std::string("ffma probe: ") + cudaGetErrorString(e)); return -1.0; }
+  const double flops = 2.0 * 8 * 16 * (double)iters * threads * blocks;
+  return flops / (ms * 1e-3) / 1e12;
+}
+
+const char* pinn_last_error(void) { return g_err.c_str(); }
+
+const char* pinn_build_info(void) { return "libpinn_b200 sm_100a fp32-ffma jets; configs=" "11" "; built " __DATE__ " " __TIME__; }
+
+}  // extern "C"

@@ -1,0 +1,30 @@
+// pinn_configs.h -- the (jet signature, output dim, tile shape) combinations this build instantiates.
+//   X(ID, H, M, T, TN, orders...)
+// ID  problem classes
+//  0  Poisson1D                                    (2)
+//  1  Burgers1D                                    (2,1)
+//  2  Poisson2D_Classic, PoissonBoltzmann2D, Poisson2D_ManyArea, Wave1D, Helmholtz2D   (2,2)
+//  3  NS2D_LidDriven / BackStep / Classic          (2,2)  m=3
+//  4  Heat2D_{Multiscale,VaryingCoef,ComplexGeometry,LongTime}   (2,2,1)
+//  5  Burgers2D, GrayScott                         (2,2,1) m=2
+//  6  NS2D_LongTime                                (2,2,1) m=3
+//  7  Poisson3D_ComplexGeometry, Wave2D_*          (2,2,2)
+//  8  KuramotoSivashinsky                          (4,1)
+//  9  PoissonND                                    (2,2,2,2,2)
+// 10  HeatND                                       (2,2,2,2,2,1)
+#pragma once
+
+#define PINN_FOR_EACH_CONFIG(X)        \
+  X(0, 100, 1, 32, 4, 2)               \
+  X(1, 100, 1, 32, 4, 2, 1)            \
+  X(2, 100, 1, 32, 4, 2, 2)            \
+  X(3, 100, 3, 32, 4, 2, 2)            \
+  X(4, 100, 1, 32, 4, 2, 2, 1)         \
+  X(5, 100, 2, 32, 4, 2, 2, 1)         \
+  X(6, 100, 3, 32, 4, 2, 2, 1)         \
+  X(7, 100, 1, 16, 2, 2, 2, 2)         \
+  X(8, 100, 1, 32, 4, 4, 1)            \
+  X(9, 100, 1, 16, 2, 2, 2, 2, 2, 2)   \
+  X(10, 100, 1, 16, 2, 2, 2, 2, 2, 2, 1)
+
+#define PINN_NUM_CONFIGS 11

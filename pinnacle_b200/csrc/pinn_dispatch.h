@@ -1,0 +1,24 @@
+// pinn_dispatch.h -- type-erased handle to one instantiated kernel configuration.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pinn_kernels.cuh"
+
+namespace pinn {
+
+struct ConfigInfo {
+  int id, H, m, d, C;
+  int order[PINN_MAX_DIM];
+  int T, NT, NTP, E4;
+  size_t smem_fwd, smem_bwd;
+  bool (*valid_kind)(int);
+  cudaError_t (*prepare)();
+  cudaError_t (*launch)(const LaunchParams&, bool bwd, int grid, cudaStream_t);
+};
+
+template <int ID>
+const ConfigInfo* get_config();
+
+#define PINN_DECLARE_CONFIG(ID, ...) template <> const ConfigInfo* get_config<ID>();
+
+}  // namespace pinn

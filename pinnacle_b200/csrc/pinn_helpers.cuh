@@ -1,0 +1,60 @@
+// pinn_helpers.cuh -- small non-template kernels (weight packing, partial reduction, FFMA probe).
+// Included by pinn_api.cu only.
+#pragma once
+#include "pinn_kernels.cuh"
+
+namespace pinn {
+
+// ------------------------------------------------------------------------------------------
+// small helper kernels
+// ------------------------------------------------------------------------------------------
+// wpack <- [W_l^T (l=2..L) | W_l (l=2..L)] from the flat parameter vector
+__global__ void pinn_pack_weights(const float* __restrict__ params, float* __restrict__ wpack, int H, int D, int L) {
+  const long long offHid = (long long)H * D + H;
+  const long long strideHid = (long long)H * H + H;
+  const int HH = H * H;
+  const int total = (L - 1) * HH;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int l = i / HH, e = i % HH;
+    const int a = e / H, b = e % H;
+    const float* W = params + offHid + (long long)l * strideHid;
+    wpack[i] = W[b * H + a];                              // transposed: [k][n] = W[n][k]
+    wpack[(size_t)total + i] = W[e];                      // native
+  }
+}
+
+// out[s*P + i] = sum_cta gpart[cta][s][i];  out[S*P + k] = inv_n * sum_cta lpart[cta][k]
+__global__ void pinn_reduce_partials(const float* __restrict__ gpart, const double* __restrict__ lpart, int grid, long long SP,
+                                     int n_pde, double inv_n, float* __restrict__ grad_out, float* __restrict__ loss_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < SP) {
+    double s = 0.0;
+    for (int c = 0; c < grid; ++c) s += (double)gpart[(size_t)c * SP + i];
+    grad_out[i] = (float)s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n_pde) {
+    double s = 0.0;
+    for (int c = 0; c < grid; ++c) s += lpart[(size_t)c * PINN_MAX_PDE + threadIdx.x];
+    loss_out[threadIdx.x] = (float)(s * inv_n);
+  }
+}
+
+// FP32 FFMA throughput probe (roofline denominator)
+__global__ void pinn_ffma_probe(float* out, int iters) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = 0.001f * (float)(threadIdx.x + i);
+  const float b = 1.0000001f, c = 1e-7f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], b, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 12345.678f) out[0] = s;
+}
+
+}  // namespace pinn

@@ -1,0 +1,48 @@
+// pinn_inst.inl -- instantiates the forward and forward+reverse kernels of ONE configuration.
+// Included by the generated inst_<ID>.cu files (see build.py), which specialise get_config<ID>().
+#include "pinn_configs.h"
+#include "pinn_dispatch.h"
+
+namespace pinn {
+namespace {
+
+template <int ID, int H, int M, int T, int TN, int... KS>
+struct Inst {
+  using SIG = JetSig<KS...>;
+  using CF = KCfg<SIG, M, H, T, TN, false>;
+  using CB = KCfg<SIG, M, H, T, TN, true>;
+
+  static bool valid_kind(int kind) { return Residual<SIG, M>::valid(kind); }
+
+  static cudaError_t prepare() {
+    cudaError_t e = cudaFuncSetAttribute(pinn_fused_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(pinn_fused_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB::smem_bytes);
+  }
+
+  static cudaError_t launch(const LaunchParams& p, bool bwd, int grid, cudaStream_t st) {
+    if (bwd)
+      pinn_fused_kernel<CB><<<grid, CB::NTP, CB::smem_bytes, st>>>(p);
+    else
+      pinn_fused_kernel<CF><<<grid, CF::NTP, CF::smem_bytes, st>>>(p);
+    return cudaGetLastError();
+  }
+
+  static const ConfigInfo* info() {
+    static const ConfigInfo ci = [] {
+      ConfigInfo c{};
+      c.id = ID; c.H = H; c.m = M; c.d = SIG::D; c.C = SIG::C;
+      const int o[] = {KS...};
+      for (int j = 0; j < PINN_MAX_DIM; ++j) c.order[j] = j < SIG::D ? o[j] : 0;
+      c.T = T; c.NT = CB::NT; c.NTP = CB::NTP; c.E4 = CB::E4;
+      c.smem_fwd = CF::smem_bytes; c.smem_bwd = CB::smem_bytes;
+      c.valid_kind = &valid_kind; c.prepare = &prepare; c.launch = &launch;
+      return c;
+    }();
+    return &ci;
+  }
+};
+
+}  // namespace
+
+}  // namespace pinn

@@ -1,0 +1,151 @@
+// TEST INFRASTRUCTURE -- host build of the device math (pinnacle_b200/csrc/jet_math.cuh).
+//
+// Runs the same tanh-jet recurrences, hand-derived adjoints and residual functors the CUDA kernels
+// use, but with plain per-point loops for the layer contractions, so the MATH can be checked against
+// the autograd oracle in the build container (no GPU).  Never linked into the product.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../pinnacle_b200/csrc/jet_math.cuh"
+#include "../../pinnacle_b200/csrc/pinn_configs.h"
+
+using namespace pinn;
+
+template <class SIG, int M>
+static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x, const float* aux, long long n, double inv_n,
+                    const float* seeds, int S, double* grad, double* loss, float* resid) {
+  constexpr int C = SIG::C, D = SIG::D;
+  const int H = d->H, L = d->L;
+  const long long P = (long long)D * H + H + (long long)(L - 1) * ((long long)H * H + H) + (long long)H * M + M;
+  std::vector<long long> offW(L + 2), offB(L + 2);
+  offW[1] = 0; offB[1] = (long long)H * D;
+  for (int l = 2; l <= L; ++l) { offW[l] = (long long)H * D + H + (long long)(l - 2) * ((long long)H * H + H); offB[l] = offW[l] + (long long)H * H; }
+  offW[L + 1] = (long long)H * D + H + (long long)(L - 1) * ((long long)H * H + H); offB[L + 1] = offW[L + 1] + (long long)M * H;
+  KindParams kp;
+  kp.kind = d->kind;
+  for (int i = 0; i < PINN_MAX_AUXSEL; ++i) kp.aux_sel[i] = d->aux_sel[i];
+  for (int i = 0; i < PINN_MAX_CONSTS; ++i) kp.c[i] = d->consts[i];
+  for (int k = 0; k < PINN_MAX_PDE; ++k) loss[k] = 0.0;
+  for (long long i = 0; i < (long long)S * P; ++i) grad[i] = 0.0;
+
+  std::vector<float> z((size_t)(L + 1) * H * C), a((size_t)(L + 1) * H * C), ab((size_t)H * C), zb((size_t)H * C), abp((size_t)H * C);
+  for (long long pt = 0; pt < n; ++pt) {
+    const float* xp = x + pt * D;
+    float auxv[PINN_MAX_AUX] = {0, 0, 0, 0};
+    for (int q = 0; q < d->n_aux; ++q) auxv[q] = aux[pt * d->n_aux + q];
+    // ---- forward
+    for (int nn = 0; nn < H; ++nn) {
+      float zz[C];
+      for (int c = 0; c < C; ++c) zz[c] = 0.f;
+      float z0 = params[offB[1] + nn];
+      for (int j = 0; j < D; ++j) z0 = fmaf(params[offW[1] + nn * D + j], xp[j], z0);
+      zz[0] = z0;
+      static_for<D>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        if constexpr (SIG::order(j) >= 1) zz[SIG::base(j)] = params[offW[1] + nn * D + j];
+      });
+      float aa[C];
+      tanh_jet_fwd<SIG>(zz, aa);
+      for (int c = 0; c < C; ++c) { z[((size_t)1 * H + nn) * C + c] = zz[c]; a[((size_t)1 * H + nn) * C + c] = aa[c]; }
+    }
+    for (int l = 2; l <= L; ++l) {
+      for (int nn = 0; nn < H; ++nn) {
+        float zz[C];
+        for (int c = 0; c < C; ++c) zz[c] = 0.f;
+        for (int k = 0; k < H; ++k) {
+          const float w = params[offW[l] + (long long)nn * H + k];
+          for (int c = 0; c < C; ++c) zz[c] = fmaf(a[((size_t)(l - 1) * H + k) * C + c], w, zz[c]);
+        }
+        zz[0] += params[offB[l] + nn];
+        float aa[C];
+        tanh_jet_fwd<SIG>(zz, aa);
+        for (int c = 0; c < C; ++c) { z[((size_t)l * H + nn) * C + c] = zz[c]; a[((size_t)l * H + nn) * C + c] = aa[c]; }
+      }
+    }
+    float U[M][C];
+    for (int o = 0; o < M; ++o)
+      for (int c = 0; c < C; ++c) {
+        float s = (c == 0) ? params[offB[L + 1] + o] : 0.f;
+        for (int k = 0; k < H; ++k) s = fmaf(params[offW[L + 1] + (long long)o * H + k], a[((size_t)L * H + k) * C + c], s);
+        U[o][c] = s;
+      }
+    float r[PINN_MAX_PDE];
+    Residual<SIG, M>::eval(kp, auxv, U, r);
+    for (int k = 0; k < d->n_pde; ++k) {
+      loss[k] += (double)r[k] * (double)r[k];
+      if (resid) resid[pt * d->n_pde + k] = r[k];
+    }
+    // ---- reverse, per seed
+    for (int s = 0; s < S; ++s) {
+      double* g = grad + (size_t)s * P;
+      float rb[PINN_MAX_PDE] = {0, 0, 0};
+      for (int k = 0; k < d->n_pde; ++k) rb[k] = seeds[s * d->n_pde + k] * 2.0f * r[k] * (float)inv_n;
+      float Ub[M][C];
+      Residual<SIG, M>::adjoint(kp, auxv, U, rb, Ub);
+      for (int o = 0; o < M; ++o) {
+        g[offB[L + 1] + o] += Ub[o][0];
+        for (int k = 0; k < H; ++k)
+          for (int c = 0; c < C; ++c) g[offW[L + 1] + (long long)o * H + k] += (double)Ub[o][c] * a[((size_t)L * H + k) * C + c];
+      }
+      for (int k = 0; k < H; ++k)
+        for (int c = 0; c < C; ++c) {
+          float v = 0.f;
+          for (int o = 0; o < M; ++o) v = fmaf(Ub[o][c], params[offW[L + 1] + (long long)o * H + k], v);
+          ab[(size_t)k * C + c] = v;
+        }
+      for (int l = L; l >= 1; --l) {
+        for (int nn = 0; nn < H; ++nn) {
+          float zz[C], aa[C], zz_b[C];
+          for (int c = 0; c < C; ++c) { zz[c] = z[((size_t)l * H + nn) * C + c]; aa[c] = ab[(size_t)nn * C + c]; zz_b[c] = 0.f; }
+          tanh_jet_bwd<SIG>(zz, aa, zz_b);
+          for (int c = 0; c < C; ++c) zb[(size_t)nn * C + c] = zz_b[c];
+          g[offB[l] + nn] += zz_b[0];
+        }
+        if (l == 1) {
+          for (int nn = 0; nn < H; ++nn) {
+            static_for<D>([&](auto J) {
+              constexpr int j = decltype(J)::value;
+              double v = (double)zb[(size_t)nn * C + 0] * xp[j];
+              if constexpr (SIG::order(j) >= 1) v += zb[(size_t)nn * C + SIG::base(j)];
+              g[offW[1] + nn * D + j] += v;
+            });
+          }
+        } else {
+          for (int nn = 0; nn < H; ++nn)
+            for (int k = 0; k < H; ++k) {
+              double v = 0.0;
+              for (int c = 0; c < C; ++c) v += (double)zb[(size_t)nn * C + c] * a[((size_t)(l - 1) * H + k) * C + c];
+              g[offW[l] + (long long)nn * H + k] += v;
+            }
+          for (int k = 0; k < H; ++k)
+            for (int c = 0; c < C; ++c) {
+              float v = 0.f;
+              for (int nn = 0; nn < H; ++nn) v = fmaf(zb[(size_t)nn * C + c], params[offW[l] + (long long)nn * H + k], v);
+              abp[(size_t)k * C + c] = v;
+            }
+          ab.swap(abp);
+        }
+      }
+    }
+  }
+  for (int k = 0; k < PINN_MAX_PDE; ++k) loss[k] *= inv_n;
+}
+
+extern "C" int harness_run(const pinn_kind_desc* d, const float* params, const float* x, const float* aux, long long n, double inv_n,
+                           const float* seeds, int S, double* grad, double* loss, float* resid) {
+#define TRY(ID, H_, M_, T_, TN_, ...)                                                                  \
+  {                                                                                                    \
+    using SIG = JetSig<__VA_ARGS__>;                                                                   \
+    const int o[] = {__VA_ARGS__};                                                                     \
+    bool same = (SIG::D == d->d) && (M_ == d->m);                                                      \
+    for (int j = 0; same && j < SIG::D; ++j) same = (o[j] == d->order[j]);                             \
+    if (same && Residual<SIG, M_>::valid(d->kind)) {                                                   \
+      run_cfg<SIG, M_>(d, params, x, aux, n, inv_n, seeds, S, grad, loss, resid);                      \
+      return 0;                                                                                        \
+    }                                                                                                  \
+  }
+  PINN_FOR_EACH_CONFIG(TRY)
+#undef TRY
+  return 1;
+}
