@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- train-step collocation points / second of the fused PDE-residual + gradient path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--points P] [--impl fused|reference]
+
+One "step" = one pass of the hot path (per-term losses + full flat parameter gradient, + the
+all-reduce when N > 1) over the synthetic collocation sets of BASELINE.json configs[1]:
+Poisson2D_Classic AND Heat2D_Multiscale, `--points` (default 1 Mi) uniform points each, 5x100 tanh
+MLP at seeded Glorot-normal weights with N(0, 0.1^2) biases.  N > 1: one process per GPU under
+torchrun, every rank holds the same per-GPU point count (weak scaling), one NCCL all-reduce of the
+flat [grads | losses] buffer per problem per step.
+
+`value`   device-resident inputs, CUDA-event time of the K steps, max over ranks.
+`e2e`     the same metric through the public API (FusedPDESolver.train_step: H2D of the step's
+          points from pinned host memory, fused op, autograd backward, Adam update, D2H of the losses).
+`--impl reference` times the reference algorithm (nested reverse-mode autograd, oracle/autograd_ref.py --
+the reference is pure Python/PyTorch, so there is nothing to compile into oracle/_ref) on the host cores
+with every thread torch can use, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "train-step collocation pts/sec"
+UNIT = "points/s"
+WORKLOAD_PROBLEMS = ("Poisson2D_Classic", "Heat2D_Multiscale")
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+def _seeded_params(desc, seed=0):
+    """Glorot-normal weights + N(0,0.1^2) biases ("trained-like" variant), flat fp32."""
+    g = torch.Generator().manual_seed(seed)
+    parts = []
+    for (n_out, n_in) in desc.layer_shapes():
+        std = (2.0 / (n_in + n_out)) ** 0.5
+        parts.append((torch.randn(n_out, n_in, generator=g) * std).reshape(-1))
+        parts.append(torch.randn(n_out, generator=g) * 0.1)
+    return torch.cat(parts).float()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [t.strip() for t in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(points_per_problem: int, steps: int, warmup: int):
+    from oracle import autograd_ref as O
+    from pinnacle_b200 import problems
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # Deep-layer jet terms go denormal on some inputs and the x86 denormal slow path costs the CPU path
+    # 10-50x; flushing them is the setting most favourable to the CPU baseline (the reference leaves it off).
+    torch.set_flush_denormal(True)
+    specs = [problems.make(n) for n in WORKLOAD_PROBLEMS]
+    work = []
+    for i, spec in enumerate(specs):
+        flat = _seeded_params(spec.desc, seed=i)
+        x = torch.as_tensor(spec.sample(points_per_problem, seed=100 + i))
+        work.append((spec.desc, flat, x))
+
+    def step():
+        for desc, flat, x in work:
+            O.train_step_cpu(desc, flat, x, None)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    pts = points_per_problem * len(specs)
+    return pts / dt, dt * 1e3, cores, pts
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_points
+    value, ms, cores, pts = cpu_reference_run(n, max(1, args.steps), max(1, args.warmup))
+    sample = f"{n} points of each of {'+'.join(WORKLOAD_PROBLEMS)} per step (reference holds the whole autograd graph in RAM; pts/s is flat in N); denormals flushed"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "+".join(WORKLOAD_PROBLEMS) + f" x{n} pts (bounded CPU sample of the 1Mi-point config), 5x100 tanh MLP",
+                   "device": "host CPU", "threads": cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused arm
+# ------------------------------------------------------------------------------------------------
+def run_fused(args):
+    import torch.distributed as dist
+    from pinnacle_b200 import capi, problems
+    from pinnacle_b200.fused import FusedPDEResidual
+    from pinnacle_b200.nn import FNN
+    from pinnacle_b200.solver import FusedPDESolver
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (fused arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    capi.load()
+
+    n_per = args.points                      # per problem, per GPU (weak scaling)
+    specs = [problems.make(n) for n in WORKLOAD_PROBLEMS]
+    ops, params, seeds, outs = [], [], [], []
+    for i, spec in enumerate(specs):
+        op = FusedPDEResidual(spec, 100, 5, device=dev)
+        x_local = torch.as_tensor(spec.sample(n_per, seed=100 + i + 1000 * rank))
+        op.set_points(x_local, shard=False)
+        op.n_global = n_per * world
+        op.inv_n_global = 1.0 / op.n_global
+        ops.append(op)
+        params.append(_seeded_params(spec.desc, seed=i).to(dev))
+        seeds.append(torch.ones(1, spec.desc.n_pde, device=dev))
+        outs.append(torch.empty(spec.desc.n_params + spec.desc.n_pde, device=dev))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    launches = [0]
+
+    def one_step(ev=None):
+        for i, op in enumerate(ops):
+            if ev is not None:
+                ev[i][0].record()
+            capi.fwd_bwd(op.desc, params[i], op.x, op.aux, op.inv_n_global, seeds[i], out=outs[i])
+            launches[0] += capi.last_launch_count()
+            if ev is not None:
+                ev[i][1].record()
+            if world > 1:
+                dist.all_reduce(outs[i])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        one_step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    K = args.steps
+    step_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kern_ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ops] for _ in range(K)]
+    launches[0] = 0
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(K):
+        flush.zero_()                         # L2 flush between timed iterations (outside the event pair)
+        step_ev[k][0].record()
+        one_step(kern_ev[k])
+        step_ev[k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = sum(a.elapsed_time(b) for a, b in step_ev)
+    kern_ms = [sum(kern_ev[k][i][0].elapsed_time(kern_ev[k][i][1]) for k in range(K)) / K for i in range(len(ops))]
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / K
+    pts_step = n_per * len(ops) * world
+    value = pts_step / (ms_step * 1e-3)
+    gpu_launches = launches[0]
+
+    # ---------------- e2e through the public API: host points -> losses on host ----------------
+    solvers = []
+    for i, spec in enumerate(specs):
+        net = FNN([spec.desc.d] + [100] * 5 + [spec.desc.m]).to(dev)
+        off = 0
+        with torch.no_grad():
+            for p in net.parameters():
+                p.copy_(params[i][off:off + p.numel()].view_as(p))
+                off += p.numel()
+        xh = torch.as_tensor(spec.sample(n_per, seed=100 + i + 1000 * rank)).pin_memory()
+        # cache_points=False: the step's points cross PCIe every step, as in the reference (model.py:263)
+        s = FusedPDESolver(spec, net, xh, cache_points=False, n_global=n_per * world)
+        s.compile(torch.optim.Adam(net.parameters(), 1e-3))
+        solvers.append(s)
+
+    def e2e_step2():
+        tot = 0.0
+        for s in solvers:
+            s.train_step()                                        # H2D (pinned) + fused op + backward + Adam
+            tot += float(s.opt.losses.detach().cpu().sum())       # D2H read of the step's result
+        return tot
+
+    for _ in range(2):
+        e2e_step2()
+    barrier()
+    Ke = max(2, min(K, 5))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(Ke):
+        e2e_step2()
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item()) / Ke
+    h2d = sum(n_per * s.spec.desc.d * 4 for s in solvers)
+    d2h = sum(s.num_loss * 4 for s in solvers)
+    e2e = {"value": pts_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "api": "FusedPDESolver.train_step (Adam update included), points from pinned host memory"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks, peak_src = _peaks()
+    dom = int(np.argmax(kern_ms))
+    desc = specs[dom].desc
+    flops_launch = desc.flops_step_per_point() * n_per
+    ach = flops_launch / (kern_ms[dom] * 1e-3) / 1e12
+    try:
+        ffma_peak = capi.ffma_peak_tflops(8192)
+    except Exception as e:  # noqa: BLE001
+        ffma_peak = None
+    tensor_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    roofline = {
+        "bound": "fp32_ffma", "achieved": ach, "peak": ffma_peak, "unit": "TFLOP/s", "frac": (ach / ffma_peak) if ffma_peak else None,
+        "traffic": None,
+        "kernel": f"pinn_fused_kernel<{specs[dom].name}, fwd+reverse>", "launch_ms": kern_ms[dom],
+        "algorithmic_flops_per_point": desc.flops_step_per_point(), "points_per_launch": n_per,
+        "peak_source": "FP32 FFMA probe kernel run in this process (pinn_ffma_peak_tflops); nominal 148*128*2*f_SM",
+        "tensor_peak_bf16": tensor_peak, "frac_of_tensor_peak_bf16": ach / tensor_peak if tensor_peak else None,
+        "tensor_peak_source": peak_src,
+        "per_kernel": [{"problem": specs[i].name, "launch_ms": kern_ms[i],
+                        "achieved_tflops": specs[i].desc.flops_step_per_point() * n_per / (kern_ms[i] * 1e-3) / 1e12,
+                        "hbm_gbs_algorithmic": specs[i].desc.bytes_per_point() * n_per / (kern_ms[i] * 1e-3) / 1e9} for i in range(len(ops))],
+    }
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, ms, cores, pts = cpu_reference_run(args.cpu_points, 2, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
+               "sample": f"{args.cpu_points} points of each of {'+'.join(WORKLOAD_PROBLEMS)} per step, 1 warm-up + 2 timed steps, torch autograd (reference algorithm) on the host cores, denormals flushed"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"Poisson2D_Classic + Heat2D_Multiscale, {n_per} synthetic collocation points each per GPU, 5x100 tanh MLP, "
+                               "losses + flat parameter gradient (+ NCCL all-reduce when N>1)",
+                   "points_per_step": pts_step, "l2": "flushed between timed iterations (256 MiB write outside the event pair)",
+                   "parallelism": f"dp{world} over collocation points", "wall_s_timed_region": t_wall},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--points", type=int, default=1 << 20, help="collocation points per problem per GPU")
+    ap.add_argument("--cpu-points", type=int, default=16384, help="points per problem of the bounded CPU sample")
+    ap.add_argument("--impl", choices=["fused", "reference"], default="fused")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_fused(args)
+
+
+if __name__ == "__main__":
+    main()

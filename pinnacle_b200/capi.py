@@ -1,0 +1,202 @@
+"""ctypes binding of ``libpinn_b200.so`` (C ABI declared in ``include/pinn_b200.h``).
+
+The library is the product's only compute path.  If it has not been built
+(``python pinnacle_b200/csrc/build.py`` or ``__graft_entry__.build()``) loading raises
+``FusedLibraryMissing`` -- there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+from .kinds import CKindDesc, KindDesc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpinn_b200.so")
+
+EXPORTS = (
+    "pinn_param_count", "pinn_supported", "pinn_workspace_bytes", "pinn_fwd", "pinn_fwd_bwd",
+    "pinn_last_launch_count", "pinn_ffma_peak_tflops", "pinn_last_error", "pinn_build_info",
+)
+
+
+class FusedLibraryMissing(RuntimeError):
+    pass
+
+
+class FusedOpError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FusedLibraryMissing(
+            f"{LIB_PATH} not found: build it with `python pinnacle_b200/csrc/build.py` "
+            "(nvcc, sm_100a). The fused path has no fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    P = ctypes.POINTER(CKindDesc)
+    vp = ctypes.c_void_p
+    lib.pinn_param_count.argtypes = [P]
+    lib.pinn_param_count.restype = ctypes.c_int64
+    lib.pinn_supported.argtypes = [P]
+    lib.pinn_supported.restype = ctypes.c_int
+    lib.pinn_workspace_bytes.argtypes = [P, ctypes.c_int]
+    lib.pinn_workspace_bytes.restype = ctypes.c_size_t
+    lib.pinn_fwd.argtypes = [P, vp, vp, vp, ctypes.c_int64, ctypes.c_double, vp, vp, vp, ctypes.c_size_t, vp]
+    lib.pinn_fwd.restype = ctypes.c_int
+    lib.pinn_fwd_bwd.argtypes = [P, vp, vp, vp, ctypes.c_int64, ctypes.c_double, vp, ctypes.c_int, vp, vp, ctypes.c_size_t, vp]
+    lib.pinn_fwd_bwd.restype = ctypes.c_int
+    lib.pinn_last_launch_count.argtypes = []
+    lib.pinn_last_launch_count.restype = ctypes.c_int
+    lib.pinn_ffma_peak_tflops.argtypes = [ctypes.c_int]
+    lib.pinn_ffma_peak_tflops.restype = ctypes.c_double
+    lib.pinn_last_error.argtypes = []
+    lib.pinn_last_error.restype = ctypes.c_char_p
+    lib.pinn_build_info.argtypes = []
+    lib.pinn_build_info.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().pinn_last_error().decode()
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise FusedOpError(f"{what}: {last_error()}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float32):
+    if not t.is_cuda:
+        raise FusedOpError(f"{name} must be a CUDA tensor (got {t.device}); the fused path has no CPU implementation")
+    if t.dtype != dtype:
+        raise FusedOpError(f"{name} must be {dtype} (got {t.dtype})")
+    if not t.is_contiguous():
+        raise FusedOpError(f"{name} must be contiguous")
+
+
+def supported(desc: KindDesc) -> bool:
+    c = desc.to_c()
+    return load().pinn_supported(ctypes.byref(c)) == 0
+
+
+def check_supported(desc: KindDesc):
+    c = desc.to_c()
+    _check(load().pinn_supported(ctypes.byref(c)), f"descriptor {desc.name or desc.kind} unsupported")
+
+
+def workspace_bytes(desc: KindDesc, n_seeds: int) -> int:
+    c = desc.to_c()
+    n = load().pinn_workspace_bytes(ctypes.byref(c), int(n_seeds))
+    if n == 0:
+        raise FusedOpError(f"pinn_workspace_bytes: {last_error()}")
+    return int(n)
+
+
+class Workspace:
+    """Caller-owned device scratch (torch caching allocator), grown on demand, one per device."""
+
+    def __init__(self):
+        self._buf = {}
+
+    def get(self, device: torch.device, nbytes: int) -> torch.Tensor:
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        b = self._buf.get(key)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+            self._buf[key] = b
+        off = (-b.data_ptr()) % 256
+        return b[off:off + nbytes]
+
+
+_WS = Workspace()
+
+
+def _stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def fwd(desc: KindDesc, params: torch.Tensor, x: torch.Tensor, aux: Optional[torch.Tensor], inv_n_global: float,
+        want_residual: bool = False):
+    """pinn_fwd: returns (loss[n_pde] device tensor, residual[n_rows,n_pde] or None)."""
+    lib = load()
+    _req(params, "params"); _req(x, "x")
+    if aux is not None:
+        _req(aux, "aux")
+    n = x.shape[0]
+    if params.numel() != desc.n_params:
+        raise FusedOpError(f"params has {params.numel()} elements, descriptor needs {desc.n_params}")
+    if x.dim() != 2 or x.shape[1] != desc.d:
+        raise FusedOpError(f"x must be [N,{desc.d}]")
+    if desc.n_aux and (aux is None or tuple(aux.shape) != (n, desc.n_aux)):
+        raise FusedOpError(f"aux must be [N,{desc.n_aux}]")
+    c = desc.to_c()
+    with torch.cuda.device(x.device):
+        ws = _WS.get(x.device, workspace_bytes(desc, 0))
+        loss = torch.empty(desc.n_pde, dtype=torch.float32, device=x.device)
+        resid = torch.empty((n, desc.n_pde), dtype=torch.float32, device=x.device) if want_residual else None
+        rc = lib.pinn_fwd(ctypes.byref(c), _ptr(params), _ptr(x), _ptr(aux), n, float(inv_n_global), _ptr(loss), _ptr(resid),
+                          _ptr(ws), ws.numel(), _stream_ptr(x.device))
+    _check(rc, "pinn_fwd")
+    return loss, resid
+
+
+def fwd_bwd(desc: KindDesc, params: torch.Tensor, x: torch.Tensor, aux: Optional[torch.Tensor], inv_n_global: float,
+            seeds: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """pinn_fwd_bwd: returns the flat device buffer [S*P grads | n_pde losses]."""
+    lib = load()
+    _req(params, "params"); _req(x, "x"); _req(seeds, "seeds")
+    if aux is not None:
+        _req(aux, "aux")
+    n = x.shape[0]
+    if params.numel() != desc.n_params:
+        raise FusedOpError(f"params has {params.numel()} elements, descriptor needs {desc.n_params}")
+    if x.dim() != 2 or x.shape[1] != desc.d:
+        raise FusedOpError(f"x must be [N,{desc.d}]")
+    if desc.n_aux and (aux is None or tuple(aux.shape) != (n, desc.n_aux)):
+        raise FusedOpError(f"aux must be [N,{desc.n_aux}]")
+    if seeds.dim() != 2 or seeds.shape[1] != desc.n_pde:
+        raise FusedOpError(f"seeds must be [S,{desc.n_pde}]")
+    S = seeds.shape[0]
+    c = desc.to_c()
+    with torch.cuda.device(x.device):
+        ws = _WS.get(x.device, workspace_bytes(desc, S))
+        if out is None:
+            out = torch.empty(S * desc.n_params + desc.n_pde, dtype=torch.float32, device=x.device)
+        else:
+            _req(out, "out")
+            if out.numel() != S * desc.n_params + desc.n_pde:
+                raise FusedOpError("out has the wrong size")
+        rc = lib.pinn_fwd_bwd(ctypes.byref(c), _ptr(params), _ptr(x), _ptr(aux), n, float(inv_n_global), _ptr(seeds), S,
+                              _ptr(out), _ptr(ws), ws.numel(), _stream_ptr(x.device))
+    _check(rc, "pinn_fwd_bwd")
+    return out
+
+
+def last_launch_count() -> int:
+    return int(load().pinn_last_launch_count())
+
+
+def ffma_peak_tflops(iters: int = 4096) -> float:
+    v = float(load().pinn_ffma_peak_tflops(int(iters)))
+    if v < 0:
+        raise FusedOpError(f"pinn_ffma_peak_tflops: {last_error()}")
+    return v
+
+
+def build_info() -> str:
+    return load().pinn_build_info().decode()

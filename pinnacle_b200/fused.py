@@ -1,0 +1,221 @@
+"""The fused PDE-loss op as a differentiable PyTorch node.
+
+``FusedPDEResidual`` owns one problem's descriptor and its device-resident collocation points
+(+ per-point aux columns) and exposes ``losses(params)``: a vector of per-term mean-square PDE
+losses whose ``backward`` can be called repeatedly with different ``grad_output`` vectors, exactly
+like the list of 0-d loss tensors ``dde.data.PDE.losses`` builds (``deepxde/data/pde.py:147-152``)
+and the reference optimizers back-propagate through (``deepxde/model.py:306-315``,
+``src/optimizer/lr_adaptor.py:33-62``, ``src/optimizer/multiadam.py:247-261``).
+
+Two gradient policies:
+
+* ``eager``  -- forward runs ``pinn_fwd_bwd`` with the identity as seed matrix and keeps
+  G[n_pde, P]; every later backward is ``g @ G`` (one kernel pass serves all backward calls);
+* ``lazy``   -- forward runs ``pinn_fwd``; each backward runs ``pinn_fwd_bwd`` with the incoming
+  ``grad_output`` as the single seed row (cached per distinct seed within one forward).
+
+``auto`` picks eager for n_pde == 1, lazy otherwise.
+
+Multi-GPU: every rank holds a contiguous shard of the rows and the same parameters; the flat
+``[grads | losses]`` buffer the kernels write is all-reduced once (``torch.distributed``, NCCL over
+NVLink) inside the op, so optimizers that compute non-linear statistics of per-term gradients
+(``lr_adaptor.py:37-56``, ``ntk.py:38-63``) see global values.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import capi
+from .kinds import KindDesc
+from .problems import ProblemSpec
+
+# The compute backend: always the C ABI.  Kept as module attributes so the gloo/CPU tests of the
+# sharding + all-reduce plumbing can substitute a checker explicitly; nothing in the product does.
+_backend_fwd = capi.fwd
+_backend_fwd_bwd = capi.fwd_bwd
+
+
+def shard_bounds(n_rows: int, rank: int, world: int):
+    """Contiguous row block of rank ``rank`` (sizes differ by at most one row)."""
+    base, rem = divmod(n_rows, world)
+    beg = rank * base + min(rank, rem)
+    return beg, beg + base + (1 if rank < rem else 0)
+
+
+def _all_reduce(buf: torch.Tensor, group):
+    import torch.distributed as dist
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+
+
+class _FusedLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, op: "FusedPDEResidual", *params: torch.Tensor):
+        flat = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
+        desc = op.desc
+        need_grad = any(ctx.needs_input_grad[1:])
+        ctx.op = op
+        ctx.shapes = [p.shape for p in params]
+        ctx.mode = "none"
+        if need_grad and op.policy_resolved == "eager":
+            out = _backend_fwd_bwd(desc, flat, op.x, op.aux, op.inv_n_global, op._eye())
+            op.stats["fwd_bwd_calls"] += 1
+            if op.world > 1:
+                _all_reduce(out, op.group)
+                op.stats["allreduce_calls"] += 1
+            S, P = desc.n_pde, desc.n_params
+            ctx.G = out[:S * P].view(S, P)
+            ctx.mode = "eager"
+            return out[S * P:].clone()
+        loss, _ = _backend_fwd(desc, flat, op.x, op.aux, op.inv_n_global)
+        op.stats["fwd_calls"] += 1
+        if op.world > 1:
+            _all_reduce(loss, op.group)
+            op.stats["allreduce_calls"] += 1
+        if need_grad:
+            ctx.mode = "lazy"
+            ctx.flat = flat
+            ctx.cache = []
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        op = ctx.op
+        desc = op.desc
+        if ctx.mode == "none":
+            return (None,) + tuple(None for _ in ctx.shapes)
+        g = g.detach().to(torch.float32).contiguous()
+        if ctx.mode == "eager":
+            flat_grad = g @ ctx.G
+        else:
+            flat_grad = None
+            for seed, grad in ctx.cache:
+                if torch.equal(seed, g):
+                    flat_grad = grad
+                    break
+            if flat_grad is None:
+                out = _backend_fwd_bwd(desc, ctx.flat, op.x, op.aux, op.inv_n_global, g.view(1, -1))
+                op.stats["fwd_bwd_calls"] += 1
+                if op.world > 1:
+                    _all_reduce(out, op.group)
+                    op.stats["allreduce_calls"] += 1
+                flat_grad = out[:desc.n_params]
+                ctx.cache.append((g.clone(), flat_grad))
+        grads, off = [], 0
+        for i, shp in enumerate(ctx.shapes):
+            n = int(np.prod(shp))
+            grads.append(flat_grad[off:off + n].view(shp) if ctx.needs_input_grad[1 + i] else None)
+            off += n
+        return (None,) + tuple(grads)
+
+
+class FusedPDEResidual:
+    """Device-resident state of the fused op for one problem and one net shape."""
+
+    def __init__(self, spec: ProblemSpec, H: int = 100, L: int = 5, policy: str = "auto", device=None, group=None,
+                 check_library: bool = True):
+        if policy not in ("auto", "eager", "lazy"):
+            raise ValueError(f"unknown policy {policy!r}")
+        self.spec = spec
+        self.desc: KindDesc = spec.desc.with_net(H, L)
+        self.policy = policy
+        self.policy_resolved = ("eager" if self.desc.n_pde == 1 else "lazy") if policy == "auto" else policy
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.group = group
+        self.world, self.rank = 1, 0
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            self.world = dist.get_world_size(group)
+            self.rank = dist.get_rank(group)
+        if check_library:
+            capi.check_supported(self.desc)      # unsupported descriptor => error now, never a fallback
+        self.x: Optional[torch.Tensor] = None
+        self.aux: Optional[torch.Tensor] = None
+        self.n_global = 0
+        self.inv_n_global = 0.0
+        self._eye_t = None
+        self.stats = dict(fwd_calls=0, fwd_bwd_calls=0, allreduce_calls=0, h2d_bytes=0, uploads=0)
+
+    def _eye(self):
+        if self._eye_t is None or self._eye_t.device != self.device:
+            self._eye_t = torch.eye(self.desc.n_pde, dtype=torch.float32, device=self.device)
+        return self._eye_t
+
+    def set_points(self, x, shard: bool = True, n_global: Optional[int] = None):
+        """Upload the PDE rows and evaluate the per-point aux columns once.
+
+        ``x``: numpy array or CPU/GPU tensor [N, d].  Default (``n_global=None``): every rank passes the
+        same GLOBAL array and keeps its contiguous shard.  With ``n_global`` given the rows are already
+        this rank's own share of ``n_global`` rows in total (no slicing)."""
+        xt = torch.as_tensor(x)
+        if xt.dim() != 2 or xt.shape[1] != self.desc.d:
+            raise ValueError(f"points must be [N,{self.desc.d}], got {tuple(xt.shape)}")
+        if n_global is not None:
+            self.n_global = int(n_global)
+        else:
+            self.n_global = int(xt.shape[0])
+            if shard and self.world > 1:
+                beg, end = shard_bounds(self.n_global, self.rank, self.world)
+                xt = xt[beg:end]
+        if self.n_global == 0:
+            raise ValueError("empty point set")
+        self.inv_n_global = 1.0 / self.n_global
+        xt = xt.to(torch.float32)
+        if xt.device != self.device:
+            self.stats["h2d_bytes"] += xt.numel() * 4
+            self.stats["uploads"] += 1
+            xt = xt.contiguous().to(self.device, non_blocking=True)
+        self.x = xt.contiguous()
+        self.aux = None
+        if self.desc.n_aux:
+            self.aux = self.spec.aux(self.x).to(torch.float32).contiguous()
+        return self
+
+    def losses(self, params: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Per-term mean-square PDE losses [n_pde] (global mean over all ranks' rows)."""
+        if self.x is None:
+            raise RuntimeError("set_points() has not been called")
+        return _FusedLossFn.apply(self, *params)
+
+    @torch.no_grad()
+    def residual(self, params: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Residual matrix [n_local_rows, n_pde] (forward only; model.predict(operator=pde) analogue)."""
+        flat = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
+        _, res = _backend_fwd(self.desc, flat, self.x, self.aux, self.inv_n_global, True)
+        self.stats["fwd_calls"] += 1
+        return res
+
+
+def net_linear_params(net) -> List[torch.Tensor]:
+    """The 2(L+1) nn.Linear tensors of a dde.nn.FNN-style net, in net.parameters() order
+    (deepxde/nn/pytorch/fnn.py:25-33), after checking the net is one the fused path supports."""
+    linears = getattr(net, "linears", None)
+    if linears is None:
+        raise capi.FusedOpError("fused path needs an FNN with a `.linears` ModuleList (deepxde/nn/pytorch/fnn.py)")
+    if getattr(net, "_input_transform", None) is not None or getattr(net, "_output_transform", None) is not None:
+        raise capi.FusedOpError("fused path does not support input/output transforms (deepxde/nn/pytorch/nn.py:13-23)")
+    act = getattr(net, "activation", None)
+    if isinstance(act, list) or act is None or getattr(act, "__name__", "") != "tanh":
+        raise capi.FusedOpError(f"fused path supports the tanh activation only (got {act!r})")
+    out = []
+    for lin in linears:
+        if lin.bias is None:
+            raise capi.FusedOpError("fused path needs biased Linear layers")
+        out += [lin.weight, lin.bias]
+    return out
+
+
+def net_shape(net):
+    """(d, H, L, m) of an FNN; raises when hidden widths differ."""
+    lins = list(net.linears)
+    d = lins[0].in_features
+    H = lins[0].out_features
+    m = lins[-1].out_features
+    for lin in lins[1:-1]:
+        if lin.in_features != H or lin.out_features != H:
+            raise capi.FusedOpError("fused path needs equal hidden widths")
+    if lins[-1].in_features != H:
+        raise capi.FusedOpError("fused path needs equal hidden widths")
+    return d, H, len(lins) - 1, m

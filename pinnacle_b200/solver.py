@@ -1,0 +1,238 @@
+"""Drop-in boundary: the fused replacement for ``outputs_losses`` / ``train_step`` of
+``deepxde.Model._compile_pytorch`` (deepxde/model.py:243-329).
+
+* ``enable_fused(model)`` patches a compiled reference ``dde.Model`` in place: it re-assigns
+  ``model.outputs_losses_train``, ``model.outputs_losses_test`` and ``model.train_step`` (the closure
+  the reference builds calls the *local* ``outputs_losses_train``, model.py:309, so all three must be
+  replaced).  ``model.opt``, ``model.lr_scheduler`` and every caller
+  (``Model.train``, ``_test``, callbacks, the optimizers in src/optimizer) stay untouched.
+* ``FusedPDESolver`` is the same step logic without the reference package: it is what the GPU
+  tests and ``bench.py`` drive, and it keeps the reference's names (``compile``, ``train_step``,
+  ``outputs_losses_train``, ``opt.losses``, ``closure(*, skip_backward)``).
+
+PDE residual terms come from the fused CUDA op on the residual rows only; boundary/initial terms
+remain stock PyTorch on the (small) BC rows, evaluated by the reference's own ``bc.error``.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import capi
+from .fused import FusedPDEResidual, net_linear_params, net_shape
+from .problems import ProblemSpec, describe_reference
+
+
+def _mse(err: torch.Tensor) -> torch.Tensor:
+    # deepxde/losses.py:16-23 with y_true = zeros
+    return torch.mean(torch.square(err))
+
+
+class _StepCore:
+    """State shared by both front ends: the fused op, the point cache and the loss assembly."""
+
+    def __init__(self, spec: ProblemSpec, net, policy="auto", device=None, group=None, cache_points=True, n_global=None):
+        d, H, L, m = net_shape(net)
+        if d != spec.desc.d or m != spec.desc.m:
+            raise capi.FusedOpError(f"net maps {d}->{m} but problem {spec.name} needs {spec.desc.d}->{spec.desc.m}")
+        self.params = net_linear_params(net)
+        self.net = net
+        dev = self.params[0].device if device is None else torch.device(device)
+        self.op = FusedPDEResidual(spec, H, L, policy=policy, device=dev, group=group)
+        self.cache_points = cache_points
+        self.n_global = n_global        # set => the rows handed to stage() are this rank's own share
+        self._key = None
+        self._x_bc = None
+
+    def stage(self, inputs, n_bc: int):
+        """Make the rows of ``inputs`` device-resident: BC rows -> self._x_bc, residual rows -> fused op.
+        Keyed on the identity of the host array, as the reference keeps one array per (re)sample
+        (data/pde.py:160-171); a new array (PDEPointResampler, add_anchors) re-uploads."""
+        if isinstance(inputs, torch.Tensor):
+            key = (inputs.data_ptr(), tuple(inputs.shape), n_bc)
+        else:
+            inputs = np.asarray(inputs)
+            key = (inputs.__array_interface__["data"][0], inputs.shape, n_bc)
+        if self.cache_points and key == self._key:
+            return
+        xt = torch.as_tensor(inputs)
+        self.op.set_points(xt[n_bc:], n_global=self.n_global)
+        self._x_bc = xt[:n_bc].to(torch.float32).to(self.op.device) if n_bc > 0 else None
+        if n_bc > 0 and xt.device != self.op.device:
+            self.op.stats["h2d_bytes"] += n_bc * xt.shape[1] * 4
+        self._key = key
+
+
+class FusedPDESolver:
+    """Reference-free front end with the reference's step semantics (model.py:258-323).
+
+    bc_terms: callables ``f(x_bc, y_bc) -> error tensor`` evaluated with stock PyTorch on the BC rows
+    (``x_bc`` requires grad so Neumann/Robin terms can differentiate), in loss order after the PDE terms.
+    """
+
+    def __init__(self, spec: ProblemSpec, net, x_pde, x_bc=None, bc_terms: Sequence[Callable] = (), policy="auto",
+                 device=None, group=None, cache_points=True, n_global=None):
+        self.spec, self.net = spec, net
+        self.core = _StepCore(spec, net, policy, device, group, cache_points, n_global)
+        self.bc_terms = list(bc_terms)
+        n_bc = 0 if x_bc is None else len(x_bc)
+        self.n_bc = n_bc
+        if n_bc == 0:
+            # keep the caller's buffer (numpy array or pinned CPU tensor): it is the host side of the H2D copy
+            self.train_x = x_pde if isinstance(x_pde, torch.Tensor) else np.asarray(x_pde, dtype=np.float32)
+        else:
+            self.train_x = np.vstack([np.asarray(x_bc, dtype=np.float32), np.asarray(x_pde, dtype=np.float32)])
+        self.opt = None
+        self.lr_scheduler = None
+        self.loss_weights = None
+
+    @property
+    def num_loss(self):
+        return self.spec.desc.n_pde + len(self.bc_terms)
+
+    def compile(self, optimizer, lr=None, loss_weights=None, lr_scheduler=None):
+        if isinstance(optimizer, str):
+            if optimizer.lower() != "adam":
+                raise ValueError("pass a torch.optim.Optimizer instance (as benchmark.py does) or 'adam'")
+            optimizer = torch.optim.Adam(self.net.parameters(), lr=lr or 1e-3)
+        self.opt = optimizer
+        self.lr_scheduler = lr_scheduler
+        self.loss_weights = loss_weights       # kept by reference: LRA/NTK mutate it in place (lr_adaptor.py:57)
+        return self
+
+    def outputs_losses(self, training: bool, inputs, targets=None):
+        self.net.train(mode=training)
+        core = self.core
+        core.stage(inputs, self.n_bc)
+        pde_losses = core.op.losses(core.params)
+        terms = [pde_losses]
+        outputs_ = None
+        if self.n_bc > 0:
+            x_bc = core._x_bc.detach().requires_grad_(True)
+            y_bc = self.net(x_bc)
+            outputs_ = y_bc
+            if self.bc_terms:
+                terms.append(torch.stack([_mse(f(x_bc, y_bc)) for f in self.bc_terms]))
+        losses = torch.cat(terms)
+        if self.loss_weights is not None:
+            losses = losses * torch.as_tensor(self.loss_weights, dtype=losses.dtype, device=losses.device)
+        return outputs_, losses
+
+    def outputs_losses_train(self, inputs=None, targets=None):
+        return self.outputs_losses(True, self.train_x if inputs is None else inputs, targets)
+
+    def outputs_losses_test(self, inputs=None, targets=None):
+        return self.outputs_losses(False, self.train_x if inputs is None else inputs, targets)
+
+    def train_step(self, inputs=None, targets=None):
+        inputs = self.train_x if inputs is None else inputs
+
+        def closure(*, skip_backward=False):
+            losses = self.outputs_losses_train(inputs, targets)[1]
+            self.opt.losses = losses
+            total_loss = torch.sum(losses)
+            if not skip_backward:
+                self.opt.zero_grad()
+                total_loss.backward()
+            return total_loss
+
+        loss = self.opt.step(closure)
+        if self.lr_scheduler is not None:
+            if type(self.lr_scheduler).__name__ == "ReduceLROnPlateau":
+                self.lr_scheduler.step(loss)
+            else:
+                self.lr_scheduler.step()
+        return loss
+
+
+def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto", cache_points: bool = True, group=None):
+    """Swap a COMPILED reference ``dde.Model`` onto the fused path (call after ``model.compile``).
+
+    Raises (never falls back) when the problem class, the net or the data object is outside what
+    the fused path covers."""
+    if getattr(model, "opt", None) is None or not hasattr(model, "train_step"):
+        raise capi.FusedOpError("enable_fused() must be called after model.compile()")
+    data, net = model.data, model.net
+    if spec is None:
+        pde_obj = getattr(model, "pde", None)
+        if pde_obj is None:
+            raise capi.FusedOpError("model.pde is not set (src/pde/baseclass.py:194); pass spec= explicitly")
+        spec = describe_reference(pde_obj)
+    for attr in ("bcs", "num_bcs", "train_x"):
+        if not hasattr(data, attr):
+            raise capi.FusedOpError(f"model.data has no attribute {attr!r}: not a dde.data.PDE/TimePDE problem")
+    if getattr(data, "auxiliary_var_fn", None) is not None:
+        raise capi.FusedOpError("auxiliary_var_function problems are not supported by the fused path")
+    if getattr(model, "external_trainable_variables", None):
+        raise capi.FusedOpError("external trainable variables (inverse problems) are not supported by the fused path")
+    core = _StepCore(spec, net, policy, None, group, cache_points)
+    n_pde = spec.desc.n_pde
+    loss_weights = model.losshistory.loss_weights       # the live array compile() closed over (model.py:117,275)
+
+    def outputs_losses(training, inputs, targets):
+        net.train(mode=training)
+        n_bc = int(np.sum(data.num_bcs))
+        core.stage(inputs, n_bc)
+        pde_losses = core.op.losses(core.params)
+        terms = [pde_losses]
+        training_graph = any(p.requires_grad for p in core.params)
+        outputs_ = None
+        if n_bc > 0:
+            x_bc = core._x_bc.detach().requires_grad_(True)
+            y_bc = net(x_bc)
+            bcs_start = np.cumsum([0] + list(data.num_bcs))
+            errs = []
+            for i, bc in enumerate(data.bcs):
+                beg, end = int(bcs_start[i]), int(bcs_start[i + 1])
+                errs.append(_mse(bc.error(data.train_x, x_bc, y_bc, beg, end)))   # data/pde.py:153-157
+            terms.append(torch.stack(errs))
+            outputs_ = y_bc
+        if not training_graph:
+            # _test()/predict bookkeeping wants outputs for every row (model.py:767-780): plain forward
+            with torch.no_grad():
+                outputs_ = net(torch.as_tensor(inputs, dtype=torch.float32).to(core.op.device))
+        losses = torch.cat(terms)
+        if loss_weights is not None:
+            losses = losses * torch.as_tensor(loss_weights, dtype=losses.dtype, device=losses.device)
+        _clear_dde_grad_cache()
+        return outputs_, losses
+
+    def outputs_losses_train(inputs, targets):
+        return outputs_losses(True, inputs, targets)
+
+    def outputs_losses_test(inputs, targets):
+        return outputs_losses(False, inputs, targets)
+
+    def train_step(inputs, targets):
+        def closure(*, skip_backward=False):
+            losses = outputs_losses_train(inputs, targets)[1]
+            model.opt.losses = losses
+            total_loss = torch.sum(losses)
+            if not skip_backward:
+                model.opt.zero_grad()
+                total_loss.backward()
+            return total_loss
+
+        loss = model.opt.step(closure)
+        if model.lr_scheduler is not None:
+            if type(model.lr_scheduler).__name__ == "ReduceLROnPlateau":
+                model.lr_scheduler.step(loss)
+            else:
+                model.lr_scheduler.step()
+
+    model.outputs_losses_train = outputs_losses_train
+    model.outputs_losses_test = outputs_losses_test
+    model.train_step = train_step
+    model.fused_core = core
+    return model
+
+
+def _clear_dde_grad_cache():
+    """BC terms that differentiate (Neumann/Robin/Periodic) go through dde.grad's identity-keyed
+    caches; the reference clears them after every evaluation (model.py:278)."""
+    import sys
+    dde = sys.modules.get("deepxde")
+    if dde is not None:
+        dde.grad.clear()

@@ -1,0 +1,85 @@
+"""Shared test helpers (golden fixtures, error metrics, the oracle-backed test double)."""
+from __future__ import annotations
+
+import glob
+import os
+
+import numpy as np
+import torch
+
+from golden import common
+from pinnacle_b200 import kinds as K
+
+GOLDEN_NAMES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(common.GOLDEN_DIR, "*.npz")))
+
+# Parity tolerances (BASELINE.json north_star: residuals, losses and gradients within 1e-5 relative in fp32)
+RTOL = 1e-5
+
+
+class Golden:
+    def __init__(self, name):
+        g = np.load(common.fixture_path(name))
+        self.name = name
+        self.g = g
+        self.desc = K.KindDesc(int(g["kind"]), int(g["d"]), int(g["m"]), tuple(int(k) for k in g["order"]), int(g["n_pde"]),
+                               int(g["n_aux"]), [float(c) for c in g["consts"]], [int(a) for a in g["aux_sel"]], name=name)
+        self.seed = int(g["seed"])
+        self.flat64 = common.golden_params(self.desc.layer_shapes(), self.seed)
+        self.idx = g["idx"]
+        self.probes = common.probe_vectors(self.desc.n_params, self.seed)
+
+    def inputs(self, dtype):
+        nd = np.float32 if dtype == torch.float32 else np.float64
+        tag = "32" if dtype == torch.float32 else "64"
+        flat = torch.as_tensor(self.flat64.astype(nd))
+        x = torch.as_tensor(self.g["x"].astype(nd))
+        aux = torch.as_tensor(self.g[f"aux{tag}"].astype(nd)) if self.desc.n_aux else None
+        return flat, x, aux
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def rel_max(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def assert_parity(got, ref, what, rtol=RTOL):
+    """||got-ref||_2 <= rtol ||ref||_2  and  max|got-ref| <= rtol max|ref|  (SURVEY.md §8c recipe)."""
+    e2, em = rel_l2(got, ref), rel_max(got, ref)
+    assert e2 <= rtol and em <= rtol, f"{what}: rel-L2 {e2:.3e}, rel-max {em:.3e} exceed {rtol:g}"
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle-backed stand-in for the C ABI, used ONLY by CPU tests of host-side plumbing
+# (sharding, all-reduce, autograd semantics, the dde.Model patch).  Never used by the product.
+# ---------------------------------------------------------------------------------------------
+def oracle_fwd(desc, params, x, aux, inv_n_global, want_residual=False):
+    from oracle import autograd_ref as O
+    losses, res, _ = O.pde_losses(desc, params.detach(), x, aux, inv_n=inv_n_global)
+    return losses.detach().to(torch.float32), (res.detach() if want_residual else None)
+
+
+def oracle_fwd_bwd(desc, params, x, aux, inv_n_global, seeds, out=None):
+    from oracle import autograd_ref as O
+    losses, grads, _ = O.losses_and_grads(desc, params.detach(), x, aux, seeds=seeds, inv_n=inv_n_global)
+    return torch.cat([grads.reshape(-1), losses]).to(torch.float32)
+
+
+class oracle_backend:
+    """Context manager swapping pinnacle_b200.fused's backend for the oracle (CPU tests only)."""
+
+    def __enter__(self):
+        from pinnacle_b200 import fused
+        self._saved = (fused._backend_fwd, fused._backend_fwd_bwd)
+        fused._backend_fwd, fused._backend_fwd_bwd = oracle_fwd, oracle_fwd_bwd
+        return self
+
+    def __exit__(self, *a):
+        from pinnacle_b200 import fused
+        fused._backend_fwd, fused._backend_fwd_bwd = self._saved
