@@ -1,0 +1,116 @@
+"""N>1 host path on CPU: world_size-2 gloo.  The sharding + all-reduce plumbing of the fused op is exercised
+with the oracle standing in for the C ABI (explicitly injected by the test; the product never does this)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, name, policy, n, q):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pinnacle_b200 import problems
+        from pinnacle_b200.fused import FusedPDEResidual, shard_bounds
+        from pinnacle_b200.nn import FNN
+        from util import oracle_backend
+        torch.manual_seed(0)
+        torch.set_num_threads(2)
+        spec = problems.make(name)
+        desc = spec.desc
+        net = FNN([desc.d] + [100] * 5 + [desc.m])
+        with torch.no_grad():
+            for lin in net.linears:
+                lin.bias.normal_(0, 0.1)
+        params = [t for lin in net.linears for t in (lin.weight, lin.bias)]
+        x = spec.sample(n, seed=4)
+        with oracle_backend():
+            op = FusedPDEResidual(spec, 100, 5, policy=policy, device="cpu", check_library=False)
+            assert (op.world, op.rank) == (world, rank)
+            op.set_points(x)
+            beg, end = shard_bounds(n, rank, world)
+            assert op.x.shape[0] == end - beg and op.n_global == n
+            losses = op.losses(params)
+            w = torch.tensor([0.5, 2.0, 1.5][:desc.n_pde])
+            net.zero_grad()
+            (losses * w).sum().backward(retain_graph=True)
+            g1 = torch.cat([p.grad.reshape(-1) for p in params]).clone()
+            net.zero_grad()
+            losses[0].backward(retain_graph=True)          # a second backward with another seed (LRA pattern)
+            g2 = torch.cat([p.grad.reshape(-1) for p in params]).clone()
+            stats = dict(op.stats)
+        q.put((rank, losses.detach().numpy(), g1.numpy(), g2.numpy(), stats))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,policy", [("Poisson2D_Classic", "auto"), ("NS2D_LidDriven", "auto"), ("NS2D_LidDriven", "eager")])
+def test_two_rank_sharding_matches_single_process(name, policy):
+    from oracle import autograd_ref as O
+    from pinnacle_b200 import problems
+    from pinnacle_b200.nn import FNN
+    n, world = 203, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, policy, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort(key=lambda t: t[0])
+    # single-process reference on ALL rows
+    torch.manual_seed(0)
+    spec = problems.make(name)
+    desc = spec.desc
+    net = FNN([desc.d] + [100] * 5 + [desc.m])
+    with torch.no_grad():
+        for lin in net.linears:
+            lin.bias.normal_(0, 0.1)
+    flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    x = torch.as_tensor(spec.sample(n, seed=4))
+    w = [0.5, 2.0, 1.5][:desc.n_pde]
+    e0 = [1.0] + [0.0] * (desc.n_pde - 1)
+    ol, og, _ = O.losses_and_grads(desc, flat, x, None, seeds=[w, e0])
+    for rank, losses, g1, g2, stats in res:
+        np.testing.assert_allclose(losses, ol.numpy(), rtol=2e-5)
+        assert np.linalg.norm(g1 - og[0].numpy()) <= 2e-5 * np.linalg.norm(og[0].numpy())
+        assert np.linalg.norm(g2 - og[1].numpy()) <= 2e-5 * np.linalg.norm(og[1].numpy())
+        if policy == "eager" or desc.n_pde == 1:
+            assert stats["fwd_bwd_calls"] == 1 and stats["allreduce_calls"] == 1     # one pass serves both backwards
+        else:
+            assert stats["fwd_calls"] == 1 and stats["fwd_bwd_calls"] == 2 and stats["allreduce_calls"] == 3
+    # ranks end up bit-identical (same all-reduced buffer) => replicated optimizers stay in lock-step
+    assert np.array_equal(res[0][2], res[1][2]) and np.array_equal(res[0][1], res[1][1])
+
+
+def test_shard_bounds_cover_all_rows():
+    from pinnacle_b200.fused import shard_bounds
+    for n in (1, 7, 64, 1000003):
+        for world in (1, 2, 3, 8):
+            segs = [shard_bounds(n, r, world) for r in range(world)]
+            assert segs[0][0] == 0 and segs[-1][1] == n
+            assert all(segs[i][1] == segs[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in segs]
+            assert max(sizes) - min(sizes) <= 1

@@ -61,13 +61,15 @@ def assert_parity(got, ref, what, rtol=RTOL):
 # ---------------------------------------------------------------------------------------------
 def oracle_fwd(desc, params, x, aux, inv_n_global, want_residual=False):
     from oracle import autograd_ref as O
-    losses, res, _ = O.pde_losses(desc, params.detach(), x, aux, inv_n=inv_n_global)
+    with torch.enable_grad():          # called from inside autograd.Function.forward (grad mode off there)
+        losses, res, _ = O.pde_losses(desc, params.detach(), x, aux, inv_n=inv_n_global)
     return losses.detach().to(torch.float32), (res.detach() if want_residual else None)
 
 
 def oracle_fwd_bwd(desc, params, x, aux, inv_n_global, seeds, out=None):
     from oracle import autograd_ref as O
-    losses, grads, _ = O.losses_and_grads(desc, params.detach(), x, aux, seeds=seeds, inv_n=inv_n_global)
+    with torch.enable_grad():
+        losses, grads, _ = O.losses_and_grads(desc, params.detach(), x, aux, seeds=seeds, inv_n=inv_n_global)
     return torch.cat([grads.reshape(-1), losses]).to(torch.float32)
 
 
