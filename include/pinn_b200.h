@@ -105,6 +105,12 @@ int pinn_last_launch_count(void);
  * FFMA per thread on every SM and returns achieved TFLOP/s (negative on error). Synchronous. */
 double pinn_ffma_peak_tflops(int iters);
 
+/* Hardware self-test of the tcgen05 descriptor conventions the fused kernels rely on: one CTA computes
+ * D[128][N] = A[128][K] * B[K][N] (tf32 x tf32 -> fp32, row-major device arrays) with the operands staged exactly
+ * as the fused kernels stage them.  mode 0: A in TMEM, B in shared memory MN-major; mode 1: A and B in shared
+ * memory, K-major.  variant bit 0 swaps the descriptor LBO/SBO fields (diagnostic).  K % 8 == 0, N % 16 == 0. */
+int pinn_debug_umma_gemm(int mode, int variant, int K, int N, const float* A, const float* B, float* D, void* stream);
+
 const char* pinn_last_error(void);
 const char* pinn_build_info(void);
 

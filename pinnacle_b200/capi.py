@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpinn_b200.so")
 
 EXPORTS = (
     "pinn_param_count", "pinn_supported", "pinn_workspace_bytes", "pinn_fwd", "pinn_fwd_bwd",
-    "pinn_last_launch_count", "pinn_ffma_peak_tflops", "pinn_last_error", "pinn_build_info",
+    "pinn_last_launch_count", "pinn_ffma_peak_tflops", "pinn_last_error", "pinn_build_info", "pinn_debug_umma_gemm",
 )
 
 
@@ -59,6 +59,8 @@ def load() -> ctypes.CDLL:
     lib.pinn_last_launch_count.restype = ctypes.c_int
     lib.pinn_ffma_peak_tflops.argtypes = [ctypes.c_int]
     lib.pinn_ffma_peak_tflops.restype = ctypes.c_double
+    lib.pinn_debug_umma_gemm.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+    lib.pinn_debug_umma_gemm.restype = ctypes.c_int
     lib.pinn_last_error.argtypes = []
     lib.pinn_last_error.restype = ctypes.c_char_p
     lib.pinn_build_info.argtypes = []

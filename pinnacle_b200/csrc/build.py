@@ -20,7 +20,7 @@ LIB = os.path.join(HERE, "libpinn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
-HEADERS = ["jet_math.cuh", "pinn_kernels.cuh", "pinn_configs.h", "pinn_dispatch.h", "pinn_inst.inl", "pinn_helpers.cuh",
+HEADERS = ["jet_math.cuh", "pinn_kernels.cuh", "pinn_configs.h", "pinn_dispatch.h", "pinn_inst.inl", "pinn_helpers.cuh", "umma.cuh",
            os.path.join("..", "..", "include", "pinn_b200.h")]
 
 
@@ -68,6 +68,7 @@ def build(force=False, jobs=None, verbose=False):
                 f.write(body)
         units.append((src, os.path.join(BUILD, f"inst_{cid}.o")))
     units.append((os.path.join(HERE, "pinn_api.cu"), os.path.join(BUILD, "pinn_api.o")))
+    units.append((os.path.join(HERE, "pinn_umma_test.cu"), os.path.join(BUILD, "pinn_umma_test.o")))
     todo = [(s, o) for s, o in units if force or _newer(o, deps + [s])]
     if todo:
         with cf.ThreadPoolExecutor(max_workers=jobs or os.cpu_count()) as ex:
