@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpinn_b200.so")
 
 EXPORTS = (
     "pinn_param_count", "pinn_supported", "pinn_workspace_bytes", "pinn_fwd", "pinn_fwd_bwd",
-    "pinn_last_launch_count", "pinn_ffma_peak_tflops", "pinn_last_error", "pinn_build_info", "pinn_debug_umma_gemm",
+    "pinn_last_launch_count", "pinn_ffma_peak_tflops", "pinn_last_error", "pinn_build_info", "pinn_debug_umma_gemm", "pinn_set_impl", "pinn_has_tensor_core_kernel",
 )
 
 
@@ -61,6 +61,10 @@ def load() -> ctypes.CDLL:
     lib.pinn_ffma_peak_tflops.restype = ctypes.c_double
     lib.pinn_debug_umma_gemm.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
     lib.pinn_debug_umma_gemm.restype = ctypes.c_int
+    lib.pinn_set_impl.argtypes = [ctypes.c_int]
+    lib.pinn_set_impl.restype = ctypes.c_int
+    lib.pinn_has_tensor_core_kernel.argtypes = [P]
+    lib.pinn_has_tensor_core_kernel.restype = ctypes.c_int
     lib.pinn_last_error.argtypes = []
     lib.pinn_last_error.restype = ctypes.c_char_p
     lib.pinn_build_info.argtypes = []
@@ -187,6 +191,19 @@ def fwd_bwd(desc: KindDesc, params: torch.Tensor, x: torch.Tensor, aux: Optional
                               _ptr(out), _ptr(ws), ws.numel(), _stream_ptr(x.device))
     _check(rc, "pinn_fwd_bwd")
     return out
+
+
+IMPL_AUTO, IMPL_FFMA, IMPL_TC = 0, 1, 2
+
+
+def set_impl(impl: int):
+    """0 = auto (tensor cores where instantiated), 1 = FP32 FFMA kernel, 2 = tcgen05 tensor-core kernel."""
+    _check(load().pinn_set_impl(int(impl)), "pinn_set_impl")
+
+
+def has_tensor_core_kernel(desc: KindDesc) -> bool:
+    c = desc.to_c()
+    return bool(load().pinn_has_tensor_core_kernel(ctypes.byref(c)))
 
 
 def last_launch_count() -> int:

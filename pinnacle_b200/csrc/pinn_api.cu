@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -27,6 +28,17 @@ static const ConfigInfo* const* all_configs() {
 
 static thread_local std::string g_err;
 static thread_local int g_launches = 0;
+static int g_impl = 0;   // 0 = auto (tensor cores where instantiated), 1 = FP32 FFMA kernel, 2 = tensor cores (error if absent)
+
+static int effective_impl() {
+  if (g_impl != 0) return g_impl;
+  const char* e = getenv("PINN_IMPL");
+  if (e != nullptr) {
+    if (strcmp(e, "ffma") == 0) return 1;
+    if (strcmp(e, "tc") == 0) return 2;
+  }
+  return 0;
+}
 
 static int fail(const std::string& msg) {
   g_err = msg;
@@ -102,21 +114,37 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
   size_t off_wpack, off_stash, off_gpart, off_lpart, total;
+  long long pstride;
 };
 
-static Workspace carve(const pinn_kind_desc* d, const ConfigInfo* c, int grid, int n_seeds) {
+static Workspace carve(const pinn_kind_desc* d, const ConfigInfo* c, int grid, int n_seeds, bool tc) {
   Workspace w;
   size_t o = 0;
   w.off_wpack = o;
-  o = align_up(o + (size_t)2 * (d->L - 1) * d->H * d->H * sizeof(float), 256);
+  if (tc)
+    o = align_up(o + (size_t)(2 * (d->L - 1) + 1) * kTcRows * kTcHP * sizeof(float), 256);
+  else
+    o = align_up(o + (size_t)2 * (d->L - 1) * d->H * d->H * sizeof(float), 256);
   w.off_stash = o;
-  o = align_up(o + (size_t)grid * d->L * c->E4 * c->NT * 16, 256);
+  if (tc)
+    o = align_up(o + (size_t)grid * d->L * c->tc_NQ * c->C * 512 * 16, 256);
+  else
+    o = align_up(o + (size_t)grid * d->L * c->E4 * c->NT * 16, 256);
   w.off_gpart = o;
-  o = align_up(o + (size_t)grid * (n_seeds > 0 ? n_seeds : 0) * param_count(d) * sizeof(float), 256);
+  w.pstride = (param_count(d) + 3) / 4 * 4;
+  o = align_up(o + (size_t)grid * (n_seeds > 0 ? n_seeds : 0) * w.pstride * sizeof(float), 256);
   w.off_lpart = o;
   o = align_up(o + (size_t)grid * PINN_MAX_PDE * sizeof(double), 256);
   w.total = o;
   return w;
+}
+
+static bool want_tc(const ConfigInfo* c, std::string* why) {
+  const int impl = effective_impl();
+  if (impl == 1) return false;
+  if (c->tc_T > 0) return true;
+  if (impl == 2) *why = "PINN_IMPL=tc but this configuration has no tensor-core kernel";
+  return false;
 }
 
 static int run(const pinn_kind_desc* desc, const float* params, const float* x, const float* aux, int64_t n_rows, double inv_n,
@@ -138,25 +166,50 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
   if (!di.ok) return fail(di.err);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
   const int max_grid = di.sms;
-  const Workspace ws = carve(desc, c, max_grid, n_seeds);
+  std::string why_tc;
+  const bool tc = want_tc(c, &why_tc);
+  if (!why_tc.empty()) return fail(why_tc);
+  const Workspace ws = carve(desc, c, max_grid, n_seeds, tc);
   if (workspace_bytes < ws.total) return fail("workspace too small: need " + std::to_string(ws.total) + " bytes");
 
   static thread_local bool prepared[PINN_NUM_CONFIGS] = {};
   if (!prepared[c->id]) {
     cudaError_t e = c->prepare();
+    if (e == cudaSuccess && c->tc_T > 0) e = c->tc_prepare();
     if (e != cudaSuccess) return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     prepared[c->id] = true;
   }
 
   const long long P = param_count(desc);
-  const long long ntiles = (n_rows + c->T - 1) / c->T;
+  const int tileT = tc ? c->tc_T : c->T;
+  const long long ntiles = (n_rows + tileT - 1) / tileT;
   int grid = (int)(ntiles < max_grid ? ntiles : max_grid);
   char* wsb = static_cast<char*>(workspace);
   float* wpack = reinterpret_cast<float*>(wsb + ws.off_wpack);
   float* gpart = reinterpret_cast<float*>(wsb + ws.off_gpart);
   double* lpart = reinterpret_cast<double*>(wsb + ws.off_lpart);
 
-  if (grid > 0) {
+  if (grid > 0 && tc) {
+    const size_t per = (size_t)kTcRows * kTcHP;
+    float* wn = wpack;
+    float* wt = wpack + (size_t)(desc->L - 1) * per;
+    float* w6p = wpack + (size_t)2 * (desc->L - 1) * per;
+    const int total = (int)((desc->L) * per);
+    pinn_pack_weights_tc<<<(total + 255) / 256, 256, 0, st>>>(params, wn, wt, w6p, desc->H, desc->d, desc->L, desc->m);
+    ++g_launches;
+    TcLaunchParams lp{};
+    lp.kp.kind = desc->kind;
+    for (int i = 0; i < PINN_MAX_AUXSEL; ++i) lp.kp.aux_sel[i] = desc->aux_sel[i];
+    for (int i = 0; i < PINN_MAX_CONSTS; ++i) lp.kp.c[i] = desc->consts[i];
+    lp.L = desc->L; lp.n_aux = desc->n_aux; lp.n_pde = desc->n_pde; lp.n_seeds = n_seeds;
+    lp.n_rows = n_rows; lp.P = P; lp.Ppad = ws.pstride; lp.inv_n = (float)inv_n;
+    lp.params = params; lp.wn = wn; lp.wt = wt; lp.w6p = w6p; lp.x = x; lp.aux = aux; lp.seeds = seeds;
+    lp.stash = reinterpret_cast<float*>(wsb + ws.off_stash);
+    lp.gpart = gpart; lp.lpart = lpart; lp.resid_out = resid_out;
+    cudaError_t e = c->tc_launch(lp, bwd, grid, st);
+    if (e != cudaSuccess) return fail(std::string("tensor-core kernel launch: ") + cudaGetErrorString(e));
+    ++g_launches;
+  } else if (grid > 0) {
     const int total = (desc->L - 1) * desc->H * desc->H;
     pinn_pack_weights<<<(total + 255) / 256, 256, 0, st>>>(params, wpack, desc->H, desc->d, desc->L);
     ++g_launches;
@@ -170,7 +223,7 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
     lp.n_pde = desc->n_pde;
     lp.n_seeds = n_seeds;
     lp.n_rows = n_rows;
-    lp.P = P;
+    lp.P = ws.pstride;
     lp.inv_n = (float)inv_n;
     lp.params = params;
     lp.wpack = wpack;
@@ -187,7 +240,8 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
   }
   const long long SP = (long long)n_seeds * P;
   const long long work = SP > 0 ? SP : 1;
-  pinn_reduce_partials<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(gpart, lpart, grid, SP, desc->n_pde, inv_n, grad_out, loss_out);
+  pinn_reduce_partials<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(gpart, lpart, grid, n_seeds, P, ws.pstride, desc->n_pde, inv_n, grad_out,
+                                                                       loss_out);
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(std::string("reduce launch: ") + cudaGetErrorString(e));
@@ -215,7 +269,9 @@ size_t pinn_workspace_bytes(const pinn_kind_desc* desc, int n_seeds) {
   if (n_seeds < 0 || n_seeds > PINN_MAX_SEEDS) { fail("n_seeds out of range"); return 0; }
   const DeviceInfo& di = device_info();
   if (!di.ok) { fail(di.err); return 0; }
-  return carve(desc, c, di.sms, n_seeds).total;
+  const size_t a = carve(desc, c, di.sms, n_seeds, false).total;
+  const size_t b = c->tc_T > 0 ? carve(desc, c, di.sms, n_seeds, true).total : 0;
+  return a > b ? a : b;
 }
 
 int pinn_fwd(const pinn_kind_desc* desc, const float* params, const float* x, const float* aux, int64_t n_rows, double inv_n_global,
@@ -233,6 +289,18 @@ int pinn_fwd_bwd(const pinn_kind_desc* desc, const float* params, const float* x
 }
 
 int pinn_last_launch_count(void) { return g_launches; }
+
+int pinn_set_impl(int impl) {
+  if (impl < 0 || impl > 2) return fail("impl must be 0 (auto), 1 (ffma) or 2 (tensor cores)");
+  g_impl = impl;
+  return 0;
+}
+
+int pinn_has_tensor_core_kernel(const pinn_kind_desc* desc) {
+  std::string why;
+  const ConfigInfo* c = find_config(desc, &why);
+  return (c != nullptr && c->tc_T > 0) ? 1 : 0;
+}
 
 double pinn_ffma_peak_tflops(int iters) {
   const DeviceInfo& di = device_info();
@@ -261,6 +329,6 @@ double pinn_ffma_peak_tflops(int iters) {
 
 const char* pinn_last_error(void) { return g_err.c_str(); }
 
-const char* pinn_build_info(void) { return "libpinn_b200 sm_100a fp32-ffma jets; configs=" "11" "; built " __DATE__ " " __TIME__; }
+const char* pinn_build_info(void) { return "libpinn_b200 sm_100a fp32-ffma + tcgen05 bf16x3 jets; configs=" "11" "; built " __DATE__ " " __TIME__; }
 
 }  // extern "C"

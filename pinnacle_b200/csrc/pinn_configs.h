@@ -1,5 +1,5 @@
 // pinn_configs.h -- the (jet signature, output dim, tile shape) combinations this build instantiates.
-//   X(ID, H, M, T, TN, orders...)
+//   X(ID, H, M, T, TN, TCT, orders...)   T/TN: FFMA kernel tile; TCT: points per tile of the tcgen05 kernel (0 = none)
 // ID  problem classes
 //  0  Poisson1D                                    (2)
 //  1  Burgers1D                                    (2,1)
@@ -15,16 +15,16 @@
 #pragma once
 
 #define PINN_FOR_EACH_CONFIG(X)        \
-  X(0, 100, 1, 32, 4, 2)               \
-  X(1, 100, 1, 32, 4, 2, 1)            \
-  X(2, 100, 1, 32, 4, 2, 2)            \
-  X(3, 100, 3, 32, 4, 2, 2)            \
-  X(4, 100, 1, 32, 4, 2, 2, 1)         \
-  X(5, 100, 2, 32, 4, 2, 2, 1)         \
-  X(6, 100, 3, 32, 4, 2, 2, 1)         \
-  X(7, 100, 1, 16, 2, 2, 2, 2)         \
-  X(8, 100, 1, 32, 4, 4, 1)            \
-  X(9, 100, 1, 16, 2, 2, 2, 2, 2, 2)   \
-  X(10, 100, 1, 16, 2, 2, 2, 2, 2, 2, 1)
+  X(0, 100, 1, 32, 4, 32, 2)               \
+  X(1, 100, 1, 32, 4, 32, 2, 1)            \
+  X(2, 100, 1, 32, 4, 32, 2, 2)            \
+  X(3, 100, 3, 32, 4, 32, 2, 2)            \
+  X(4, 100, 1, 32, 4, 16, 2, 2, 1)         \
+  X(5, 100, 2, 32, 4, 16, 2, 2, 1)         \
+  X(6, 100, 3, 32, 4, 16, 2, 2, 1)         \
+  X(7, 100, 1, 16, 2, 16, 2, 2, 2)         \
+  X(8, 100, 1, 32, 4, 16, 4, 1)            \
+  X(9, 100, 1, 16, 2, 0, 2, 2, 2, 2, 2)   \
+  X(10, 100, 1, 16, 2, 0, 2, 2, 2, 2, 2, 1)
 
 #define PINN_NUM_CONFIGS 11

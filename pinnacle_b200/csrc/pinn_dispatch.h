@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "pinn_kernels.cuh"
+#include "pinn_tc_kernels.cuh"
 
 namespace pinn {
 
@@ -14,6 +15,11 @@ struct ConfigInfo {
   bool (*valid_kind)(int);
   cudaError_t (*prepare)();
   cudaError_t (*launch)(const LaunchParams&, bool bwd, int grid, cudaStream_t);
+  // tensor-core (tcgen05) variant; tc_T == 0 when this configuration has none
+  int tc_T, tc_NQ;
+  size_t tc_smem_fwd, tc_smem_bwd;
+  cudaError_t (*tc_prepare)();
+  cudaError_t (*tc_launch)(const TcLaunchParams&, bool bwd, int grid, cudaStream_t);
 };
 
 template <int ID>

@@ -23,13 +23,37 @@ __global__ void pinn_pack_weights(const float* __restrict__ params, float* __res
   }
 }
 
-// out[s*P + i] = sum_cta gpart[cta][s][i];  out[S*P + k] = inv_n * sum_cta lpart[cta][k]
-__global__ void pinn_reduce_partials(const float* __restrict__ gpart, const double* __restrict__ lpart, int grid, long long SP,
-                                     int n_pde, double inv_n, float* __restrict__ grad_out, float* __restrict__ loss_out) {
+// tensor-core path: zero-padded [128][112] copies of W_l, W_l^T (l = 2..L) and of the output layer
+__global__ void pinn_pack_weights_tc(const float* __restrict__ params, float* __restrict__ wn, float* __restrict__ wt, float* __restrict__ w6p,
+                                     int H, int D, int L, int M) {
+  const long long offHid = (long long)H * D + H;
+  const long long strideHid = (long long)H * H + H;
+  const long long offW6 = offHid + (long long)(L - 1) * strideHid;
+  const int per = 128 * 112;
+  const int total = (L - 1) * per;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total + per; i += gridDim.x * blockDim.x) {
+    const int l = i / per, e = i % per;
+    const int row = e / 112, col = e % 112;
+    if (l < L - 1) {
+      const float* W = params + offHid + (long long)l * strideHid;
+      const bool in = row < H && col < H;
+      wn[i] = in ? W[row * H + col] : 0.f;
+      wt[i] = in ? W[col * H + row] : 0.f;
+    } else {
+      w6p[e] = (row < M && col < H) ? params[offW6 + row * H + col] : 0.f;
+    }
+  }
+}
+
+// out[s*P + i] = sum_cta gpart[cta][s*Pstride + i];  out[S*P + k] = inv_n * sum_cta lpart[cta][k]
+__global__ void pinn_reduce_partials(const float* __restrict__ gpart, const double* __restrict__ lpart, int grid, int S, long long P,
+                                     long long Pstride, int n_pde, double inv_n, float* __restrict__ grad_out,
+                                     float* __restrict__ loss_out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < SP) {
+  if (i < (long long)S * P) {
+    const long long sidx = i / P, e = i % P;
     double s = 0.0;
-    for (int c = 0; c < grid; ++c) s += (double)gpart[(size_t)c * SP + i];
+    for (int c = 0; c < grid; ++c) s += (double)gpart[((size_t)c * S + sidx) * Pstride + e];
     grad_out[i] = (float)s;
   }
   if (blockIdx.x == 0 && threadIdx.x < n_pde) {

@@ -6,7 +6,7 @@
 namespace pinn {
 namespace {
 
-template <int ID, int H, int M, int T, int TN, int... KS>
+template <int ID, int H, int M, int T, int TN, int TCT, int... KS>
 struct Inst {
   using SIG = JetSig<KS...>;
   using CF = KCfg<SIG, M, H, T, TN, false>;
@@ -28,6 +28,28 @@ struct Inst {
     return cudaGetLastError();
   }
 
+  template <int TT>
+  struct Tc {
+    using TF = TCfg<SIG, M, H, TT, false>;
+    using TB = TCfg<SIG, M, H, TT, true>;
+    static cudaError_t prepare() {
+      cudaError_t e = cudaFuncSetAttribute(pinn_tc_kernel<TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF::smem_bytes);
+      if (e != cudaSuccess) return e;
+      return cudaFuncSetAttribute(pinn_tc_kernel<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB::smem_bytes);
+    }
+    static cudaError_t launch(const TcLaunchParams& p, bool bwd, int grid, cudaStream_t st) {
+      if (bwd)
+        pinn_tc_kernel<TB><<<grid, TB::NTH, TB::smem_bytes, st>>>(p);
+      else
+        pinn_tc_kernel<TF><<<grid, TF::NTH, TF::smem_bytes, st>>>(p);
+      return cudaGetLastError();
+    }
+    static void fill(ConfigInfo& c) {
+      c.tc_T = TT; c.tc_NQ = TB::NQ; c.tc_smem_fwd = TF::smem_bytes; c.tc_smem_bwd = TB::smem_bytes;
+      c.tc_prepare = &prepare; c.tc_launch = &launch;
+    }
+  };
+
   static const ConfigInfo* info() {
     static const ConfigInfo ci = [] {
       ConfigInfo c{};
@@ -37,6 +59,8 @@ struct Inst {
       c.T = T; c.NT = CB::NT; c.NTP = CB::NTP; c.E4 = CB::E4;
       c.smem_fwd = CF::smem_bytes; c.smem_bwd = CB::smem_bytes;
       c.valid_kind = &valid_kind; c.prepare = &prepare; c.launch = &launch;
+      c.tc_T = 0; c.tc_NQ = 0; c.tc_smem_fwd = c.tc_smem_bwd = 0; c.tc_prepare = nullptr; c.tc_launch = nullptr;
+      if constexpr (TCT > 0) Tc<TCT>::fill(c);
       return c;
     }();
     return &ci;

@@ -1,0 +1,606 @@
+// pinn_tc_kernels.cuh -- tensor-core (tcgen05 / TMEM) formulation of the fused PDE-residual step, sm_100a.
+//
+// Same algorithm and interface as pinn_fused_kernel (pinn_kernels.cuh); the H x H layer contractions run on the
+// 5th-generation tensor cores with split-precision operands:  x = b1 + b2 + b3 (three bf16 terms, 24 mantissa
+// bits), products b1b1 + b1b2 + b2b1 + b2b2 + b1b3 + b3b1 accumulated in fp32 in TMEM ("bf16x3", 6 MMAs per
+// k-step, relative product error ~2^-26 -- at least the accuracy of 3xTF32; bf16 is used instead of tf32 because
+// un-swizzled MN-major operands exist only for 16-bit types, which lets ONE shared-memory copy of an activation
+// matrix serve all three contractions; validated on hardware by pinn_debug_umma_gemm).
+//
+// Orientation: neurons on the M axis / TMEM lanes, (jet channel, point) pairs on the N axis / TMEM columns:
+//     forward      Z^l [n][r]    = W_l   [n][k] * A^{l-1}[k][r]     A-operand W_l   in TMEM,  B = A^{l-1} smem, MN-major
+//     reverse (ii) Abar^{l-1}[k][r] = W_l^T[k][n] * Zbar^l[n][r]     A-operand W_l^T in TMEM,  B = Zbar^l  smem, MN-major
+//     reverse (i)  dW_l[n][k]    = Zbar^l[n][r] * A^{l-1}[k][r]^T    A = Zbar^l smem K-major,  B = A^{l-1} smem K-major
+// so thread (lane j, column group g) of the 16 epilogue warps owns neuron j for a quad of points and all jet
+// channels -- exactly what the element-wise tanh-jet stage needs.  Shared-memory storage of every activation
+// matrix ("X16"):  addr(r, j) = (j/8)*JB + (r/8)*128 + (j%8)*16 + (r%8)*2 bytes, JB = (R/8)*128.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "jet_math.cuh"
+#include "pinn_kernels.cuh"
+#include "umma.cuh"
+
+namespace pinn {
+
+constexpr int kTcHP = 112;   // neuron count padded to a multiple of 16 (K of the bf16 MMA, N of the dW MMA)
+constexpr int kTcRows = 128; // UMMA M
+
+struct TcLaunchParams {
+  KindParams kp;
+  int L, n_aux, n_pde, n_seeds;
+  long long n_rows, P, Ppad;
+  float inv_n;
+  const float* params;
+  const float* wn;     // [(L-1)][128][112] zero-padded W_l          (row = out neuron, col = in neuron)
+  const float* wt;     // [(L-1)][128][112] zero-padded W_l^T
+  const float* w6p;    // [128][112] zero-padded output layer (rows o < m)
+  const float* x;
+  const float* aux;
+  const float* seeds;
+  float* stash;        // [grid][L][NQ][C][512] float4
+  float* gpart;        // [grid][n_seeds][Ppad]
+  double* lpart;
+  float* resid_out;
+};
+
+template <class SIG_, int M_, int H_, int T_, bool BWD_>
+struct TCfg {
+  using SIG = SIG_;
+  static constexpr int M = M_, H = H_, T = T_;
+  static constexpr bool BWD = BWD_;
+  static constexpr int C = SIG::C, D = SIG::D;
+  static constexpr int NTH = 512;
+  static constexpr int R = C * T;                 // rows = N of the forward MMA
+  static constexpr int NQ = T / 16;               // quads of 4 points per thread
+  static constexpr int JB = (R / 8) * 128;        // bytes between 8-neuron blocks
+  static constexpr int ARR = 14 * JB;             // one bf16 split array (112 neuron rows)
+  static constexpr int NARR = BWD ? 6 : 3;
+  // TMEM columns
+  static constexpr int tcD = 0, tcDW = 160, tcW = 272, tcTotal = 512;
+  // shared memory carve-up (bytes)
+  static constexpr int oArr = 0;
+  static constexpr int oSmall = NARR * ARR;
+  static constexpr int oW1 = oSmall;                           // float [H*D]
+  static constexpr int oBias = oW1 + H * D * 4;                // float [kMaxLayers*H]
+  static constexpr int oW6 = oBias + kMaxLayers * H * 4;       // float [M*H]
+  static constexpr int oB6 = oW6 + M * H * 4;                  // float [4]
+  static constexpr int oX = oB6 + 16;                          // float [T*D]
+  static constexpr int oAux = oX + T * D * 4;                  // float [T*4]
+  static constexpr int oUo = oAux + T * PINN_MAX_AUX * 4;      // float [M*R]
+  static constexpr int oUb = oUo + M * R * 4;                  // float [M*R]
+  static constexpr int oRs = oUb + M * R * 4;                  // float [3*T]
+  static constexpr int oRed = oRs + PINN_MAX_PDE * T * 4;      // float [4*128]
+  static constexpr int oLred = (oRed + 4 * 128 * 4 + 7) / 8 * 8;  // double [3*T]
+  static constexpr int oBar = oLred + PINN_MAX_PDE * T * 8;    // 2 x uint64 + tmem slot
+  static constexpr int oKp = oBar + 32;
+  static constexpr int nBytes = oKp + (int)((sizeof(KindParams) + 15) / 16 * 16);
+  static constexpr size_t smem_bytes = (size_t)nBytes;
+
+  static_assert(H == 100, "tensor-core path is instantiated for H = 100");
+  static_assert(T == 16 || T == 32, "T");
+  static_assert(R % 16 == 0 && R <= 160, "R = C*T must be a multiple of 16 and fit the TMEM map");
+  static_assert(oSmall % 16 == 0 && oUo % 16 == 0, "alignment");
+  static_assert(nBytes - oSmall >= 2 * JB, "A-operand over-read of the last Zbar array must stay inside the allocation");
+  static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
+};
+
+// ------------------------------------------------------------------------------------------------
+// bf16x3 split helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x (low 16 bits) = lo
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+// (x0, x1) -> three packed bf16 pairs p1 + p2 + p3 ~= x
+__device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+  p1 = pack_bf16x2(x0, x1);
+  float r0 = x0 - __uint_as_float(p1 << 16);
+  float r1 = x1 - __uint_as_float(p1 & 0xFFFF0000u);
+  p2 = pack_bf16x2(r0, r1);
+  r0 -= __uint_as_float(p2 << 16);
+  r1 -= __uint_as_float(p2 & 0xFFFF0000u);
+  p3 = pack_bf16x2(r0, r1);
+}
+
+__device__ __forceinline__ void tmem_ld4u(uint32_t taddr, float (&v)[4]) { umma::tmem_ld4(taddr, v); }
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+      "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_init_n(uint64_t* bar, uint32_t n) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(umma::smem_addr(bar)), "r"(n) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <class CFG>
+__global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchParams p) {
+  using SIG = typename CFG::SIG;
+  constexpr int C = CFG::C, D = CFG::D, M = CFG::M, H = CFG::H, T = CFG::T, R = CFG::R, NQ = CFG::NQ, JB = CFG::JB, ARR = CFG::ARR,
+                NTH = CFG::NTH;
+  constexpr bool BWD = CFG::BWD;
+
+  extern __shared__ __align__(1024) unsigned char smraw[];
+  unsigned char* arrA[3] = {smraw + 0 * ARR, smraw + 1 * ARR, smraw + 2 * ARR};   // A^{l} splits
+  unsigned char* arrZ[3] = {smraw + 3 * ARR, smraw + 4 * ARR, smraw + 5 * ARR};   // Zbar^{l} splits (BWD)
+  float* W1s = reinterpret_cast<float*>(smraw + CFG::oW1);
+  float* bs = reinterpret_cast<float*>(smraw + CFG::oBias);
+  float* W6s = reinterpret_cast<float*>(smraw + CFG::oW6);
+  float* b6s = reinterpret_cast<float*>(smraw + CFG::oB6);
+  float* xs = reinterpret_cast<float*>(smraw + CFG::oX);
+  float* auxs = reinterpret_cast<float*>(smraw + CFG::oAux);
+  float* uo = reinterpret_cast<float*>(smraw + CFG::oUo);
+  float* ub = reinterpret_cast<float*>(smraw + CFG::oUb);
+  float* rs = reinterpret_cast<float*>(smraw + CFG::oRs);
+  float* redbuf = reinterpret_cast<float*>(smraw + CFG::oRed);
+  double* lred = reinterpret_cast<double*>(smraw + CFG::oLred);
+  uint64_t* bar0 = reinterpret_cast<uint64_t*>(smraw + CFG::oBar);        // forward / (ii) / output MMAs
+  uint64_t* bar1 = bar0 + 1;                                              // dW MMAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar0 + 2);
+  KindParams* kps = reinterpret_cast<KindParams*>(smraw + CFG::oKp);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, g = warp >> 2;         // TMEM lane quarter, column group
+  const int j = 32 * q + lane;                   // neuron owned by this thread
+  const bool act = j < H;
+  const uint32_t lane_off = (uint32_t)(32 * q) << 16;
+  const int L = p.L;
+  const int S = BWD ? p.n_seeds : 0;
+  const long long P = p.P;
+
+  const long long offB1 = (long long)H * D;
+  const long long offHid = offB1 + H;
+  const long long strideHid = (long long)H * H + H;
+  const long long offW6 = offHid + (long long)(L - 1) * strideHid;
+  const long long offB6 = offW6 + (long long)M * H;
+
+  // ---------------- one-time setup ----------------
+  for (int i = tid; i < H * D; i += NTH) W1s[i] = p.params[i];
+  for (int i = tid; i < H; i += NTH) bs[i] = p.params[offB1 + i];
+  for (int l = 2; l <= L; ++l)
+    for (int i = tid; i < H; i += NTH) bs[(l - 1) * H + i] = p.params[offHid + (long long)(l - 2) * strideHid + (long long)H * H + i];
+  for (int i = tid; i < M * H; i += NTH) W6s[i] = p.params[offW6 + i];
+  if (tid < M) b6s[tid] = p.params[offB6 + tid];
+  for (int i = tid; i < CFG::NARR * ARR / 16; i += NTH) reinterpret_cast<uint4*>(smraw)[i] = make_uint4(0u, 0u, 0u, 0u);   // pad rows stay zero
+  if (tid == 0) {
+    mbar_init_n(bar0, 1);
+    mbar_init_n(bar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    *kps = p.kp;
+  }
+  if (warp == 0) umma::tmem_alloc(tmem_slot, CFG::tcTotal);
+  float* gp = nullptr;
+  if constexpr (BWD) {
+    gp = p.gpart + (size_t)blockIdx.x * S * p.Ppad;
+    for (long long i = tid; i < (long long)S * p.Ppad; i += NTH) gp[i] = 0.f;
+    __threadfence();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const uint32_t tD = tbase + CFG::tcD, tDW = tbase + CFG::tcDW, tW = tbase + CFG::tcW;
+
+  float4* stash = reinterpret_cast<float4*>(p.stash) + (size_t)blockIdx.x * L * NQ * C * NTH;
+  auto stash_at = [&](int l /*1-based layer*/, int qi, int c) -> float4* { return stash + ((size_t)((l - 1) * NQ + qi) * C + c) * NTH + tid; };
+
+  uint32_t ph0 = 0, ph1 = 0;
+  double lacc[PINN_MAX_PDE] = {0.0, 0.0, 0.0};
+
+  // W (128 x 112 fp32, zero padded, row j) -> three bf16 splits in TMEM columns tW + s*56 + k/2
+  auto load_W = [&](const float* Wp) {
+    const int kb = 32 * g;                         // this warp group's K slice: [kb, kb + 32) (g = 3: 16 valid)
+    const int len = (g < 3) ? 32 : 16;
+    const float4* src = reinterpret_cast<const float4*>(Wp + (size_t)j * kTcHP + kb);
+    uint32_t s1[16], s2[16], s3[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (4 * i < len) v = src[i];
+      split3_pair(v.x, v.y, s1[2 * i], s2[2 * i], s3[2 * i]);
+      split3_pair(v.z, v.w, s1[2 * i + 1], s2[2 * i + 1], s3[2 * i + 1]);
+    }
+    const uint32_t col = tW + lane_off + kb / 2;
+    if (g < 3) {
+      tmem_st16(col, s1);
+      tmem_st16(col + 56, s2);
+      tmem_st16(col + 112, s3);
+    } else {
+      tmem_st8u(col, s1);
+      tmem_st8u(col + 56, s2);
+      tmem_st8u(col + 112, s3);
+    }
+    umma::wait_st();
+  };
+
+  // four consecutive rows r0..r0+3 of neuron j -> the three split arrays (8-byte stores)
+  auto store_quad = [&](unsigned char* const (&arr)[3], int r0, float v0, float v1, float v2, float v3) {
+    uint32_t a1, a2, a3, b1, b2, b3;
+    split3_pair(v0, v1, a1, a2, a3);
+    split3_pair(v2, v3, b1, b2, b3);
+    const int off = (j >> 3) * JB + (r0 >> 3) * 128 + (j & 7) * 16 + (r0 & 7) * 2;
+    *reinterpret_cast<uint2*>(arr[0] + off) = make_uint2(a1, b1);
+    *reinterpret_cast<uint2*>(arr[1] + off) = make_uint2(a2, b2);
+    *reinterpret_cast<uint2*>(arr[2] + off) = make_uint2(a3, b3);
+  };
+
+  // D (+)= Wop[TMEM] * B[smem, MN-major]: 7 k-steps x 6 split products, small terms first
+  auto issue_rows = [&](unsigned char* const (&barr)[3], uint64_t* bar) {
+    constexpr uint32_t idesc = umma::make_idesc_bf16(kTcRows, R, 0, 1);
+    const int wa[6] = {0, 2, 1, 0, 1, 0};
+    const int ab[6] = {2, 0, 1, 1, 0, 0};
+    // Split-product major, k-step minor: the five correction products are summed while the accumulator is still
+    // ~2^-8 of its final size, so only the last 7 MMAs (b1*b1) round at full magnitude (the tensor core truncates
+    // its fp32 accumulate; 42 full-magnitude truncations cost ~10x the FFMA path's error, 7 do not).
+    uint32_t accum = 0;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+#pragma unroll 1
+      for (int ks = 0; ks < kTcHP / 16; ++ks) {
+        const uint64_t bd = umma::make_smem_desc(umma::smem_addr(barr[ab[t]]) + ks * 2 * JB, JB, 128);
+        umma::mma_bf16_ts(tD, tW + wa[t] * 56 + ks * 8, bd, idesc, accum);
+        accum = 1;
+      }
+    }
+    umma::commit(bar);
+  };
+  // DW = Zbar[smem, K-major] * A[smem, K-major]^T : R/16 k-steps x 6 split products
+  auto issue_dw = [&](uint64_t* bar) {
+    constexpr uint32_t idesc = umma::make_idesc_bf16(kTcRows, kTcHP, 0, 0);
+    const int za[6] = {0, 2, 1, 0, 1, 0};
+    const int ab[6] = {2, 0, 1, 1, 0, 0};
+    uint32_t accum = 0;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+#pragma unroll 1
+      for (int ks = 0; ks < R / 16; ++ks) {
+        const uint64_t ad = umma::make_smem_desc(umma::smem_addr(arrZ[za[t]]) + ks * 256, 128, JB);
+        const uint64_t bd = umma::make_smem_desc(umma::smem_addr(arrA[ab[t]]) + ks * 256, 128, JB);
+        umma::mma_bf16_ss(tDW, ad, bd, idesc, accum);
+        accum = 1;
+      }
+    }
+    umma::commit(bar);
+  };
+  // all threads: publish generic-proxy smem writes + TMEM stores, sync, then one thread issues
+  auto sync_for_mma = [&]() {
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+  };
+  auto wait_bar = [&](uint64_t* bar, uint32_t& ph) {
+    mbar_wait(bar, ph);
+    ph ^= 1;
+    umma::fence_after_sync();
+  };
+  // sum a per-thread partial over the 4 column groups (fixed order) and RED it to one address
+  auto reduce_groups_red = [&](float v, float* dst) {
+    redbuf[g * 128 + j] = v;
+    __syncthreads();
+    if (g == 0 && act) atomicAdd(dst, (redbuf[j] + redbuf[128 + j]) + (redbuf[256 + j] + redbuf[384 + j]));
+    __syncthreads();
+  };
+
+  const long long ntiles = (p.n_rows + T - 1) / T;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * T;
+    for (int i = tid; i < T * D; i += NTH) {
+      const long long r = row0 + i / D;
+      xs[i] = (r < p.n_rows) ? p.x[row0 * D + i] : 0.f;
+    }
+    if (p.n_aux > 0) {
+      for (int i = tid; i < T * p.n_aux; i += NTH) {
+        const int pt = i / p.n_aux, a = i % p.n_aux;
+        const long long r = row0 + pt;
+        auxs[pt * PINN_MAX_AUX + a] = (r < p.n_rows) ? p.aux[r * p.n_aux + a] : 0.f;
+      }
+    }
+    __syncthreads();
+
+    // ================= layer 1 (d -> H), CUDA cores =================
+    if (act) {
+      float w[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) w[i] = W1s[j * D + i];
+      const float b = bs[j];
+#pragma unroll
+      for (int qi = 0; qi < NQ; ++qi) {
+        const int pb = 4 * (NQ * g + qi);
+        float a[C][4];
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {
+          float z0 = b;
+#pragma unroll
+          for (int i = 0; i < D; ++i) z0 = fmaf(w[i], xs[(pb + pp) * D + i], z0);
+#pragma unroll
+          for (int c = 0; c < C; ++c) a[c][pp] = 0.f;
+          a[0][pp] = z0;
+          static_for<D>([&](auto J) {
+            constexpr int jj = decltype(J)::value;
+            if constexpr (SIG::order(jj) >= 1) a[SIG::base(jj)][pp] = w[jj];
+          });
+        }
+        if constexpr (BWD) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) *stash_at(1, qi, c) = make_float4(a[c][0], a[c][1], a[c][2], a[c][3]);
+        }
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {
+          float z[C], av[C];
+#pragma unroll
+          for (int c = 0; c < C; ++c) z[c] = a[c][pp];
+          tanh_jet_fwd<SIG>(z, av);
+#pragma unroll
+          for (int c = 0; c < C; ++c) a[c][pp] = av[c];
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) store_quad(arrA, c * T + pb, a[c][0], a[c][1], a[c][2], a[c][3]);
+      }
+    }
+
+    // ================= layers 2..L (+ output layer as one more "layer" with W6 padded) =================
+    for (int l = 2; l <= L + 1; ++l) {
+      load_W(l <= L ? p.wn + (size_t)(l - 2) * kTcRows * kTcHP : p.w6p);
+      sync_for_mma();
+      if (tid == 0) issue_rows(arrA, bar0);
+      wait_bar(bar0, ph0);
+      if (l <= L) {
+        const float b = act ? bs[(l - 1) * H + j] : 0.f;
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+          const int pb = 4 * (NQ * g + qi);
+          float zq[C][4];
+#pragma unroll
+          for (int c = 0; c < C; ++c) umma::tmem_ld4(tD + lane_off + c * T + pb, zq[c]);
+          umma::wait_ld();
+          if (act) {
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) zq[0][pp] += b;
+            if constexpr (BWD) {
+#pragma unroll
+              for (int c = 0; c < C; ++c) *stash_at(l, qi, c) = make_float4(zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
+            }
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+              float z[C], av[C];
+#pragma unroll
+              for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
+              tanh_jet_fwd<SIG>(z, av);
+#pragma unroll
+              for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) store_quad(arrA, c * T + pb, zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
+          }
+        }
+      } else {
+        // output jets: lanes o < M of D hold u[o][r]
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+          const int pb = 4 * (NQ * g + qi);
+          float uq[C][4];
+#pragma unroll
+          for (int c = 0; c < C; ++c) umma::tmem_ld4(tD + lane_off + c * T + pb, uq[c]);
+          umma::wait_ld();
+          if (j < M) {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+              for (int pp = 0; pp < 4; ++pp) uo[j * R + c * T + pb + pp] = uq[c][pp] + (c == 0 ? b6s[j] : 0.f);
+          }
+        }
+      }
+      umma::fence_before_sync();
+      __syncthreads();
+    }
+
+    // ================= residual + loss =================
+    if (tid < T) {
+      float U[M][C];
+#pragma unroll
+      for (int o = 0; o < M; ++o)
+#pragma unroll
+        for (int c = 0; c < C; ++c) U[o][c] = uo[o * R + c * T + tid];
+      float r[PINN_MAX_PDE];
+      Residual<SIG, M>::eval(*kps, auxs + tid * PINN_MAX_AUX, U, r);
+      const bool valid = row0 + tid < p.n_rows;
+#pragma unroll
+      for (int k = 0; k < PINN_MAX_PDE; ++k) {
+        const float rk = valid ? r[k] : 0.f;
+        rs[k * T + tid] = rk;
+        lacc[k] += (double)rk * (double)rk;
+      }
+      if (p.resid_out != nullptr && valid)
+        for (int k = 0; k < p.n_pde; ++k) p.resid_out[(row0 + tid) * p.n_pde + k] = r[k];
+    }
+
+    if constexpr (BWD) {
+      for (int s = 0; s < S; ++s) {
+        float* gs = gp + (size_t)s * p.Ppad;
+        // ---- adjoint of the residual
+        if (tid < T) {
+          float U[M][C], Ub[M][C];
+#pragma unroll
+          for (int o = 0; o < M; ++o)
+#pragma unroll
+            for (int c = 0; c < C; ++c) U[o][c] = uo[o * R + c * T + tid];
+          float rb[PINN_MAX_PDE];
+#pragma unroll
+          for (int k = 0; k < PINN_MAX_PDE; ++k) rb[k] = (k < p.n_pde) ? p.seeds[s * p.n_pde + k] * 2.0f * rs[k * T + tid] * p.inv_n : 0.f;
+          Residual<SIG, M>::adjoint(*kps, auxs + tid * PINN_MAX_AUX, U, rb, Ub);
+#pragma unroll
+          for (int o = 0; o < M; ++o)
+#pragma unroll
+            for (int c = 0; c < C; ++c) ub[o * R + c * T + tid] = Ub[o][c];
+        }
+        __syncthreads();
+        if (tid < M) {
+          float sacc = 0.f;
+          for (int pq = 0; pq < T; ++pq) sacc += ub[tid * R + pq];
+          atomicAdd(gs + offB6 + tid, sacc);
+        }
+
+        // ---- layers L..1.  abar^l comes from ub/W6 (l == L) or from D (written by (ii) of layer l+1)
+        for (int l = L; l >= 1; --l) {
+          float dbias = 0.f;
+          float dw6[M];
+#pragma unroll
+          for (int o = 0; o < M; ++o) dw6[o] = 0.f;
+          float dw1[D];
+#pragma unroll
+          for (int i = 0; i < D; ++i) dw1[i] = 0.f;
+#pragma unroll
+          for (int qi = 0; qi < NQ; ++qi) {
+            const int pb = 4 * (NQ * g + qi);
+            float ab[C][4];
+            if (l < L) {
+#pragma unroll
+              for (int c = 0; c < C; ++c) umma::tmem_ld4(tD + lane_off + c * T + pb, ab[c]);
+              umma::wait_ld();
+            }
+            if (act) {
+              float zq[C][4];
+#pragma unroll
+              for (int c = 0; c < C; ++c) {
+                const float4 v = *stash_at(l, qi, c);
+                zq[c][0] = v.x; zq[c][1] = v.y; zq[c][2] = v.z; zq[c][3] = v.w;
+              }
+              if (l == L) {
+                // abar^L = W6^T ubar ; dW6 = ubar a^L
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {
+                  float z[C], av[C];
+#pragma unroll
+                  for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
+                  tanh_jet_fwd<SIG>(z, av);
+#pragma unroll
+                  for (int c = 0; c < C; ++c) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int o = 0; o < M; ++o) {
+                      const float u = ub[o * R + c * T + pb + pp];
+                      v = fmaf(u, W6s[o * H + j], v);
+                      dw6[o] = fmaf(u, av[c], dw6[o]);
+                    }
+                    ab[c][pp] = v;
+                  }
+                }
+              }
+#pragma unroll
+              for (int pp = 0; pp < 4; ++pp) {
+                float z[C], a_[C], zb[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                  z[c] = zq[c][pp];
+                  a_[c] = ab[c][pp];
+                  zb[c] = 0.f;
+                }
+                tanh_jet_bwd<SIG>(z, a_, zb);
+                dbias += zb[0];
+                if (l == 1) {
+                  static_for<D>([&](auto J) {
+                    constexpr int jj = decltype(J)::value;
+                    dw1[jj] = fmaf(zb[0], xs[(pb + pp) * D + jj], dw1[jj]);
+                    if constexpr (SIG::order(jj) >= 1) dw1[jj] += zb[SIG::base(jj)];
+                  });
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) ab[c][pp] = zb[c];
+              }
+              if (l > 1) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) store_quad(arrZ, c * T + pb, ab[c][0], ab[c][1], ab[c][2], ab[c][3]);
+                // a^{l-1} from the stash
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                  const float4 v = *stash_at(l - 1, qi, c);
+                  zq[c][0] = v.x; zq[c][1] = v.y; zq[c][2] = v.z; zq[c][3] = v.w;
+                }
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {
+                  float z[C], av[C];
+#pragma unroll
+                  for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
+                  tanh_jet_fwd<SIG>(z, av);
+#pragma unroll
+                  for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) store_quad(arrA, c * T + pb, zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
+              }
+            }
+          }
+          // small gradients: bias of layer l (+ output weights at l == L, first-layer weights at l == 1)
+          float* gb = gs + ((l == 1) ? offB1 : offHid + (long long)(l - 2) * strideHid + (long long)H * H);
+          reduce_groups_red(dbias, gb + j);
+          if (l == L) {
+#pragma unroll
+            for (int o = 0; o < M; ++o) reduce_groups_red(dw6[o], gs + offW6 + o * H + j);
+          }
+          if (l == 1) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) reduce_groups_red(dw1[i], gs + j * D + i);
+            break;
+          }
+          // ---- tensor-core contractions of layer l
+          load_W(p.wt + (size_t)(l - 2) * kTcRows * kTcHP);
+          sync_for_mma();
+          if (tid == 0) {
+            issue_dw(bar1);
+            issue_rows(arrZ, bar0);
+          }
+          wait_bar(bar1, ph1);
+          {
+            // flush dW_l[n = j][k] from TMEM: this group's 28-column slice, as float4 REDs
+            float* gw = gs + offHid + (long long)(l - 2) * strideHid + (long long)j * H;
+            const int k0 = 28 * g;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+              float v[4];
+              umma::tmem_ld4(tDW + lane_off + k0 + 4 * i, v);
+              umma::wait_ld();
+              if (act && k0 + 4 * i < H) atomicAdd(reinterpret_cast<float4*>(gw + k0 + 4 * i), make_float4(v[0], v[1], v[2], v[3]));
+            }
+          }
+          wait_bar(bar0, ph0);       // abar^{l-1} is now in D
+          umma::fence_before_sync();
+          __syncthreads();
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---------------- per-CTA loss partials ----------------
+  if (tid < T) {
+#pragma unroll
+    for (int k = 0; k < PINN_MAX_PDE; ++k) lred[k * T + tid] = lacc[k];
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (tid < PINN_MAX_PDE) {
+    double ssum = 0.0;
+    for (int pq = 0; pq < T; ++pq) ssum += lred[tid * T + pq];
+    p.lpart[(size_t)blockIdx.x * PINN_MAX_PDE + tid] = ssum;
+  }
+  if (warp == 0) umma::tmem_dealloc(tbase, CFG::tcTotal);
+}
+
+}  // namespace pinn

@@ -134,7 +134,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
 
 extern "C" int harness_run(const pinn_kind_desc* d, const float* params, const float* x, const float* aux, long long n, double inv_n,
                            const float* seeds, int S, double* grad, double* loss, float* resid) {
-#define TRY(ID, H_, M_, T_, TN_, ...)                                                                  \
+#define TRY(ID, H_, M_, T_, TN_, TCT_, ...)                                                                \
   {                                                                                                    \
     using SIG = JetSig<__VA_ARGS__>;                                                                   \
     const int o[] = {__VA_ARGS__};                                                                     \

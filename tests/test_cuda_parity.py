@@ -19,12 +19,32 @@ def _to(dev, *ts):
     return [None if t is None else t.to(dev).contiguous() for t in ts]
 
 
+IMPLS = ["ffma", "tc"]
+
+
+def _select_impl(impl, desc):
+    """Both kernels (FP32 FFMA, tcgen05 bf16x3) implement the same C-ABI call; run the parity suite on each."""
+    from pinnacle_b200 import capi
+    if impl == "tc" and not capi.has_tensor_core_kernel(desc):
+        pytest.skip("no tensor-core kernel instantiated for this jet signature")
+    capi.set_impl(capi.IMPL_TC if impl == "tc" else capi.IMPL_FFMA)
+
+
+@pytest.fixture(autouse=True)
+def _reset_impl():
+    yield
+    from pinnacle_b200 import capi
+    capi.set_impl(capi.IMPL_AUTO)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
-def test_fwd_bwd_matches_reference_golden(name):
+def test_fwd_bwd_matches_reference_golden(name, impl):
     from pinnacle_b200 import capi
     dev = _cuda()
     G = Golden(name)
     desc = G.desc
+    _select_impl(impl, desc)
     flat, x, aux = _to(dev, *G.inputs(torch.float32))
     S, P = desc.n_pde, desc.n_params
     seeds = torch.eye(S, device=dev)
@@ -46,13 +66,15 @@ def test_fwd_bwd_matches_reference_golden(name):
 @pytest.mark.parametrize("name,n", [("Poisson2D_Classic", 1), ("Poisson2D_Classic", 32), ("Poisson2D_Classic", 33),
                                     ("Burgers1D", 4099), ("NS2D_LidDriven", 5000), ("KuramotoSivashinskyEquation", 4800),
                                     ("Heat2D_Multiscale", 9001), ("Poisson3D_ComplexGeometry", 2500), ("HeatND", 1111)])
-def test_matches_oracle_ragged_sizes(name, n):
+@pytest.mark.parametrize("impl", IMPLS)
+def test_matches_oracle_ragged_sizes(name, n, impl):
     """Many tiles per CTA, ragged tails, single point; trained-like weights (x1.5, saturating tanh)."""
     from oracle import autograd_ref as O
     from pinnacle_b200 import capi, problems
     dev = _cuda()
     G = Golden(name)
     desc = G.desc
+    _select_impl(impl, desc)
     spec = problems.make(name) if desc.n_aux == 0 or name in ("Poisson3D_ComplexGeometry", "HeatND") else None
     rng = np.random.RandomState(n)
     flat64 = G.flat64 * 1.2
@@ -74,10 +96,12 @@ def test_matches_oracle_ragged_sizes(name, n):
     assert_parity(resid.cpu().numpy(), orr.numpy(), "residual")
 
 
-def test_bitwise_deterministic():
+@pytest.mark.parametrize("impl", IMPLS)
+def test_bitwise_deterministic(impl):
     from pinnacle_b200 import capi, problems
     dev = _cuda()
     spec = problems.make("Poisson2D_Classic")
+    _select_impl(impl, spec.desc)
     G = Golden("Poisson2D_Classic")
     x = torch.as_tensor(spec.sample(70001, seed=3)).to(dev)
     flat = torch.as_tensor(G.flat64).float().to(dev)
