@@ -201,30 +201,36 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
   auto stash_at = [&](int l /*1-based layer*/, int qi, int c) -> float4* { return stash + ((size_t)((l - 1) * NQ + qi) * C + c) * NTH + tid; };
 
   uint32_t ph0 = 0, ph1 = 0;
+  bool w_ready = false;      // W_2 already staged in TMEM by the previous tile's tail
   double lacc[PINN_MAX_PDE] = {0.0, 0.0, 0.0};
 
-  // W (128 x 112 fp32, zero padded, row j) -> three bf16 splits in TMEM columns tW + s*56 + k/2
-  auto load_W = [&](const float* Wp) {
+  // W (128 x 112 fp32, zero padded, row j) -> three bf16 splits in TMEM columns tW + s*56 + k/2.
+  // Split in two steps so the global-load latency hides behind the wait for the MMAs that still read the
+  // previous W: fetch_W() right after an MMA batch is issued, put_W() once that batch has completed.
+  uint32_t ws1[16], ws2[16], ws3[16];
+  auto fetch_W = [&](const float* Wp) {
     const int kb = 32 * g;                         // this warp group's K slice: [kb, kb + 32) (g = 3: 16 valid)
     const int len = (g < 3) ? 32 : 16;
     const float4* src = reinterpret_cast<const float4*>(Wp + (size_t)j * kTcHP + kb);
-    uint32_t s1[16], s2[16], s3[16];
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (4 * i < len) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (4 * i < len) v = src[i];
-      split3_pair(v.x, v.y, s1[2 * i], s2[2 * i], s3[2 * i]);
-      split3_pair(v.z, v.w, s1[2 * i + 1], s2[2 * i + 1], s3[2 * i + 1]);
+      split3_pair(v[i].x, v[i].y, ws1[2 * i], ws2[2 * i], ws3[2 * i]);
+      split3_pair(v[i].z, v[i].w, ws1[2 * i + 1], ws2[2 * i + 1], ws3[2 * i + 1]);
     }
-    const uint32_t col = tW + lane_off + kb / 2;
+  };
+  auto put_W = [&]() {
+    const uint32_t col = tW + lane_off + 16 * g;
     if (g < 3) {
-      tmem_st16(col, s1);
-      tmem_st16(col + 56, s2);
-      tmem_st16(col + 112, s3);
+      tmem_st16(col, ws1);
+      tmem_st16(col + 56, ws2);
+      tmem_st16(col + 112, ws3);
     } else {
-      tmem_st8u(col, s1);
-      tmem_st8u(col + 56, s2);
-      tmem_st8u(col + 112, s3);
+      tmem_st8u(col, ws1);
+      tmem_st8u(col + 56, ws2);
+      tmem_st8u(col + 112, ws3);
     }
     umma::wait_st();
   };
@@ -356,11 +362,23 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
     }
 
     // ================= layers 2..L (+ output layer as one more "layer" with W6 padded) =================
+    if (!w_ready) {
+      fetch_W(p.wn);
+      put_W();
+    }
+    w_ready = false;
     for (int l = 2; l <= L + 1; ++l) {
-      load_W(l <= L ? p.wn + (size_t)(l - 2) * kTcRows * kTcHP : p.w6p);
       sync_for_mma();
       if (tid == 0) issue_rows(arrA, bar0);
+      // operand of the next MMA batch: W_{l+1}, the padded output layer, or (reverse sweep) W_L^T
+      const float* nextW = (l < L) ? p.wn + (size_t)(l - 1) * kTcRows * kTcHP
+                                   : (l == L) ? p.w6p
+                                              : (BWD ? p.wt + (size_t)(L - 2) * kTcRows * kTcHP
+                                                     : (tile + gridDim.x < ntiles ? p.wn : nullptr));
+      if (nextW != nullptr) fetch_W(nextW);
       wait_bar(bar0, ph0);
+      if (nextW != nullptr) put_W();
+      if (!BWD && l == L + 1 && nextW != nullptr) w_ready = true;
       if (l <= L) {
         const float b = act ? bs[(l - 1) * H + j] : 0.f;
 #pragma unroll
@@ -559,13 +577,18 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
             for (int i = 0; i < D; ++i) reduce_groups_red(dw1[i], gs + j * D + i);
             break;
           }
-          // ---- tensor-core contractions of layer l
-          load_W(p.wt + (size_t)(l - 2) * kTcRows * kTcHP);
+          // ---- tensor-core contractions of layer l (W_l^T is already in TMEM)
           sync_for_mma();
           if (tid == 0) {
             issue_dw(bar1);
             issue_rows(arrZ, bar0);
           }
+          // next operand: W_{l-1}^T, or W_L^T again for the next seed, or W_2 for the next tile's forward
+          const float* nextW = (l - 1 >= 2) ? p.wt + (size_t)(l - 3) * kTcRows * kTcHP
+                                            : (s + 1 < S) ? p.wt + (size_t)(L - 2) * kTcRows * kTcHP
+                                                          : (tile + gridDim.x < ntiles ? p.wn : nullptr);
+          if (nextW != nullptr) fetch_W(nextW);
+          if (l == 2 && s + 1 >= S && nextW != nullptr) w_ready = true;
           wait_bar(bar1, ph1);
           {
             // flush dW_l[n = j][k] from TMEM: this group's 28-column slice, as float4 REDs
@@ -580,6 +603,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
             }
           }
           wait_bar(bar0, ph0);       // abar^{l-1} is now in D
+          if (nextW != nullptr) put_W();
           umma::fence_before_sync();
           __syncthreads();
         }
