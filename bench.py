@@ -184,6 +184,7 @@ def run_fused(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     capi.load()
+    capi.set_impl({"auto": capi.IMPL_AUTO, "ffma": capi.IMPL_FFMA, "tc": capi.IMPL_TC}[args.kernel])
 
     n_per = args.points                      # per problem, per GPU (weak scaling)
     specs = [problems.make(n) for n in WORKLOAD_PROBLEMS]
@@ -300,25 +301,52 @@ def run_fused(args):
     peaks, peak_src = _peaks()
     dom = int(np.argmax(kern_ms))
     desc = specs[dom].desc
+    on_tc = args.kernel != "ffma" and capi.has_tensor_core_kernel(ops[dom].desc)
     flops_launch = desc.flops_step_per_point() * n_per
     ach = flops_launch / (kern_ms[dom] * 1e-3) / 1e12
     try:
         ffma_peak = capi.ffma_peak_tflops(8192)
-    except Exception as e:  # noqa: BLE001
+    except Exception:  # noqa: BLE001
         ffma_peak = None
     tensor_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
-    roofline = {
-        "bound": "fp32_ffma", "achieved": ach, "peak": ffma_peak, "unit": "TFLOP/s", "frac": (ach / ffma_peak) if ffma_peak else None,
-        "traffic": None,
-        "kernel": f"pinn_fused_kernel<{specs[dom].name}, fwd+reverse>", "launch_ms": kern_ms[dom],
-        "algorithmic_flops_per_point": desc.flops_step_per_point(), "points_per_launch": n_per,
-        "peak_source": "FP32 FFMA probe kernel run in this process (pinn_ffma_peak_tflops); nominal 148*128*2*f_SM",
-        "tensor_peak_bf16": tensor_peak, "frac_of_tensor_peak_bf16": ach / tensor_peak if tensor_peak else None,
-        "tensor_peak_source": peak_src,
-        "per_kernel": [{"problem": specs[i].name, "launch_ms": kern_ms[i],
-                        "achieved_tflops": specs[i].desc.flops_step_per_point() * n_per / (kern_ms[i] * 1e-3) / 1e12,
-                        "hbm_gbs_algorithmic": specs[i].desc.bytes_per_point() * n_per / (kern_ms[i] * 1e-3) / 1e9} for i in range(len(ops))],
-    }
+
+    def kinfo(i):
+        d = ops[i].desc
+        tc_i = args.kernel != "ffma" and capi.has_tensor_core_kernel(d)
+        t = kern_ms[i] * 1e-3
+        out = {"problem": specs[i].name, "kernel": "pinn_tc_kernel (tcgen05 bf16x3)" if tc_i else "pinn_fused_kernel (FP32 FFMA)",
+               "launch_ms": kern_ms[i], "achieved_tflops": d.flops_step_per_point() * n_per / t / 1e12,
+               "hbm_gbs_algorithmic": d.bytes_per_point() * n_per / t / 1e9}
+        if tc_i:
+            out["executed_tensor_tflops"] = d.tc_executed_flops_per_point(1) * n_per / t / 1e12
+        return out
+
+    if on_tc:
+        exe = desc.tc_executed_flops_per_point(1) * n_per / (kern_ms[dom] * 1e-3) / 1e12
+        roofline = {
+            "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak if tensor_peak else None,
+            "traffic": None,
+            "kernel": f"pinn_tc_kernel<{specs[dom].name}, fwd+reverse> (tcgen05 kind::f16, bf16x3 split precision, TMEM accumulators)",
+            "launch_ms": kern_ms[dom], "algorithmic_flops_per_point": desc.flops_step_per_point(), "points_per_launch": n_per,
+            "peak_source": peak_src + " bf16 dense, sustained",
+            "executed_tensor_flops_per_point": desc.tc_executed_flops_per_point(1), "executed_tensor_tflops": exe,
+            "tensor_pipe_frac_executed": exe / tensor_peak if tensor_peak else None,
+            "note": "fp32-accuracy contraction = 6 bf16 MMAs per k-step on a 128x112-padded 100x100 layer: executed/algorithmic = "
+                    f"{desc.tc_executed_flops_per_point(1) / desc.flops_step_per_point():.2f}x",
+            "ffma_peak_tflops": ffma_peak, "frac_of_ffma_peak": ach / ffma_peak if ffma_peak else None,
+            "per_kernel": [kinfo(i) for i in range(len(ops))],
+        }
+    else:
+        roofline = {
+            "bound": "fp32_ffma", "achieved": ach, "peak": ffma_peak, "unit": "TFLOP/s", "frac": (ach / ffma_peak) if ffma_peak else None,
+            "traffic": None,
+            "kernel": f"pinn_fused_kernel<{specs[dom].name}, fwd+reverse>", "launch_ms": kern_ms[dom],
+            "algorithmic_flops_per_point": desc.flops_step_per_point(), "points_per_launch": n_per,
+            "peak_source": "FP32 FFMA probe kernel run in this process (pinn_ffma_peak_tflops); nominal 148*128*2*f_SM",
+            "tensor_peak_bf16": tensor_peak, "frac_of_tensor_peak_bf16": ach / tensor_peak if tensor_peak else None,
+            "tensor_peak_source": peak_src,
+            "per_kernel": [kinfo(i) for i in range(len(ops))],
+        }
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -333,7 +361,7 @@ def run_fused(args):
         "config": {"workload": f"Poisson2D_Classic + Heat2D_Multiscale, {n_per} synthetic collocation points each per GPU, 5x100 tanh MLP, "
                                "losses + flat parameter gradient (+ NCCL all-reduce when N>1)",
                    "points_per_step": pts_step, "l2": "flushed between timed iterations (256 MiB write outside the event pair)",
-                   "parallelism": f"dp{world} over collocation points", "wall_s_timed_region": t_wall},
+                   "parallelism": f"dp{world} over collocation points", "wall_s_timed_region": t_wall, "kernel": args.kernel},
         "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -349,6 +377,8 @@ def main():
     ap.add_argument("--points", type=int, default=1 << 20, help="collocation points per problem per GPU")
     ap.add_argument("--cpu-points", type=int, default=16384, help="points per problem of the bounded CPU sample")
     ap.add_argument("--impl", choices=["fused", "reference"], default="fused")
+    ap.add_argument("--kernel", choices=["auto", "ffma", "tc"], default="auto",
+                    help="fused arm only: tcgen05 tensor-core kernel (auto/tc) or the FP32 FFMA kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -82,9 +82,19 @@ PINN_HD void tanh_series(const float (&zz)[K + 1], float t0, float w0, float (&t
   }
 }
 
+// t0 = tanh(z[0]) supplied by the caller (a[0] of the forward pass, stashed by the tensor-core kernel)
+template <class SIG>
+PINN_HD void tanh_jet_fwd_t0(const float (&z)[SIG::C], float t0, float (&a)[SIG::C]);
+template <class SIG>
+PINN_HD void tanh_jet_bwd_t0(const float (&z)[SIG::C], float t0, const float (&abar)[SIG::C], float (&zbar)[SIG::C]);
+
 template <class SIG>
 PINN_HD void tanh_jet_fwd(const float (&z)[SIG::C], float (&a)[SIG::C]) {
-  const float t0 = tanhf(z[0]);
+  tanh_jet_fwd_t0<SIG>(z, tanhf(z[0]), a);
+}
+
+template <class SIG>
+PINN_HD void tanh_jet_fwd_t0(const float (&z)[SIG::C], float t0, float (&a)[SIG::C]) {
   const float w0 = fmaf(-t0, t0, 1.0f);
   a[0] = t0;
   static_for<SIG::D>([&](auto J) {
@@ -106,7 +116,11 @@ PINN_HD void tanh_jet_fwd(const float (&z)[SIG::C], float (&a)[SIG::C]) {
 // Adjoint of tanh_jet_fwd: given z and abar = dLoss/da, returns zbar = dLoss/dz.
 template <class SIG>
 PINN_HD void tanh_jet_bwd(const float (&z)[SIG::C], const float (&abar)[SIG::C], float (&zbar)[SIG::C]) {
-  const float t0 = tanhf(z[0]);
+  tanh_jet_bwd_t0<SIG>(z, tanhf(z[0]), abar, zbar);
+}
+
+template <class SIG>
+PINN_HD void tanh_jet_bwd_t0(const float (&z)[SIG::C], float t0, const float (&abar)[SIG::C], float (&zbar)[SIG::C]) {
   const float w0 = fmaf(-t0, t0, 1.0f);
   float t0bar = abar[0];
   float w0bar = 0.f;
