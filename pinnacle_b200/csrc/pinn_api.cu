@@ -122,7 +122,7 @@ static Workspace carve(const pinn_kind_desc* d, const ConfigInfo* c, int grid, i
   size_t o = 0;
   w.off_wpack = o;
   if (tc)
-    o = align_up(o + (size_t)(2 * (d->L - 1) + 1) * kTcRows * kTcHP * sizeof(float), 256);
+    o = align_up(o + (size_t)(2 * (d->L - 1) + 1) * kTcWMat * sizeof(uint4), 256);
   else
     o = align_up(o + (size_t)2 * (d->L - 1) * d->H * d->H * sizeof(float), 256);
   w.off_stash = o;
@@ -190,12 +190,12 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
   double* lpart = reinterpret_cast<double*>(wsb + ws.off_lpart);
 
   if (grid > 0 && tc) {
-    const size_t per = (size_t)kTcRows * kTcHP;
-    float* wn = wpack;
-    float* wt = wpack + (size_t)(desc->L - 1) * per;
-    float* w6p = wpack + (size_t)2 * (desc->L - 1) * per;
-    const int total = (int)((desc->L) * per);
-    pinn_pack_weights_tc<<<(total + 255) / 256, 256, 0, st>>>(params, wn, wt, w6p, desc->H, desc->d, desc->L, desc->m);
+    uint4* wperm = reinterpret_cast<uint4*>(wpack);
+    const uint4* wn = wperm;
+    const uint4* wt = wperm + (size_t)(desc->L - 1) * kTcWMat;
+    const uint4* w6p = wperm + (size_t)2 * (desc->L - 1) * kTcWMat;
+    const int total = (2 * (desc->L - 1) + 1) * 4 * 512;
+    pinn_pack_weights_tc<<<(total + 255) / 256, 256, 0, st>>>(params, wperm, desc->H, desc->d, desc->L, desc->m);
     ++g_launches;
     TcLaunchParams lp{};
     lp.kp.kind = desc->kind;

@@ -1,6 +1,8 @@
 // pinn_helpers.cuh -- small non-template kernels (weight packing, partial reduction, FFMA probe).
 // Included by pinn_api.cu only.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "pinn_kernels.cuh"
 
 namespace pinn {
@@ -23,25 +25,56 @@ __global__ void pinn_pack_weights(const float* __restrict__ params, float* __res
   }
 }
 
-// tensor-core path: zero-padded [128][112] copies of W_l, W_l^T (l = 2..L) and of the output layer
-__global__ void pinn_pack_weights_tc(const float* __restrict__ params, float* __restrict__ wn, float* __restrict__ wt, float* __restrict__ w6p,
-                                     int H, int D, int L, int M) {
+// Tensor-core path: every MMA A-operand matrix (W_l, W_l^T for l = 2..L, and the output layer zero-padded) is
+// pre-split into its three bf16 terms and stored in the exact per-thread order the kernel's fetch_W() consumes:
+//   wperm[((mat*12 + slot)*512 + tid)] (uint4),  tid = 128*g + 32*q + lane  <->  row j = 32*q + lane, K slice [32*g, 32*g+32)
+//   slot = 4*split + quarter  holds packed pairs (k, k+1) for k = 32*g + 8*quarter + {0,2,4,6}
+// so one warp-wide 128-bit load is 512 contiguous bytes.  mat order: W_2..W_L, W_2^T..W_L^T, W_out(padded).
+__device__ __forceinline__ uint32_t pack_bf16x2_h(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__global__ void pinn_pack_weights_tc(const float* __restrict__ params, uint4* __restrict__ wperm, int H, int D, int L, int M) {
   const long long offHid = (long long)H * D + H;
   const long long strideHid = (long long)H * H + H;
   const long long offW6 = offHid + (long long)(L - 1) * strideHid;
-  const int per = 128 * 112;
-  const int total = (L - 1) * per;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total + per; i += gridDim.x * blockDim.x) {
-    const int l = i / per, e = i % per;
-    const int row = e / 112, col = e % 112;
-    if (l < L - 1) {
-      const float* W = params + offHid + (long long)l * strideHid;
-      const bool in = row < H && col < H;
-      wn[i] = in ? W[row * H + col] : 0.f;
-      wt[i] = in ? W[col * H + row] : 0.f;
-    } else {
-      w6p[e] = (row < M && col < H) ? params[offW6 + row * H + col] : 0.f;
+  const int nmat = 2 * (L - 1) + 1;
+  const int total = nmat * 4 * 512;                 // one work item = (mat, quarter, tid): 8 consecutive k of one row
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
+    const int tid = it % 512, quarter = (it / 512) % 4, mat = it / 2048;
+    const int warp = tid >> 5, lane = tid & 31, q = warp & 3, g = warp >> 2;
+    const int row = 32 * q + lane, k0 = 32 * g + 8 * quarter;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = k0 + i;
+      float x = 0.f;
+      if (k < H) {
+        if (mat < L - 1) {
+          if (row < H) x = params[offHid + (long long)mat * strideHid + (long long)row * H + k];            // W_l[row][k]
+        } else if (mat < 2 * (L - 1)) {
+          if (row < H) x = params[offHid + (long long)(mat - (L - 1)) * strideHid + (long long)k * H + row];  // W_l^T[row][k] = W_l[k][row]
+        } else {
+          if (row < M) x = params[offW6 + (long long)row * H + k];
+        }
+      }
+      v[i] = x;
     }
+    uint32_t p1[4], p2[4], p3[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float x0 = v[2 * i], x1 = v[2 * i + 1];
+      p1[i] = pack_bf16x2_h(x0, x1);
+      float r0 = x0 - __uint_as_float(p1[i] << 16), r1 = x1 - __uint_as_float(p1[i] & 0xFFFF0000u);
+      p2[i] = pack_bf16x2_h(r0, r1);
+      r0 -= __uint_as_float(p2[i] << 16);
+      r1 -= __uint_as_float(p2[i] & 0xFFFF0000u);
+      p3[i] = pack_bf16x2_h(r0, r1);
+    }
+    uint4* dst = wperm + (size_t)mat * 12 * 512 + tid;
+    dst[(0 * 4 + quarter) * 512] = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+    dst[(1 * 4 + quarter) * 512] = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+    dst[(2 * 4 + quarter) * 512] = make_uint4(p3[0], p3[1], p3[2], p3[3]);
   }
 }
 

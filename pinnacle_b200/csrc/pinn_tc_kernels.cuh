@@ -28,6 +28,7 @@ namespace pinn {
 
 constexpr int kTcHP = 112;   // neuron count padded to a multiple of 16 (K of the bf16 MMA, N of the dW MMA)
 constexpr int kTcRows = 128; // UMMA M
+constexpr int kTcWMat = 12 * 512;   // uint4 per pre-split operand matrix
 
 struct TcLaunchParams {
   KindParams kp;
@@ -35,9 +36,10 @@ struct TcLaunchParams {
   long long n_rows, P, Ppad;
   float inv_n;
   const float* params;
-  const float* wn;     // [(L-1)][128][112] zero-padded W_l          (row = out neuron, col = in neuron)
-  const float* wt;     // [(L-1)][128][112] zero-padded W_l^T
-  const float* w6p;    // [128][112] zero-padded output layer (rows o < m)
+  // pre-split bf16x3 A-operands in per-thread fetch order (pinn_pack_weights_tc): 12*512 uint4 per matrix
+  const uint4* wn;     // W_l,   l = 2..L
+  const uint4* wt;     // W_l^T, l = 2..L
+  const uint4* w6p;    // output layer, zero-padded to 128 x 112
   const float* x;
   const float* aux;
   const float* seeds;
@@ -208,17 +210,14 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
   // Split in two steps so the global-load latency hides behind the wait for the MMAs that still read the
   // previous W: fetch_W() right after an MMA batch is issued, put_W() once that batch has completed.
   uint32_t ws1[16], ws2[16], ws3[16];
-  auto fetch_W = [&](const float* Wp) {
-    const int kb = 32 * g;                         // this warp group's K slice: [kb, kb + 32) (g = 3: 16 valid)
-    const int len = (g < 3) ? 32 : 16;
-    const float4* src = reinterpret_cast<const float4*>(Wp + (size_t)j * kTcHP + kb);
-    float4 v[8];
+  auto fetch_W = [&](const uint4* Wp) {
+    const uint4* src = Wp + tid;                   // slot-major, thread-minor: every warp load is 512 contiguous bytes
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (4 * i < len) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      split3_pair(v[i].x, v[i].y, ws1[2 * i], ws2[2 * i], ws3[2 * i]);
-      split3_pair(v[i].z, v[i].w, ws1[2 * i + 1], ws2[2 * i + 1], ws3[2 * i + 1]);
+    for (int qd = 0; qd < 4; ++qd) {
+      const uint4 a = src[(0 * 4 + qd) * NTH], b = src[(1 * 4 + qd) * NTH], c = src[(2 * 4 + qd) * NTH];
+      ws1[4 * qd] = a.x; ws1[4 * qd + 1] = a.y; ws1[4 * qd + 2] = a.z; ws1[4 * qd + 3] = a.w;
+      ws2[4 * qd] = b.x; ws2[4 * qd + 1] = b.y; ws2[4 * qd + 2] = b.z; ws2[4 * qd + 3] = b.w;
+      ws3[4 * qd] = c.x; ws3[4 * qd + 1] = c.y; ws3[4 * qd + 2] = c.z; ws3[4 * qd + 3] = c.w;
     }
   };
   auto put_W = [&]() {
@@ -371,9 +370,9 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
       sync_for_mma();
       if (tid == 0) issue_rows(arrA, bar0);
       // operand of the next MMA batch: W_{l+1}, the padded output layer, or (reverse sweep) W_L^T
-      const float* nextW = (l < L) ? p.wn + (size_t)(l - 1) * kTcRows * kTcHP
+      const uint4* nextW = (l < L) ? p.wn + (size_t)(l - 1) * kTcWMat
                                    : (l == L) ? p.w6p
-                                              : (BWD ? p.wt + (size_t)(L - 2) * kTcRows * kTcHP
+                                              : (BWD ? p.wt + (size_t)(L - 2) * kTcWMat
                                                      : (tile + gridDim.x < ntiles ? p.wn : nullptr));
       if (nextW != nullptr) fetch_W(nextW);
       wait_bar(bar0, ph0);
@@ -584,8 +583,8 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
             issue_rows(arrZ, bar0);
           }
           // next operand: W_{l-1}^T, or W_L^T again for the next seed, or W_2 for the next tile's forward
-          const float* nextW = (l - 1 >= 2) ? p.wt + (size_t)(l - 3) * kTcRows * kTcHP
-                                            : (s + 1 < S) ? p.wt + (size_t)(L - 2) * kTcRows * kTcHP
+          const uint4* nextW = (l - 1 >= 2) ? p.wt + (size_t)(l - 3) * kTcWMat
+                                            : (s + 1 < S) ? p.wt + (size_t)(L - 2) * kTcWMat
                                                           : (tile + gridDim.x < ntiles ? p.wn : nullptr);
           if (nextW != nullptr) fetch_W(nextW);
           if (l == 2 && s + 1 >= S && nextW != nullptr) w_ready = true;
@@ -594,13 +593,13 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
             // flush dW_l[n = j][k] from TMEM: this group's 28-column slice, as float4 REDs
             float* gw = gs + offHid + (long long)(l - 2) * strideHid + (long long)j * H;
             const int k0 = 28 * g;
+            float v[7][4];
 #pragma unroll
-            for (int i = 0; i < 7; ++i) {
-              float v[4];
-              umma::tmem_ld4(tDW + lane_off + k0 + 4 * i, v);
-              umma::wait_ld();
-              if (act && k0 + 4 * i < H) atomicAdd(reinterpret_cast<float4*>(gw + k0 + 4 * i), make_float4(v[0], v[1], v[2], v[3]));
-            }
+            for (int i = 0; i < 7; ++i) umma::tmem_ld4(tDW + lane_off + k0 + 4 * i, v[i]);
+            umma::wait_ld();
+#pragma unroll
+            for (int i = 0; i < 7; ++i)
+              if (act && k0 + 4 * i < H) atomicAdd(reinterpret_cast<float4*>(gw + k0 + 4 * i), make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
           }
           wait_bar(bar0, ph0);       // abar^{l-1} is now in D
           if (nextW != nullptr) put_W();
