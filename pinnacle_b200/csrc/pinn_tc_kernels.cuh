@@ -57,7 +57,8 @@ struct TCfg {
   static constexpr int C = SIG::C, D = SIG::D;
   static constexpr int NTH = 512;
   static constexpr int R = C * T;                 // rows = N of the forward MMA
-  static constexpr int NQ = T / 16;               // quads of 4 points per thread
+  static constexpr int NQUADS = T / 4;            // quads of 4 points in a tile, dealt round-robin to the 4 column groups
+  static constexpr int NQ = (NQUADS + 3) / 4;     // quads per thread (groups g >= NQUADS % 4 may own one less)
   static constexpr int JB = (R / 8) * 128;        // bytes between 8-neuron blocks
   static constexpr int ARR = 14 * JB;             // one bf16 split array (112 neuron rows)
   static constexpr int NARR = BWD ? 6 : 3;
@@ -83,7 +84,7 @@ struct TCfg {
   static constexpr size_t smem_bytes = (size_t)nBytes;
 
   static_assert(H == 100, "tensor-core path is instantiated for H = 100");
-  static_assert(T == 16 || T == 32, "T");
+  static_assert(T % 4 == 0 && T >= 16 && T <= 48, "T");
   static_assert(R % 16 == 0 && R <= 160, "R = C*T must be a multiple of 16 and fit the TMEM map");
   static_assert(oSmall % 16 == 0 && oUo % 16 == 0, "alignment");
   static_assert(nBytes - oSmall >= 2 * JB, "A-operand over-read of the last Zbar array must stay inside the allocation");
@@ -327,7 +328,8 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
       const float b = bs[j];
 #pragma unroll
       for (int qi = 0; qi < NQ; ++qi) {
-        const int pb = 4 * (NQ * g + qi);
+        if (4 * qi + g >= CFG::NQUADS) continue;      // warp-uniform: this group owns no quad in this slot
+        const int pb = 4 * (4 * qi + g);
         float a[C][4];
 #pragma unroll
         for (int pp = 0; pp < 4; ++pp) {
@@ -382,7 +384,8 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
         const float b = act ? bs[(l - 1) * H + j] : 0.f;
 #pragma unroll
         for (int qi = 0; qi < NQ; ++qi) {
-          const int pb = 4 * (NQ * g + qi);
+          if (4 * qi + g >= CFG::NQUADS) continue;      // warp-uniform: this group owns no quad in this slot
+          const int pb = 4 * (4 * qi + g);
           float zq[C][4];
 #pragma unroll
           for (int c = 0; c < C; ++c) umma::tmem_ld4(tD + lane_off + c * T + pb, zq[c]);
@@ -411,7 +414,8 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
         // output jets: lanes o < M of D hold u[o][r]
 #pragma unroll
         for (int qi = 0; qi < NQ; ++qi) {
-          const int pb = 4 * (NQ * g + qi);
+          if (4 * qi + g >= CFG::NQUADS) continue;      // warp-uniform: this group owns no quad in this slot
+          const int pb = 4 * (4 * qi + g);
           float uq[C][4];
 #pragma unroll
           for (int c = 0; c < C; ++c) umma::tmem_ld4(tD + lane_off + c * T + pb, uq[c]);
@@ -485,7 +489,8 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
           for (int i = 0; i < D; ++i) dw1[i] = 0.f;
 #pragma unroll
           for (int qi = 0; qi < NQ; ++qi) {
-            const int pb = 4 * (NQ * g + qi);
+            if (4 * qi + g >= CFG::NQUADS) continue;      // warp-uniform: this group owns no quad in this slot
+            const int pb = 4 * (4 * qi + g);
             float ab[C][4];
             if (l < L) {
 #pragma unroll

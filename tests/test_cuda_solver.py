@@ -1,0 +1,119 @@
+"""The drop-in boundary on the GPU: FusedPDESolver (reference step semantics, model.py:258-323) driving the CUDA
+path, compared with the oracle (reference algorithm on CPU) on identical weights and points."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _net(desc, dev, seed=0):
+    from pinnacle_b200.nn import FNN
+    torch.manual_seed(seed)
+    net = FNN([desc.d] + [100] * 5 + [desc.m])
+    with torch.no_grad():
+        for lin in net.linears:
+            lin.bias.normal_(0, 0.1)
+    return net.to(dev)
+
+
+def _flat(net):
+    return torch.cat([p.detach().reshape(-1) for p in net.parameters()]).cpu()
+
+
+@pytest.mark.parametrize("name,policy", [("NS2D_LidDriven", "lazy"), ("NS2D_LidDriven", "eager"), ("Burgers1D", "auto")])
+def test_per_term_backward_like_lra(name, policy):
+    """losses[k].backward(retain_graph=True) per term and sum(...).backward() twice accumulate into p.grad like
+    autograd does (lr_adaptor.py:36,49,62; multiadam.py:248)."""
+    from oracle import autograd_ref as O
+    from pinnacle_b200 import problems
+    from pinnacle_b200.fused import FusedPDEResidual, net_linear_params
+    dev = torch.device("cuda:0")
+    spec = problems.make(name)
+    net = _net(spec.desc, dev)
+    params = net_linear_params(net)
+    x = spec.sample(3000, seed=2)
+    ol, og, _ = O.losses_and_grads(spec.desc, _flat(net).double(), torch.as_tensor(x).double(), None)
+    op = FusedPDEResidual(spec, policy=policy, device=dev).set_points(x)
+    losses = op.losses(params)
+    np.testing.assert_allclose(losses.detach().cpu().numpy(), ol.numpy(), rtol=1e-5)
+    for k in range(spec.desc.n_pde):
+        net.zero_grad()
+        losses[k].backward(retain_graph=True)
+        g = torch.cat([p.grad.reshape(-1) for p in params]).cpu().double()
+        assert (g - og[k]).norm() <= 1e-5 * og[k].norm()
+    net.zero_grad()
+    w = torch.linspace(0.5, 2.0, spec.desc.n_pde, device=dev)
+    (losses * w).sum().backward(retain_graph=True)
+    (losses * w).sum().backward()
+    g = torch.cat([p.grad.reshape(-1) for p in params]).cpu().double()
+    ref = 2 * (w.cpu().double()[:, None] * og).sum(0)
+    assert (g - ref).norm() <= 1e-5 * ref.norm()
+    if policy == "eager" or spec.desc.n_pde == 1:
+        assert op.stats["fwd_bwd_calls"] == 1
+
+
+def test_frozen_params_forward_only_and_residual_service():
+    from oracle import autograd_ref as O
+    from pinnacle_b200 import problems
+    from pinnacle_b200.fused import FusedPDEResidual, net_linear_params
+    dev = torch.device("cuda:0")
+    spec = problems.make("Heat2D_LongTime")
+    net = _net(spec.desc, dev)
+    x = spec.sample(2049, seed=5)
+    op = FusedPDEResidual(spec, device=dev).set_points(x)
+    net.requires_grad_(False)
+    losses = op.losses(net_linear_params(net))
+    assert not losses.requires_grad and op.stats["fwd_bwd_calls"] == 0
+    res = op.residual(net_linear_params(net))
+    xt = torch.as_tensor(x).double()
+    ol, _, orr = O.losses_and_grads(spec.desc, _flat(net).double(), xt, spec.aux(xt))
+    assert (res.cpu().double() - orr).norm() <= 1e-5 * orr.norm()
+    np.testing.assert_allclose(losses.cpu().numpy(), ol.numpy(), rtol=1e-5)
+
+
+def test_fixed_seed_training_run_matches_reference_algorithm():
+    """Fixed seed, fixed steps, same points (BASELINE north star: final error within 5 % of the reference): 150 Adam
+    steps of Burgers1D with an initial-condition term, fused path on the GPU vs the reference algorithm on the CPU.
+    Compared: the loss trajectory and the relative L2 distance between the two trained networks' outputs on a grid."""
+    from oracle import autograd_ref as O
+    from pinnacle_b200 import problems
+    from pinnacle_b200.solver import FusedPDESolver
+    dev = torch.device("cuda:0")
+    spec = problems.make("Burgers1D")
+    x = spec.sample(2048, seed=3)
+    x_ic = spec.sample(256, seed=4)
+    x_ic[:, 1] = 0.0
+    target_np = np.sin(-np.pi * x_ic[:, 0:1]).astype(np.float32)
+    steps = 150
+    net_a, net_b = _net(spec.desc, dev, 7), _net(spec.desc, torch.device("cpu"), 7)
+    tgt_dev = torch.as_tensor(target_np, device=dev)
+    solver = FusedPDESolver(spec, net_a, x, x_ic, [lambda xb, yb: yb[:, 0:1] - tgt_dev])
+    solver.compile(torch.optim.Adam(net_a.parameters(), 1e-3))
+    hist_a = []
+    for _ in range(steps):
+        solver.train_step()
+        hist_a.append(solver.opt.losses.detach().cpu().numpy().copy())
+    opt = torch.optim.Adam(net_b.parameters(), 1e-3)
+    xt, xi, tg = torch.as_tensor(x), torch.as_tensor(x_ic), torch.as_tensor(target_np)
+    hist_b = []
+    torch.set_flush_denormal(True)
+    for _ in range(steps):
+        opt.zero_grad()
+        flat = torch.cat([p.reshape(-1) for p in net_b.parameters()])
+        losses, _, _ = O.pde_losses(spec.desc, flat, xt, None)
+        bc = torch.mean(torch.square(net_b(xi)[:, 0:1] - tg))
+        all_l = torch.cat([losses, bc.reshape(1)])
+        all_l.sum().backward()
+        opt.step()
+        hist_b.append(all_l.detach().numpy().copy())
+    hist_a, hist_b = np.array(hist_a), np.array(hist_b)
+    # trajectories: identical at the start, within 5 % at the end (fp32 summation-order noise grows)
+    np.testing.assert_allclose(hist_a[0], hist_b[0], rtol=1e-4)
+    np.testing.assert_allclose(hist_a[-1], hist_b[-1], rtol=5e-2)
+    grid = spec.sample(4096, seed=9)
+    ya = net_a(torch.as_tensor(grid, device=dev)).detach().cpu().double()
+    yb = net_b(torch.as_tensor(grid)).detach().double()
+    rel = float((ya - yb).norm() / yb.norm())
+    assert rel < 5e-2, rel
+    assert hist_a[-1].sum() < 0.7 * hist_a[0].sum()      # it actually trained
