@@ -113,7 +113,7 @@ static const DeviceInfo& device_info() {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
-  size_t off_wpack, off_stash, off_gpart, off_lpart, total;
+  size_t off_wpack, off_stash, off_gpart, off_gwt, off_lpart, total;
   long long pstride;
 };
 
@@ -133,6 +133,8 @@ static Workspace carve(const pinn_kind_desc* d, const ConfigInfo* c, int grid, i
   w.off_gpart = o;
   w.pstride = (param_count(d) + 3) / 4 * 4;
   o = align_up(o + (size_t)grid * (n_seeds > 0 ? n_seeds : 0) * w.pstride * sizeof(float), 256);
+  w.off_gwt = o;
+  if (tc) o = align_up(o + (size_t)grid * (n_seeds > 0 ? n_seeds : 0) * (d->L - 1) * kTcGwtLayer4 * 16, 256);
   w.off_lpart = o;
   o = align_up(o + (size_t)grid * PINN_MAX_PDE * sizeof(double), 256);
   w.total = o;
@@ -206,6 +208,7 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
     lp.params = params; lp.wn = wn; lp.wt = wt; lp.w6p = w6p; lp.x = x; lp.aux = aux; lp.seeds = seeds;
     lp.stash = reinterpret_cast<float*>(wsb + ws.off_stash);
     lp.gpart = gpart; lp.lpart = lpart; lp.resid_out = resid_out;
+    lp.gwt = reinterpret_cast<float*>(wsb + ws.off_gwt);
     cudaError_t e = c->tc_launch(lp, bwd, grid, st);
     if (e != cudaSuccess) return fail(std::string("tensor-core kernel launch: ") + cudaGetErrorString(e));
     ++g_launches;
@@ -241,7 +244,8 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
   const long long SP = (long long)n_seeds * P;
   const long long work = SP > 0 ? SP : 1;
   pinn_reduce_partials<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(gpart, lpart, grid, n_seeds, P, ws.pstride, desc->n_pde, inv_n, grad_out,
-                                                                       loss_out);
+                                                                       loss_out, (tc && bwd && c->tc_rmw) ? reinterpret_cast<const float*>(wsb + ws.off_gwt) : nullptr,
+                                                                       desc->H, desc->d, desc->L);
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(std::string("reduce launch: ") + cudaGetErrorString(e));

@@ -16,7 +16,7 @@ struct ConfigInfo {
   cudaError_t (*prepare)();
   cudaError_t (*launch)(const LaunchParams&, bool bwd, int grid, cudaStream_t);
   // tensor-core (tcgen05) variant; tc_T == 0 when this configuration has none
-  int tc_T, tc_NQ;
+  int tc_T, tc_NQ, tc_rmw;
   size_t tc_smem_fwd, tc_smem_bwd;
   cudaError_t (*tc_prepare)();
   cudaError_t (*tc_launch)(const TcLaunchParams&, bool bwd, int grid, cudaStream_t);

@@ -78,15 +78,33 @@ __global__ void pinn_pack_weights_tc(const float* __restrict__ params, uint4* __
   }
 }
 
-// out[s*P + i] = sum_cta gpart[cta][s*Pstride + i];  out[S*P + k] = inv_n * sum_cta lpart[cta][k]
+// out[s*P + i] = sum_cta gpart[cta][s*Pstride + i];  out[S*P + k] = inv_n * sum_cta lpart[cta][k].
+// When gwt != nullptr (tensor-core path) the hidden-layer weight entries come from the transposed partials
+// gwt[cta][s][l][k/4][n][k%4] instead.
 __global__ void pinn_reduce_partials(const float* __restrict__ gpart, const double* __restrict__ lpart, int grid, int S, long long P,
                                      long long Pstride, int n_pde, double inv_n, float* __restrict__ grad_out,
-                                     float* __restrict__ loss_out) {
+                                     float* __restrict__ loss_out, const float* __restrict__ gwt, int H, int D, int L) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < (long long)S * P) {
     const long long sidx = i / P, e = i % P;
+    const long long offHid = (long long)H * D + H, strideHid = (long long)H * H + H;
     double s = 0.0;
-    for (int c = 0; c < grid; ++c) s += (double)gpart[((size_t)c * S + sidx) * Pstride + e];
+    bool hidden_w = false;
+    long long toff = 0;
+    if (gwt != nullptr && e >= offHid && e < offHid + (long long)(L - 1) * strideHid) {
+      const long long r = (e - offHid) % strideHid, l = (e - offHid) / strideHid;
+      if (r < (long long)H * H) {
+        hidden_w = true;
+        const int n = (int)(r / H), k = (int)(r % H);
+        toff = (l * 25 + k / 4) * 512 + n * 4 + (k % 4);
+      }
+    }
+    if (hidden_w) {
+      const size_t per = (size_t)(L - 1) * 25 * 512;
+      for (int c = 0; c < grid; ++c) s += (double)gwt[((size_t)c * S + sidx) * per + toff];
+    } else {
+      for (int c = 0; c < grid; ++c) s += (double)gpart[((size_t)c * S + sidx) * Pstride + e];
+    }
     grad_out[i] = (float)s;
   }
   if (blockIdx.x == 0 && threadIdx.x < n_pde) {

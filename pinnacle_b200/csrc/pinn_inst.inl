@@ -45,7 +45,7 @@ struct Inst {
       return cudaGetLastError();
     }
     static void fill(ConfigInfo& c) {
-      c.tc_T = TT; c.tc_NQ = TB::NQ; c.tc_smem_fwd = TF::smem_bytes; c.tc_smem_bwd = TB::smem_bytes;
+      c.tc_T = TT; c.tc_NQ = TB::NQ; c.tc_rmw = TB::RMW_FLUSH ? 1 : 0; c.tc_smem_fwd = TF::smem_bytes; c.tc_smem_bwd = TB::smem_bytes;
       c.tc_prepare = &prepare; c.tc_launch = &launch;
     }
   };
@@ -59,7 +59,7 @@ struct Inst {
       c.T = T; c.NT = CB::NT; c.NTP = CB::NTP; c.E4 = CB::E4;
       c.smem_fwd = CF::smem_bytes; c.smem_bwd = CB::smem_bytes;
       c.valid_kind = &valid_kind; c.prepare = &prepare; c.launch = &launch;
-      c.tc_T = 0; c.tc_NQ = 0; c.tc_smem_fwd = c.tc_smem_bwd = 0; c.tc_prepare = nullptr; c.tc_launch = nullptr;
+      c.tc_T = 0; c.tc_NQ = 0; c.tc_rmw = 0; c.tc_smem_fwd = c.tc_smem_bwd = 0; c.tc_prepare = nullptr; c.tc_launch = nullptr;
       if constexpr (TCT > 0) Tc<TCT>::fill(c);
       return c;
     }();

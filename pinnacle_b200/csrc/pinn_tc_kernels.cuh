@@ -29,6 +29,7 @@ namespace pinn {
 constexpr int kTcHP = 112;   // neuron count padded to a multiple of 16 (K of the bf16 MMA, N of the dW MMA)
 constexpr int kTcRows = 128; // UMMA M
 constexpr int kTcWMat = 12 * 512;   // uint4 per pre-split operand matrix
+constexpr int kTcGwtLayer4 = 25 * 128;   // float4 per hidden-layer weight-gradient partial, layout [k/4][n (128)][k%4]
 
 struct TcLaunchParams {
   KindParams kp;
@@ -44,7 +45,8 @@ struct TcLaunchParams {
   const float* aux;
   const float* seeds;
   float* stash;        // [grid][L][NQ][C][512] float4
-  float* gpart;        // [grid][n_seeds][Ppad]
+  float* gpart;        // [grid][n_seeds][Ppad]   (hidden-layer weight entries unused on this path)
+  float* gwt;          // [grid][n_seeds][L-1][25][128][4]  hidden-layer weight-gradient partials
   double* lpart;
   float* resid_out;
 };
@@ -62,6 +64,9 @@ struct TCfg {
   static constexpr int JB = (R / 8) * 128;        // bytes between 8-neuron blocks
   static constexpr int ARR = 14 * JB;             // one bf16 split array (112 neuron rows)
   static constexpr int NARR = BWD ? 6 : 3;
+  // dW flush: private read-modify-write partial (cheaper per element, needs the longer MMA window of a 32-point
+  // tile to hide its load latency) or 128-bit REDs (fire-and-forget; better for 16-point tiles)
+  static constexpr bool RMW_FLUSH = (NQ >= 2);
   // TMEM columns
   static constexpr int tcD = 0, tcDW = 160, tcW = 272, tcTotal = 512;
   // shared memory carve-up (bytes)
@@ -100,6 +105,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 // (x0, x1) -> three packed bf16 pairs p1 + p2 + p3 ~= x
 __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+#ifdef PINN_EXP_NO_SPLIT    // what-if timing experiment only
+  p1 = pack_bf16x2(x0, x1); p2 = p1; p3 = p1;
+  return;
+#endif
   p1 = pack_bf16x2(x0, x1);
   float r0 = x0 - __uint_as_float(p1 << 16);
   float r1 = x1 - __uint_as_float(p1 & 0xFFFF0000u);
@@ -192,6 +201,10 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
   if constexpr (BWD) {
     gp = p.gpart + (size_t)blockIdx.x * S * p.Ppad;
     for (long long i = tid; i < (long long)S * p.Ppad; i += NTH) gp[i] = 0.f;
+    if constexpr (CFG::RMW_FLUSH) {
+      float4* gz = reinterpret_cast<float4*>(p.gwt) + (size_t)blockIdx.x * S * (L - 1) * kTcGwtLayer4;
+      for (long long i = tid; i < (long long)S * (L - 1) * kTcGwtLayer4; i += NTH) gz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     __threadfence();
   }
   umma::fence_before_sync();
@@ -201,7 +214,12 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
   const uint32_t tD = tbase + CFG::tcD, tDW = tbase + CFG::tcDW, tW = tbase + CFG::tcW;
 
   float4* stash = reinterpret_cast<float4*>(p.stash) + (size_t)blockIdx.x * L * NQ * C * NTH;
+#ifdef PINN_EXP_NO_STASH   // what-if: no stash memory traffic at all (results wrong)
+  float4 fake_stash_reg = make_float4(0.1f, 0.2f, 0.3f, 0.4f);
+  auto stash_at = [&](int l, int qi, int c) -> float4* { return &fake_stash_reg; };
+#else
   auto stash_at = [&](int l /*1-based layer*/, int qi, int c) -> float4* { return stash + ((size_t)((l - 1) * NQ + qi) * C + c) * NTH + tid; };
+#endif
 
   uint32_t ph0 = 0, ph1 = 0;
   bool w_ready = false;      // W_2 already staged in TMEM by the previous tile's tail
@@ -212,6 +230,9 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
   // previous W: fetch_W() right after an MMA batch is issued, put_W() once that batch has completed.
   uint32_t ws1[16], ws2[16], ws3[16];
   auto fetch_W = [&](const uint4* Wp) {
+#ifdef PINN_EXP_NO_W
+    return;
+#endif
     const uint4* src = Wp + tid;                   // slot-major, thread-minor: every warp load is 512 contiguous bytes
 #pragma unroll
     for (int qd = 0; qd < 4; ++qd) {
@@ -222,6 +243,9 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
     }
   };
   auto put_W = [&]() {
+#ifdef PINN_EXP_NO_W
+    return;
+#endif
     const uint32_t col = tW + lane_off + 16 * g;
     if (g < 3) {
       tmem_st16(col, ws1);
@@ -241,9 +265,13 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
     split3_pair(v0, v1, a1, a2, a3);
     split3_pair(v2, v3, b1, b2, b3);
     const int off = (j >> 3) * JB + (r0 >> 3) * 128 + (j & 7) * 16 + (r0 & 7) * 2;
+#ifdef PINN_EXP_NO_STS      // what-if timing experiment only (results wrong)
+    if (a1 == 0x12345678u) *reinterpret_cast<uint2*>(arr[0] + off) = make_uint2(a1 ^ a2 ^ a3, b1 ^ b2 ^ b3);
+#else
     *reinterpret_cast<uint2*>(arr[0] + off) = make_uint2(a1, b1);
     *reinterpret_cast<uint2*>(arr[1] + off) = make_uint2(a2, b2);
     *reinterpret_cast<uint2*>(arr[2] + off) = make_uint2(a3, b3);
+#endif
   };
 
   // D (+)= Wop[TMEM] * B[smem, MN-major]: 7 k-steps x 6 split products, small terms first
@@ -260,6 +288,9 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
 #pragma unroll 1
       for (int ks = 0; ks < kTcHP / 16; ++ks) {
         const uint64_t bd = umma::make_smem_desc(umma::smem_addr(barr[ab[t]]) + ks * 2 * JB, JB, 128);
+#ifdef PINN_EXP_ONE_MMA     // what-if: (almost) no tensor work
+        if (t != 5 || ks != 0) continue;
+#endif
         umma::mma_bf16_ts(tD, tW + wa[t] * 56 + ks * 8, bd, idesc, accum);
         accum = 1;
       }
@@ -278,6 +309,9 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
       for (int ks = 0; ks < R / 16; ++ks) {
         const uint64_t ad = umma::make_smem_desc(umma::smem_addr(arrZ[za[t]]) + ks * 256, 128, JB);
         const uint64_t bd = umma::make_smem_desc(umma::smem_addr(arrA[ab[t]]) + ks * 256, 128, JB);
+#ifdef PINN_EXP_ONE_MMA
+        if (t != 5 || ks != 0) continue;
+#endif
         umma::mma_bf16_ss(tDW, ad, bd, idesc, accum);
         accum = 1;
       }
@@ -298,6 +332,10 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
   };
   // sum a per-thread partial over the 4 column groups (fixed order) and RED it to one address
   auto reduce_groups_red = [&](float v, float* dst) {
+#ifdef PINN_EXP_NO_RED
+    if (v == 12345.f) atomicAdd(dst, v);
+    return;
+#endif
     redbuf[g * 128 + j] = v;
     __syncthreads();
     if (g == 0 && act) atomicAdd(dst, (redbuf[j] + redbuf[128 + j]) + (redbuf[256 + j] + redbuf[384 + j]));
@@ -595,16 +633,30 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
           if (l == 2 && s + 1 >= S && nextW != nullptr) w_ready = true;
           wait_bar(bar1, ph1);
           {
-            // flush dW_l[n = j][k] from TMEM: this group's 28-column slice, as float4 REDs
-            float* gw = gs + offHid + (long long)(l - 2) * strideHid + (long long)j * H;
             const int k0 = 28 * g;
             float v[7][4];
 #pragma unroll
             for (int i = 0; i < 7; ++i) umma::tmem_ld4(tDW + lane_off + k0 + 4 * i, v[i]);
             umma::wait_ld();
+            if constexpr (CFG::RMW_FLUSH) {
+              // Flush dW_l into this CTA's private partial by plain read-modify-write (single writer, so no atomics:
+              // 10^4 scalar-equivalent REDs per layer cost ~10k cycles per tile).  Partial layout [k/4][n = j][k%4]:
+              // consecutive lanes touch consecutive 16-byte words.
+              float4* gt = reinterpret_cast<float4*>(p.gwt) + ((size_t)(blockIdx.x * S + s) * (L - 1) + (l - 2)) * kTcGwtLayer4;
+              float4 old[7];
 #pragma unroll
-            for (int i = 0; i < 7; ++i)
-              if (act && k0 + 4 * i < H) atomicAdd(reinterpret_cast<float4*>(gw + k0 + 4 * i), make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
+              for (int i = 0; i < 7; ++i)
+                if (k0 + 4 * i < H) old[i] = gt[(size_t)(k0 / 4 + i) * 128 + j];
+#pragma unroll
+              for (int i = 0; i < 7; ++i)
+                if (k0 + 4 * i < H)
+                  gt[(size_t)(k0 / 4 + i) * 128 + j] = make_float4(old[i].x + v[i][0], old[i].y + v[i][1], old[i].z + v[i][2], old[i].w + v[i][3]);
+            } else {
+              float* gw = gs + offHid + (long long)(l - 2) * strideHid + (long long)j * H;
+#pragma unroll
+              for (int i = 0; i < 7; ++i)
+                if (act && k0 + 4 * i < H) atomicAdd(reinterpret_cast<float4*>(gw + k0 + 4 * i), make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
+            }
           }
           wait_bar(bar0, ph0);       // abar^{l-1} is now in D
           if (nextW != nullptr) put_W();
