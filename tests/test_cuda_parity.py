@@ -148,6 +148,26 @@ def test_full_size_properties(name):
     assert abs(float((resid.double() ** 2).sum(0).cpu()[0]) / n - float(full[P].cpu())) <= 1e-5 * float(full[P].cpu())
 
 
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("L", [2, 3, 7])
+def test_other_depths_match_oracle(L, impl):
+    """--hidden-layers 100*L for L != 5 (benchmark.py:65): depth is a run-time parameter of both kernels."""
+    from oracle import autograd_ref as O
+    from pinnacle_b200 import capi, problems
+    from golden import common
+    dev = _cuda()
+    spec = problems.make("Burgers1D")
+    desc = spec.desc.with_net(100, L)
+    _select_impl(impl, desc)
+    flat64 = common.golden_params(desc.layer_shapes(), 11 + L)
+    x64 = spec.sample(1500, seed=L, dtype=np.float32).astype(np.float64)
+    ol, og, orr = O.losses_and_grads(desc, torch.as_tensor(flat64), torch.as_tensor(x64), None)
+    out = capi.fwd_bwd(desc, torch.as_tensor(flat64).float().to(dev), torch.as_tensor(x64).float().to(dev), None, 1.0 / 1500,
+                       torch.ones(1, 1, device=dev))
+    assert_parity(out[desc.n_params:].cpu().numpy(), ol.numpy(), "loss")
+    assert_parity(out[:desc.n_params].cpu().numpy(), og[0].numpy(), "grad")
+
+
 def test_errors_are_loud():
     from pinnacle_b200 import capi, kinds
     dev = _cuda()
