@@ -144,6 +144,33 @@ def cpu_reference_run(points_per_problem: int, steps: int, warmup: int):
     return pts / dt, dt * 1e3, cores, pts
 
 
+def gpu_autograd_run(points_per_problem: int, steps: int, warmup: int, dev):
+    """The reference ALGORITHM (nested reverse-mode autograd, oracle/autograd_ref.py) with stock PyTorch CUDA kernels on
+    the same GPU -- what a PINNacle user runs today.  Bounded sample: the retained graph is ~70 KB/point."""
+    from oracle import autograd_ref as O
+    from pinnacle_b200 import problems
+    specs = [problems.make(n) for n in WORKLOAD_PROBLEMS]
+    work = []
+    for i, spec in enumerate(specs):
+        work.append((spec.desc, _seeded_params(spec.desc, seed=i).to(dev), torch.as_tensor(spec.sample(points_per_problem, seed=100 + i)).to(dev)))
+
+    def step():
+        for desc, flat, x in work:
+            O.train_step_cpu(desc, flat, x, None)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return points_per_problem * len(specs) / (ms * 1e-3), ms
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -354,6 +381,16 @@ def run_fused(args):
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
                "sample": f"{args.cpu_points} points of each of {'+'.join(WORKLOAD_PROBLEMS)} per step, 1 warm-up + 2 timed steps, torch autograd (reference algorithm) on the host cores, denormals flushed"}
 
+    gpu_ref = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, ms = gpu_autograd_run(args.gpu_ref_points, 3, 2, dev)
+            gpu_ref = {"value": v, "unit": UNIT, "ms_per_step": ms, "kind": "port",
+                       "sample": f"{args.gpu_ref_points} points of each problem per step; reference algorithm (nested torch.autograd) with stock "
+                                 "PyTorch CUDA kernels on this GPU"}
+        except Exception as e:  # noqa: BLE001
+            gpu_ref = {"error": repr(e)[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -363,6 +400,7 @@ def run_fused(args):
                    "points_per_step": pts_step, "l2": "flushed between timed iterations (256 MiB write outside the event pair)",
                    "parallelism": f"dp{world} over collocation points", "wall_s_timed_region": t_wall, "kernel": args.kernel},
         "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_autograd_baseline": gpu_ref,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -379,7 +417,8 @@ def main():
     ap.add_argument("--impl", choices=["fused", "reference"], default="fused")
     ap.add_argument("--kernel", choices=["auto", "ffma", "tc"], default="auto",
                     help="fused arm only: tcgen05 tensor-core kernel (auto/tc) or the FP32 FFMA kernel")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gpu-ref-points", type=int, default=131072, help="points per problem of the stock-PyTorch-on-GPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU and stock-PyTorch-GPU baselines")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

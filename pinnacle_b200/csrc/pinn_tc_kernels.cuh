@@ -170,7 +170,11 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
   const int warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, g = warp >> 2;         // TMEM lane quarter, column group
   const int j = 32 * q + lane;                   // neuron owned by this thread
+#ifdef PINN_EXP_NO_ELEMENTWISE   // what-if: only MMAs, syncs, operand staging, flush
+  const bool act = false;
+#else
   const bool act = j < H;
+#endif
   const uint32_t lane_off = (uint32_t)(32 * q) << 16;
   const int L = p.L;
   const int S = BWD ? p.n_seeds : 0;
