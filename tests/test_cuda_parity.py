@@ -111,6 +111,24 @@ def test_bitwise_deterministic(impl):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("impl", IMPLS)
+def test_repeated_runs_stay_bitwise_identical(impl):
+    """Poor man's race check (compute-sanitizer is closed on this pool): 12 repeats x 3 problem shapes x ragged sizes."""
+    from pinnacle_b200 import capi, problems
+    dev = _cuda()
+    for name, n in (("NS2D_LidDriven", 9973), ("Heat2D_Multiscale", 20011), ("KuramotoSivashinskyEquation", 4801)):
+        spec = problems.make(name)
+        _select_impl(impl, spec.desc)
+        x = torch.as_tensor(spec.sample(n, seed=n)).to(dev)
+        flat = torch.as_tensor(Golden(name).flat64).float().to(dev)
+        seeds = torch.ones(2, spec.desc.n_pde, device=dev)
+        seeds[1] *= 0.5
+        first = capi.fwd_bwd(spec.desc, flat, x, None, 1.0 / n, seeds).clone()
+        assert torch.isfinite(first).all()
+        for _ in range(12):
+            assert torch.equal(capi.fwd_bwd(spec.desc, flat, x, None, 1.0 / n, seeds), first)
+
+
 @pytest.mark.parametrize("name", ["Poisson2D_Classic", "Heat2D_Multiscale", "NS2D_LidDriven"])
 def test_full_size_properties(name):
     """At BASELINE.json's 1M-point size the oracle is out of reach; check size-independent properties:
