@@ -55,7 +55,10 @@ enum pinn_kind {
   PINN_KIND_NS2D_UNSTEADY = 4, /* ns.py:330-352      + u_t, v_t, aux[aux_sel[0]] added to mom-y  */
   PINN_KIND_HEAT_NLSRC = 5,    /* heat.py:214-222    u_t - c0 lap u - c1 sin(c2 u^2) aux          */
   PINN_KIND_GRAYSCOTT = 6,     /* chaotic.py:21-31   c0,c1 = eps; c2 = b; c3 = d                  */
-  PINN_KIND_KS = 7             /* chaotic.py:77-83   u_t + c0 u u_x + c1 u_xx + c2 u_xxxx         */
+  PINN_KIND_KS = 7,            /* chaotic.py:77-83   u_t + c0 u u_x + c1 u_xx + c2 u_xxxx         */
+  /* value-type boundary / initial / point-set term: r = u_c - g(x), c = (int)consts[0], g = aux[aux_sel[0]]
+   * (deepxde/icbc/boundary_conditions.py:73-80,214-241; initial_conditions.py:29-36).  Jet-free signature (all orders 0). */
+  PINN_KIND_VALUE = 8
 };
 
 typedef struct pinn_kind_desc {

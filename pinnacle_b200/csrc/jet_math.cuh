@@ -212,6 +212,7 @@ struct Residual {
       case PINN_KIND_HEAT_NLSRC: return M == 1 && D == 3 && sig22() && SIG::order(D - 1) >= 1;
       case PINN_KIND_GRAYSCOTT: return M == 2 && D == 3 && sig22() && SIG::order(D - 1) >= 1;
       case PINN_KIND_KS: return M == 1 && D == 2 && SIG::order(0) >= 4 && SIG::order(1) >= 1;
+      case PINN_KIND_VALUE: return C == 1;
       default: return false;
     }
   }
@@ -308,6 +309,13 @@ struct Residual {
             r[0] = U[0][SIG::chan(1, 1)] + c[0] * u * ux + c[1] * 2.0f * U[0][SIG::chan(0, 2)] + c[2] * 24.0f * U[0][SIG::chan(0, 4)];
           }
         }
+      } break;
+      case PINN_KIND_VALUE: {
+        const int comp = (int)c[0];
+        float u = U[0][0];
+#pragma unroll
+        for (int o = 1; o < M; ++o) u = (comp == o) ? U[o][0] : u;
+        r[0] = u - aux[kp.aux_sel[0]];
       } break;
       default: break;
     }
@@ -430,6 +438,11 @@ struct Residual {
             Ub[0][SIG::chan(1, 1)] = g;
           }
         }
+      } break;
+      case PINN_KIND_VALUE: {
+        const int comp = (int)c[0];
+#pragma unroll
+        for (int o = 0; o < M; ++o) Ub[o][0] = (comp == o) ? rb[0] : 0.f;
       } break;
       default: break;
     }

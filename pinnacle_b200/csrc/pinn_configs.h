@@ -12,6 +12,7 @@
 //  8  KuramotoSivashinsky                          (4,1)
 //  9  PoissonND                                    (2,2,2,2,2)
 // 10  HeatND                                       (2,2,2,2,2,1)
+// 11-18 value-type BC/IC/point-set terms (PINN_KIND_VALUE): jet-free signatures (0,..,0), d x m = 2x1 2x3 3x1 3x2 3x3 1x1 5x1 6x1
 #pragma once
 
 #define PINN_FOR_EACH_CONFIG(X)        \
@@ -25,6 +26,14 @@
   X(7, 100, 1, 16, 2, 16, 2, 2, 2)         \
   X(8, 100, 1, 32, 4, 16, 4, 1)            \
   X(9, 100, 1, 16, 2, 0, 2, 2, 2, 2, 2)   \
-  X(10, 100, 1, 16, 2, 0, 2, 2, 2, 2, 2, 1)
+  X(10, 100, 1, 16, 2, 0, 2, 2, 2, 2, 2, 1) \
+  X(11, 100, 1, 32, 4, 0, 0, 0)            \
+  X(12, 100, 3, 32, 4, 0, 0, 0)            \
+  X(13, 100, 1, 32, 4, 0, 0, 0, 0)         \
+  X(14, 100, 2, 32, 4, 0, 0, 0, 0)         \
+  X(15, 100, 3, 32, 4, 0, 0, 0, 0)         \
+  X(16, 100, 1, 32, 4, 0, 0)               \
+  X(17, 100, 1, 32, 4, 0, 0, 0, 0, 0, 0)   \
+  X(18, 100, 1, 32, 4, 0, 0, 0, 0, 0, 0, 0)
 
-#define PINN_NUM_CONFIGS 11
+#define PINN_NUM_CONFIGS 19

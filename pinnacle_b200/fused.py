@@ -173,6 +173,14 @@ class FusedPDEResidual:
             self.aux = self.spec.aux(self.x).to(torch.float32).contiguous()
         return self
 
+    def set_rows(self, x_dev: torch.Tensor, aux_dev: Optional[torch.Tensor], n_global: Optional[int] = None):
+        """Install already device-resident rows and aux columns (used for fused boundary terms)."""
+        self.x = x_dev.to(torch.float32).contiguous()
+        self.aux = None if aux_dev is None else aux_dev.to(torch.float32).contiguous()
+        self.n_global = int(n_global if n_global is not None else self.x.shape[0])
+        self.inv_n_global = 1.0 / max(self.n_global, 1)
+        return self
+
     def losses(self, params: Sequence[torch.Tensor]) -> torch.Tensor:
         """Per-term mean-square PDE losses [n_pde] (global mean over all ranks' rows)."""
         if self.x is None:

@@ -30,6 +30,7 @@ KIND_NS2D_UNSTEADY = 4   # src/pde/ns.py:330-352
 KIND_HEAT_NLSRC = 5      # src/pde/heat.py:214-222
 KIND_GRAYSCOTT = 6       # src/pde/chaotic.py:21-31
 KIND_KS = 7              # src/pde/chaotic.py:77-83
+KIND_VALUE = 8           # value-type BC/IC/point-set term: u_c - g(x)  (icbc/boundary_conditions.py:73-80,214-241)
 
 KIND_NAMES = {
     KIND_LINEAR: "linear",
@@ -40,6 +41,7 @@ KIND_NAMES = {
     KIND_HEAT_NLSRC: "heat_nlsrc",
     KIND_GRAYSCOTT: "grayscott",
     KIND_KS: "ks",
+    KIND_VALUE: "value",
 }
 
 # LINEAR kind constant layout
@@ -159,6 +161,13 @@ class KindDesc:
         for i in range(PINN_MAX_CONSTS):
             c.consts[i] = self.consts[i]
         return c
+
+
+def value_desc(d: int, m: int, component: int, name: str = "") -> KindDesc:
+    """Descriptor of a value-type boundary / initial / point-set term r = u_component - target (target = aux column 0)."""
+    if not 0 <= component < m:
+        raise ValueError(f"component {component} outside 0..{m - 1}")
+    return KindDesc(KIND_VALUE, d, m, (0,) * d, 1, 1, [float(component)], [0], name=name)
 
 
 def linear_desc(d: int, order: Sequence[int], cu: float = 0.0, c1: Sequence[float] = (), c2: Sequence[float] = (),

@@ -20,9 +20,16 @@ from typing import Callable, List, Optional, Sequence
 import numpy as np
 import torch
 
+from collections import namedtuple
+
 from . import capi
 from .fused import FusedPDEResidual, net_linear_params, net_shape
+from .kinds import value_desc
 from .problems import ProblemSpec, describe_reference
+
+# A value-type boundary / initial / point-set term on BC rows [beg, end):  u[:, component] - values
+# (DirichletBC / IC / PointSetBC of deepxde/icbc).  Evaluated by the fused op (kind VALUE) instead of stock autograd.
+ValueBC = namedtuple("ValueBC", ["beg", "end", "component", "values"])
 
 
 def _mse(err: torch.Tensor) -> torch.Tensor:
@@ -45,6 +52,30 @@ class _StepCore:
         self.n_global = n_global        # set => the rows handed to stage() are this rank's own share
         self._key = None
         self._x_bc = None
+        self._shape = (d, H, L, m)
+        self._policy = policy
+        self._value_ops = {}            # (term index) -> FusedPDEResidual of kind VALUE
+        self.generation = 0             # bumped whenever new rows are staged
+
+    def value_term_loss(self, idx: int, beg: int, end: int, component: int, values_fn):
+        """Mean-square of u[beg:end, component] - values on the staged BC rows through the fused op.
+        `values_fn()` is called once per staged point set and must return an array/tensor broadcastable to [n, 1]."""
+        d, H, L, m = self._shape
+        ent = self._value_ops.get(idx)
+        if ent is None or ent[1] != self.generation:
+            op = ent[0] if ent is not None else FusedPDEResidual(
+                ProblemSpec(f"value_bc_{idx}", value_desc(d, m, int(component)), [0, 1] * d), H, L, policy="eager", device=self.op.device)
+            op.world, op.rank = 1, 0              # BC rows are replicated on every rank (SURVEY.md §8e)
+            n = end - beg
+            vals = torch.as_tensor(values_fn(), dtype=torch.float32).to(self.op.device).reshape(-1, 1) if n > 0 else torch.zeros(0, 1)
+            if vals.shape[0] == 1 and n != 1:
+                vals = vals.expand(n, 1)
+            if vals.shape[0] != n:
+                raise capi.FusedOpError(f"boundary term {idx}: {vals.shape[0]} target values for {n} rows")
+            op.set_rows(self._x_bc[beg:end], vals.contiguous(), n)
+            self._value_ops[idx] = (op, self.generation)
+            ent = self._value_ops[idx]
+        return ent[0].losses(self.params)
 
     def stage(self, inputs, n_bc: int):
         """Make the rows of ``inputs`` device-resident: BC rows -> self._x_bc, residual rows -> fused op.
@@ -63,6 +94,7 @@ class _StepCore:
         if n_bc > 0 and xt.device != self.op.device:
             self.op.stats["h2d_bytes"] += n_bc * xt.shape[1] * 4
         self._key = key
+        self.generation += 1
 
 
 class FusedPDESolver:
@@ -110,11 +142,20 @@ class FusedPDESolver:
         terms = [pde_losses]
         outputs_ = None
         if self.n_bc > 0:
-            x_bc = core._x_bc.detach().requires_grad_(True)
-            y_bc = self.net(x_bc)
-            outputs_ = y_bc
-            if self.bc_terms:
-                terms.append(torch.stack([_mse(f(x_bc, y_bc)) for f in self.bc_terms]))
+            need_torch = any(not isinstance(f, ValueBC) for f in self.bc_terms) or not self.bc_terms
+            x_bc = y_bc = None
+            if need_torch:
+                x_bc = core._x_bc.detach().requires_grad_(True)
+                y_bc = self.net(x_bc)
+                outputs_ = y_bc
+            for i, f in enumerate(self.bc_terms):
+                if isinstance(f, ValueBC):
+                    if f.end - f.beg == 0:
+                        terms.append(torch.full((1,), float("nan"), device=pde_losses.device))   # mean over no rows, as the reference
+                    else:
+                        terms.append(core.value_term_loss(i, f.beg, f.end, f.component, lambda f=f: f.values))
+                else:
+                    terms.append(_mse(f(x_bc, y_bc)).reshape(1))
         losses = torch.cat(terms)
         if self.loss_weights is not None:
             losses = losses * torch.as_tensor(self.loss_weights, dtype=losses.dtype, device=losses.device)
@@ -192,11 +233,13 @@ class FusedPDESolver:
         return loss
 
 
-def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto", cache_points: bool = True, group=None):
+def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto", cache_points: bool = True, group=None,
+                 fuse_bcs: bool = True):
     """Swap a COMPILED reference ``dde.Model`` onto the fused path (call after ``model.compile``).
 
     Raises (never falls back) when the problem class, the net or the data object is outside what
-    the fused path covers."""
+    the fused path covers.  With ``fuse_bcs`` (default) value-type boundary terms (DirichletBC, IC, PointSetBC) also run
+    through the fused op (kind VALUE); Neumann / Robin / Periodic / Operator terms stay stock PyTorch on the BC rows."""
     if getattr(model, "opt", None) is None or not hasattr(model, "train_step"):
         raise capi.FusedOpError("enable_fused() must be called after model.compile()")
     data, net = model.data, model.net
@@ -225,15 +268,24 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
         training_graph = any(p.requires_grad for p in core.params)
         outputs_ = None
         if n_bc > 0:
-            x_bc = core._x_bc.detach().requires_grad_(True)
-            y_bc = net(x_bc)
             bcs_start = np.cumsum([0] + list(data.num_bcs))
-            errs = []
+            fused_ok = [fuse_bcs and _value_bc_info(bc) is not None for bc in data.bcs]
+            x_bc = y_bc = None
+            if not all(fused_ok):
+                x_bc = core._x_bc.detach().requires_grad_(True)
+                y_bc = net(x_bc)
+                outputs_ = y_bc
             for i, bc in enumerate(data.bcs):
                 beg, end = int(bcs_start[i]), int(bcs_start[i + 1])
-                errs.append(_mse(bc.error(data.train_x, x_bc, y_bc, beg, end)))   # data/pde.py:153-157
-            terms.append(torch.stack(errs))
-            outputs_ = y_bc
+                if fused_ok[i]:
+                    # DirichletBC / IC / PointSetBC: u[beg:end, c] - values, values evaluated once per point set
+                    comp, values_fn = _value_bc_info(bc)
+                    if end == beg:
+                        terms.append(torch.full((1,), float("nan"), device=pde_losses.device))   # mean over no rows, as the reference
+                    else:
+                        terms.append(core.value_term_loss(i, beg, end, comp, lambda vf=values_fn, b=beg, e=end: vf(data.train_x, b, e)))
+                else:
+                    terms.append(_mse(bc.error(data.train_x, x_bc, y_bc, beg, end)).reshape(1))   # data/pde.py:153-157
         if not training_graph:
             # _test()/predict bookkeeping wants outputs for every row (model.py:767-780): plain forward
             with torch.no_grad():
@@ -272,6 +324,32 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
     model.train_step = train_step
     model.fused_core = core
     return model
+
+
+def _value_bc_info(bc):
+    """(component, values_fn(X, beg, end)) when `bc` is a value-type term u[:, c] - g, else None.
+    Mirrors DirichletBC.error / IC.error / PointSetBC.error (icbc/boundary_conditions.py:73-80,214-241;
+    initial_conditions.py:29-36)."""
+    name = type(bc).__name__
+    comp = getattr(bc, "component", None)
+    if not isinstance(comp, (int, np.integer)):
+        return None
+    if name in ("DirichletBC", "IC"):
+        func = bc.func
+
+        def values(X, beg, end):
+            v = func(X, beg, end, None)
+            return v.detach() if isinstance(v, torch.Tensor) else v
+
+        return int(comp), values
+    if name == "PointSetBC" and getattr(bc, "batch_size", None) is None:
+        vals = bc.values
+
+        def values(X, beg, end):
+            return vals.detach() if isinstance(vals, torch.Tensor) else vals
+
+        return int(comp), values
+    return None
 
 
 def _clear_dde_grad_cache():

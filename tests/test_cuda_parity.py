@@ -186,6 +186,25 @@ def test_other_depths_match_oracle(L, impl):
     assert_parity(out[:desc.n_params].cpu().numpy(), og[0].numpy(), "grad")
 
 
+@pytest.mark.parametrize("d,m,comp,n", [(2, 1, 0, 129), (2, 3, 2, 1), (3, 2, 1, 2049), (3, 3, 0, 513), (1, 1, 0, 77), (5, 1, 0, 300), (6, 1, 0, 300)])
+def test_value_bc_kind_matches_oracle(d, m, comp, n):
+    """Fused value-type boundary / initial / point-set term (kind VALUE) vs the oracle restatement of DirichletBC.error."""
+    from oracle import autograd_ref as O
+    from golden import common
+    from pinnacle_b200 import capi, kinds
+    dev = _cuda()
+    desc = kinds.value_desc(d, m, comp)
+    rs = np.random.RandomState(n)
+    flat = common.golden_params(desc.layer_shapes(), 5)
+    x = rs.uniform(-1, 1, (n, d)).astype(np.float32).astype(np.float64)
+    tgt = rs.standard_normal((n, 1)).astype(np.float32).astype(np.float64)
+    ol, og, orr = O.losses_and_grads(desc, torch.as_tensor(flat), torch.as_tensor(x), torch.as_tensor(tgt))
+    out = capi.fwd_bwd(desc, torch.as_tensor(flat).float().to(dev), torch.as_tensor(x).float().to(dev), torch.as_tensor(tgt).float().to(dev),
+                       1.0 / n, torch.ones(1, 1, device=dev))
+    assert_parity(out[desc.n_params:].cpu().numpy(), ol.numpy(), "loss")
+    assert_parity(out[:desc.n_params].cpu().numpy(), og[0].numpy(), "grad")
+
+
 def test_errors_are_loud():
     from pinnacle_b200 import capi, kinds
     dev = _cuda()

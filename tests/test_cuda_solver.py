@@ -88,7 +88,9 @@ def test_fixed_seed_training_run_matches_reference_algorithm():
     steps = 150
     net_a, net_b = _net(spec.desc, dev, 7), _net(spec.desc, torch.device("cpu"), 7)
     tgt_dev = torch.as_tensor(target_np, device=dev)
-    solver = FusedPDESolver(spec, net_a, x, x_ic, [lambda xb, yb: yb[:, 0:1] - tgt_dev])
+    from pinnacle_b200.solver import ValueBC
+    # initial condition as a FUSED value-type term on the first 128 rows and as a stock-PyTorch term on the rest
+    solver = FusedPDESolver(spec, net_a, x, x_ic, [ValueBC(0, 128, 0, target_np[:128]), lambda xb, yb: (yb[:, 0:1] - tgt_dev)[128:]])
     solver.compile(torch.optim.Adam(net_a.parameters(), 1e-3))
     hist_a = []
     for _ in range(steps):
@@ -102,8 +104,8 @@ def test_fixed_seed_training_run_matches_reference_algorithm():
         opt.zero_grad()
         flat = torch.cat([p.reshape(-1) for p in net_b.parameters()])
         losses, _, _ = O.pde_losses(spec.desc, flat, xt, None)
-        bc = torch.mean(torch.square(net_b(xi)[:, 0:1] - tg))
-        all_l = torch.cat([losses, bc.reshape(1)])
+        err = net_b(xi)[:, 0:1] - tg
+        all_l = torch.cat([losses, torch.mean(torch.square(err[:128])).reshape(1), torch.mean(torch.square(err[128:])).reshape(1)])
         all_l.sum().backward()
         opt.step()
         hist_b.append(all_l.detach().numpy().copy())

@@ -45,3 +45,28 @@ def test_structural_zero_output_bias(harness_lib):
     G = Golden("Poisson2D_Classic")
     _, grad, _ = _run(harness_lib, G, np.eye(1, dtype=np.float32))
     assert grad[0, -1] == 0.0
+
+
+def test_value_kind_matches_oracle(harness_lib):
+    """Value-type boundary term (kind VALUE, jet-free signature) of the device math vs the oracle."""
+    from oracle import autograd_ref as O
+    from golden import common
+    from pinnacle_b200 import kinds
+    for d, m, comp in ((2, 1, 0), (2, 3, 2), (3, 2, 1)):
+        desc = kinds.value_desc(d, m, comp)
+        rs = np.random.RandomState(d * 10 + m)
+        flat = common.golden_params(desc.layer_shapes(), 5).astype(np.float32)
+        x = rs.uniform(-1, 1, (53, d)).astype(np.float32)
+        tgt = rs.standard_normal((53, 1)).astype(np.float32)
+        ol, og, orr = O.losses_and_grads(desc, torch.as_tensor(flat).double(), torch.as_tensor(x).double(), torch.as_tensor(tgt).double())
+        n, P = 53, desc.n_params
+        grad = np.zeros((1, P)); loss = np.zeros(3); resid = np.zeros((n, 1), np.float32)
+        cd = desc.to_c()
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        seeds = np.ones((1, 1), np.float32)
+        rc = harness_lib.harness_run(ctypes.byref(cd), vp(flat), vp(x), vp(tgt), ctypes.c_longlong(n), ctypes.c_double(1.0 / n), vp(seeds), 1,
+                                     vp(grad), vp(loss), vp(resid))
+        assert rc == 0
+        assert_parity(resid, orr.numpy(), "residual")
+        assert_parity(loss[:1], ol.numpy(), "loss")
+        assert_parity(grad, og.numpy(), "grad")
