@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pinnacle_b200 import problems
 from pinnacle_b200.nn import FNN
-from pinnacle_b200.solver import FusedPDESolver
+from pinnacle_b200.solver import FusedPDESolver, ValueBC
 from oracle import autograd_ref as O
 dev = torch.device("cuda:0")
 for name, n_pde, n_bc in (("Burgers1D", 12288, 4096), ("Poisson2D_Classic", 10240, 2048), ("NS2D_LidDriven", 10240, 4097), ("Heat2D_Multiscale", 49152, 16385)):
@@ -16,7 +16,7 @@ for name, n_pde, n_bc in (("Burgers1D", 12288, 4096), ("Poisson2D_Classic", 1024
     x = spec.sample(n_pde, seed=1)
     xb = spec.sample(n_bc, seed=2)
     tgt = torch.zeros(n_bc, 1, device=dev)
-    solver = FusedPDESolver(spec, net, x, xb, [lambda a, y: y[:, 0:1] - tgt]).compile(torch.optim.Adam(net.parameters(), 1e-3))
+    solver = FusedPDESolver(spec, net, x, xb, [ValueBC(0, n_bc, 0, np.zeros((n_bc, 1), np.float32))]).compile(torch.optim.Adam(net.parameters(), 1e-3))
     for _ in range(20):
         solver.train_step()
     torch.cuda.synchronize()
@@ -48,7 +48,7 @@ for name, n_pde, n_bc in (("Burgers1D", 12288, 4096), ("Poisson2D_Classic", 1024
     # same step replayed from a CUDA graph
     torch.manual_seed(0)
     net3 = FNN([d.d] + [100] * 5 + [d.m]).to(dev)
-    s3 = FusedPDESolver(spec, net3, x, xb, [lambda a, y: y[:, 0:1] - tgt]).compile(torch.optim.Adam(net3.parameters(), 1e-3, capturable=True))
+    s3 = FusedPDESolver(spec, net3, x, xb, [ValueBC(0, n_bc, 0, np.zeros((n_bc, 1), np.float32))]).compile(torch.optim.Adam(net3.parameters(), 1e-3, capturable=True))
     s3.capture_step()
     for _ in range(20):
         s3.train_step()

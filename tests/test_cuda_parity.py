@@ -197,7 +197,8 @@ def test_value_bc_kind_matches_oracle(d, m, comp, n):
     rs = np.random.RandomState(n)
     flat = common.golden_params(desc.layer_shapes(), 5)
     x = rs.uniform(-1, 1, (n, d)).astype(np.float32).astype(np.float64)
-    tgt = rs.standard_normal((n, 1)).astype(np.float32).astype(np.float64)
+    # targets offset so a single-row term (PointSetBC at one point, ns.py:196-201) is not a u ~ g cancellation
+    tgt = (rs.standard_normal((n, 1)) + 2.0).astype(np.float32).astype(np.float64)
     ol, og, orr = O.losses_and_grads(desc, torch.as_tensor(flat), torch.as_tensor(x), torch.as_tensor(tgt))
     out = capi.fwd_bwd(desc, torch.as_tensor(flat).float().to(dev), torch.as_tensor(x).float().to(dev), torch.as_tensor(tgt).float().to(dev),
                        1.0 / n, torch.ones(1, 1, device=dev))
