@@ -211,7 +211,7 @@ def run_fused(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     capi.load()
-    capi.set_impl({"auto": capi.IMPL_AUTO, "ffma": capi.IMPL_FFMA, "tc": capi.IMPL_TC}[args.kernel])
+    capi.set_impl({"auto": capi.IMPL_AUTO, "ffma": capi.IMPL_FFMA, "tc": capi.IMPL_TC, "tc2": capi.IMPL_TC_PIPELINED}[args.kernel])
 
     n_per = args.points                      # per problem, per GPU (weak scaling)
     specs = [problems.make(n) for n in WORKLOAD_PROBLEMS]
@@ -415,7 +415,7 @@ def main():
     ap.add_argument("--points", type=int, default=1 << 20, help="collocation points per problem per GPU")
     ap.add_argument("--cpu-points", type=int, default=16384, help="points per problem of the bounded CPU sample")
     ap.add_argument("--impl", choices=["fused", "reference"], default="fused")
-    ap.add_argument("--kernel", choices=["auto", "ffma", "tc"], default="auto",
+    ap.add_argument("--kernel", choices=["auto", "ffma", "tc", "tc2"], default="auto",
                     help="fused arm only: tcgen05 tensor-core kernel (auto/tc) or the FP32 FFMA kernel")
     ap.add_argument("--gpu-ref-points", type=int, default=131072, help="points per problem of the stock-PyTorch-on-GPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU and stock-PyTorch-GPU baselines")

@@ -193,11 +193,11 @@ def fwd_bwd(desc: KindDesc, params: torch.Tensor, x: torch.Tensor, aux: Optional
     return out
 
 
-IMPL_AUTO, IMPL_FFMA, IMPL_TC = 0, 1, 2
+IMPL_AUTO, IMPL_FFMA, IMPL_TC, IMPL_TC_PIPELINED = 0, 1, 2, 3
 
 
 def set_impl(impl: int):
-    """0 = auto (tensor cores where instantiated), 1 = FP32 FFMA kernel, 2 = tcgen05 tensor-core kernel."""
+    """0 = auto, 1 = FP32 FFMA kernel, 2 = tcgen05 tensor-core kernel, 3 = pipelined tcgen05 kernel (falls back to 2 where not instantiated)."""
     _check(load().pinn_set_impl(int(impl)), "pinn_set_impl")
 
 

@@ -20,7 +20,7 @@ LIB = os.path.join(HERE, "libpinn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("PINN_EXTRA_NVCC_FLAGS", "").split()
-HEADERS = ["jet_math.cuh", "pinn_kernels.cuh", "pinn_configs.h", "pinn_dispatch.h", "pinn_inst.inl", "pinn_helpers.cuh", "umma.cuh", "pinn_tc_kernels.cuh",
+HEADERS = ["jet_math.cuh", "pinn_kernels.cuh", "pinn_configs.h", "pinn_dispatch.h", "pinn_inst.inl", "pinn_helpers.cuh", "umma.cuh", "pinn_tc_kernels.cuh", "pinn_tc2_kernels.cuh",
            os.path.join("..", "..", "include", "pinn_b200.h")]
 
 

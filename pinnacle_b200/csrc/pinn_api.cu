@@ -28,16 +28,21 @@ static const ConfigInfo* const* all_configs() {
 
 static thread_local std::string g_err;
 static thread_local int g_launches = 0;
+int g_tc_pipelined = 0;
 static int g_impl = 0;   // 0 = auto (tensor cores where instantiated), 1 = FP32 FFMA kernel, 2 = tensor cores (error if absent)
 
 static int effective_impl() {
-  if (g_impl != 0) return g_impl;
-  const char* e = getenv("PINN_IMPL");
-  if (e != nullptr) {
-    if (strcmp(e, "ffma") == 0) return 1;
-    if (strcmp(e, "tc") == 0) return 2;
+  int impl = g_impl;
+  if (impl == 0) {
+    const char* e = getenv("PINN_IMPL");
+    if (e != nullptr) {
+      if (strcmp(e, "ffma") == 0) impl = 1;
+      if (strcmp(e, "tc") == 0) impl = 2;
+      if (strcmp(e, "tc2") == 0) impl = 3;
+    }
   }
-  return 0;
+  g_tc_pipelined = (impl == 3) ? 1 : 0;
+  return impl;
 }
 
 static int fail(const std::string& msg) {
@@ -145,7 +150,7 @@ static bool want_tc(const ConfigInfo* c, std::string* why) {
   const int impl = effective_impl();
   if (impl == 1) return false;
   if (c->tc_T > 0) return true;
-  if (impl == 2) *why = "PINN_IMPL=tc but this configuration has no tensor-core kernel";
+  if (impl >= 2) *why = "PINN_IMPL=tc but this configuration has no tensor-core kernel";
   return false;
 }
 
@@ -295,7 +300,7 @@ int pinn_fwd_bwd(const pinn_kind_desc* desc, const float* params, const float* x
 int pinn_last_launch_count(void) { return g_launches; }
 
 int pinn_set_impl(int impl) {
-  if (impl < 0 || impl > 2) return fail("impl must be 0 (auto), 1 (ffma) or 2 (tensor cores)");
+  if (impl < 0 || impl > 3) return fail("impl must be 0 (auto), 1 (ffma), 2 (tensor cores) or 3 (pipelined tensor cores)");
   g_impl = impl;
   return 0;
 }

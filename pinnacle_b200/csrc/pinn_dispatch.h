@@ -4,8 +4,11 @@
 
 #include "pinn_kernels.cuh"
 #include "pinn_tc_kernels.cuh"
+#include "pinn_tc2_kernels.cuh"
 
 namespace pinn {
+
+extern int g_tc_pipelined;   // 1 = use the pipelined tensor-core kernel where instantiated (defined in pinn_api.cu)
 
 struct ConfigInfo {
   int id, H, m, d, C;

@@ -32,12 +32,33 @@ struct Inst {
   struct Tc {
     using TF = TCfg<SIG, M, H, TT, false>;
     using TB = TCfg<SIG, M, H, TT, true>;
+    // the pipelined two-sub-tile kernel (pinn_tc2_kernels.cuh) exists where two sub-tiles fit in shared memory
+    static constexpr bool kPipe = (TT == 32 && SIG::C <= 5);
     static cudaError_t prepare() {
       cudaError_t e = cudaFuncSetAttribute(pinn_tc_kernel<TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF::smem_bytes);
       if (e != cudaSuccess) return e;
+      if constexpr (kPipe) {
+        using PF = TC2fg<SIG, M, H, false>;
+        using PB = TC2fg<SIG, M, H, true>;
+        e = cudaFuncSetAttribute(pinn_tc2_kernel<PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF::smem_bytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(pinn_tc2_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB::smem_bytes);
+        if (e != cudaSuccess) return e;
+      }
       return cudaFuncSetAttribute(pinn_tc_kernel<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB::smem_bytes);
     }
     static cudaError_t launch(const TcLaunchParams& p, bool bwd, int grid, cudaStream_t st) {
+      if constexpr (kPipe) {
+        if (g_tc_pipelined) {
+          using PF = TC2fg<SIG, M, H, false>;
+          using PB = TC2fg<SIG, M, H, true>;
+          if (bwd)
+            pinn_tc2_kernel<PB><<<grid, PB::NTHALL, PB::smem_bytes, st>>>(p);
+          else
+            pinn_tc2_kernel<PF><<<grid, PF::NTHALL, PF::smem_bytes, st>>>(p);
+          return cudaGetLastError();
+        }
+      }
       if (bwd)
         pinn_tc_kernel<TB><<<grid, TB::NTH, TB::smem_bytes, st>>>(p);
       else

@@ -1,0 +1,619 @@
+// pinn_tc2_kernels.cuh -- warp-specialised, software-pipelined variant of the tcgen05 kernel (pinn_tc_kernels.cuh).
+//
+// Same math, same operand formats (bf16x3, X16 shared-memory layout, weight operand in TMEM).  What changes is the
+// schedule: a tile is two 16-point sub-tiles A and B that are always one MMA batch apart, so that the tensor core
+// works on one sub-tile while the 16 element-wise warps work on the other:
+//
+//   element-wise warps (0..15)   EW(A,l)  EW(B,l)  EW(A,l+1)  EW(B,l+1) ...      signal rdy[h] after each stage
+//   tensor core                       MMA(A,l+1)  MMA(B,l+1)  MMA(A,l+2) ...      commit -> bars[h]
+//   producer warps (16..19)      after every B batch: flush dW (reverse sweep), stage the next weight operand in
+//                                TMEM, signal wrdy; lane 0 of warp 16 is also the MMA issuer.
+//
+// The element-wise warps never touch weights, never issue MMAs and never flush dW.  Needs 2 x 6 split arrays in
+// shared memory, i.e. C <= 5 (R = C*16 <= 80).
+#pragma once
+
+#include "pinn_tc_kernels.cuh"
+
+namespace pinn {
+
+template <class SIG_, int M_, int H_, bool BWD_>
+struct TC2fg {
+  using SIG = SIG_;
+  static constexpr int M = M_, H = H_;
+  static constexpr bool BWD = BWD_;
+  static constexpr int C = SIG::C, D = SIG::D;
+  static constexpr int NEW = 512;                 // element-wise threads (16 warps)
+  static constexpr int NPR = 128;                 // producer threads (4 warps, one per TMEM lane quarter)
+  static constexpr int NTHALL = NEW + NPR;
+  static constexpr int TS = 16, NSUB = 2, T = TS * NSUB;
+  static constexpr int R = C * TS;
+  static constexpr int JB = (R / 8) * 128;
+  static constexpr int ARR = 14 * JB;
+  static constexpr int APS = BWD ? 6 : 3;         // split arrays per sub-tile
+  static constexpr int NARR = APS * NSUB;
+  static constexpr int tcD = 0, tcDstride = 80, tcDW = 160, tcW = 272, tcTotal = 512;
+  static constexpr int oSmall = NARR * ARR;
+  static constexpr int oW1 = oSmall;
+  static constexpr int oBias = oW1 + H * D * 4;
+  static constexpr int oW6 = oBias + kMaxLayers * H * 4;
+  static constexpr int oB6 = oW6 + M * H * 4;
+  static constexpr int oX = oB6 + 16;
+  static constexpr int oAux = oX + T * D * 4;
+  static constexpr int oUo = oAux + T * PINN_MAX_AUX * 4;
+  static constexpr int oUb = oUo + NSUB * M * R * 4;
+  static constexpr int oRs = oUb + NSUB * M * R * 4;
+  static constexpr int oRed = oRs + PINN_MAX_PDE * T * 4;
+  static constexpr int oLred = (oRed + 4 * 128 * 4 + 7) / 8 * 8;
+  static constexpr int oBar = oLred + PINN_MAX_PDE * T * 8;    // bars[2], rdy[2], wrdy, tmem slot
+  static constexpr int oKp = oBar + 64;
+  static constexpr int nBytes = oKp + (int)((sizeof(KindParams) + 15) / 16 * 16);
+  static constexpr size_t smem_bytes = (size_t)nBytes;
+
+  static_assert(H == 100, "tensor-core path is instantiated for H = 100");
+  static_assert(R % 16 == 0 && R <= 80, "two sub-tiles in flight need R = C*16 <= 80");
+  static_assert(oSmall % 16 == 0 && oUo % 16 == 0, "alignment");
+  static_assert(nBytes - oSmall >= 2 * JB, "A-operand over-read of the last Zbar array must stay inside the allocation");
+  static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <class CFG>
+__global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunchParams p) {
+  using SIG = typename CFG::SIG;
+  constexpr int C = CFG::C, D = CFG::D, M = CFG::M, H = CFG::H, T = CFG::T, TS = CFG::TS, NSUB = CFG::NSUB, R = CFG::R, JB = CFG::JB,
+                ARR = CFG::ARR, NEW = CFG::NEW, NTHALL = CFG::NTHALL, APS = CFG::APS;
+  constexpr bool BWD = CFG::BWD;
+
+  extern __shared__ __align__(1024) unsigned char smraw[];
+  float* W1s = reinterpret_cast<float*>(smraw + CFG::oW1);
+  float* bs = reinterpret_cast<float*>(smraw + CFG::oBias);
+  float* W6s = reinterpret_cast<float*>(smraw + CFG::oW6);
+  float* b6s = reinterpret_cast<float*>(smraw + CFG::oB6);
+  float* xs = reinterpret_cast<float*>(smraw + CFG::oX);
+  float* auxs = reinterpret_cast<float*>(smraw + CFG::oAux);
+  float* uo = reinterpret_cast<float*>(smraw + CFG::oUo);
+  float* ub = reinterpret_cast<float*>(smraw + CFG::oUb);
+  float* rs = reinterpret_cast<float*>(smraw + CFG::oRs);
+  float* redbuf = reinterpret_cast<float*>(smraw + CFG::oRed);
+  double* lred = reinterpret_cast<double*>(smraw + CFG::oLred);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + CFG::oBar);   // [h] MMA batch of sub-tile h complete (tcgen05.commit)
+  uint64_t* rdy = bars + 2;                                           // [h] operands of sub-tile h's next batch in place (512 arrivals)
+  uint64_t* wrdy = bars + 4;                                          // next weight operand staged + dW flushed (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  KindParams* kps = reinterpret_cast<KindParams*>(smraw + CFG::oKp);
+  auto arr_ptr = [&](int h, int a) -> unsigned char* { return smraw + (size_t)(h * APS + a) * ARR; };
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3;                        // TMEM lane quarter of this warp
+  const int g = (warp >> 2) & 3;                 // element-wise warps: column group (quad of points)
+  const int j = 32 * q + lane;                   // neuron (TMEM lane) owned by this thread
+#ifdef PINN_EXP_NO_ELEMENTWISE   // what-if timing experiment only
+  const bool act = false;
+#else
+  const bool act = j < H;
+#endif
+  const bool is_ew = warp < NEW / 32;
+  const uint32_t lane_off = (uint32_t)(32 * q) << 16;
+  const int pb = 4 * g;
+  const int L = p.L;
+  const int S = BWD ? p.n_seeds : 0;
+
+  const long long offB1 = (long long)H * D;
+  const long long offHid = offB1 + H;
+  const long long strideHid = (long long)H * H + H;
+  const long long offW6 = offHid + (long long)(L - 1) * strideHid;
+  const long long offB6 = offW6 + (long long)M * H;
+
+  // ---------------- one-time setup (all 20 warps) ----------------
+  for (int i = tid; i < H * D; i += NTHALL) W1s[i] = p.params[i];
+  for (int i = tid; i < H; i += NTHALL) bs[i] = p.params[offB1 + i];
+  for (int l = 2; l <= L; ++l)
+    for (int i = tid; i < H; i += NTHALL) bs[(l - 1) * H + i] = p.params[offHid + (long long)(l - 2) * strideHid + (long long)H * H + i];
+  for (int i = tid; i < M * H; i += NTHALL) W6s[i] = p.params[offW6 + i];
+  if (tid < M) b6s[tid] = p.params[offB6 + tid];
+  for (int i = tid; i < CFG::NARR * ARR / 16; i += NTHALL) reinterpret_cast<uint4*>(smraw)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) {
+    mbar_init_n(&bars[0], 1);
+    mbar_init_n(&bars[1], 1);
+    mbar_init_n(&rdy[0], NEW);
+    mbar_init_n(&rdy[1], NEW);
+    mbar_init_n(wrdy, CFG::NPR);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    *kps = p.kp;
+  }
+  if (warp == 0) umma::tmem_alloc(tmem_slot, CFG::tcTotal);
+  float* gp = nullptr;
+  if constexpr (BWD) {
+    gp = p.gpart + (size_t)blockIdx.x * S * p.Ppad;
+    for (long long i = tid; i < (long long)S * p.Ppad; i += NTHALL) gp[i] = 0.f;
+    float4* gz = reinterpret_cast<float4*>(p.gwt) + (size_t)blockIdx.x * S * (L - 1) * kTcGwtLayer4;
+    for (long long i = tid; i < (long long)S * (L - 1) * kTcGwtLayer4; i += NTHALL) gz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __threadfence();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tbase = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // shfl: lets ptxas treat TMEM addresses as warp-uniform
+  const uint32_t tDW = tbase + CFG::tcDW, tW = tbase + CFG::tcW;
+  auto tD = [&](int h) -> uint32_t { return tbase + CFG::tcD + h * CFG::tcDstride; };
+  const long long ntiles = (p.n_rows + T - 1) / T;
+
+  if (!is_ew) {
+    // =====================================================================================================
+    // producer warps: weight operands + dW flush; lane 0 of the first one also issues the MMAs
+    // =====================================================================================================
+    const bool issuer_warp = (warp == NEW / 32);
+    uint32_t bph = 0;                     // parity of bars[1] (B batch complete)
+    uint32_t rph[2] = {0, 0}, wph = 0;    // issuer-side parities
+
+    // stage one pre-split operand matrix (12*512 uint4, fetch order of pinn_pack_weights_tc) into TMEM lanes 32q..32q+31
+    auto stage_W = [&](const uint4* Wp) {
+#ifdef PINN_EXP_NO_W
+      return;
+#endif
+      // one split (56 columns) per round, all 14 loads of a round in flight together: the operand is L2-resident and
+      // four warps have to cover the L2 latency with their own memory-level parallelism
+#pragma unroll
+      for (int sp = 0; sp < 3; ++sp) {
+        uint4 a[14];
+#pragma unroll
+        for (int i = 0; i < 14; ++i) {
+          const int gg = i >> 2, qd = i & 3;
+          a[i] = Wp[(size_t)(4 * sp + qd) * 512 + 128 * gg + 32 * q + lane];
+        }
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+          uint32_t v[16];
+#pragma unroll
+          for (int qd = 0; qd < (gg < 3 ? 4 : 2); ++qd) {
+            v[4 * qd] = a[4 * gg + qd].x; v[4 * qd + 1] = a[4 * gg + qd].y; v[4 * qd + 2] = a[4 * gg + qd].z; v[4 * qd + 3] = a[4 * gg + qd].w;
+          }
+          const uint32_t col = tW + lane_off + 56 * sp + 16 * gg;
+          if (gg < 3) tmem_st16(col, v);
+          else tmem_st8u(col, v);
+        }
+      }
+      umma::wait_st();
+    };
+    // dW_l (TMEM, 100 x 100 used) -> this CTA's private partial [k/4][n][k%4], plain read-modify-write (single writer).
+    // Three rounds of 32 / 32 / 36 columns; the global loads of a round are all in flight together.
+    auto flush_dw = [&](int s, int l) {
+#ifdef PINN_EXP_NO_FLUSH
+      return;
+#endif
+      float4* gt = reinterpret_cast<float4*>(p.gwt) + ((size_t)(blockIdx.x * S + s) * (L - 1) + (l - 2)) * kTcGwtLayer4 + j;
+#pragma unroll
+      for (int rd = 0; rd < 3; ++rd) {
+        constexpr int NV = 9;
+        const int c0 = 32 * rd;
+        const int nv = (rd < 2) ? 8 : 9;
+        float4 old[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (i < nv) old[i] = gt[(size_t)(c0 / 4 + i) * 128];
+        float v[NV][4];
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (i < nv) umma::tmem_ld4(tDW + lane_off + c0 + 4 * i, v[i]);
+        umma::wait_ld();
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (i < nv)
+            gt[(size_t)(c0 / 4 + i) * 128] = make_float4(old[i].x + v[i][0], old[i].y + v[i][1], old[i].z + v[i][2], old[i].w + v[i][3]);
+      }
+    };
+    auto signal_wrdy = [&]() {
+      umma::fence_before_sync();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(wrdy)) : "memory");
+    };
+    auto wait_b_done = [&]() {
+      mbar_wait(&bars[1], bph);
+      bph ^= 1;
+      umma::fence_after_sync();
+    };
+    // ---- MMA issue helpers (same instruction sequences as pinn_tc_kernel; run by the whole issuer warp) ----
+    auto issue_rows = [&](int h, unsigned char* bbase, uint32_t el) {
+      constexpr uint32_t idesc = umma::make_idesc_bf16(kTcRows, R, 0, 1);
+      const int wa[6] = {0, 2, 1, 0, 1, 0};
+      const int ab[6] = {2, 0, 1, 1, 0, 0};
+      const uint32_t d = tD(h);
+      uint32_t accum = 0;
+#pragma unroll
+      for (int t = 0; t < 6; ++t) {
+#pragma unroll
+        for (int ks = 0; ks < kTcHP / 16; ++ks) {
+          const uint64_t bd = umma::make_smem_desc(umma::smem_addr(bbase + ab[t] * ARR) + ks * 2 * JB, JB, 128);
+          umma::mma_bf16_ts_e(d, tW + wa[t] * 56 + ks * 8, bd, idesc, accum, el);
+          accum = 1;
+        }
+      }
+    };
+    auto issue_dw = [&](int h, uint32_t accum, uint32_t el) {
+      constexpr uint32_t idesc = umma::make_idesc_bf16(kTcRows, kTcHP, 0, 0);
+      const int za[6] = {0, 2, 1, 0, 1, 0};
+      const int ab[6] = {2, 0, 1, 1, 0, 0};
+      unsigned char* zbase = arr_ptr(h, 3);
+      unsigned char* abase = arr_ptr(h, 0);
+#pragma unroll
+      for (int t = 0; t < 6; ++t) {
+#pragma unroll
+        for (int ks = 0; ks < R / 16; ++ks) {
+          const uint64_t ad = umma::make_smem_desc(umma::smem_addr(zbase + za[t] * ARR) + ks * 256, 128, JB);
+          const uint64_t bd = umma::make_smem_desc(umma::smem_addr(abase + ab[t] * ARR) + ks * 256, 128, JB);
+          umma::mma_bf16_ss_e(tDW, ad, bd, idesc, accum, el);
+          accum = 1;
+        }
+      }
+    };
+    // one pipeline step = the batches of both sub-tiles for one layer
+    auto issue_step = [&](bool reverse) {
+      if (!issuer_warp) return;
+      mbar_wait(wrdy, wph);                 // operand staged (and previous dW flushed) by all 4 producer warps
+      wph ^= 1;
+      umma::fence_after_sync();
+#pragma unroll
+      for (int h = 0; h < NSUB; ++h) {
+        mbar_wait(&rdy[h], rph[h]);
+        rph[h] ^= 1;
+        umma::fence_after_sync();
+        const uint32_t el = umma::elect_one();
+        if (reverse) {
+          issue_dw(h, h == 0 ? 0u : 1u, el);
+          issue_rows(h, arr_ptr(h, 3), el);
+        } else {
+          issue_rows(h, arr_ptr(h, 0), el);
+        }
+        umma::commit_e(&bars[h], el);
+      }
+    };
+
+    bool first = true;
+    int pend_s = -1, pend_l = -1;          // dW of the previous reverse step still sitting in TMEM
+    auto producer_step = [&](const uint4* Wp, bool reverse, int s, int l) {
+      if (!first) {
+        wait_b_done();                     // every MMA that reads the current operand / accumulates the current dW is done
+        if (pend_l >= 2) flush_dw(pend_s, pend_l);
+      }
+      first = false;
+      pend_s = reverse ? s : -1;
+      pend_l = reverse ? l : -1;
+      stage_W(Wp);
+      signal_wrdy();
+      issue_step(reverse);
+    };
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int l = 2; l <= L + 1; ++l) producer_step(l <= L ? p.wn + (size_t)(l - 2) * kTcWMat : p.w6p, false, 0, 0);
+      if constexpr (BWD) {
+        for (int s = 0; s < S; ++s)
+          for (int l = L; l >= 2; --l) producer_step(p.wt + (size_t)(l - 2) * kTcWMat, true, s, l);
+      }
+    }
+    if (!first) {
+      wait_b_done();
+      if (pend_l >= 2) flush_dw(pend_s, pend_l);
+    }
+  } else {
+    // =====================================================================================================
+    // element-wise warps
+    // =====================================================================================================
+    float4* stash = reinterpret_cast<float4*>(p.stash) + (size_t)blockIdx.x * L * NSUB * C * NEW;
+    auto stash_at = [&](int l, int h, int c) -> float4* { return stash + ((size_t)((l - 1) * NSUB + h) * C + c) * NEW + tid; };
+    uint32_t ph[2] = {0, 0};
+    double lacc[PINN_MAX_PDE] = {0.0, 0.0, 0.0};
+
+    auto store_quad = [&](unsigned char* base, int r0, float v0, float v1, float v2, float v3) {
+      uint32_t a1, a2, a3, b1, b2, b3;
+      split3_pair(v0, v1, a1, a2, a3);
+      split3_pair(v2, v3, b1, b2, b3);
+      const int off = (j >> 3) * JB + (r0 >> 3) * 128 + (j & 7) * 16 + (r0 & 7) * 2;
+      *reinterpret_cast<uint2*>(base + off) = make_uint2(a1, b1);
+      *reinterpret_cast<uint2*>(base + ARR + off) = make_uint2(a2, b2);
+      *reinterpret_cast<uint2*>(base + 2 * ARR + off) = make_uint2(a3, b3);
+    };
+    auto signal_ready = [&](int h) {
+      umma::fence_async_smem();
+      umma::fence_before_sync();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(&rdy[h])) : "memory");
+    };
+    auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NEW) : "memory"); };
+    auto wait_bar = [&](int h) {
+      mbar_wait(&bars[h], ph[h]);
+      ph[h] ^= 1;
+      umma::fence_after_sync();
+    };
+    auto reduce_groups_red = [&](float v, float* dst) {
+      redbuf[g * 128 + j] = v;
+      epi_sync();
+      if (g == 0 && act) atomicAdd(dst, (redbuf[j] + redbuf[128 + j]) + (redbuf[256 + j] + redbuf[384 + j]));
+      epi_sync();
+    };
+    auto epi_layer1 = [&](int h) {
+      if (!act) return;
+      float w[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) w[i] = W1s[j * D + i];
+      const float b = bs[j];
+      float a[C][4];
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) {
+        float z0 = b;
+#pragma unroll
+        for (int i = 0; i < D; ++i) z0 = fmaf(w[i], xs[(h * TS + pb + pp) * D + i], z0);
+#pragma unroll
+        for (int c = 0; c < C; ++c) a[c][pp] = 0.f;
+        a[0][pp] = z0;
+        static_for<D>([&](auto J) {
+          constexpr int jj = decltype(J)::value;
+          if constexpr (SIG::order(jj) >= 1) a[SIG::base(jj)][pp] = w[jj];
+        });
+      }
+      if constexpr (BWD) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) *stash_at(1, h, c) = make_float4(a[c][0], a[c][1], a[c][2], a[c][3]);
+      }
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) {
+        float z[C], av[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) z[c] = a[c][pp];
+        tanh_jet_fwd<SIG>(z, av);
+#pragma unroll
+        for (int c = 0; c < C; ++c) a[c][pp] = av[c];
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) store_quad(arr_ptr(h, 0), c * TS + pb, a[c][0], a[c][1], a[c][2], a[c][3]);
+    };
+    auto epi_hidden = [&](int h, int l) {
+      float zq[C][4];
+#pragma unroll
+      for (int c = 0; c < C; ++c) umma::tmem_ld4(tD(h) + lane_off + c * TS + pb, zq[c]);
+      umma::wait_ld();
+      if (!act) return;
+      const float b = bs[(l - 1) * H + j];
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) zq[0][pp] += b;
+      if constexpr (BWD) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) *stash_at(l, h, c) = make_float4(zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
+      }
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) {
+        float z[C], av[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
+        tanh_jet_fwd<SIG>(z, av);
+#pragma unroll
+        for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) store_quad(arr_ptr(h, 0), c * TS + pb, zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
+    };
+    auto epi_output = [&](int h) {
+      float uq[C][4];
+#pragma unroll
+      for (int c = 0; c < C; ++c) umma::tmem_ld4(tD(h) + lane_off + c * TS + pb, uq[c]);
+      umma::wait_ld();
+      if (j < M) {
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) uo[(h * M + j) * R + c * TS + pb + pp] = uq[c][pp] + (c == 0 ? b6s[j] : 0.f);
+      }
+    };
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long row0 = tile * T;
+      for (int i = tid; i < T * D; i += NEW) {
+        const long long r = row0 + i / D;
+        xs[i] = (r < p.n_rows) ? p.x[row0 * D + i] : 0.f;
+      }
+      if (p.n_aux > 0) {
+        for (int i = tid; i < T * p.n_aux; i += NEW) {
+          const int pt = i / p.n_aux, a = i % p.n_aux;
+          const long long r = row0 + pt;
+          auxs[pt * PINN_MAX_AUX + a] = (r < p.n_rows) ? p.aux[r * p.n_aux + a] : 0.f;
+        }
+      }
+      epi_sync();
+
+      // ================= forward =================
+#pragma unroll
+      for (int h = 0; h < NSUB; ++h) {
+        epi_layer1(h);
+        signal_ready(h);
+      }
+      for (int l = 2; l <= L + 1; ++l) {
+#pragma unroll
+        for (int h = 0; h < NSUB; ++h) {
+          wait_bar(h);
+          if (l <= L) {
+            epi_hidden(h, l);
+            signal_ready(h);
+          } else {
+            epi_output(h);
+          }
+        }
+      }
+      epi_sync();
+
+      // ================= residual + loss =================
+      if (tid < T) {
+        const int h = tid / TS, pt = tid % TS;
+        float U[M][C];
+#pragma unroll
+        for (int o = 0; o < M; ++o)
+#pragma unroll
+          for (int c = 0; c < C; ++c) U[o][c] = uo[(h * M + o) * R + c * TS + pt];
+        float r[PINN_MAX_PDE];
+        Residual<SIG, M>::eval(*kps, auxs + tid * PINN_MAX_AUX, U, r);
+        const bool valid = row0 + tid < p.n_rows;
+#pragma unroll
+        for (int k = 0; k < PINN_MAX_PDE; ++k) {
+          const float rk = valid ? r[k] : 0.f;
+          rs[k * T + tid] = rk;
+          lacc[k] += (double)rk * (double)rk;
+        }
+        if (p.resid_out != nullptr && valid)
+          for (int k = 0; k < p.n_pde; ++k) p.resid_out[(row0 + tid) * p.n_pde + k] = r[k];
+      }
+
+      if constexpr (BWD) {
+        for (int s = 0; s < S; ++s) {
+          float* gs = gp + (size_t)s * p.Ppad;
+          if (tid < T) {
+            const int h = tid / TS, pt = tid % TS;
+            float U[M][C], Ub[M][C];
+#pragma unroll
+            for (int o = 0; o < M; ++o)
+#pragma unroll
+              for (int c = 0; c < C; ++c) U[o][c] = uo[(h * M + o) * R + c * TS + pt];
+            float rb[PINN_MAX_PDE];
+#pragma unroll
+            for (int k = 0; k < PINN_MAX_PDE; ++k) rb[k] = (k < p.n_pde) ? p.seeds[s * p.n_pde + k] * 2.0f * rs[k * T + tid] * p.inv_n : 0.f;
+            Residual<SIG, M>::adjoint(*kps, auxs + tid * PINN_MAX_AUX, U, rb, Ub);
+#pragma unroll
+            for (int o = 0; o < M; ++o)
+#pragma unroll
+              for (int c = 0; c < C; ++c) ub[(h * M + o) * R + c * TS + pt] = Ub[o][c];
+          }
+          epi_sync();
+          if (tid < M) {
+            float sacc = 0.f;
+            for (int h = 0; h < NSUB; ++h)
+              for (int pq = 0; pq < TS; ++pq) sacc += ub[(h * M + tid) * R + pq];
+            atomicAdd(gs + offB6 + tid, sacc);
+          }
+
+          for (int l = L; l >= 1; --l) {
+            float dbias = 0.f;
+            float dw6[M];
+#pragma unroll
+            for (int o = 0; o < M; ++o) dw6[o] = 0.f;
+            float dw1[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) dw1[i] = 0.f;
+#pragma unroll
+            for (int h = 0; h < NSUB; ++h) {
+              if (l < L) wait_bar(h);                     // (i) and (ii) of layer l+1, sub-tile h: abar^l(h) is in D_h
+              float ab[C][4];
+              if (l < L) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) umma::tmem_ld4(tD(h) + lane_off + c * TS + pb, ab[c]);
+                umma::wait_ld();
+              }
+              if (act) {
+                float zq[C][4];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                  const float4 v = *stash_at(l, h, c);
+                  zq[c][0] = v.x; zq[c][1] = v.y; zq[c][2] = v.z; zq[c][3] = v.w;
+                }
+                if (l == L) {
+#pragma unroll
+                  for (int pp = 0; pp < 4; ++pp) {
+                    float z[C], av[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
+                    tanh_jet_fwd<SIG>(z, av);
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                      float v = 0.f;
+#pragma unroll
+                      for (int o = 0; o < M; ++o) {
+                        const float u = ub[(h * M + o) * R + c * TS + pb + pp];
+                        v = fmaf(u, W6s[o * H + j], v);
+                        dw6[o] = fmaf(u, av[c], dw6[o]);
+                      }
+                      ab[c][pp] = v;
+                    }
+                  }
+                }
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {
+                  float z[C], a_[C], zb[C];
+#pragma unroll
+                  for (int c = 0; c < C; ++c) {
+                    z[c] = zq[c][pp];
+                    a_[c] = ab[c][pp];
+                    zb[c] = 0.f;
+                  }
+                  tanh_jet_bwd<SIG>(z, a_, zb);
+                  dbias += zb[0];
+                  if (l == 1) {
+                    static_for<D>([&](auto J) {
+                      constexpr int jj = decltype(J)::value;
+                      dw1[jj] = fmaf(zb[0], xs[(h * TS + pb + pp) * D + jj], dw1[jj]);
+                      if constexpr (SIG::order(jj) >= 1) dw1[jj] += zb[SIG::base(jj)];
+                    });
+                  }
+#pragma unroll
+                  for (int c = 0; c < C; ++c) ab[c][pp] = zb[c];
+                }
+                if (l > 1) {
+#pragma unroll
+                  for (int c = 0; c < C; ++c) store_quad(arr_ptr(h, 3), c * TS + pb, ab[c][0], ab[c][1], ab[c][2], ab[c][3]);
+#pragma unroll
+                  for (int c = 0; c < C; ++c) {
+                    const float4 v = *stash_at(l - 1, h, c);
+                    zq[c][0] = v.x; zq[c][1] = v.y; zq[c][2] = v.z; zq[c][3] = v.w;
+                  }
+#pragma unroll
+                  for (int pp = 0; pp < 4; ++pp) {
+                    float z[C], av[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
+                    tanh_jet_fwd<SIG>(z, av);
+#pragma unroll
+                    for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
+                  }
+#pragma unroll
+                  for (int c = 0; c < C; ++c) store_quad(arr_ptr(h, 0), c * TS + pb, zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
+                }
+              }
+              if (l >= 2) signal_ready(h);
+            }
+            float* gb = gs + ((l == 1) ? offB1 : offHid + (long long)(l - 2) * strideHid + (long long)H * H);
+            reduce_groups_red(dbias, gb + j);
+            if (l == L) {
+#pragma unroll
+              for (int o = 0; o < M; ++o) reduce_groups_red(dw6[o], gs + offW6 + o * H + j);
+            }
+            if (l == 1) {
+#pragma unroll
+              for (int i = 0; i < D; ++i) reduce_groups_red(dw1[i], gs + j * D + i);
+            }
+          }
+        }
+      }
+      epi_sync();
+    }
+    if (tid < T) {
+#pragma unroll
+      for (int k = 0; k < PINN_MAX_PDE; ++k) lred[k * T + tid] = lacc[k];
+    }
+  }
+
+  // ---------------- per-CTA loss partials ----------------
+  umma::fence_before_sync();
+  __syncthreads();
+  if (tid < PINN_MAX_PDE) {
+    double ssum = 0.0;
+    for (int pq = 0; pq < T; ++pq) ssum += lred[tid * T + pq];
+    p.lpart[(size_t)blockIdx.x * PINN_MAX_PDE + tid] = ssum;
+  }
+  if (warp == 0) umma::tmem_dealloc(tbase, CFG::tcTotal);
+}
+
+}  // namespace pinn

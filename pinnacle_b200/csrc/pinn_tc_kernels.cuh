@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
-  const uint32_t tbase = *tmem_slot;
+  const uint32_t tbase = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // shfl: lets ptxas treat TMEM addresses as warp-uniform
   const uint32_t tD = tbase + CFG::tcD, tDW = tbase + CFG::tcDW, tW = tbase + CFG::tcW;
 
   float4* stash = reinterpret_cast<float4*>(p.stash) + (size_t)blockIdx.x * L * NQ * C * NTH;
@@ -278,8 +278,10 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
 #endif
   };
 
-  // D (+)= Wop[TMEM] * B[smem, MN-major]: 7 k-steps x 6 split products, small terms first
+  // D (+)= Wop[TMEM] * B[smem, MN-major]: 7 k-steps x 6 split products, small terms first.
+  // Issue functions are called by all of warp 0 (see umma::mma_bf16_ts_e).
   auto issue_rows = [&](unsigned char* const (&barr)[3], uint64_t* bar) {
+    const uint32_t el = umma::elect_one();
     constexpr uint32_t idesc = umma::make_idesc_bf16(kTcRows, R, 0, 1);
     const int wa[6] = {0, 2, 1, 0, 1, 0};
     const int ab[6] = {2, 0, 1, 1, 0, 0};
@@ -289,38 +291,39 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
     uint32_t accum = 0;
 #pragma unroll
     for (int t = 0; t < 6; ++t) {
-#pragma unroll 1
+#pragma unroll
       for (int ks = 0; ks < kTcHP / 16; ++ks) {
         const uint64_t bd = umma::make_smem_desc(umma::smem_addr(barr[ab[t]]) + ks * 2 * JB, JB, 128);
 #ifdef PINN_EXP_ONE_MMA     // what-if: (almost) no tensor work
         if (t != 5 || ks != 0) continue;
 #endif
-        umma::mma_bf16_ts(tD, tW + wa[t] * 56 + ks * 8, bd, idesc, accum);
+        umma::mma_bf16_ts_e(tD, tW + wa[t] * 56 + ks * 8, bd, idesc, accum, el);
         accum = 1;
       }
     }
-    umma::commit(bar);
+    umma::commit_e(bar, el);
   };
   // DW = Zbar[smem, K-major] * A[smem, K-major]^T : R/16 k-steps x 6 split products
   auto issue_dw = [&](uint64_t* bar) {
     constexpr uint32_t idesc = umma::make_idesc_bf16(kTcRows, kTcHP, 0, 0);
     const int za[6] = {0, 2, 1, 0, 1, 0};
     const int ab[6] = {2, 0, 1, 1, 0, 0};
+    const uint32_t el = umma::elect_one();
     uint32_t accum = 0;
 #pragma unroll
     for (int t = 0; t < 6; ++t) {
-#pragma unroll 1
+#pragma unroll
       for (int ks = 0; ks < R / 16; ++ks) {
         const uint64_t ad = umma::make_smem_desc(umma::smem_addr(arrZ[za[t]]) + ks * 256, 128, JB);
         const uint64_t bd = umma::make_smem_desc(umma::smem_addr(arrA[ab[t]]) + ks * 256, 128, JB);
 #ifdef PINN_EXP_ONE_MMA
         if (t != 5 || ks != 0) continue;
 #endif
-        umma::mma_bf16_ss(tDW, ad, bd, idesc, accum);
+        umma::mma_bf16_ss_e(tDW, ad, bd, idesc, accum, el);
         accum = 1;
       }
     }
-    umma::commit(bar);
+    umma::commit_e(bar, el);
   };
   // all threads: publish generic-proxy smem writes + TMEM stores, sync, then one thread issues
   auto sync_for_mma = [&]() {
@@ -412,7 +415,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
     w_ready = false;
     for (int l = 2; l <= L + 1; ++l) {
       sync_for_mma();
-      if (tid == 0) issue_rows(arrA, bar0);
+      if (warp == 0) issue_rows(arrA, bar0);
       // operand of the next MMA batch: W_{l+1}, the padded output layer, or (reverse sweep) W_L^T
       const uint4* nextW = (l < L) ? p.wn + (size_t)(l - 1) * kTcWMat
                                    : (l == L) ? p.w6p
@@ -625,7 +628,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
           }
           // ---- tensor-core contractions of layer l (W_l^T is already in TMEM)
           sync_for_mma();
-          if (tid == 0) {
+          if (warp == 0) {
             issue_dw(bar1);
             issue_rows(arrZ, bar0);
           }

@@ -114,6 +114,48 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
+// ---- MMA issue by a whole warp ---------------------------------------------------------------------
+// The issuing warp runs the issue code convergently with warp-uniform operands and predicates the instruction on an
+// elected lane.  ptxas then keeps descriptors and TMEM addresses in uniform registers (a handful of uniform-datapath
+// ops per MMA); issuing from inside `if (lane == 0)` instead costs a ~20-instruction R2UR/ELECT "waterfall" per MMA
+// (~110 clk), which is longer than a 128 x 80 x 16 MMA itself.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void mma_bf16_ts_e(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate,
+                                              uint32_t elected) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 e, %5, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ss_e(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate,
+                                              uint32_t elected) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 e, %5, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void commit_e(uint64_t* bar, uint32_t elected) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %1, 0;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_addr(bar)),
+      "r"(elected)
+      : "memory");
+}
+
 // ---- TMEM <-> registers (warp-collective; a warp touches lanes 32*(warp%4) .. +31) --------------
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
   uint32_t r0, r1, r2, r3;

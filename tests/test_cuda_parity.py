@@ -19,15 +19,15 @@ def _to(dev, *ts):
     return [None if t is None else t.to(dev).contiguous() for t in ts]
 
 
-IMPLS = ["ffma", "tc"]
+IMPLS = ["ffma", "tc", "tc2"]
 
 
 def _select_impl(impl, desc):
     """Both kernels (FP32 FFMA, tcgen05 bf16x3) implement the same C-ABI call; run the parity suite on each."""
     from pinnacle_b200 import capi
-    if impl == "tc" and not capi.has_tensor_core_kernel(desc):
+    if impl in ("tc", "tc2") and not capi.has_tensor_core_kernel(desc):
         pytest.skip("no tensor-core kernel instantiated for this jet signature")
-    capi.set_impl(capi.IMPL_TC if impl == "tc" else capi.IMPL_FFMA)
+    capi.set_impl({"tc": capi.IMPL_TC, "tc2": capi.IMPL_TC_PIPELINED, "ffma": capi.IMPL_FFMA}[impl])
 
 
 @pytest.fixture(autouse=True)
