@@ -101,10 +101,12 @@ int pinn_fwd_bwd(const pinn_kind_desc* desc, const float* params, const float* x
                  int64_t n_rows, double inv_n_global, const float* seeds, int n_seeds, float* out,
                  void* workspace, size_t workspace_bytes, void* stream);
 
-/* Kernel selection: 0 = automatic (tcgen05 tensor-core kernel where one is instantiated, else the FP32 FFMA
- * kernel), 1 = FP32 FFMA kernel, 2 = tensor-core kernel (calls fail where none exists).  The environment variable
- * PINN_IMPL=ffma|tc has the same effect when this is left at 0.  Both kernels implement the same interface to the
- * same tolerance; the switch exists so they can be measured against each other. */
+/* Kernel selection: 0 = automatic (tcgen05 tensor-core kernel where one is instantiated -- its pipelined variant
+ * where that exists -- else the FP32 FFMA kernel), 1 = FP32 FFMA kernel, 2 = tensor-core kernel, one tile at a time
+ * (calls fail where none exists), 3 = pipelined tensor-core kernel (two sub-tiles in flight, warp-specialised;
+ * falls back to 2 for configurations it is not instantiated for).  The environment variable
+ * PINN_IMPL=ffma|tc|tc2 has the same effect when this is left at 0.  All kernels implement the same interface to
+ * the same tolerance; the switch exists so they can be measured against each other. */
 int pinn_set_impl(int impl);
 /* 1 if the descriptor's configuration has a tensor-core kernel in this build. */
 int pinn_has_tensor_core_kernel(const pinn_kind_desc* desc);

@@ -29,7 +29,8 @@ static const ConfigInfo* const* all_configs() {
 static thread_local std::string g_err;
 static thread_local int g_launches = 0;
 int g_tc_pipelined = 0;
-static int g_impl = 0;   // 0 = auto (tensor cores where instantiated), 1 = FP32 FFMA kernel, 2 = tensor cores (error if absent)
+static int g_impl = 0;   // 0 = auto (tensor cores, pipelined where instantiated), 1 = FP32 FFMA kernel, 2 = tensor cores, one tile at a time
+                         // (error if absent), 3 = pipelined tensor-core kernel (falls back to 2 where not instantiated)
 
 static int effective_impl() {
   int impl = g_impl;
@@ -41,7 +42,7 @@ static int effective_impl() {
       if (strcmp(e, "tc2") == 0) impl = 3;
     }
   }
-  g_tc_pipelined = (impl == 3) ? 1 : 0;
+  g_tc_pipelined = (impl == 3 || impl == 0) ? 1 : 0;   // auto prefers the pipelined kernel where it is instantiated
   return impl;
 }
 

@@ -5,9 +5,10 @@
 // works on one sub-tile while the 16 element-wise warps work on the other:
 //
 //   element-wise warps (0..15)   EW(A,l)  EW(B,l)  EW(A,l+1)  EW(B,l+1) ...      signal rdy[h] after each stage
-//   tensor core                       MMA(A,l+1)  MMA(B,l+1)  MMA(A,l+2) ...      commit -> bars[h]
-//   producer warps (16..19)      after every B batch: flush dW (reverse sweep), stage the next weight operand in
-//                                TMEM, signal wrdy; lane 0 of warp 16 is also the MMA issuer.
+//   tensor core                       MMA(A,l+1)  MMA(B,l+1)  MMA(A,l+2) ...      commit -> bars[h] (, dwd[h])
+//   producer warps (16..19)      stage the next weight operand in TMEM as soon as the rows MMAs of B are complete
+//                                (wfree -> wrdy), then flush the previous step's dW partial (dwd[1] -> dwfree)
+//   issuer warp (20)             per step: wait wrdy; per sub-tile: wait rdy[h], rows MMAs, (wait dwfree,) dW MMAs
 //
 // The element-wise warps never touch weights, never issue MMAs and never flush dW.  Needs 2 x 6 split arrays in
 // shared memory, i.e. C <= 5 (R = C*16 <= 80).
@@ -17,7 +18,10 @@
 
 namespace pinn {
 
-template <class SIG_, int M_, int H_, bool BWD_>
+#ifndef PINN_TC2_NIS
+#define PINN_TC2_NIS 32
+#endif
+template <class SIG_, int M_, int H_, bool BWD_, int NIS_ = PINN_TC2_NIS>
 struct TC2fg {
   using SIG = SIG_;
   static constexpr int M = M_, H = H_;
@@ -25,7 +29,8 @@ struct TC2fg {
   static constexpr int C = SIG::C, D = SIG::D;
   static constexpr int NEW = 512;                 // element-wise threads (16 warps)
   static constexpr int NPR = 128;                 // producer threads (4 warps, one per TMEM lane quarter)
-  static constexpr int NTHALL = NEW + NPR;
+  static constexpr int NIS = NIS_;                // 32: separate MMA issuer warp (21 warps, 80 registers/thread); 0: first producer warp issues
+  static constexpr int NTHALL = NEW + NPR + NIS;
   static constexpr int TS = 16, NSUB = 2, T = TS * NSUB;
   static constexpr int R = C * TS;
   static constexpr int JB = (R / 8) * 128;
@@ -46,7 +51,7 @@ struct TC2fg {
   static constexpr int oRed = oRs + PINN_MAX_PDE * T * 4;
   static constexpr int oLred = (oRed + 4 * 128 * 4 + 7) / 8 * 8;
   static constexpr int oBar = oLred + PINN_MAX_PDE * T * 8;    // bars[2], rdy[2], wrdy, tmem slot
-  static constexpr int oKp = oBar + 64;
+  static constexpr int oKp = oBar + 96;
   static constexpr int nBytes = oKp + (int)((sizeof(KindParams) + 15) / 16 * 16);
   static constexpr size_t smem_bytes = (size_t)nBytes;
 
@@ -89,8 +94,11 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
   double* lred = reinterpret_cast<double*>(smraw + CFG::oLred);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + CFG::oBar);   // [h] MMA batch of sub-tile h complete (tcgen05.commit)
   uint64_t* rdy = bars + 2;                                           // [h] operands of sub-tile h's next batch in place (512 arrivals)
-  uint64_t* wrdy = bars + 4;                                          // next weight operand staged + dW flushed (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* wrdy = bars + 4;                                          // next weight operand staged (128 arrivals)
+  uint64_t* wfree = bars + 5;                                         // all MMAs reading the current weight operand complete
+  uint64_t* dwd = bars + 6;                                           // [h] dW MMAs of sub-tile h complete: its arrays may be rewritten
+  uint64_t* dwfree = bars + 8;                                        // dW flushed out of TMEM (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   KindParams* kps = reinterpret_cast<KindParams*>(smraw + CFG::oKp);
   auto arr_ptr = [&](int h, int a) -> unsigned char* { return smraw + (size_t)(h * APS + a) * ARR; };
 
@@ -104,7 +112,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
 #else
   const bool act = j < H;
 #endif
-  const bool is_ew = warp < NEW / 32;
+  const int role = warp < NEW / 32 ? 0 : (warp < (NEW + CFG::NPR) / 32 ? 1 : 2);   // 0 element-wise, 1 producer, 2 MMA issuer
   const uint32_t lane_off = (uint32_t)(32 * q) << 16;
   const int pb = 4 * g;
   const int L = p.L;
@@ -130,6 +138,10 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
     mbar_init_n(&rdy[0], NEW);
     mbar_init_n(&rdy[1], NEW);
     mbar_init_n(wrdy, CFG::NPR);
+    mbar_init_n(wfree, 1);
+    mbar_init_n(&dwd[0], 1);
+    mbar_init_n(&dwd[1], 1);
+    mbar_init_n(dwfree, CFG::NPR);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     *kps = p.kp;
   }
@@ -150,92 +162,124 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
   auto tD = [&](int h) -> uint32_t { return tbase + CFG::tcD + h * CFG::tcDstride; };
   const long long ntiles = (p.n_rows + T - 1) / T;
 
-  if (!is_ew) {
+  // the (W operand, reverse?) sequence of one tile, identical for the producer warps and the issuer warp:
+  //   forward  l = 2..L+1 : W_l (W_{L+1} = zero-padded output layer)
+  //   reverse  s, l = L..2: W_l^T, plus the dW_l contraction
+  if (role != 0) {
     // =====================================================================================================
-    // producer warps: weight operands + dW flush; lane 0 of the first one also issues the MMAs
+    // producer warps: stage weight operands in TMEM, flush dW partials.
+    // MMA issuer: its own warp (CFG::NIS == 32) or the first producer warp, after its producer work of the step.
     // =====================================================================================================
-    const bool issuer_warp = (warp == NEW / 32);
-    uint32_t bph = 0;                     // parity of bars[1] (B batch complete)
-    uint32_t rph[2] = {0, 0}, wph = 0;    // issuer-side parities
-
-    // stage one pre-split operand matrix (12*512 uint4, fetch order of pinn_pack_weights_tc) into TMEM lanes 32q..32q+31
-    auto stage_W = [&](const uint4* Wp) {
-#ifdef PINN_EXP_NO_W
-      return;
+#ifdef PINN_TC2_REGS_ISSUER
+    if (CFG::NIS > 0 && role == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PINN_TC2_REGS_ISSUER));
 #endif
-      // one split (56 columns) per round, all 14 loads of a round in flight together: the operand is L2-resident and
-      // four warps have to cover the L2 latency with their own memory-level parallelism
+#ifdef PINN_TC2_REGS_PROD
+    if (CFG::NIS > 0 && role == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PINN_TC2_REGS_PROD));
+#endif
+    const bool do_prod = (role == 1);
+    const bool do_issue = (CFG::NIS > 0) ? (role == 2) : (warp == NEW / 32);
+    uint32_t wfph = 0, dwph = 0;          // parities of wfree / dwd[1]
+    uint4 a[14];
+    auto load_split = [&](const uint4* Wp, int sp) {
+      // one split (56 columns), all 14 loads in flight together: the operand is L2-resident and four warps have to
+      // cover the L2 latency with their own memory-level parallelism
 #pragma unroll
-      for (int sp = 0; sp < 3; ++sp) {
-        uint4 a[14];
-#pragma unroll
-        for (int i = 0; i < 14; ++i) {
-          const int gg = i >> 2, qd = i & 3;
-          a[i] = Wp[(size_t)(4 * sp + qd) * 512 + 128 * gg + 32 * q + lane];
-        }
-#pragma unroll
-        for (int gg = 0; gg < 4; ++gg) {
-          uint32_t v[16];
-#pragma unroll
-          for (int qd = 0; qd < (gg < 3 ? 4 : 2); ++qd) {
-            v[4 * qd] = a[4 * gg + qd].x; v[4 * qd + 1] = a[4 * gg + qd].y; v[4 * qd + 2] = a[4 * gg + qd].z; v[4 * qd + 3] = a[4 * gg + qd].w;
-          }
-          const uint32_t col = tW + lane_off + 56 * sp + 16 * gg;
-          if (gg < 3) tmem_st16(col, v);
-          else tmem_st8u(col, v);
-        }
+      for (int i = 0; i < 14; ++i) {
+        const int gg = i >> 2, qd = i & 3;
+        a[i] = Wp[(size_t)(4 * sp + qd) * 512 + 128 * gg + 32 * q + lane];
       }
-      umma::wait_st();
+    };
+    auto store_split = [&](int sp) {
+#pragma unroll
+      for (int gg = 0; gg < 4; ++gg) {
+        uint32_t v[16];
+#pragma unroll
+        for (int qd = 0; qd < (gg < 3 ? 4 : 2); ++qd) {
+          v[4 * qd] = a[4 * gg + qd].x; v[4 * qd + 1] = a[4 * gg + qd].y; v[4 * qd + 2] = a[4 * gg + qd].z; v[4 * qd + 3] = a[4 * gg + qd].w;
+        }
+        const uint32_t col = tW + lane_off + 56 * sp + 16 * gg;
+        if (gg < 3) tmem_st16(col, v);
+        else tmem_st8u(col, v);
+      }
     };
     // dW_l (TMEM, 100 x 100 used) -> this CTA's private partial [k/4][n][k%4], plain read-modify-write (single writer).
-    // Three rounds of 32 / 32 / 36 columns; the global loads of a round are all in flight together.
+    // Two rounds of 52 / 48 columns; the global loads of a round are all in flight together.
     auto flush_dw = [&](int s, int l) {
 #ifdef PINN_EXP_NO_FLUSH
       return;
 #endif
       float4* gt = reinterpret_cast<float4*>(p.gwt) + ((size_t)(blockIdx.x * S + s) * (L - 1) + (l - 2)) * kTcGwtLayer4 + j;
 #pragma unroll
-      for (int rd = 0; rd < 3; ++rd) {
-        constexpr int NV = 9;
-        const int c0 = 32 * rd;
-        const int nv = (rd < 2) ? 8 : 9;
-        float4 old[NV];
+      for (int rd = 0; rd < 2; ++rd) {
+        constexpr int NV = 13;
+        const int c0 = 52 * rd;
+        const int nv = (rd == 0) ? 13 : 12;
+        float4 acc[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i)
-          if (i < nv) old[i] = gt[(size_t)(c0 / 4 + i) * 128];
-        float v[NV][4];
+          if (i < nv) acc[i] = gt[(size_t)(c0 / 4 + i) * 128];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          if (i < nv) {
+            float v[4];
+            umma::tmem_ld4(tDW + lane_off + c0 + 4 * i, v);
+            umma::wait_ld();
+            acc[i].x += v[0]; acc[i].y += v[1]; acc[i].z += v[2]; acc[i].w += v[3];
+          }
+        }
 #pragma unroll
         for (int i = 0; i < NV; ++i)
-          if (i < nv) umma::tmem_ld4(tDW + lane_off + c0 + 4 * i, v[i]);
-        umma::wait_ld();
-#pragma unroll
-        for (int i = 0; i < NV; ++i)
-          if (i < nv)
-            gt[(size_t)(c0 / 4 + i) * 128] = make_float4(old[i].x + v[i][0], old[i].y + v[i][1], old[i].z + v[i][2], old[i].w + v[i][3]);
+          if (i < nv) gt[(size_t)(c0 / 4 + i) * 128] = acc[i];
       }
     };
-    auto signal_wrdy = [&]() {
+    bool first = true;
+    int pend_s = -1, pend_l = -1;          // dW of the previous reverse step, still in TMEM
+    auto producer_stage = [&](const uint4* Wp) {
+#ifndef PINN_EXP_NO_W
+      load_split(Wp, 0);                   // in flight while the previous step's MMAs still read the old operand
+#endif
+      if (!first) {
+        mbar_wait(wfree, wfph);            // every MMA that reads the current operand is done
+        wfph ^= 1;
+        umma::fence_after_sync();
+      }
+#ifndef PINN_EXP_NO_W
+      store_split(0);
+      load_split(Wp, 1);
+      store_split(1);
+      load_split(Wp, 2);
+      store_split(2);
+      umma::wait_st();
+#endif
       umma::fence_before_sync();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(wrdy)) : "memory");
+      first = false;
     };
-    auto wait_b_done = [&]() {
-      mbar_wait(&bars[1], bph);
-      bph ^= 1;
+    // the flush owed for the previous reverse step
+    auto producer_flush = [&]() {
+      mbar_wait(&dwd[1], dwph);            // dW of the previous step is complete
+      dwph ^= 1;
       umma::fence_after_sync();
+      flush_dw(pend_s, pend_l);
+      umma::fence_before_sync();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(dwfree)) : "memory");
+      pend_l = -1;
     };
-    // ---- MMA issue helpers (same instruction sequences as pinn_tc_kernel; run by the whole issuer warp) ----
+    uint32_t rph[2] = {0, 0}, wph = 0, fph = 0;
+    bool flush_pending = false;
     auto issue_rows = [&](int h, unsigned char* bbase, uint32_t el) {
       constexpr uint32_t idesc = umma::make_idesc_bf16(kTcRows, R, 0, 1);
       const int wa[6] = {0, 2, 1, 0, 1, 0};
       const int ab[6] = {2, 0, 1, 1, 0, 0};
       const uint32_t d = tD(h);
+      const uint32_t lo0 = umma::smem_desc_lo(umma::smem_addr(bbase), JB);
+      constexpr uint32_t hi = umma::smem_desc_hi(128);
       uint32_t accum = 0;
 #pragma unroll
       for (int t = 0; t < 6; ++t) {
 #pragma unroll
         for (int ks = 0; ks < kTcHP / 16; ++ks) {
-          const uint64_t bd = umma::make_smem_desc(umma::smem_addr(bbase + ab[t] * ARR) + ks * 2 * JB, JB, 128);
-          umma::mma_bf16_ts_e(d, tW + wa[t] * 56 + ks * 8, bd, idesc, accum, el);
+          umma::mma_bf16_ts_e2(d, tW + wa[t] * 56 + ks * 8, lo0 + (uint32_t)((ab[t] * ARR + ks * 2 * JB) >> 4), hi, idesc, accum, el);
           accum = 1;
         }
       }
@@ -244,73 +288,96 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       constexpr uint32_t idesc = umma::make_idesc_bf16(kTcRows, kTcHP, 0, 0);
       const int za[6] = {0, 2, 1, 0, 1, 0};
       const int ab[6] = {2, 0, 1, 1, 0, 0};
-      unsigned char* zbase = arr_ptr(h, 3);
-      unsigned char* abase = arr_ptr(h, 0);
+      const uint32_t zlo0 = umma::smem_desc_lo(umma::smem_addr(arr_ptr(h, 3)), 128);
+      const uint32_t alo0 = umma::smem_desc_lo(umma::smem_addr(arr_ptr(h, 0)), 128);
+      constexpr uint32_t hi = umma::smem_desc_hi(JB);
 #pragma unroll
       for (int t = 0; t < 6; ++t) {
 #pragma unroll
         for (int ks = 0; ks < R / 16; ++ks) {
-          const uint64_t ad = umma::make_smem_desc(umma::smem_addr(zbase + za[t] * ARR) + ks * 256, 128, JB);
-          const uint64_t bd = umma::make_smem_desc(umma::smem_addr(abase + ab[t] * ARR) + ks * 256, 128, JB);
-          umma::mma_bf16_ss_e(tDW, ad, bd, idesc, accum, el);
+          umma::mma_bf16_ss_e2(tDW, zlo0 + (uint32_t)((za[t] * ARR + ks * 256) >> 4), hi, alo0 + (uint32_t)((ab[t] * ARR + ks * 256) >> 4), hi, idesc,
+                               accum, el);
           accum = 1;
         }
       }
     };
-    // one pipeline step = the batches of both sub-tiles for one layer
-    auto issue_step = [&](bool reverse) {
-      if (!issuer_warp) return;
-      mbar_wait(wrdy, wph);                 // operand staged (and previous dW flushed) by all 4 producer warps
-      wph ^= 1;
+    // one pipeline step = the batches of both sub-tiles for one layer.  The rows MMAs (the only readers of the weight
+    // operand) go first so that the producers can restage it while the dW MMAs run.
+    // One pipeline step = the batches of both sub-tiles for one layer.  The rows MMAs (the only readers of the weight
+    // operand) go first so that the producers can restage it while the dW MMAs run.
+    auto issue_sub = [&](int h, bool reverse) {
+      mbar_wait(&rdy[h], rph[h]);
+      rph[h] ^= 1;
       umma::fence_after_sync();
-#pragma unroll
-      for (int h = 0; h < NSUB; ++h) {
-        mbar_wait(&rdy[h], rph[h]);
-        rph[h] ^= 1;
-        umma::fence_after_sync();
-        const uint32_t el = umma::elect_one();
-        if (reverse) {
-          issue_dw(h, h == 0 ? 0u : 1u, el);
-          issue_rows(h, arr_ptr(h, 3), el);
-        } else {
-          issue_rows(h, arr_ptr(h, 0), el);
-        }
-        umma::commit_e(&bars[h], el);
-      }
+      const uint32_t el = umma::elect_one();
+      issue_rows(h, reverse ? arr_ptr(h, 3) : arr_ptr(h, 0), el);
+      umma::commit_e(&bars[h], el);
+      if (h == NSUB - 1) umma::commit_e(wfree, el);
+      return el;
     };
-
-    bool first = true;
-    int pend_s = -1, pend_l = -1;          // dW of the previous reverse step still sitting in TMEM
-    auto producer_step = [&](const uint4* Wp, bool reverse, int s, int l) {
-      if (!first) {
-        wait_b_done();                     // every MMA that reads the current operand / accumulates the current dW is done
-        if (pend_l >= 2) flush_dw(pend_s, pend_l);
+    auto issue_sub_dw = [&](int h, uint32_t el) {
+      if (h == 0 && flush_pending) {
+        mbar_wait(dwfree, fph);            // the previous reverse step's dW has left TMEM
+        fph ^= 1;
+        umma::fence_after_sync();
       }
-      first = false;
-      pend_s = reverse ? s : -1;
-      pend_l = reverse ? l : -1;
-      stage_W(Wp);
-      signal_wrdy();
-      issue_step(reverse);
+      issue_dw(h, h == 0 ? 0u : 1u, el);
+      umma::commit_e(&dwd[h], el);
+    };
+    auto step = [&](const uint4* Wp, bool reverse, int s, int l) {
+      if (do_prod) producer_stage(Wp);
+      bool owe = do_prod && pend_l >= 2;
+      if (do_issue) {
+        if (owe) {
+          // this warp is also a producer: flush first only if the element-wise warps are not ready for the MMAs anyway
+          uint32_t ok;
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(ok)
+                       : "r"(umma::smem_addr(&rdy[0])), "r"(rph[0])
+                       : "memory");
+          if (__any_sync(0xffffffffu, ok == 0)) {
+            producer_flush();
+            owe = false;
+          }
+        }
+        mbar_wait(wrdy, wph);
+        wph ^= 1;
+        umma::fence_after_sync();
+        const uint32_t el0 = issue_sub(0, reverse);
+        if (owe) producer_flush();
+        if (reverse) issue_sub_dw(0, el0);
+        const uint32_t el1 = issue_sub(1, reverse);
+        if (reverse) {
+          issue_sub_dw(1, el1);
+          flush_pending = true;
+        }
+      } else if (owe) {
+        producer_flush();
+      }
+      if (do_prod && reverse) {
+        pend_s = s;
+        pend_l = l;
+      }
     };
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      for (int l = 2; l <= L + 1; ++l) producer_step(l <= L ? p.wn + (size_t)(l - 2) * kTcWMat : p.w6p, false, 0, 0);
+      for (int l = 2; l <= L + 1; ++l) step(l <= L ? p.wn + (size_t)(l - 2) * kTcWMat : p.w6p, false, 0, 0);
       if constexpr (BWD) {
         for (int s = 0; s < S; ++s)
-          for (int l = L; l >= 2; --l) producer_step(p.wt + (size_t)(l - 2) * kTcWMat, true, s, l);
+          for (int l = L; l >= 2; --l) step(p.wt + (size_t)(l - 2) * kTcWMat, true, s, l);
       }
     }
-    if (!first) {
-      wait_b_done();
-      if (pend_l >= 2) flush_dw(pend_s, pend_l);
-    }
+    if (do_prod && pend_l >= 2) producer_flush();
   } else {
     // =====================================================================================================
     // element-wise warps
     // =====================================================================================================
+#ifdef PINN_TC2_REGS_EW
+    if (CFG::NIS > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PINN_TC2_REGS_EW));
+#endif
     float4* stash = reinterpret_cast<float4*>(p.stash) + (size_t)blockIdx.x * L * NSUB * C * NEW;
     auto stash_at = [&](int l, int h, int c) -> float4* { return stash + ((size_t)((l - 1) * NSUB + h) * C + c) * NEW + tid; };
-    uint32_t ph[2] = {0, 0};
+    uint32_t ph[2] = {0, 0}, dph[2] = {0, 0};
+    bool dwp[2] = {false, false};          // a dW contraction that reads sub-tile h's arrays may still be running
     double lacc[PINN_MAX_PDE] = {0.0, 0.0, 0.0};
 
     auto store_quad = [&](unsigned char* base, int r0, float v0, float v1, float v2, float v3) {
@@ -333,6 +400,14 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       ph[h] ^= 1;
       umma::fence_after_sync();
     };
+    // before rewriting sub-tile h's arrays: the last dW contraction that reads them must be complete
+    auto guard_arrays = [&](int h) {
+      if (dwp[h]) {
+        mbar_wait(&dwd[h], dph[h]);
+        dph[h] ^= 1;
+        dwp[h] = false;
+      }
+    };
     auto reduce_groups_red = [&](float v, float* dst) {
       redbuf[g * 128 + j] = v;
       epi_sync();
@@ -340,6 +415,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       epi_sync();
     };
     auto epi_layer1 = [&](int h) {
+      guard_arrays(h);
       if (!act) return;
       float w[D];
 #pragma unroll
@@ -513,6 +589,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                 for (int c = 0; c < C; ++c) umma::tmem_ld4(tD(h) + lane_off + c * TS + pb, ab[c]);
                 umma::wait_ld();
               }
+              if (l > 1) guard_arrays(h);
               if (act) {
                 float zq[C][4];
 #pragma unroll
@@ -582,7 +659,10 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                   for (int c = 0; c < C; ++c) store_quad(arr_ptr(h, 0), c * TS + pb, zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
                 }
               }
-              if (l >= 2) signal_ready(h);
+              if (l >= 2) {
+                signal_ready(h);
+                dwp[h] = true;
+              }
             }
             float* gb = gs + ((l == 1) ? offB1 : offHid + (long long)(l - 2) * strideHid + (long long)H * H);
             reduce_groups_red(dbias, gb + j);

@@ -288,16 +288,17 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
     // Split-product major, k-step minor: the five correction products are summed while the accumulator is still
     // ~2^-8 of its final size, so only the last 7 MMAs (b1*b1) round at full magnitude (the tensor core truncates
     // its fp32 accumulate; 42 full-magnitude truncations cost ~10x the FFMA path's error, 7 do not).
+    const uint32_t lo0 = umma::smem_desc_lo(umma::smem_addr(barr[0]), JB);   // the three split arrays are ARR bytes apart
+    constexpr uint32_t hi = umma::smem_desc_hi(128);
     uint32_t accum = 0;
 #pragma unroll
     for (int t = 0; t < 6; ++t) {
 #pragma unroll
       for (int ks = 0; ks < kTcHP / 16; ++ks) {
-        const uint64_t bd = umma::make_smem_desc(umma::smem_addr(barr[ab[t]]) + ks * 2 * JB, JB, 128);
 #ifdef PINN_EXP_ONE_MMA     // what-if: (almost) no tensor work
         if (t != 5 || ks != 0) continue;
 #endif
-        umma::mma_bf16_ts_e(tD, tW + wa[t] * 56 + ks * 8, bd, idesc, accum, el);
+        umma::mma_bf16_ts_e2(tD, tW + wa[t] * 56 + ks * 8, lo0 + (uint32_t)((ab[t] * ARR + ks * 2 * JB) >> 4), hi, idesc, accum, el);
         accum = 1;
       }
     }
@@ -309,17 +310,19 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
     const int za[6] = {0, 2, 1, 0, 1, 0};
     const int ab[6] = {2, 0, 1, 1, 0, 0};
     const uint32_t el = umma::elect_one();
+    const uint32_t zlo0 = umma::smem_desc_lo(umma::smem_addr(arrZ[0]), 128);
+    const uint32_t alo0 = umma::smem_desc_lo(umma::smem_addr(arrA[0]), 128);
+    constexpr uint32_t hi = umma::smem_desc_hi(JB);
     uint32_t accum = 0;
 #pragma unroll
     for (int t = 0; t < 6; ++t) {
 #pragma unroll
       for (int ks = 0; ks < R / 16; ++ks) {
-        const uint64_t ad = umma::make_smem_desc(umma::smem_addr(arrZ[za[t]]) + ks * 256, 128, JB);
-        const uint64_t bd = umma::make_smem_desc(umma::smem_addr(arrA[ab[t]]) + ks * 256, 128, JB);
 #ifdef PINN_EXP_ONE_MMA
         if (t != 5 || ks != 0) continue;
 #endif
-        umma::mma_bf16_ss_e(tDW, ad, bd, idesc, accum, el);
+        umma::mma_bf16_ss_e2(tDW, zlo0 + (uint32_t)((za[t] * ARR + ks * 256) >> 4), hi, alo0 + (uint32_t)((ab[t] * ARR + ks * 256) >> 4), hi, idesc,
+                             accum, el);
         accum = 1;
       }
     }
