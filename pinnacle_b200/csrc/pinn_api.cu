@@ -28,7 +28,7 @@ static const ConfigInfo* const* all_configs() {
 
 static thread_local std::string g_err;
 static thread_local int g_launches = 0;
-int g_tc_pipelined = 0;
+static int g_tc_pipelined = 0;
 static int g_impl = 0;   // 0 = auto (tensor cores, pipelined where instantiated), 1 = FP32 FFMA kernel, 2 = tensor cores, one tile at a time
                          // (error if absent), 3 = pipelined tensor-core kernel (falls back to 2 where not instantiated)
 
@@ -133,7 +133,7 @@ static Workspace carve(const pinn_kind_desc* d, const ConfigInfo* c, int grid, i
     o = align_up(o + (size_t)2 * (d->L - 1) * d->H * d->H * sizeof(float), 256);
   w.off_stash = o;
   if (tc)
-    o = align_up(o + (size_t)grid * d->L * c->tc_NQ * c->C * 512 * 16, 256);
+    o = align_up(o + (size_t)grid * d->L * (c->tc_pipe && c->tc_NQ < 2 ? 2 : c->tc_NQ) * c->C * 512 * 16, 256);
   else
     o = align_up(o + (size_t)grid * d->L * c->E4 * c->NT * 16, 256);
   w.off_gpart = o;
@@ -189,7 +189,8 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
   }
 
   const long long P = param_count(desc);
-  const int tileT = tc ? c->tc_T : c->T;
+  const bool pipe = tc && c->tc_pipe && g_tc_pipelined;
+  const int tileT = tc ? (pipe ? 32 : c->tc_T) : c->T;
   const long long ntiles = (n_rows + tileT - 1) / tileT;
   int grid = (int)(ntiles < max_grid ? ntiles : max_grid);
   char* wsb = static_cast<char*>(workspace);
@@ -215,7 +216,7 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
     lp.stash = reinterpret_cast<float*>(wsb + ws.off_stash);
     lp.gpart = gpart; lp.lpart = lpart; lp.resid_out = resid_out;
     lp.gwt = reinterpret_cast<float*>(wsb + ws.off_gwt);
-    cudaError_t e = c->tc_launch(lp, bwd, grid, st);
+    cudaError_t e = c->tc_launch(lp, bwd, pipe, grid, st);
     if (e != cudaSuccess) return fail(std::string("tensor-core kernel launch: ") + cudaGetErrorString(e));
     ++g_launches;
   } else if (grid > 0) {
@@ -250,7 +251,7 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
   const long long SP = (long long)n_seeds * P;
   const long long work = SP > 0 ? SP : 1;
   pinn_reduce_partials<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(gpart, lpart, grid, n_seeds, P, ws.pstride, desc->n_pde, inv_n, grad_out,
-                                                                       loss_out, (tc && bwd && c->tc_rmw) ? reinterpret_cast<const float*>(wsb + ws.off_gwt) : nullptr,
+                                                                       loss_out, (tc && bwd && (pipe || c->tc_rmw)) ? reinterpret_cast<const float*>(wsb + ws.off_gwt) : nullptr,
                                                                        desc->H, desc->d, desc->L);
   ++g_launches;
   cudaError_t e = cudaGetLastError();

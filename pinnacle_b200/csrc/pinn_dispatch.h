@@ -8,8 +8,6 @@
 
 namespace pinn {
 
-extern int g_tc_pipelined;   // 1 = use the pipelined tensor-core kernel where instantiated (defined in pinn_api.cu)
-
 struct ConfigInfo {
   int id, H, m, d, C;
   int order[PINN_MAX_DIM];
@@ -20,9 +18,10 @@ struct ConfigInfo {
   cudaError_t (*launch)(const LaunchParams&, bool bwd, int grid, cudaStream_t);
   // tensor-core (tcgen05) variant; tc_T == 0 when this configuration has none
   int tc_T, tc_NQ, tc_rmw;
+  int tc_pipe;   // 1: the pipelined kernel (pinn_tc2_kernels.cuh: 32-point tiles, 2 stash quads per thread, RMW dW partials) exists too
   size_t tc_smem_fwd, tc_smem_bwd;
   cudaError_t (*tc_prepare)();
-  cudaError_t (*tc_launch)(const TcLaunchParams&, bool bwd, int grid, cudaStream_t);
+  cudaError_t (*tc_launch)(const TcLaunchParams&, bool bwd, bool pipelined, int grid, cudaStream_t);
 };
 
 template <int ID>

@@ -33,7 +33,7 @@ struct Inst {
     using TF = TCfg<SIG, M, H, TT, false>;
     using TB = TCfg<SIG, M, H, TT, true>;
     // the pipelined two-sub-tile kernel (pinn_tc2_kernels.cuh) exists where two sub-tiles fit in shared memory
-    static constexpr bool kPipe = (TT == 32 && SIG::C <= 5);
+    static constexpr bool kPipe = (TT == 32 && SIG::C <= 5) || (TT == 16 && SIG::C == 6);
     static cudaError_t prepare() {
       cudaError_t e = cudaFuncSetAttribute(pinn_tc_kernel<TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF::smem_bytes);
       if (e != cudaSuccess) return e;
@@ -47,9 +47,9 @@ struct Inst {
       }
       return cudaFuncSetAttribute(pinn_tc_kernel<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB::smem_bytes);
     }
-    static cudaError_t launch(const TcLaunchParams& p, bool bwd, int grid, cudaStream_t st) {
+    static cudaError_t launch(const TcLaunchParams& p, bool bwd, bool pipelined, int grid, cudaStream_t st) {
       if constexpr (kPipe) {
-        if (g_tc_pipelined) {
+        if (pipelined) {
           using PF = TC2fg<SIG, M, H, false>;
           using PB = TC2fg<SIG, M, H, true>;
           if (bwd)
@@ -66,7 +66,7 @@ struct Inst {
       return cudaGetLastError();
     }
     static void fill(ConfigInfo& c) {
-      c.tc_T = TT; c.tc_NQ = TB::NQ; c.tc_rmw = TB::RMW_FLUSH ? 1 : 0; c.tc_smem_fwd = TF::smem_bytes; c.tc_smem_bwd = TB::smem_bytes;
+      c.tc_T = TT; c.tc_NQ = TB::NQ; c.tc_rmw = TB::RMW_FLUSH ? 1 : 0; c.tc_pipe = kPipe ? 1 : 0; c.tc_smem_fwd = TF::smem_bytes; c.tc_smem_bwd = TB::smem_bytes;
       c.tc_prepare = &prepare; c.tc_launch = &launch;
     }
   };
@@ -80,7 +80,7 @@ struct Inst {
       c.T = T; c.NT = CB::NT; c.NTP = CB::NTP; c.E4 = CB::E4;
       c.smem_fwd = CF::smem_bytes; c.smem_bwd = CB::smem_bytes;
       c.valid_kind = &valid_kind; c.prepare = &prepare; c.launch = &launch;
-      c.tc_T = 0; c.tc_NQ = 0; c.tc_rmw = 0; c.tc_smem_fwd = c.tc_smem_bwd = 0; c.tc_prepare = nullptr; c.tc_launch = nullptr;
+      c.tc_T = 0; c.tc_NQ = 0; c.tc_rmw = 0; c.tc_pipe = 0; c.tc_smem_fwd = c.tc_smem_bwd = 0; c.tc_prepare = nullptr; c.tc_launch = nullptr;
       if constexpr (TCT > 0) Tc<TCT>::fill(c);
       return c;
     }();

@@ -35,9 +35,12 @@ struct TC2fg {
   static constexpr int R = C * TS;
   static constexpr int JB = (R / 8) * 128;
   static constexpr int ARR = 14 * JB;
-  static constexpr int APS = BWD ? 6 : 3;         // split arrays per sub-tile
-  static constexpr int NARR = APS * NSUB;
-  static constexpr int tcD = 0, tcDstride = 80, tcDW = 160, tcW = 272, tcTotal = 512;
+  // Split arrays: a^{l}/a^{l-1} (3 per sub-tile) and, for the reverse sweep, zbar^{l} (3 per sub-tile, or 3 shared by
+  // both sub-tiles when two private sets do not fit: C = 6).  With the shared set the element-wise warps of one
+  // sub-tile still overlap the other's MMAs with everything except their final zbar stores.
+  static constexpr bool SHZ = (C > 5);
+  static constexpr int NARR = 3 * NSUB + (BWD ? (SHZ ? 3 : 3 * NSUB) : 0);
+  static constexpr int tcD = 0, tcDstride = R, tcDW = 2 * R, tcW = 2 * R + 112, tcTotal = 512;
   static constexpr int oSmall = NARR * ARR;
   static constexpr int oW1 = oSmall;
   static constexpr int oBias = oW1 + H * D * 4;
@@ -56,7 +59,8 @@ struct TC2fg {
   static constexpr size_t smem_bytes = (size_t)nBytes;
 
   static_assert(H == 100, "tensor-core path is instantiated for H = 100");
-  static_assert(R % 16 == 0 && R <= 80, "two sub-tiles in flight need R = C*16 <= 80");
+  static_assert(R % 16 == 0 && R <= 96, "two sub-tiles in flight need R = C*16 <= 96");
+  static_assert(tcW + 168 <= tcTotal, "TMEM budget");
   static_assert(oSmall % 16 == 0 && oUo % 16 == 0, "alignment");
   static_assert(nBytes - oSmall >= 2 * JB, "A-operand over-read of the last Zbar array must stay inside the allocation");
   static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
@@ -77,7 +81,7 @@ template <class CFG>
 __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunchParams p) {
   using SIG = typename CFG::SIG;
   constexpr int C = CFG::C, D = CFG::D, M = CFG::M, H = CFG::H, T = CFG::T, TS = CFG::TS, NSUB = CFG::NSUB, R = CFG::R, JB = CFG::JB,
-                ARR = CFG::ARR, NEW = CFG::NEW, NTHALL = CFG::NTHALL, APS = CFG::APS;
+                ARR = CFG::ARR, NEW = CFG::NEW, NTHALL = CFG::NTHALL;
   constexpr bool BWD = CFG::BWD;
 
   extern __shared__ __align__(1024) unsigned char smraw[];
@@ -100,7 +104,10 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
   uint64_t* dwfree = bars + 8;                                        // dW flushed out of TMEM (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   KindParams* kps = reinterpret_cast<KindParams*>(smraw + CFG::oKp);
-  auto arr_ptr = [&](int h, int a) -> unsigned char* { return smraw + (size_t)(h * APS + a) * ARR; };
+  // a = 0..2: splits of a^{l} / a^{l-1} of sub-tile h; a = 3..5: splits of zbar^{l}
+  auto arr_ptr = [&](int h, int a) -> unsigned char* {
+    return smraw + (size_t)(a < 3 ? h * 3 + a : 3 * NSUB + (CFG::SHZ ? 0 : h * 3) + (a - 3)) * ARR;
+  };
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -582,14 +589,37 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
             for (int i = 0; i < D; ++i) dw1[i] = 0.f;
 #pragma unroll
             for (int h = 0; h < NSUB; ++h) {
-              if (l < L) wait_bar(h);                     // (i) and (ii) of layer l+1, sub-tile h: abar^l(h) is in D_h
+              // ---- part 1, independent of the tensor core: splits of a^{l-1} (operand of the dW contraction)
+              if (l > 1) {
+                guard_arrays(h);
+                if (act) {
+                  float zq[C][4];
+#pragma unroll
+                  for (int c = 0; c < C; ++c) {
+                    const float4 v = *stash_at(l - 1, h, c);
+                    zq[c][0] = v.x; zq[c][1] = v.y; zq[c][2] = v.z; zq[c][3] = v.w;
+                  }
+#pragma unroll
+                  for (int pp = 0; pp < 4; ++pp) {
+                    float z[C], av[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
+                    tanh_jet_fwd<SIG>(z, av);
+#pragma unroll
+                    for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
+                  }
+#pragma unroll
+                  for (int c = 0; c < C; ++c) store_quad(arr_ptr(h, 0), c * TS + pb, zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
+                }
+              }
+              // ---- part 2: abar^l (from D_h, written by the rows MMAs of layer l+1) -> zbar^l
+              if (l < L) wait_bar(h);
               float ab[C][4];
               if (l < L) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) umma::tmem_ld4(tD(h) + lane_off + c * TS + pb, ab[c]);
                 umma::wait_ld();
               }
-              if (l > 1) guard_arrays(h);
               if (act) {
                 float zq[C][4];
 #pragma unroll
@@ -638,28 +668,16 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
 #pragma unroll
                   for (int c = 0; c < C; ++c) ab[c][pp] = zb[c];
                 }
-                if (l > 1) {
+              }
+              if (l > 1) {
+                if constexpr (CFG::SHZ) {
+                  // shared zbar arrays: the other sub-tile's MMAs (its pending dwd phase) must be done reading them
+                  if (dwp[1 - h]) mbar_wait(&dwd[1 - h], dph[1 - h]);
+                }
+                if (act) {
 #pragma unroll
                   for (int c = 0; c < C; ++c) store_quad(arr_ptr(h, 3), c * TS + pb, ab[c][0], ab[c][1], ab[c][2], ab[c][3]);
-#pragma unroll
-                  for (int c = 0; c < C; ++c) {
-                    const float4 v = *stash_at(l - 1, h, c);
-                    zq[c][0] = v.x; zq[c][1] = v.y; zq[c][2] = v.z; zq[c][3] = v.w;
-                  }
-#pragma unroll
-                  for (int pp = 0; pp < 4; ++pp) {
-                    float z[C], av[C];
-#pragma unroll
-                    for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-                    tanh_jet_fwd<SIG>(z, av);
-#pragma unroll
-                    for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
-                  }
-#pragma unroll
-                  for (int c = 0; c < C; ++c) store_quad(arr_ptr(h, 0), c * TS + pb, zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
                 }
-              }
-              if (l >= 2) {
                 signal_ready(h);
                 dwp[h] = true;
               }
