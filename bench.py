@@ -341,7 +341,7 @@ def run_fused(args):
         d = ops[i].desc
         tc_i = args.kernel != "ffma" and capi.has_tensor_core_kernel(d)
         t = kern_ms[i] * 1e-3
-        out = {"problem": specs[i].name, "kernel": "pinn_tc_kernel (tcgen05 bf16x3)" if tc_i else "pinn_fused_kernel (FP32 FFMA)",
+        out = {"problem": specs[i].name, "kernel": capi.IMPL_NAMES.get(capi.selected_impl(d), "?"),
                "launch_ms": kern_ms[i], "achieved_tflops": d.flops_step_per_point() * n_per / t / 1e12,
                "hbm_gbs_algorithmic": d.bytes_per_point() * n_per / t / 1e9}
         if tc_i:
@@ -353,7 +353,8 @@ def run_fused(args):
         roofline = {
             "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak if tensor_peak else None,
             "traffic": None,
-            "kernel": f"pinn_tc_kernel<{specs[dom].name}, fwd+reverse> (tcgen05 kind::f16, bf16x3 split precision, TMEM accumulators)",
+            "kernel": f"{'pinn_tc2_kernel' if capi.selected_impl(desc) == 3 else 'pinn_tc_kernel'}<{specs[dom].name}, fwd+reverse> "
+                      "(tcgen05 kind::f16, bf16x3 split precision, TMEM accumulators)",
             "launch_ms": kern_ms[dom], "algorithmic_flops_per_point": desc.flops_step_per_point(), "points_per_launch": n_per,
             "peak_source": peak_src + " bf16 dense, sustained",
             "executed_tensor_flops_per_point": desc.tc_executed_flops_per_point(1), "executed_tensor_tflops": exe,

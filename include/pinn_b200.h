@@ -110,6 +110,9 @@ int pinn_fwd_bwd(const pinn_kind_desc* desc, const float* params, const float* x
 int pinn_set_impl(int impl);
 /* 1 if the descriptor's configuration has a tensor-core kernel in this build. */
 int pinn_has_tensor_core_kernel(const pinn_kind_desc* desc);
+/* The kernel pinn_fwd / pinn_fwd_bwd would run for this descriptor under the current selection: 1 = FP32 FFMA,
+ * 2 = tensor cores (one tile at a time), 3 = tensor cores (pipelined); 0 = unsupported descriptor / selection. */
+int pinn_selected_impl(const pinn_kind_desc* desc);
 
 /* Number of kernel launches the last pinn_fwd / pinn_fwd_bwd call of this thread enqueued. */
 int pinn_last_launch_count(void);

@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpinn_b200.so")
 EXPORTS = (
     "pinn_param_count", "pinn_supported", "pinn_workspace_bytes", "pinn_fwd", "pinn_fwd_bwd",
     "pinn_last_launch_count", "pinn_ffma_peak_tflops", "pinn_last_error", "pinn_build_info", "pinn_debug_umma_gemm", "pinn_set_impl", "pinn_has_tensor_core_kernel",
+    "pinn_selected_impl",
 )
 
 
@@ -65,6 +66,8 @@ def load() -> ctypes.CDLL:
     lib.pinn_set_impl.restype = ctypes.c_int
     lib.pinn_has_tensor_core_kernel.argtypes = [P]
     lib.pinn_has_tensor_core_kernel.restype = ctypes.c_int
+    lib.pinn_selected_impl.argtypes = [P]
+    lib.pinn_selected_impl.restype = ctypes.c_int
     lib.pinn_last_error.argtypes = []
     lib.pinn_last_error.restype = ctypes.c_char_p
     lib.pinn_build_info.argtypes = []
@@ -204,6 +207,16 @@ def set_impl(impl: int):
 def has_tensor_core_kernel(desc: KindDesc) -> bool:
     c = desc.to_c()
     return bool(load().pinn_has_tensor_core_kernel(ctypes.byref(c)))
+
+
+def selected_impl(desc: KindDesc) -> int:
+    """Kernel the next call would run for ``desc``: IMPL_FFMA, IMPL_TC or IMPL_TC_PIPELINED (0 = unsupported)."""
+    c = desc.to_c()
+    return int(load().pinn_selected_impl(ctypes.byref(c)))
+
+
+IMPL_NAMES = {1: "pinn_fused_kernel (FP32 FFMA)", 2: "pinn_tc_kernel (tcgen05 bf16x3)",
+              3: "pinn_tc2_kernel (tcgen05 bf16x3, warp-specialised, two sub-tiles in flight)"}
 
 
 def last_launch_count() -> int:

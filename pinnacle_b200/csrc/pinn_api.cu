@@ -313,6 +313,15 @@ int pinn_has_tensor_core_kernel(const pinn_kind_desc* desc) {
   return (c != nullptr && c->tc_T > 0) ? 1 : 0;
 }
 
+int pinn_selected_impl(const pinn_kind_desc* desc) {
+  std::string why;
+  const ConfigInfo* c = find_config(desc, &why);
+  if (c == nullptr) return 0;
+  std::string why_tc;
+  if (!want_tc(c, &why_tc)) return why_tc.empty() ? 1 : 0;
+  return (c->tc_pipe && g_tc_pipelined) ? 3 : 2;
+}
+
 double pinn_ffma_peak_tflops(int iters) {
   const DeviceInfo& di = device_info();
   if (!di.ok) { fail(di.err); return -1.0; }
