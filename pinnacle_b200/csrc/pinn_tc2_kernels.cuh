@@ -14,6 +14,8 @@
 // shared memory, i.e. C <= 5 (R = C*16 <= 80).
 #pragma once
 
+#include <cstdio>
+
 #include "pinn_tc_kernels.cuh"
 
 namespace pinn {
@@ -77,6 +79,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// -DPINN_TRACE (debug builds only, see scripts/trace_timeline.py): lane 0 of one element-wise warp, one producer warp
+// and the issuer warp of CTA 0 record clock() at the events below for one steady-state tile and print them at exit.
+#ifdef PINN_TRACE
+#define PINN_TR(ev)                                                                                      \
+  do {                                                                                                   \
+    if (tr_on && tr_n < 160) tr_buf[tr_n++] = ((unsigned)(ev) << 24) | ((unsigned)clock() & 0xffffffu); \
+  } while (0)
+#else
+#define PINN_TR(ev) \
+  do {              \
+  } while (0)
+#endif
+
 template <class CFG>
 __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunchParams p) {
   using SIG = typename CFG::SIG;
@@ -125,20 +140,22 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
   const int L = p.L;
   const int S = BWD ? p.n_seeds : 0;
 
-  const long long offB1 = (long long)H * D;
-  const long long offHid = offB1 + H;
-  const long long strideHid = (long long)H * H + H;
-  const long long offW6 = offHid + (long long)(L - 1) * strideHid;
-  const long long offB6 = offW6 + (long long)M * H;
+  // parameter offsets (nn.Linear order); P < 2^31, 32-bit keeps them out of register pairs
+  const int offB1 = H * D;
+  const int offHid = offB1 + H;
+  const int strideHid = H * H + H;
+  const int offW6 = offHid + (L - 1) * strideHid;
+  const int offB6 = offW6 + M * H;
 
   // ---------------- one-time setup (all 20 warps) ----------------
   for (int i = tid; i < H * D; i += NTHALL) W1s[i] = p.params[i];
   for (int i = tid; i < H; i += NTHALL) bs[i] = p.params[offB1 + i];
   for (int l = 2; l <= L; ++l)
-    for (int i = tid; i < H; i += NTHALL) bs[(l - 1) * H + i] = p.params[offHid + (long long)(l - 2) * strideHid + (long long)H * H + i];
+    for (int i = tid; i < H; i += NTHALL) bs[(l - 1) * H + i] = p.params[offHid + (l - 2) * strideHid + H * H + i];
   for (int i = tid; i < M * H; i += NTHALL) W6s[i] = p.params[offW6 + i];
   if (tid < M) b6s[tid] = p.params[offB6 + tid];
   for (int i = tid; i < CFG::NARR * ARR / 16; i += NTHALL) reinterpret_cast<uint4*>(smraw)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < PINN_MAX_PDE * T) lred[tid] = 0.0;
   if (tid == 0) {
     mbar_init_n(&bars[0], 1);
     mbar_init_n(&bars[1], 1);
@@ -168,6 +185,12 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
   const uint32_t tDW = tbase + CFG::tcDW, tW = tbase + CFG::tcW;
   auto tD = [&](int h) -> uint32_t { return tbase + CFG::tcD + h * CFG::tcDstride; };
   const long long ntiles = (p.n_rows + T - 1) / T;
+#ifdef PINN_TRACE
+  unsigned tr_buf[160];
+  int tr_n = 0;
+  bool tr_on = false;
+  const bool tr_thread = blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 16 || warp == 20);
+#endif
 
   // the (W operand, reverse?) sequence of one tile, identical for the producer warps and the issuer warp:
   //   forward  l = 2..L+1 : W_l (W_{L+1} = zero-padded output layer)
@@ -245,11 +268,13 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
 #ifndef PINN_EXP_NO_W
       load_split(Wp, 0);                   // in flight while the previous step's MMAs still read the old operand
 #endif
+      PINN_TR(40);
       if (!first) {
         mbar_wait(wfree, wfph);            // every MMA that reads the current operand is done
         wfph ^= 1;
         umma::fence_after_sync();
       }
+      PINN_TR(41);
 #ifndef PINN_EXP_NO_W
       store_split(0);
       load_split(Wp, 1);
@@ -260,6 +285,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
 #endif
       umma::fence_before_sync();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(wrdy)) : "memory");
+      PINN_TR(42);
       first = false;
     };
     // the flush owed for the previous reverse step
@@ -267,7 +293,9 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       mbar_wait(&dwd[1], dwph);            // dW of the previous step is complete
       dwph ^= 1;
       umma::fence_after_sync();
+      PINN_TR(43);
       flush_dw(pend_s, pend_l);
+      PINN_TR(44);
       umma::fence_before_sync();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(dwfree)) : "memory");
       pend_l = -1;
@@ -313,12 +341,15 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
     // One pipeline step = the batches of both sub-tiles for one layer.  The rows MMAs (the only readers of the weight
     // operand) go first so that the producers can restage it while the dW MMAs run.
     auto issue_sub = [&](int h, bool reverse) {
+      PINN_TR(60 + h);
       mbar_wait(&rdy[h], rph[h]);
       rph[h] ^= 1;
       umma::fence_after_sync();
+      PINN_TR(62 + h);
       const uint32_t el = umma::elect_one();
       issue_rows(h, reverse ? arr_ptr(h, 3) : arr_ptr(h, 0), el);
       umma::commit_e(&bars[h], el);
+      PINN_TR(64 + h);
       if (h == NSUB - 1) umma::commit_e(wfree, el);
       return el;
     };
@@ -328,8 +359,10 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         fph ^= 1;
         umma::fence_after_sync();
       }
+      PINN_TR(66 + h);
       issue_dw(h, h == 0 ? 0u : 1u, el);
       umma::commit_e(&dwd[h], el);
+      PINN_TR(68 + h);
     };
     auto step = [&](const uint4* Wp, bool reverse, int s, int l) {
       if (do_prod) producer_stage(Wp);
@@ -347,9 +380,11 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
             owe = false;
           }
         }
+        PINN_TR(58);
         mbar_wait(wrdy, wph);
         wph ^= 1;
         umma::fence_after_sync();
+        PINN_TR(59);
         const uint32_t el0 = issue_sub(0, reverse);
         if (owe) producer_flush();
         if (reverse) issue_sub_dw(0, el0);
@@ -367,6 +402,9 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       }
     };
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#ifdef PINN_TRACE
+      tr_on = tr_thread && (tile / gridDim.x == 3);
+#endif
       for (int l = 2; l <= L + 1; ++l) step(l <= L ? p.wn + (size_t)(l - 2) * kTcWMat : p.w6p, false, 0, 0);
       if constexpr (BWD) {
         for (int s = 0; s < S; ++s)
@@ -385,7 +423,6 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
     auto stash_at = [&](int l, int h, int c) -> float4* { return stash + ((size_t)((l - 1) * NSUB + h) * C + c) * NEW + tid; };
     uint32_t ph[2] = {0, 0}, dph[2] = {0, 0};
     bool dwp[2] = {false, false};          // a dW contraction that reads sub-tile h's arrays may still be running
-    double lacc[PINN_MAX_PDE] = {0.0, 0.0, 0.0};
 
     auto store_quad = [&](unsigned char* base, int r0, float v0, float v1, float v2, float v3) {
       uint32_t a1, a2, a3, b1, b2, b3;
@@ -497,6 +534,9 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
     };
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#ifdef PINN_TRACE
+      tr_on = tr_thread && (tile / gridDim.x == 3);
+#endif
       const long long row0 = tile * T;
       for (int i = tid; i < T * D; i += NEW) {
         const long long r = row0 + i / D;
@@ -514,19 +554,24 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       // ================= forward =================
 #pragma unroll
       for (int h = 0; h < NSUB; ++h) {
+        PINN_TR(1 + h);
         epi_layer1(h);
         signal_ready(h);
+        PINN_TR(3 + h);
       }
       for (int l = 2; l <= L + 1; ++l) {
 #pragma unroll
         for (int h = 0; h < NSUB; ++h) {
+          PINN_TR(10 + h);
           wait_bar(h);
+          PINN_TR(12 + h);
           if (l <= L) {
             epi_hidden(h, l);
             signal_ready(h);
           } else {
             epi_output(h);
           }
+          PINN_TR(14 + h);
         }
       }
       epi_sync();
@@ -546,7 +591,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         for (int k = 0; k < PINN_MAX_PDE; ++k) {
           const float rk = valid ? r[k] : 0.f;
           rs[k * T + tid] = rk;
-          lacc[k] += (double)rk * (double)rk;
+          lred[k * T + tid] += (double)rk * (double)rk;   // per-point running sums live in shared memory, not in registers
         }
         if (p.resid_out != nullptr && valid)
           for (int k = 0; k < p.n_pde; ++k) p.resid_out[(row0 + tid) * p.n_pde + k] = r[k];
@@ -590,8 +635,10 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
 #pragma unroll
             for (int h = 0; h < NSUB; ++h) {
               // ---- part 1, independent of the tensor core: splits of a^{l-1} (operand of the dW contraction)
+              PINN_TR(20 + h);
               if (l > 1) {
                 guard_arrays(h);
+                PINN_TR(22 + h);
                 if (act) {
                   float zq[C][4];
 #pragma unroll
@@ -613,7 +660,9 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                 }
               }
               // ---- part 2: abar^l (from D_h, written by the rows MMAs of layer l+1) -> zbar^l
+              PINN_TR(24 + h);
               if (l < L) wait_bar(h);
+              PINN_TR(26 + h);
               float ab[C][4];
               if (l < L) {
 #pragma unroll
@@ -681,8 +730,9 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                 signal_ready(h);
                 dwp[h] = true;
               }
+              PINN_TR(28 + h);
             }
-            float* gb = gs + ((l == 1) ? offB1 : offHid + (long long)(l - 2) * strideHid + (long long)H * H);
+            float* gb = gs + ((l == 1) ? offB1 : offHid + (l - 2) * strideHid + H * H);
             reduce_groups_red(dbias, gb + j);
             if (l == L) {
 #pragma unroll
@@ -697,12 +747,12 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       }
       epi_sync();
     }
-    if (tid < T) {
-#pragma unroll
-      for (int k = 0; k < PINN_MAX_PDE; ++k) lred[k * T + tid] = lacc[k];
-    }
   }
 
+#ifdef PINN_TRACE
+  if (tr_thread)
+    for (int i = 0; i < tr_n; ++i) printf("TR %d %u %u\n", warp, tr_buf[i] >> 24, tr_buf[i] & 0xffffffu);
+#endif
   // ---------------- per-CTA loss partials ----------------
   umma::fence_before_sync();
   __syncthreads();
