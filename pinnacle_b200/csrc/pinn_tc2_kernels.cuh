@@ -6,12 +6,23 @@
 //
 //   element-wise warps (0..15)   EW(A,l)  EW(B,l)  EW(A,l+1)  EW(B,l+1) ...      signal rdy[h] after each stage
 //   tensor core                       MMA(A,l+1)  MMA(B,l+1)  MMA(A,l+2) ...      commit -> bars[h] (, dwd[h])
-//   producer warps (16..19)      stage the next weight operand in TMEM as soon as the rows MMAs of B are complete
-//                                (wfree -> wrdy), then flush the previous step's dW partial (dwd[1] -> dwfree)
-//   issuer warp (20)             per step: wait wrdy; per sub-tile: wait rdy[h], rows MMAs, (wait dwfree,) dW MMAs
+//   producer warps (16..19)      restage the weight operand split by split as the previous step's last MMAs release
+//                                it, then flush the previous reverse step's dW partial (dwd[1] -> dwfree)
+//   issuer warp (20)             per sub-tile: wait rdy[h]; rows MMAs, group by group as the splits become ready
+//                                (wr[0..2]); (wait dwfree,) dW MMAs
 //
-// The element-wise warps never touch weights, never issue MMAs and never flush dW.  Needs 2 x 6 split arrays in
-// shared memory, i.e. C <= 5 (R = C*16 <= 80).
+// Weight operand hand-over.  Both sub-tiles use the same layer's operand, so step n+1's operand can only replace
+// step n's once B's rows MMAs are through with it -- and A's next rows MMAs (hence the element-wise warps) wait
+// for that.  To keep that gap short the three bf16 splits w1, w2, w3 are handed over individually:
+//   * the rows MMAs run in three groups  G0 = w2*(a2, a1),  G1 = w3*a1,  G2 = w1*(a3, a2, a1)  (main term last);
+//     B's batch commits wf1 after G0 and wf2 after G1, so w2 and w3 are restaged while B's batch is still running;
+//   * w1 alternates between two TMEM slots from step to step, so the next w1 is staged a whole step early;
+//   * the issuer waits per group, so G0 of the next step runs while w3 is still in flight.
+// Four 52-column slots fit next to 2 x D and dW because a split only has 50 live columns: the last k-step of a slot
+// reads 4 columns of its right-hand neighbour, which multiply the zero pad rows 100..111 of the activation arrays
+// (any finite value will do); the last slot's k-step 6 lives in a 4-column stub in front of slot 0.
+//
+// The element-wise warps never touch weights, never issue MMAs and never flush dW.
 #pragma once
 
 #include <cstdio>
@@ -20,10 +31,7 @@
 
 namespace pinn {
 
-#ifndef PINN_TC2_NIS
-#define PINN_TC2_NIS 32
-#endif
-template <class SIG_, int M_, int H_, bool BWD_, int NIS_ = PINN_TC2_NIS>
+template <class SIG_, int M_, int H_, bool BWD_>
 struct TC2fg {
   using SIG = SIG_;
   static constexpr int M = M_, H = H_;
@@ -31,7 +39,7 @@ struct TC2fg {
   static constexpr int C = SIG::C, D = SIG::D;
   static constexpr int NEW = 512;                 // element-wise threads (16 warps)
   static constexpr int NPR = 128;                 // producer threads (4 warps, one per TMEM lane quarter)
-  static constexpr int NIS = NIS_;                // 32: separate MMA issuer warp (21 warps, 80 registers/thread); 0: first producer warp issues
+  static constexpr int NIS = 32;                  // MMA issuer warp
   static constexpr int NTHALL = NEW + NPR + NIS;
   static constexpr int TS = 16, NSUB = 2, T = TS * NSUB;
   static constexpr int R = C * TS;
@@ -42,7 +50,9 @@ struct TC2fg {
   // sub-tile still overlap the other's MMAs with everything except their final zbar stores.
   static constexpr bool SHZ = (C > 5);
   static constexpr int NARR = 3 * NSUB + (BWD ? (SHZ ? 3 : 3 * NSUB) : 0);
-  static constexpr int tcD = 0, tcDstride = R, tcDW = 2 * R, tcW = 2 * R + 112, tcTotal = 512;
+  // TMEM columns: D_A | D_B | dW (112) | stub (4) | four weight-split slots at a 52-column stride (the last one 48 wide)
+  static constexpr int tcD = 0, tcDstride = R, tcDW = 2 * R, tcStub = 2 * R + 112, tcW = tcStub + 4, tcWStride = 52, tcTotal = 512;
+  static constexpr int tcWEnd = tcW + 3 * tcWStride + 48;
   static constexpr int oSmall = NARR * ARR;
   static constexpr int oW1 = oSmall;
   static constexpr int oBias = oW1 + H * D * 4;
@@ -55,14 +65,14 @@ struct TC2fg {
   static constexpr int oRs = oUb + NSUB * M * R * 4;
   static constexpr int oRed = oRs + PINN_MAX_PDE * T * 4;
   static constexpr int oLred = (oRed + 4 * 128 * 4 + 7) / 8 * 8;
-  static constexpr int oBar = oLred + PINN_MAX_PDE * T * 8;    // bars[2], rdy[2], wrdy, tmem slot
-  static constexpr int oKp = oBar + 96;
+  static constexpr int oBar = oLred + PINN_MAX_PDE * T * 8;    // 15 mbarriers + tmem slot
+  static constexpr int oKp = oBar + 128;
   static constexpr int nBytes = oKp + (int)((sizeof(KindParams) + 15) / 16 * 16);
   static constexpr size_t smem_bytes = (size_t)nBytes;
 
   static_assert(H == 100, "tensor-core path is instantiated for H = 100");
   static_assert(R % 16 == 0 && R <= 96, "two sub-tiles in flight need R = C*16 <= 96");
-  static_assert(tcW + 168 <= tcTotal, "TMEM budget");
+  static_assert(tcWEnd <= tcTotal && (tcWEnd - tcStub) % 16 == 0, "TMEM budget");
   static_assert(oSmall % 16 == 0 && oUo % 16 == 0, "alignment");
   static_assert(nBytes - oSmall >= 2 * JB, "A-operand over-read of the last Zbar array must stay inside the allocation");
   static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
@@ -113,11 +123,15 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
   double* lred = reinterpret_cast<double*>(smraw + CFG::oLred);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + CFG::oBar);   // [h] MMA batch of sub-tile h complete (tcgen05.commit)
   uint64_t* rdy = bars + 2;                                           // [h] operands of sub-tile h's next batch in place (512 arrivals)
-  uint64_t* wrdy = bars + 4;                                          // next weight operand staged (128 arrivals)
-  uint64_t* wfree = bars + 5;                                         // all MMAs reading the current weight operand complete
-  uint64_t* dwd = bars + 6;                                           // [h] dW MMAs of sub-tile h complete: its arrays may be rewritten
-  uint64_t* dwfree = bars + 8;                                        // dW flushed out of TMEM (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  // wr[0], wr[1]: w1 of an even / odd step staged (the producers may run a step ahead on w1, hence one barrier per
+  // slot); wr[2], wr[3]: w2, w3 of this step staged (128 arrivals each)
+  uint64_t* wr = bars + 4;
+  uint64_t* wfree = bars + 8;                                         // [n&1] rows MMAs of step n complete (w1's slot of step n is free)
+  uint64_t* wf1 = bars + 10;                                          // B's rows MMAs are through with w2 (after group G0)
+  uint64_t* wf2 = bars + 11;                                          // ... and with w3 (after group G1)
+  uint64_t* dwd = bars + 12;                                          // [h] dW MMAs of sub-tile h complete: its arrays may be rewritten
+  uint64_t* dwfree = bars + 14;                                       // dW flushed out of TMEM (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
   KindParams* kps = reinterpret_cast<KindParams*>(smraw + CFG::oKp);
   // a = 0..2: splits of a^{l} / a^{l-1} of sub-tile h; a = 3..5: splits of zbar^{l}
   auto arr_ptr = [&](int h, int a) -> unsigned char* {
@@ -161,8 +175,11 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
     mbar_init_n(&bars[1], 1);
     mbar_init_n(&rdy[0], NEW);
     mbar_init_n(&rdy[1], NEW);
-    mbar_init_n(wrdy, CFG::NPR);
-    mbar_init_n(wfree, 1);
+    for (int i = 0; i < 4; ++i) mbar_init_n(&wr[i], CFG::NPR);
+    mbar_init_n(&wfree[0], 1);
+    mbar_init_n(&wfree[1], 1);
+    mbar_init_n(wf1, 1);
+    mbar_init_n(wf2, 1);
     mbar_init_n(&dwd[0], 1);
     mbar_init_n(&dwd[1], 1);
     mbar_init_n(dwfree, CFG::NPR);
@@ -182,7 +199,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tbase = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // shfl: lets ptxas treat TMEM addresses as warp-uniform
-  const uint32_t tDW = tbase + CFG::tcDW, tW = tbase + CFG::tcW;
+  const uint32_t tDW = tbase + CFG::tcDW, tStub = tbase + CFG::tcStub, tW = tbase + CFG::tcW;
   auto tD = [&](int h) -> uint32_t { return tbase + CFG::tcD + h * CFG::tcDstride; };
   const long long ntiles = (p.n_rows + T - 1) / T;
 #ifdef PINN_TRACE
@@ -198,40 +215,51 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
   if (role != 0) {
     // =====================================================================================================
     // producer warps: stage weight operands in TMEM, flush dW partials.
-    // MMA issuer: its own warp (CFG::NIS == 32) or the first producer warp, after its producer work of the step.
+    // MMA issuer: its own warp.
     // =====================================================================================================
-#ifdef PINN_TC2_REGS_ISSUER
-    if (CFG::NIS > 0 && role == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PINN_TC2_REGS_ISSUER));
-#endif
-#ifdef PINN_TC2_REGS_PROD
-    if (CFG::NIS > 0 && role == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PINN_TC2_REGS_PROD));
-#endif
     const bool do_prod = (role == 1);
-    const bool do_issue = (CFG::NIS > 0) ? (role == 2) : (warp == NEW / 32);
-    uint32_t wfph = 0, dwph = 0;          // parities of wfree / dwd[1]
-    uint4 a[14];
+    uint32_t wfp[2] = {0, 0}, wf1p = 0, wf2p = 0, dwph = 0;   // producer-side parities of wfree[], wf1, wf2, dwd[1]
+    uint4 a[13];
+    // slot of split sp at step n: w1 alternates between slot 0 and slot 3, w2 -> slot 1, w3 -> slot 2
+    auto slot_of = [&](int sp, long long n) -> int { return sp == 0 ? ((n & 1) ? 3 : 0) : sp; };
     auto load_split = [&](const uint4* Wp, int sp) {
-      // one split (56 columns), all 14 loads in flight together: the operand is L2-resident and four warps have to
-      // cover the L2 latency with their own memory-level parallelism
+      // one split (52 columns incl. 2 zero pad columns), all 13 loads in flight together: the operand is L2-resident
+      // and four warps have to cover the L2 latency with their own memory-level parallelism
 #pragma unroll
-      for (int i = 0; i < 14; ++i) {
+      for (int i = 0; i < 13; ++i) {
         const int gg = i >> 2, qd = i & 3;
         a[i] = Wp[(size_t)(4 * sp + qd) * 512 + 128 * gg + 32 * q + lane];
       }
     };
-    auto store_split = [&](int sp) {
+    auto store_split = [&](int slot) {
+      const uint32_t base = tW + lane_off + (uint32_t)(CFG::tcWStride * slot);
 #pragma unroll
-      for (int gg = 0; gg < 4; ++gg) {
+      for (int gg = 0; gg < 3; ++gg) {
         uint32_t v[16];
 #pragma unroll
-        for (int qd = 0; qd < (gg < 3 ? 4 : 2); ++qd) {
+        for (int qd = 0; qd < 4; ++qd) {
           v[4 * qd] = a[4 * gg + qd].x; v[4 * qd + 1] = a[4 * gg + qd].y; v[4 * qd + 2] = a[4 * gg + qd].z; v[4 * qd + 3] = a[4 * gg + qd].w;
         }
-        const uint32_t col = tW + lane_off + 56 * sp + 16 * gg;
-        if (gg < 3) tmem_st16(col, v);
-        else tmem_st8u(col, v);
+        tmem_st16(base + 16 * gg, v);
       }
+      const uint32_t tail = (slot == 3) ? tStub + lane_off : base + 48;   // columns 48..51 (k-step 6)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tail), "r"(a[12].x), "r"(a[12].y), "r"(a[12].z), "r"(a[12].w)
+                   : "memory");
+      umma::wait_st();
     };
+    auto arrive = [&](uint64_t* bar) {
+      umma::fence_before_sync();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(bar)) : "memory");
+    };
+    if (do_prod) {
+      // every column a padded k-step may read must hold a finite value from the start
+      uint32_t z[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll 1
+      for (int c = 0; c < CFG::tcWEnd - CFG::tcStub; c += 16) tmem_st16(tStub + lane_off + c, z);
+      umma::wait_st();
+    }
     // dW_l (TMEM, 100 x 100 used) -> this CTA's private partial [k/4][n][k%4], plain read-modify-write (single writer).
     // Two rounds of 52 / 48 columns; the global loads of a round are all in flight together.
     auto flush_dw = [&](int s, int l) {
@@ -262,31 +290,49 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
           if (i < nv) gt[(size_t)(c0 / 4 + i) * 128] = acc[i];
       }
     };
-    bool first = true;
+    long long nstep = 0;                   // pipeline steps so far (forward and reverse, all tiles)
     int pend_s = -1, pend_l = -1;          // dW of the previous reverse step, still in TMEM
     auto producer_stage = [&](const uint4* Wp) {
-#ifndef PINN_EXP_NO_W
-      load_split(Wp, 0);                   // in flight while the previous step's MMAs still read the old operand
+      const long long n = nstep;
+#ifdef PINN_EXP_NO_W
+      if (n >= 2) { mbar_wait(&wfree[n & 1], wfp[n & 1]); wfp[n & 1] ^= 1; }
+      arrive(&wr[n & 1]);
+      if (n >= 1) { mbar_wait(wf1, wf1p); wf1p ^= 1; }
+      arrive(&wr[2]);
+      if (n >= 1) { mbar_wait(wf2, wf2p); wf2p ^= 1; }
+      arrive(&wr[3]);
+      return;
 #endif
+      // w1: its slot was last read by step n-2
+      load_split(Wp, 0);
       PINN_TR(40);
-      if (!first) {
-        mbar_wait(wfree, wfph);            // every MMA that reads the current operand is done
-        wfph ^= 1;
+      if (n >= 2) {
+        mbar_wait(&wfree[n & 1], wfp[n & 1]);
+        wfp[n & 1] ^= 1;
+        umma::fence_after_sync();
+      }
+      store_split(slot_of(0, n));
+      arrive(&wr[n & 1]);
+      // w2: free once group G0 of B's rows MMAs of step n-1 is complete
+      load_split(Wp, 1);
+      if (n >= 1) {
+        mbar_wait(wf1, wf1p);
+        wf1p ^= 1;
         umma::fence_after_sync();
       }
       PINN_TR(41);
-#ifndef PINN_EXP_NO_W
-      store_split(0);
-      load_split(Wp, 1);
       store_split(1);
+      arrive(&wr[2]);
+      // w3: free after group G1
       load_split(Wp, 2);
+      if (n >= 1) {
+        mbar_wait(wf2, wf2p);
+        wf2p ^= 1;
+        umma::fence_after_sync();
+      }
       store_split(2);
-      umma::wait_st();
-#endif
-      umma::fence_before_sync();
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(wrdy)) : "memory");
+      arrive(&wr[3]);
       PINN_TR(42);
-      first = false;
     };
     // the flush owed for the previous reverse step
     auto producer_flush = [&]() {
@@ -296,27 +342,41 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       PINN_TR(43);
       flush_dw(pend_s, pend_l);
       PINN_TR(44);
-      umma::fence_before_sync();
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(dwfree)) : "memory");
+      arrive(dwfree);
       pend_l = -1;
     };
-    uint32_t rph[2] = {0, 0}, wph = 0, fph = 0;
+    uint32_t rph[2] = {0, 0}, wrp[4] = {0, 0, 0, 0}, fph = 0;
     bool flush_pending = false;
-    auto issue_rows = [&](int h, unsigned char* bbase, uint32_t el) {
+    // rows MMAs of sub-tile h: D_h (+)= W[TMEM] * B[smem, MN-major], 7 k-steps x 6 split products in three groups.
+    // first: this is the step's first batch (wait for each split as its group comes up); last: it is the step's last
+    // batch (release w2 / w3 / everything as the groups retire).
+    auto issue_rows = [&](int h, unsigned char* bbase, uint32_t el, bool first, bool last) {
       constexpr uint32_t idesc = umma::make_idesc_bf16(kTcRows, R, 0, 1);
-      const int wa[6] = {0, 2, 1, 0, 1, 0};
-      const int ab[6] = {2, 0, 1, 1, 0, 0};
+      //                 G0    G1   G2
+      const int wa[6] = {1, 1, 2, 0, 0, 0};      // weight split     (w2 w2 | w3 | w1 w1 w1)
+      const int ab[6] = {1, 0, 0, 2, 1, 0};      // activation split (a2 a1 | a1 | a3 a2 a1): the main term goes last
       const uint32_t d = tD(h);
+      const uint32_t s0 = (uint32_t)(CFG::tcWStride * slot_of(0, nstep));
+      const uint32_t s0last = (nstep & 1) ? tStub : tW + s0 + 48;     // k-step 6 of w1 (slot 3 keeps it in the stub)
       const uint32_t lo0 = umma::smem_desc_lo(umma::smem_addr(bbase), JB);
       constexpr uint32_t hi = umma::smem_desc_hi(128);
       uint32_t accum = 0;
 #pragma unroll
       for (int t = 0; t < 6; ++t) {
+        if (first && (t == 0 || t == 2 || t == 3)) {
+          const int wb = (wa[t] == 0) ? (int)(nstep & 1) : wa[t] + 1;
+          mbar_wait(&wr[wb], wrp[wb]);
+          wrp[wb] ^= 1;
+          umma::fence_after_sync();
+        }
 #pragma unroll
         for (int ks = 0; ks < kTcHP / 16; ++ks) {
-          umma::mma_bf16_ts_e2(d, tW + wa[t] * 56 + ks * 8, lo0 + (uint32_t)((ab[t] * ARR + ks * 2 * JB) >> 4), hi, idesc, accum, el);
+          const uint32_t wad = (wa[t] == 0) ? (ks == 6 ? s0last : tW + s0 + (uint32_t)(ks * 8)) : tW + (uint32_t)(wa[t] * CFG::tcWStride + ks * 8);
+          umma::mma_bf16_ts_e2(d, wad, lo0 + (uint32_t)((ab[t] * ARR + ks * 2 * JB) >> 4), hi, idesc, accum, el);
           accum = 1;
         }
+        if (last && t == 1) umma::commit_e(wf1, el);
+        if (last && t == 2) umma::commit_e(wf2, el);
       }
     };
     auto issue_dw = [&](int h, uint32_t accum, uint32_t el) {
@@ -336,10 +396,8 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         }
       }
     };
-    // one pipeline step = the batches of both sub-tiles for one layer.  The rows MMAs (the only readers of the weight
-    // operand) go first so that the producers can restage it while the dW MMAs run.
-    // One pipeline step = the batches of both sub-tiles for one layer.  The rows MMAs (the only readers of the weight
-    // operand) go first so that the producers can restage it while the dW MMAs run.
+    // One pipeline step = the batches of both sub-tiles for one layer.  Within a sub-tile the rows MMAs (the only
+    // readers of the weight operand, the producers of D) go before the dW MMAs.
     auto issue_sub = [&](int h, bool reverse) {
       PINN_TR(60 + h);
       mbar_wait(&rdy[h], rph[h]);
@@ -347,59 +405,37 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       umma::fence_after_sync();
       PINN_TR(62 + h);
       const uint32_t el = umma::elect_one();
-      issue_rows(h, reverse ? arr_ptr(h, 3) : arr_ptr(h, 0), el);
+      issue_rows(h, reverse ? arr_ptr(h, 3) : arr_ptr(h, 0), el, h == 0, h == NSUB - 1);
       umma::commit_e(&bars[h], el);
+      if (h == NSUB - 1) umma::commit_e(&wfree[nstep & 1], el);
       PINN_TR(64 + h);
-      if (h == NSUB - 1) umma::commit_e(wfree, el);
-      return el;
-    };
-    auto issue_sub_dw = [&](int h, uint32_t el) {
-      if (h == 0 && flush_pending) {
-        mbar_wait(dwfree, fph);            // the previous reverse step's dW has left TMEM
-        fph ^= 1;
-        umma::fence_after_sync();
+      if (reverse) {
+        if (h == 0 && flush_pending) {
+          mbar_wait(dwfree, fph);          // the previous reverse step's dW has left TMEM
+          fph ^= 1;
+          umma::fence_after_sync();
+        }
+        PINN_TR(66 + h);
+        issue_dw(h, h == 0 ? 0u : 1u, el);
+        umma::commit_e(&dwd[h], el);
+        PINN_TR(68 + h);
       }
-      PINN_TR(66 + h);
-      issue_dw(h, h == 0 ? 0u : 1u, el);
-      umma::commit_e(&dwd[h], el);
-      PINN_TR(68 + h);
     };
     auto step = [&](const uint4* Wp, bool reverse, int s, int l) {
-      if (do_prod) producer_stage(Wp);
-      bool owe = do_prod && pend_l >= 2;
-      if (do_issue) {
-        if (owe) {
-          // this warp is also a producer: flush first only if the element-wise warps are not ready for the MMAs anyway
-          uint32_t ok;
-          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                       : "=r"(ok)
-                       : "r"(umma::smem_addr(&rdy[0])), "r"(rph[0])
-                       : "memory");
-          if (__any_sync(0xffffffffu, ok == 0)) {
-            producer_flush();
-            owe = false;
-          }
-        }
-        PINN_TR(58);
-        mbar_wait(wrdy, wph);
-        wph ^= 1;
-        umma::fence_after_sync();
-        PINN_TR(59);
-        const uint32_t el0 = issue_sub(0, reverse);
-        if (owe) producer_flush();
-        if (reverse) issue_sub_dw(0, el0);
-        const uint32_t el1 = issue_sub(1, reverse);
+      if (do_prod) {
+        producer_stage(Wp);
+        if (pend_l >= 2) producer_flush();
         if (reverse) {
-          issue_sub_dw(1, el1);
-          flush_pending = true;
+          pend_s = s;
+          pend_l = l;
         }
-      } else if (owe) {
-        producer_flush();
+      } else {
+        PINN_TR(58);
+        issue_sub(0, reverse);
+        issue_sub(1, reverse);
+        if (reverse) flush_pending = true;
       }
-      if (do_prod && reverse) {
-        pend_s = s;
-        pend_l = l;
-      }
+      ++nstep;
     };
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 #ifdef PINN_TRACE
@@ -416,9 +452,6 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
     // =====================================================================================================
     // element-wise warps
     // =====================================================================================================
-#ifdef PINN_TC2_REGS_EW
-    if (CFG::NIS > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PINN_TC2_REGS_EW));
-#endif
     float4* stash = reinterpret_cast<float4*>(p.stash) + (size_t)blockIdx.x * L * NSUB * C * NEW;
     auto stash_at = [&](int l, int h, int c) -> float4* { return stash + ((size_t)((l - 1) * NSUB + h) * C + c) * NEW + tid; };
     uint32_t ph[2] = {0, 0}, dph[2] = {0, 0};
