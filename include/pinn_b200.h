@@ -39,7 +39,7 @@ extern "C" {
 #define PINN_MAX_CONSTS 24
 #define PINN_MAX_AUXSEL 8
 #define PINN_MAX_PDE 3
-#define PINN_MAX_AUX 4
+#define PINN_MAX_AUX 8
 #define PINN_MAX_SEEDS 4
 
 /* Residual kinds.  Taylor coefficients: u_j = du/dx_j, u_jj = d2u/dx_j^2. */
@@ -58,7 +58,12 @@ enum pinn_kind {
   PINN_KIND_KS = 7,            /* chaotic.py:77-83   u_t + c0 u u_x + c1 u_xx + c2 u_xxxx         */
   /* value-type boundary / initial / point-set term: r = u_c - g(x), c = (int)consts[0], g = aux[aux_sel[0]]
    * (deepxde/icbc/boundary_conditions.py:73-80,214-241; initial_conditions.py:29-36).  Jet-free signature (all orders 0). */
-  PINN_KIND_VALUE = 8
+  PINN_KIND_VALUE = 8,
+  /* flux-type boundary term (Neumann / affine Robin): r = sum_j n_j(x) du_c/dx_j + beta(x) u_c - g(x), c = (int)consts[0];
+   * aux_sel[0] = g column, aux_sel[1] = beta column (-1: none), aux_sel[2+j] = column of the outward normal component
+   * n_j (deepxde/icbc/boundary_conditions.py:44-57,83-105: NeumannBC.error, RobinBC.error with func affine in u).
+   * First-order jets in every direction: signature (1,..,1). */
+  PINN_KIND_FLUX = 9
 };
 
 typedef struct pinn_kind_desc {

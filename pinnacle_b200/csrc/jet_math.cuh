@@ -213,6 +213,7 @@ struct Residual {
       case PINN_KIND_GRAYSCOTT: return M == 2 && D == 3 && sig22() && SIG::order(D - 1) >= 1;
       case PINN_KIND_KS: return M == 1 && D == 2 && SIG::order(0) >= 4 && SIG::order(1) >= 1;
       case PINN_KIND_VALUE: return C == 1;
+      case PINN_KIND_FLUX: return C == 1 + D && SIG::order(0) == 1;
       default: return false;
     }
   }
@@ -316,6 +317,21 @@ struct Residual {
 #pragma unroll
         for (int o = 1; o < M; ++o) u = (comp == o) ? U[o][0] : u;
         r[0] = u - aux[kp.aux_sel[0]];
+      } break;
+      case PINN_KIND_FLUX: {
+        if constexpr (C == 1 + D) {
+          const int comp = (int)c[0];
+          float acc = -aux[kp.aux_sel[0]];
+#pragma unroll
+          for (int o = 0; o < M; ++o) {
+            if (comp == o) {
+              if (kp.aux_sel[1] >= 0) acc = fmaf(aux[kp.aux_sel[1]], U[o][0], acc);
+#pragma unroll
+              for (int jj = 0; jj < D; ++jj) acc = fmaf(aux[kp.aux_sel[2 + jj]], U[o][1 + jj], acc);
+            }
+          }
+          r[0] = acc;
+        }
       } break;
       default: break;
     }
@@ -443,6 +459,19 @@ struct Residual {
         const int comp = (int)c[0];
 #pragma unroll
         for (int o = 0; o < M; ++o) Ub[o][0] = (comp == o) ? rb[0] : 0.f;
+      } break;
+      case PINN_KIND_FLUX: {
+        if constexpr (C == 1 + D) {
+          const int comp = (int)c[0];
+#pragma unroll
+          for (int o = 0; o < M; ++o) {
+            if (comp == o) {
+              Ub[o][0] = (kp.aux_sel[1] >= 0) ? aux[kp.aux_sel[1]] * rb[0] : 0.f;
+#pragma unroll
+              for (int jj = 0; jj < D; ++jj) Ub[o][1 + jj] = aux[kp.aux_sel[2 + jj]] * rb[0];
+            }
+          }
+        }
       } break;
       default: break;
     }

@@ -13,6 +13,7 @@
 //  9  PoissonND                                    (2,2,2,2,2)
 // 10  HeatND                                       (2,2,2,2,2,1)
 // 11-18 value-type BC/IC/point-set terms (PINN_KIND_VALUE): jet-free signatures (0,..,0), d x m = 2x1 2x3 3x1 3x2 3x3 1x1 5x1 6x1
+// 19-20 flux-type boundary terms (PINN_KIND_FLUX: Neumann / affine Robin): first-order signatures (1,1), (1,1,1), m = 1
 #pragma once
 
 #define PINN_FOR_EACH_CONFIG(X)        \
@@ -34,6 +35,8 @@
   X(15, 100, 3, 32, 4, 0, 0, 0, 0)         \
   X(16, 100, 1, 32, 4, 0, 0)               \
   X(17, 100, 1, 32, 4, 0, 0, 0, 0, 0, 0)   \
-  X(18, 100, 1, 32, 4, 0, 0, 0, 0, 0, 0, 0)
+  X(18, 100, 1, 32, 4, 0, 0, 0, 0, 0, 0, 0) \
+  X(19, 100, 1, 32, 4, 0, 1, 1)            \
+  X(20, 100, 1, 32, 4, 0, 1, 1, 1)
 
-#define PINN_NUM_CONFIGS 19
+#define PINN_NUM_CONFIGS 21

@@ -31,6 +31,7 @@ KIND_HEAT_NLSRC = 5      # src/pde/heat.py:214-222
 KIND_GRAYSCOTT = 6       # src/pde/chaotic.py:21-31
 KIND_KS = 7              # src/pde/chaotic.py:77-83
 KIND_VALUE = 8           # value-type BC/IC/point-set term: u_c - g(x)  (icbc/boundary_conditions.py:73-80,214-241)
+KIND_FLUX = 9            # flux-type BC term: n(x).grad u_c + beta(x) u_c - g(x)  (icbc/boundary_conditions.py:44-57,83-105)
 
 KIND_NAMES = {
     KIND_LINEAR: "linear",
@@ -42,6 +43,7 @@ KIND_NAMES = {
     KIND_GRAYSCOTT: "grayscott",
     KIND_KS: "ks",
     KIND_VALUE: "value",
+    KIND_FLUX: "flux",
 }
 
 # LINEAR kind constant layout
@@ -168,6 +170,16 @@ def value_desc(d: int, m: int, component: int, name: str = "") -> KindDesc:
     if not 0 <= component < m:
         raise ValueError(f"component {component} outside 0..{m - 1}")
     return KindDesc(KIND_VALUE, d, m, (0,) * d, 1, 1, [float(component)], [0], name=name)
+
+
+def flux_desc(d: int, m: int, component: int, with_beta: bool, name: str = "") -> KindDesc:
+    """Descriptor of a Neumann / affine-Robin boundary term r = n.grad u_c + beta u_c - g.
+    aux columns: [g, beta (if with_beta), n_0 .. n_{d-1}]."""
+    if not 0 <= component < m:
+        raise ValueError(f"component {component} outside 0..{m - 1}")
+    nb = 2 if with_beta else 1
+    sel = [0, 1 if with_beta else -1] + [nb + j for j in range(d)]
+    return KindDesc(KIND_FLUX, d, m, (1,) * d, 1, nb + d, [float(component)], sel, name=name)
 
 
 def linear_desc(d: int, order: Sequence[int], cu: float = 0.0, c1: Sequence[float] = (), c2: Sequence[float] = (),

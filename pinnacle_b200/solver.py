@@ -24,12 +24,25 @@ from collections import namedtuple
 
 from . import capi
 from .fused import FusedPDEResidual, net_linear_params, net_shape
-from .kinds import value_desc
+from .kinds import flux_desc, value_desc
 from .problems import ProblemSpec, describe_reference
 
 # A value-type boundary / initial / point-set term on BC rows [beg, end):  u[:, component] - values
 # (DirichletBC / IC / PointSetBC of deepxde/icbc).  Evaluated by the fused op (kind VALUE) instead of stock autograd.
 ValueBC = namedtuple("ValueBC", ["beg", "end", "component", "values"])
+# A flux-type boundary term on BC rows [beg, end):  normals . grad u[:, component] + beta * u[:, component] - values
+# (NeumannBC: beta = None; RobinBC dy/dn = a - b*y: values = a, beta = b).  Fused op, kind FLUX (d <= 3, one output).
+FluxBC = namedtuple("FluxBC", ["beg", "end", "component", "normals", "values", "beta"], defaults=[None])
+
+
+def _flux_aux(f: "FluxBC") -> np.ndarray:
+    """aux columns of a FLUX term: [g, beta (optional), n_0 .. n_{d-1}]."""
+    n = f.end - f.beg
+    nrm = np.asarray(f.normals, dtype=np.float64).reshape(n, -1)
+    cols = [np.broadcast_to(np.asarray(f.values, dtype=np.float64).reshape(-1, 1), (n, 1))]
+    if f.beta is not None:
+        cols.append(np.broadcast_to(np.asarray(f.beta, dtype=np.float64).reshape(-1, 1), (n, 1)))
+    return np.concatenate(cols + [nrm], axis=1)
 
 
 def _mse(err: torch.Tensor) -> torch.Tensor:
@@ -57,25 +70,31 @@ class _StepCore:
         self._value_ops = {}            # (term index) -> FusedPDEResidual of kind VALUE
         self.generation = 0             # bumped whenever new rows are staged
 
-    def value_term_loss(self, idx: int, beg: int, end: int, component: int, values_fn):
-        """Mean-square of u[beg:end, component] - values on the staged BC rows through the fused op.
-        `values_fn()` is called once per staged point set and must return an array/tensor broadcastable to [n, 1]."""
+    def fused_term_loss(self, idx: int, beg: int, end: int, desc, aux_fn):
+        """Mean-square of one boundary / initial / point-set term over the staged BC rows [beg, end) through the fused
+        op.  `desc` is the term's kind descriptor (VALUE or FLUX); `aux_fn()` is called once per staged point set and
+        returns its aux columns, broadcastable to [n, desc.n_aux]."""
         d, H, L, m = self._shape
         ent = self._value_ops.get(idx)
         if ent is None or ent[1] != self.generation:
             op = ent[0] if ent is not None else FusedPDEResidual(
-                ProblemSpec(f"value_bc_{idx}", value_desc(d, m, int(component)), [0, 1] * d), H, L, policy="eager", device=self.op.device)
+                ProblemSpec(f"bc_term_{idx}", desc, [0, 1] * d), H, L, policy="eager", device=self.op.device)
             op.world, op.rank = 1, 0              # BC rows are replicated on every rank (SURVEY.md §8e)
             n = end - beg
-            vals = torch.as_tensor(values_fn(), dtype=torch.float32).to(self.op.device).reshape(-1, 1) if n > 0 else torch.zeros(0, 1)
-            if vals.shape[0] == 1 and n != 1:
-                vals = vals.expand(n, 1)
-            if vals.shape[0] != n:
-                raise capi.FusedOpError(f"boundary term {idx}: {vals.shape[0]} target values for {n} rows")
-            op.set_rows(self._x_bc[beg:end], vals.contiguous(), n)
+            aux = torch.as_tensor(aux_fn(), dtype=torch.float32).to(self.op.device).reshape(-1, desc.n_aux) if n > 0 else torch.zeros(0, desc.n_aux)
+            if aux.shape[0] == 1 and n != 1:
+                aux = aux.expand(n, desc.n_aux)
+            if aux.shape[0] != n:
+                raise capi.FusedOpError(f"boundary term {idx}: {aux.shape[0]} rows of term data for {n} boundary rows")
+            op.set_rows(self._x_bc[beg:end], aux.contiguous(), n)
             self._value_ops[idx] = (op, self.generation)
             ent = self._value_ops[idx]
         return ent[0].losses(self.params)
+
+    def value_term_loss(self, idx: int, beg: int, end: int, component: int, values_fn):
+        """u[beg:end, component] - values (DirichletBC / IC / PointSetBC)."""
+        d, H, L, m = self._shape
+        return self.fused_term_loss(idx, beg, end, value_desc(d, m, int(component)), values_fn)
 
     def stage(self, inputs, n_bc: int):
         """Make the rows of ``inputs`` device-resident: BC rows -> self._x_bc, residual rows -> fused op.
@@ -142,7 +161,7 @@ class FusedPDESolver:
         terms = [pde_losses]
         outputs_ = None
         if self.n_bc > 0:
-            need_torch = any(not isinstance(f, ValueBC) for f in self.bc_terms) or not self.bc_terms
+            need_torch = any(not isinstance(f, (ValueBC, FluxBC)) for f in self.bc_terms) or not self.bc_terms
             x_bc = y_bc = None
             if need_torch:
                 x_bc = core._x_bc.detach().requires_grad_(True)
@@ -154,6 +173,12 @@ class FusedPDESolver:
                         terms.append(torch.full((1,), float("nan"), device=pde_losses.device))   # mean over no rows, as the reference
                     else:
                         terms.append(core.value_term_loss(i, f.beg, f.end, f.component, lambda f=f: f.values))
+                elif isinstance(f, FluxBC):
+                    if f.end - f.beg == 0:
+                        terms.append(torch.full((1,), float("nan"), device=pde_losses.device))
+                    else:
+                        terms.append(core.fused_term_loss(i, f.beg, f.end, flux_desc(core._shape[0], core._shape[3], int(f.component), f.beta is not None),
+                                                          lambda f=f: _flux_aux(f)))
                 else:
                     terms.append(_mse(f(x_bc, y_bc)).reshape(1))
         losses = torch.cat(terms)
@@ -269,7 +294,8 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
         outputs_ = None
         if n_bc > 0:
             bcs_start = np.cumsum([0] + list(data.num_bcs))
-            fused_ok = [fuse_bcs and _value_bc_info(bc) is not None for bc in data.bcs]
+            flux = [(_flux_bc_info(bc, core) if fuse_bcs else None) for bc in data.bcs]
+            fused_ok = [fuse_bcs and (_value_bc_info(bc) is not None or flux[i] is not None) for i, bc in enumerate(data.bcs)]
             x_bc = y_bc = None
             if not all(fused_ok):
                 x_bc = core._x_bc.detach().requires_grad_(True)
@@ -277,7 +303,14 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
                 outputs_ = y_bc
             for i, bc in enumerate(data.bcs):
                 beg, end = int(bcs_start[i]), int(bcs_start[i + 1])
-                if fused_ok[i]:
+                if fused_ok[i] and flux[i] is not None:
+                    # NeumannBC / affine RobinBC: n.grad u_c + beta u_c - g, term data evaluated once per point set
+                    fdesc, aux_fn = flux[i]
+                    if end == beg:
+                        terms.append(torch.full((1,), float("nan"), device=pde_losses.device))
+                    else:
+                        terms.append(core.fused_term_loss(i, beg, end, fdesc, lambda af=aux_fn, b=beg, e=end: af(data.train_x, b, e)))
+                elif fused_ok[i]:
                     # DirichletBC / IC / PointSetBC: u[beg:end, c] - values, values evaluated once per point set
                     comp, values_fn = _value_bc_info(bc)
                     if end == beg:
@@ -350,6 +383,57 @@ def _value_bc_info(bc):
 
         return int(comp), values
     return None
+
+
+def _flux_bc_info(bc, core):
+    """(descriptor, aux_fn(X, beg, end)) when `bc` is a flux-type term the FLUX kind covers, else None:
+    NeumannBC.error = n.grad u_c - func(x) and RobinBC.error = n.grad u_c - func(x, u) with func affine in u
+    (icbc/boundary_conditions.py:44-57,83-105; e.g. heat.py:176-192 `lambda _, u: 5 - u`).  Affinity is probed on the
+    actual boundary rows (u = 0, 1, 2); a non-affine closure keeps the stock autograd path."""
+    name = type(bc).__name__
+    comp = getattr(bc, "component", None)
+    d, H, L, m = core._shape
+    if name not in ("NeumannBC", "RobinBC") or not isinstance(comp, (int, np.integer)) or m != 1 or d not in (2, 3):
+        return None
+    if not capi.supported(flux_desc(d, m, int(comp), True)):
+        return None
+
+    def to_np(v, n):
+        v = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+        v = np.asarray(v, dtype=np.float64).reshape(-1, 1) if v.ndim < 2 or v.shape[-1] == 1 else np.asarray(v, dtype=np.float64)
+        return np.broadcast_to(v, (n, v.shape[1])) if v.shape[0] == 1 and n != 1 else v
+
+    if name == "NeumannBC":
+        def aux_fn(X, beg, end):
+            n = end - beg
+            return np.concatenate([to_np(bc.func(X, beg, end, None), n), to_np(bc.boundary_normal(X, beg, end, None), n)], axis=1)
+
+        return flux_desc(d, m, int(comp), False), aux_fn
+
+    def robin_parts(X, beg, end):
+        n = end - beg
+        Xs = X[beg:end]
+        probe = [to_np(bc.func(Xs, torch.full((n, m), float(v))), n) for v in (0.0, 1.0, 2.0)]
+        alpha, slope = probe[0], probe[1] - probe[0]
+        if not np.allclose(probe[2], alpha + 2.0 * slope, rtol=1e-6, atol=1e-9):
+            return None
+        return alpha, slope
+
+    def aux_fn(X, beg, end):
+        n = end - beg
+        parts = robin_parts(X, beg, end)
+        if parts is None:
+            raise capi.FusedOpError("RobinBC function stopped being affine in u on a new point set; re-run enable_fused(..., fuse_bcs=False)")
+        alpha, slope = parts
+        # n.grad u - (alpha + slope u)  ==  n.grad u + beta u - g  with beta = -slope, g = alpha
+        return np.concatenate([alpha, -slope, to_np(bc.boundary_normal(X, beg, end, None), n)], axis=1)
+
+    try:
+        probe_X = np.zeros((2, d), dtype=np.float32)
+        ok = robin_parts(probe_X, 0, 2) is not None
+    except Exception:  # noqa: BLE001  closures that need real boundary coordinates: decide on the first staged rows instead
+        ok = True
+    return (flux_desc(d, m, int(comp), True), aux_fn) if ok else None
 
 
 def _clear_dde_grad_cache():

@@ -32,7 +32,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
   std::vector<float> z((size_t)(L + 1) * H * C), a((size_t)(L + 1) * H * C), ab((size_t)H * C), zb((size_t)H * C), abp((size_t)H * C);
   for (long long pt = 0; pt < n; ++pt) {
     const float* xp = x + pt * D;
-    float auxv[PINN_MAX_AUX] = {0, 0, 0, 0};
+    float auxv[PINN_MAX_AUX] = {};
     for (int q = 0; q < d->n_aux; ++q) auxv[q] = aux[pt * d->n_aux + q];
     // ---- forward
     for (int nn = 0; nn < H; ++nn) {

@@ -206,6 +206,23 @@ def test_value_bc_kind_matches_oracle(d, m, comp, n):
     assert_parity(out[:desc.n_params].cpu().numpy(), og[0].numpy(), "grad")
 
 
+@pytest.mark.parametrize("d,with_beta,n", [(2, False, 129), (2, True, 1), (2, True, 2049), (3, False, 513), (3, True, 8193)])
+def test_flux_bc_kind_matches_oracle(d, with_beta, n):
+    """Fused flux-type boundary term (kind FLUX: NeumannBC.error / affine RobinBC.error) vs the oracle."""
+    from oracle import autograd_ref as O
+    from test_host_math import _flux_case
+    from pinnacle_b200 import capi
+    dev = _cuda()
+    desc, flat, x, aux = _flux_case(d, with_beta, 100 * d + n, n=n)
+    ol, og, orr = O.losses_and_grads(desc, torch.as_tensor(flat).double(), torch.as_tensor(x).double(), torch.as_tensor(aux).double())
+    out = capi.fwd_bwd(desc, torch.as_tensor(flat).to(dev), torch.as_tensor(x).to(dev), torch.as_tensor(aux).to(dev), 1.0 / n,
+                       torch.ones(1, 1, device=dev))
+    assert_parity(out[desc.n_params:].cpu().numpy(), ol.numpy(), "loss")
+    assert_parity(out[:desc.n_params].cpu().numpy(), og[0].numpy(), "grad")
+    loss, resid = capi.fwd(desc, torch.as_tensor(flat).to(dev), torch.as_tensor(x).to(dev), torch.as_tensor(aux).to(dev), 1.0 / n, want_residual=True)
+    assert_parity(resid.cpu().numpy(), orr.numpy(), "residual")
+
+
 def test_errors_are_loud():
     from pinnacle_b200 import capi, kinds
     dev = _cuda()

@@ -119,3 +119,41 @@ def test_fixed_seed_training_run_matches_reference_algorithm():
     rel = float((ya - yb).norm() / yb.norm())
     assert rel < 5e-2, rel
     assert hist_a[-1].sum() < 0.7 * hist_a[0].sum()      # it actually trained
+
+
+@pytest.mark.gpu
+def test_flux_term_steps_match_stock_autograd():
+    """A Robin-type boundary term dy/dn = a - b*y through the fused op (FluxBC, kind FLUX) vs the same term written with
+    torch.autograd on the boundary rows (NeumannBC/RobinBC.error of the reference): losses and one Adam step."""
+    from pinnacle_b200 import problems
+    from pinnacle_b200.solver import FluxBC, FusedPDESolver
+    dev = torch.device("cuda:0")
+    spec = problems.make("Poisson2D_Classic")
+    x = spec.sample(1024, seed=3)
+    rs = np.random.RandomState(5)
+    nb = 300
+    xb = spec.sample(nb, seed=4)
+    nrm = rs.standard_normal((nb, 2))
+    nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+    a = (rs.standard_normal((nb, 1)) + 2.0).astype(np.float32)
+    b = rs.uniform(0.5, 2.0, (nb, 1)).astype(np.float32)
+    net_a, net_b = _net(spec.desc, dev, 11), _net(spec.desc, dev, 11)
+    nt, at, bt = (torch.as_tensor(v, device=dev) for v in (nrm, a, b))
+
+    def robin_stock(xbt, ybt):      # n . grad y - (a - b y)
+        g = torch.autograd.grad(ybt, xbt, torch.ones_like(ybt), create_graph=True)[0]
+        return (g * nt).sum(1, keepdim=True) - (at - bt * ybt)
+
+    sa = FusedPDESolver(spec, net_a, x, xb, [FluxBC(0, nb, 0, nrm, a, b), FluxBC(0, 100, 0, nrm[:100], a[:100])]).compile(
+        torch.optim.Adam(net_a.parameters(), 1e-3))
+    sb = FusedPDESolver(spec, net_b, x, xb, [robin_stock, lambda xbt, ybt: ((torch.autograd.grad(ybt, xbt, torch.ones_like(ybt), create_graph=True)[0]
+                                                                             * nt).sum(1, keepdim=True) - at)[:100]]).compile(
+        torch.optim.Adam(net_b.parameters(), 1e-3))
+    for _ in range(3):
+        sa.train_step()
+        sb.train_step()
+        la, lb = sa.opt.losses.detach().cpu().numpy(), sb.opt.losses.detach().cpu().numpy()
+        np.testing.assert_allclose(la, lb, rtol=2e-4)
+    pa = torch.cat([p.detach().reshape(-1) for p in net_a.parameters()])
+    pb = torch.cat([p.detach().reshape(-1) for p in net_b.parameters()])
+    assert float((pa - pb).norm() / pb.norm()) < 1e-4

@@ -70,3 +70,38 @@ def test_value_kind_matches_oracle(harness_lib):
         assert_parity(resid, orr.numpy(), "residual")
         assert_parity(loss[:1], ol.numpy(), "loss")
         assert_parity(grad, og.numpy(), "grad")
+
+
+def _flux_case(d, with_beta, seed, n=61):
+    from golden import common
+    from pinnacle_b200 import kinds
+    desc = kinds.flux_desc(d, 1, 0, with_beta)
+    rs = np.random.RandomState(seed)
+    flat = common.golden_params(desc.layer_shapes(), 5).astype(np.float32)
+    x = rs.uniform(-1, 1, (n, d)).astype(np.float32)
+    nrm = rs.standard_normal((n, d))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    cols = [rs.standard_normal((n, 1)) + 2.0]                  # g, offset so r is not a near-cancellation
+    if with_beta:
+        cols.append(rs.uniform(0.5, 2.0, (n, 1)))
+    aux = np.concatenate(cols + [nrm], axis=1).astype(np.float32)
+    return desc, flat, x, np.ascontiguousarray(aux)
+
+
+def test_flux_kind_matches_oracle(harness_lib):
+    """Flux-type boundary term (Neumann / affine Robin: kind FLUX, first-order jets) of the device math vs the oracle."""
+    from oracle import autograd_ref as O
+    for d, with_beta in ((2, False), (2, True), (3, False), (3, True)):
+        desc, flat, x, aux = _flux_case(d, with_beta, 7 * d + with_beta)
+        ol, og, orr = O.losses_and_grads(desc, torch.as_tensor(flat).double(), torch.as_tensor(x).double(), torch.as_tensor(aux).double())
+        n, P = x.shape[0], desc.n_params
+        grad = np.zeros((1, P)); loss = np.zeros(3); resid = np.zeros((n, 1), np.float32)
+        cd = desc.to_c()
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        seeds = np.ones((1, 1), np.float32)
+        rc = harness_lib.harness_run(ctypes.byref(cd), vp(flat), vp(x), vp(aux), ctypes.c_longlong(n), ctypes.c_double(1.0 / n), vp(seeds), 1,
+                                     vp(grad), vp(loss), vp(resid))
+        assert rc == 0
+        assert_parity(resid, orr.numpy(), "residual")
+        assert_parity(loss[:1], ol.numpy(), "loss")
+        assert_parity(grad, og.numpy(), "grad")

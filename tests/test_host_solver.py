@@ -96,7 +96,8 @@ def test_solver_adam_steps_follow_oracle_training():
 
 
 @needs_ref
-@pytest.mark.parametrize("name", ["Burgers1D", "Poisson2D_Classic", "NS2D_LidDriven", "Wave1D"])
+@pytest.mark.parametrize("name", ["Burgers1D", "Poisson2D_Classic", "NS2D_LidDriven", "Wave1D", "Heat2D_ComplexGeometry", "Poisson2D_ManyArea",
+                                  "Wave2D_LongTime"])
 def test_patched_dde_model_matches_unpatched_reference_step(name):
     """Same weights, same points: losses and p.grad of the reference closure vs the patched closure."""
     import copy
@@ -166,3 +167,37 @@ def test_unsupported_problems_raise():
         bbox = [0, 1]
     with pytest.raises(problems.UnsupportedProblem):
         problems.describe_reference(Strange())
+
+
+@needs_ref
+@pytest.mark.parametrize("name,n_flux", [("Wave1D", 1), ("Heat2D_ComplexGeometry", 3), ("Poisson2D_ManyArea", 1), ("HeatND", 0)])
+def test_flux_boundary_terms_take_the_fused_path(name, n_flux):
+    """NeumannBC and affine RobinBC terms (d <= 3, m = 1) are evaluated by the fused op (kind FLUX), not by stock autograd;
+    the 6-dimensional Neumann term of HeatND stays on the stock path."""
+    dde, _ = refshim.load()
+    from pinnacle_b200 import fused, kinds
+    from pinnacle_b200.solver import enable_fused
+    torch.manual_seed(0)
+    pde = refshim.construct(name)
+    pde.training_points(domain=96, boundary=64, **({"initial": 32} if hasattr(pde, "num_initial_points") else {}))
+    net = dde.nn.FNN([pde.input_dim] + [100] * 5 + [pde.output_dim], "tanh", "Glorot normal").float()
+    model = pde.create_model(net)
+    model.compile(torch.optim.Adam(net.parameters(), 1e-3), loss_weights=np.ones(pde.num_loss))
+    net.auxiliary_vars = None
+    _, ref_losses = model.outputs_losses_train(model.data.train_x, None)
+    made = []
+    orig = fused.FusedPDEResidual.__init__
+
+    def init_cpu(self, spec, H=100, L=5, policy="auto", device=None, group=None, check_library=True):
+        made.append(spec.desc.kind)
+        orig(self, spec, H, L, policy, "cpu", group, False)
+
+    fused.FusedPDEResidual.__init__ = init_cpu
+    try:
+        with oracle_backend():
+            enable_fused(model)
+            _, losses = model.outputs_losses_train(model.data.train_x, None)
+    finally:
+        fused.FusedPDEResidual.__init__ = orig
+    assert made.count(kinds.KIND_FLUX) == n_flux
+    np.testing.assert_allclose(losses.detach().numpy(), ref_losses.detach().numpy(), rtol=2e-5)
