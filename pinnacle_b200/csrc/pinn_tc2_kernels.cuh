@@ -26,6 +26,7 @@
 #pragma once
 
 #include <cstdio>
+#include <type_traits>
 
 #include "pinn_tc_kernels.cuh"
 
@@ -49,6 +50,9 @@ struct TC2fg {
   // both sub-tiles when two private sets do not fit: C = 6).  With the shared set the element-wise warps of one
   // sub-tile still overlap the other's MMAs with everything except their final zbar stores.
   static constexpr bool SHZ = (C > 5);
+  // separate instantiations of the top / bottom reverse stages: measured -14 % (NS2D, m = 3), -1 % (C <= 5, m = 1),
+  // +5 % (C = 6, m = 1: more spills)
+  static constexpr bool PEEL = (M > 1) || (C <= 5);
   static constexpr int NARR = 3 * NSUB + (BWD ? (SHZ ? 3 : 3 * NSUB) : 0);
   // TMEM columns: D_A | D_B | dW (112) | stub (4) | four weight-split slots at a 52-column stride (the last one 48 wide)
   static constexpr int tcD = 0, tcDstride = R, tcDW = 2 * R, tcStub = 2 * R + 112, tcW = tcStub + 4, tcWStride = 52, tcTotal = 512;
@@ -657,7 +661,13 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
             atomicAdd(gs + offB6 + tid, sacc);
           }
 
-          for (int l = L; l >= 1; --l) {
+          // One reverse stage (both sub-tiles) of layer l.  The top (l == L: abar from the output adjoint, dW6) and bottom
+          // (l == 1: dW1, no MMAs) stages are separate instantiations where that helps register allocation (CFG::PEEL:
+          // their extra live state -- dw6, dw1, the W6 row -- then does not weigh on the L-2 stages in between).
+          auto rev_stage = [&](auto top_c, auto bottom_c, const int l) {
+            // 0 / 1: known at compile time; 2: decided at run time (one shared instantiation)
+            const bool IS_TOP = decltype(top_c)::value == 2 ? (l == L) : (decltype(top_c)::value == 1);
+            const bool IS_BOTTOM = decltype(bottom_c)::value == 2 ? (l == 1) : (decltype(bottom_c)::value == 1);
             float dbias = 0.f;
             float dw6[M];
 #pragma unroll
@@ -669,7 +679,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
             for (int h = 0; h < NSUB; ++h) {
               // ---- part 1, independent of the tensor core: splits of a^{l-1} (operand of the dW contraction)
               PINN_TR(20 + h);
-              if (l > 1) {
+              if (!IS_BOTTOM) {
                 guard_arrays(h);
                 PINN_TR(22 + h);
                 if (act) {
@@ -694,10 +704,10 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
               }
               // ---- part 2: abar^l (from D_h, written by the rows MMAs of layer l+1) -> zbar^l
               PINN_TR(24 + h);
-              if (l < L) wait_bar(h);
+              if (!IS_TOP) wait_bar(h);
               PINN_TR(26 + h);
               float ab[C][4];
-              if (l < L) {
+              if (!IS_TOP) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) umma::tmem_ld4(tD(h) + lane_off + c * TS + pb, ab[c]);
                 umma::wait_ld();
@@ -709,7 +719,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                   const float4 v = *stash_at(l, h, c);
                   zq[c][0] = v.x; zq[c][1] = v.y; zq[c][2] = v.z; zq[c][3] = v.w;
                 }
-                if (l == L) {
+                if (IS_TOP) {
 #pragma unroll
                   for (int pp = 0; pp < 4; ++pp) {
                     float z[C], av[C];
@@ -740,7 +750,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                   }
                   tanh_jet_bwd<SIG>(z, a_, zb);
                   dbias += zb[0];
-                  if (l == 1) {
+                  if (IS_BOTTOM) {
                     static_for<D>([&](auto J) {
                       constexpr int jj = decltype(J)::value;
                       dw1[jj] = fmaf(zb[0], xs[(h * TS + pb + pp) * D + jj], dw1[jj]);
@@ -751,7 +761,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                   for (int c = 0; c < C; ++c) ab[c][pp] = zb[c];
                 }
               }
-              if (l > 1) {
+              if (!IS_BOTTOM) {
                 if constexpr (CFG::SHZ) {
                   // shared zbar arrays: the other sub-tile's MMAs (its pending dwd phase) must be done reading them
                   if (dwp[1 - h]) mbar_wait(&dwd[1 - h], dph[1 - h]);
@@ -765,16 +775,26 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
               }
               PINN_TR(28 + h);
             }
-            float* gb = gs + ((l == 1) ? offB1 : offHid + (l - 2) * strideHid + H * H);
+            float* gb = gs + (IS_BOTTOM ? offB1 : offHid + (l - 2) * strideHid + H * H);
             reduce_groups_red(dbias, gb + j);
-            if (l == L) {
+            if (IS_TOP) {
 #pragma unroll
               for (int o = 0; o < M; ++o) reduce_groups_red(dw6[o], gs + offW6 + o * H + j);
             }
-            if (l == 1) {
+            if (IS_BOTTOM) {
 #pragma unroll
               for (int i = 0; i < D; ++i) reduce_groups_red(dw1[i], gs + j * D + i);
             }
+          };
+          using Yes = std::integral_constant<int, 1>;
+          using No = std::integral_constant<int, 0>;
+          using Rt = std::integral_constant<int, 2>;
+          if constexpr (CFG::PEEL) {
+            rev_stage(Yes{}, No{}, L);
+            for (int l = L - 1; l >= 2; --l) rev_stage(No{}, No{}, l);
+            rev_stage(No{}, Yes{}, 1);
+          } else {
+            for (int l = L; l >= 1; --l) rev_stage(Rt{}, Rt{}, l);
           }
         }
       }
