@@ -53,6 +53,8 @@ struct TC2fg {
   // separate instantiations of the top / bottom reverse stages: measured -14 % (NS2D, m = 3), -1 % (C <= 5, m = 1),
   // +5 % (C = 6, m = 1: more spills)
   static constexpr bool PEEL = (M > 1) || (C <= 5);
+  // sub-tile loop of a reverse stage: unrolled for C <= 5, rolled for C = 6 (measured: Poisson2D 11.4 vs 11.8 ms, Burgers2D 16.4 vs 15.7 ms)
+  static constexpr int REV_UNROLL = (C <= 5) ? NSUB : 1;
   static constexpr int NARR = 3 * NSUB + (BWD ? (SHZ ? 3 : 3 * NSUB) : 0);
   // TMEM columns: D_A | D_B | dW (112) | stub (4) | four weight-split slots at a 52-column stride (the last one 48 wide)
   static constexpr int tcD = 0, tcDstride = R, tcDW = 2 * R, tcStub = 2 * R + 112, tcW = tcStub + 4, tcWStride = 52, tcTotal = 512;
@@ -675,7 +677,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
             float dw1[D];
 #pragma unroll
             for (int i = 0; i < D; ++i) dw1[i] = 0.f;
-#pragma unroll
+#pragma unroll(CFG::REV_UNROLL)
             for (int h = 0; h < NSUB; ++h) {
               // ---- part 1, independent of the tensor core: splits of a^{l-1} (operand of the dW contraction)
               PINN_TR(20 + h);
