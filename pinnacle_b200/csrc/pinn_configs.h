@@ -1,5 +1,6 @@
 // pinn_configs.h -- the (jet signature, output dim, tile shape) combinations this build instantiates.
-//   X(ID, H, M, T, TN, TCT, orders...)   T/TN: FFMA kernel tile; TCT: points per tile of the tcgen05 kernel (0 = none)
+//   X(ID, H, M, T, TN, TCT, orders...)   T/TN: FFMA kernel tile; TCT: points per tile of the tcgen05 kernel (0 = none;
+//                                        8: two of the four column groups of element-wise threads own a quad)
 // ID  problem classes
 //  0  Poisson1D                                    (2)
 //  1  Burgers1D                                    (2,1)
@@ -26,8 +27,8 @@
   X(6, 100, 3, 32, 4, 16, 2, 2, 1)         \
   X(7, 100, 1, 16, 2, 16, 2, 2, 2)         \
   X(8, 100, 1, 32, 4, 16, 4, 1)            \
-  X(9, 100, 1, 16, 2, 0, 2, 2, 2, 2, 2)   \
-  X(10, 100, 1, 16, 2, 0, 2, 2, 2, 2, 2, 1) \
+  X(9, 100, 1, 16, 2, 8, 2, 2, 2, 2, 2)   \
+  X(10, 100, 1, 16, 2, 8, 2, 2, 2, 2, 2, 1) \
   X(11, 100, 1, 32, 4, 0, 0, 0)            \
   X(12, 100, 3, 32, 4, 0, 0, 0)            \
   X(13, 100, 1, 32, 4, 0, 0, 0, 0)         \

@@ -58,7 +58,7 @@ struct TCfg {
   static constexpr bool BWD = BWD_;
   static constexpr int C = SIG::C, D = SIG::D;
   static constexpr int NTH = 512;
-  static constexpr int R = C * T;                 // rows = N of the forward MMA
+  static constexpr int R = (C * T + 15) / 16 * 16;   // rows = N of the forward MMA (row c*T + p; rows >= C*T are zero padding)
   static constexpr int NQUADS = T / 4;            // quads of 4 points in a tile, dealt round-robin to the 4 column groups
   static constexpr int NQ = (NQUADS + 3) / 4;     // quads per thread (groups g >= NQUADS % 4 may own one less)
   static constexpr int JB = (R / 8) * 128;        // bytes between 8-neuron blocks
@@ -89,8 +89,8 @@ struct TCfg {
   static constexpr size_t smem_bytes = (size_t)nBytes;
 
   static_assert(H == 100, "tensor-core path is instantiated for H = 100");
-  static_assert(T % 4 == 0 && T >= 16 && T <= 48, "T");
-  static_assert(R % 16 == 0 && R <= 160, "R = C*T must be a multiple of 16 and fit the TMEM map");
+  static_assert(T % 4 == 0 && T >= 8 && T <= 48, "T");
+  static_assert(R % 16 == 0 && R <= 160, "R must fit the TMEM map");
   static_assert(oSmall % 16 == 0 && oUo % 16 == 0, "alignment");
   static_assert(nBytes - oSmall >= 2 * JB, "A-operand over-read of the last Zbar array must stay inside the allocation");
   static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
