@@ -118,6 +118,12 @@ int pinn_has_tensor_core_kernel(const pinn_kind_desc* desc);
 /* The kernel pinn_fwd / pinn_fwd_bwd would run for this descriptor under the current selection: 1 = FP32 FFMA,
  * 2 = tensor cores (one tile at a time), 3 = tensor cores (pipelined); 0 = unsupported descriptor / selection. */
 int pinn_selected_impl(const pinn_kind_desc* desc);
+/* Jet channels per neuron the kernels carry for this descriptor: 1 + sum(order) normally; d + 2 when the residual
+ * uses its second derivatives only through one weighted sum (LINEAR kind) and the forward-Laplacian signature
+ * [u, du/dx_1..d, sum_j c2_j d2u/dx_j^2] is propagated instead of separate second-order coefficients.  Same results
+ * to rounding; pinn_set_laplacian_collapse(0) (or PINN_NO_LAPLACIAN=1) switches the collapse off for comparison. */
+int pinn_effective_channels(const pinn_kind_desc* desc);
+int pinn_set_laplacian_collapse(int enable);
 
 /* Number of kernel launches the last pinn_fwd / pinn_fwd_bwd call of this thread enqueued. */
 int pinn_last_launch_count(void);

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpinn_b200.so")
 EXPORTS = (
     "pinn_param_count", "pinn_supported", "pinn_workspace_bytes", "pinn_fwd", "pinn_fwd_bwd",
     "pinn_last_launch_count", "pinn_ffma_peak_tflops", "pinn_last_error", "pinn_build_info", "pinn_debug_umma_gemm", "pinn_set_impl", "pinn_has_tensor_core_kernel",
-    "pinn_selected_impl",
+    "pinn_selected_impl", "pinn_effective_channels", "pinn_set_laplacian_collapse",
 )
 
 
@@ -66,6 +66,10 @@ def load() -> ctypes.CDLL:
     lib.pinn_set_impl.restype = ctypes.c_int
     lib.pinn_has_tensor_core_kernel.argtypes = [P]
     lib.pinn_has_tensor_core_kernel.restype = ctypes.c_int
+    lib.pinn_effective_channels.argtypes = [P]
+    lib.pinn_effective_channels.restype = ctypes.c_int
+    lib.pinn_set_laplacian_collapse.argtypes = [ctypes.c_int]
+    lib.pinn_set_laplacian_collapse.restype = ctypes.c_int
     lib.pinn_selected_impl.argtypes = [P]
     lib.pinn_selected_impl.restype = ctypes.c_int
     lib.pinn_last_error.argtypes = []
@@ -207,6 +211,16 @@ def set_impl(impl: int):
 def has_tensor_core_kernel(desc: KindDesc) -> bool:
     c = desc.to_c()
     return bool(load().pinn_has_tensor_core_kernel(ctypes.byref(c)))
+
+
+def effective_channels(desc: KindDesc) -> int:
+    """Jet channels per neuron the kernels carry for ``desc`` (d + 2 under the forward-Laplacian collapse, else 1 + sum(order))."""
+    c = desc.to_c()
+    return int(load().pinn_effective_channels(ctypes.byref(c)))
+
+
+def set_laplacian_collapse(enable: bool):
+    _check(load().pinn_set_laplacian_collapse(1 if enable else 0), "pinn_set_laplacian_collapse")
 
 
 def selected_impl(desc: KindDesc) -> int:

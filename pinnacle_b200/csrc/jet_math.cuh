@@ -45,6 +45,7 @@ PINN_HD void static_for(F&& f) {
 
 template <int... KS>
 struct JetSig {
+  static constexpr bool kLap = false;
   static constexpr int D = sizeof...(KS);
   static constexpr int C = 1 + (0 + ... + KS);
   PINN_HD static constexpr int order(int j) {
@@ -58,6 +59,22 @@ struct JetSig {
     return b;
   }
   PINN_HD static constexpr int chan(int j, int k) { return base(j) + k - 1; }
+};
+
+// Forward-Laplacian signature (SURVEY.md §8d "forward-Laplacian collapse C -> d+2"): for residuals that use the second
+// derivatives only through one weighted sum  s = sum_j w_j d2u/dx_j^2  (every LINEAR-kind class: Poisson, heat, wave,
+// Helmholtz), carry per neuron  [value, du/dx_1 .. du/dx_D, s]  instead of separate second-order coefficients per
+// direction.  Linear layers act per channel as before; tanh couples them:
+//   a_0 = t,  a_j = t' z_j,  a_s = t' z_s + t'' sum_j w_j z_j^2      (t = tanh z_0, t' = 1 - t^2, t'' = -2 t t').
+template <int D_>
+struct LapSig {
+  static constexpr bool kLap = true;
+  static constexpr int D = D_;
+  static constexpr int C = D_ + 2;
+  static constexpr int lap = D_ + 1;                        // channel of s
+  PINN_HD static constexpr int order(int) { return 1; }     // every direction carries its first derivative
+  PINN_HD static constexpr int base(int j) { return 1 + j; }
+  PINN_HD static constexpr int chan(int j, int) { return 1 + j; }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -83,29 +100,40 @@ PINN_HD void tanh_series(const float (&zz)[K + 1], float t0, float w0, float (&t
 }
 
 // t0 = tanh(z[0]) supplied by the caller (a[0] of the forward pass, stashed by the tensor-core kernel)
+// `lw`: the D direction weights of a forward-Laplacian signature (LapSig); ignored by JetSig signatures.
 template <class SIG>
-PINN_HD void tanh_jet_fwd_t0(const float (&z)[SIG::C], float t0, float (&a)[SIG::C]);
+PINN_HD void tanh_jet_fwd_t0(const float (&z)[SIG::C], float t0, float (&a)[SIG::C], const float* lw = nullptr);
 template <class SIG>
-PINN_HD void tanh_jet_bwd_t0(const float (&z)[SIG::C], float t0, const float (&abar)[SIG::C], float (&zbar)[SIG::C]);
+PINN_HD void tanh_jet_bwd_t0(const float (&z)[SIG::C], float t0, const float (&abar)[SIG::C], float (&zbar)[SIG::C], const float* lw = nullptr);
 
 template <class SIG>
-PINN_HD void tanh_jet_fwd(const float (&z)[SIG::C], float (&a)[SIG::C]) {
+PINN_HD void tanh_jet_fwd(const float (&z)[SIG::C], float (&a)[SIG::C], const float* lw = nullptr) {
 #ifdef PINN_EXP_NO_JET
-  tanh_jet_fwd_t0<SIG>(z, z[0], a);
+  tanh_jet_fwd_t0<SIG>(z, z[0], a, lw);
 #else
-  tanh_jet_fwd_t0<SIG>(z, tanhf(z[0]), a);
+  tanh_jet_fwd_t0<SIG>(z, tanhf(z[0]), a, lw);
 #endif
 }
 
 template <class SIG>
-PINN_HD void tanh_jet_fwd_t0(const float (&z)[SIG::C], float t0, float (&a)[SIG::C]) {
+PINN_HD void tanh_jet_fwd_t0(const float (&z)[SIG::C], float t0, float (&a)[SIG::C], const float* lw) {
 #ifdef PINN_EXP_NO_JET      // what-if timing experiment only
   for (int c = 0; c < SIG::C; ++c) a[c] = z[c] * 0.5f;
   return;
 #endif
   const float w0 = fmaf(-t0, t0, 1.0f);
   a[0] = t0;
-  static_for<SIG::D>([&](auto J) {
+  if constexpr (SIG::kLap) {
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < SIG::D; ++j) {
+      q = fmaf(lw[j] * z[1 + j], z[1 + j], q);
+      a[1 + j] = w0 * z[1 + j];
+    }
+    a[SIG::lap] = w0 * fmaf(-2.0f * t0, q, z[SIG::lap]);
+    return;
+  } else {
+    static_for<SIG::D>([&](auto J) {
     constexpr int j = decltype(J)::value;
     constexpr int K = SIG::order(j);
     constexpr int b = SIG::base(j);
@@ -119,20 +147,46 @@ PINN_HD void tanh_jet_fwd_t0(const float (&z)[SIG::C], float t0, float (&a)[SIG:
       for (int k = 1; k <= K; ++k) a[b + k - 1] = t[k];
     }
   });
+  }
 }
 
 // Adjoint of tanh_jet_fwd: given z and abar = dLoss/da, returns zbar = dLoss/dz.
 template <class SIG>
-PINN_HD void tanh_jet_bwd(const float (&z)[SIG::C], const float (&abar)[SIG::C], float (&zbar)[SIG::C]) {
+PINN_HD void tanh_jet_bwd(const float (&z)[SIG::C], const float (&abar)[SIG::C], float (&zbar)[SIG::C], const float* lw = nullptr) {
 #ifdef PINN_EXP_NO_JET
   for (int c = 0; c < SIG::C; ++c) zbar[c] = abar[c] * 0.5f + z[c] * 1e-9f;
 #else
-  tanh_jet_bwd_t0<SIG>(z, tanhf(z[0]), abar, zbar);
+  tanh_jet_bwd_t0<SIG>(z, tanhf(z[0]), abar, zbar, lw);
 #endif
 }
 
+// adjoint of the forward-Laplacian tanh rule
 template <class SIG>
-PINN_HD void tanh_jet_bwd_t0(const float (&z)[SIG::C], float t0, const float (&abar)[SIG::C], float (&zbar)[SIG::C]) {
+PINN_HD void tanh_lap_bwd(const float (&z)[SIG::C], float t0, const float (&abar)[SIG::C], float (&zbar)[SIG::C], const float* lw) {
+  const float w0 = fmaf(-t0, t0, 1.0f);
+  const float as = abar[SIG::lap];
+  float q = 0.f, w0bar = 0.f;
+  const float k = -4.0f * t0 * w0 * as;          // d a_s / d z_j = t'' * 2 w_j z_j = -2 t t' * 2 w_j z_j
+#pragma unroll
+  for (int j = 0; j < SIG::D; ++j) {
+    const float zj = z[1 + j];
+    q = fmaf(lw[j] * zj, zj, q);
+    w0bar = fmaf(abar[1 + j], zj, w0bar);
+    zbar[1 + j] = fmaf(w0, abar[1 + j], k * lw[j] * zj);
+  }
+  zbar[SIG::lap] = w0 * as;
+  w0bar = fmaf(as, fmaf(-2.0f * t0, q, z[SIG::lap]), w0bar);      // a_s = w0 (z_s - 2 t q)
+  float t0bar = abar[0] - 2.0f * w0 * q * as;                       // d a_s / d t (w0 fixed)
+  t0bar = fmaf(-2.0f * t0, w0bar, t0bar);                           // w0 = 1 - t^2
+  zbar[0] = w0 * t0bar;
+}
+
+template <class SIG>
+PINN_HD void tanh_jet_bwd_t0(const float (&z)[SIG::C], float t0, const float (&abar)[SIG::C], float (&zbar)[SIG::C], const float* lw) {
+  if constexpr (SIG::kLap) {
+    tanh_lap_bwd<SIG>(z, t0, abar, zbar, lw);
+    return;
+  } else {
   const float w0 = fmaf(-t0, t0, 1.0f);
   float t0bar = abar[0];
   float w0bar = 0.f;
@@ -177,6 +231,7 @@ PINN_HD void tanh_jet_bwd_t0(const float (&z)[SIG::C], float t0, const float (&a
   });
   t0bar = fmaf(-2.0f * t0, w0bar, t0bar);   // w_0 = 1 - t_0^2
   zbar[0] = w0 * t0bar;                     // t_0 = tanh(z_0)
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -203,6 +258,7 @@ struct Residual {
   PINN_HD static constexpr bool sig22() { return D >= 2 && SIG::order(0) >= 2 && SIG::order(1) >= 2; }
 
   PINN_HD static bool valid(int kind) {
+    if constexpr (SIG::kLap) return kind == PINN_KIND_LINEAR && M == 1;   // the forward-Laplacian channel only serves weighted-sum residuals
     switch (kind) {
       case PINN_KIND_LINEAR: return M == 1;
       case PINN_KIND_BURGERS1D: return M == 1 && D == 2 && SIG::order(0) >= 2 && SIG::order(1) >= 1;
@@ -224,7 +280,19 @@ struct Residual {
     const float* c = kp.c;
     switch (kp.kind) {
       case PINN_KIND_LINEAR: {
-        if constexpr (M == 1) {
+        if constexpr (M == 1 && SIG::kLap) {
+          // U[0][lap] = sum_j c2_j d2u/dx_j^2 already; the c2 terms share one per-point multiplier (host-checked)
+          float mul = 1.0f;
+#pragma unroll
+          for (int j = 0; j < D; ++j)
+            if (c[LIN_C2 + j] != 0.f && kp.aux_sel[LIN_SEL_C2 + j] >= 0) mul = aux[kp.aux_sel[LIN_SEL_C2 + j]];
+          float acc = mul * U[0][SIG::lap];
+#pragma unroll
+          for (int j = 0; j < D; ++j) acc = fmaf(c[LIN_C1 + j], U[0][1 + j], acc);
+          acc = fmaf(c[LIN_CU] * aux_or_one(aux, kp.aux_sel[LIN_SEL_CU]), U[0][0], acc);
+          if (kp.aux_sel[LIN_SEL_SRC] >= 0) acc += aux[kp.aux_sel[LIN_SEL_SRC]];
+          r[0] = acc;
+        } else if constexpr (M == 1) {
           float acc = 0.f;
           static_for<D>([&](auto J) {
             constexpr int j = decltype(J)::value;
@@ -347,7 +415,17 @@ struct Residual {
     const float* c = kp.c;
     switch (kp.kind) {
       case PINN_KIND_LINEAR: {
-        if constexpr (M == 1) {
+        if constexpr (M == 1 && SIG::kLap) {
+          const float g = rb[0];
+          float mul = 1.0f;
+#pragma unroll
+          for (int j = 0; j < D; ++j)
+            if (c[LIN_C2 + j] != 0.f && kp.aux_sel[LIN_SEL_C2 + j] >= 0) mul = aux[kp.aux_sel[LIN_SEL_C2 + j]];
+          Ub[0][SIG::lap] = mul * g;
+#pragma unroll
+          for (int j = 0; j < D; ++j) Ub[0][1 + j] = c[LIN_C1 + j] * g;
+          Ub[0][0] = c[LIN_CU] * aux_or_one(aux, kp.aux_sel[LIN_SEL_CU]) * g;
+        } else if constexpr (M == 1) {
           const float g = rb[0];
           static_for<D>([&](auto J) {
             constexpr int j = decltype(J)::value;
@@ -477,5 +555,24 @@ struct Residual {
     }
   }
 };
+
+// Host-side: can this descriptor run on the forward-Laplacian signature LapSig<d>?  LINEAR kind, one output, no
+// direction beyond second order, at least two second-order directions (else nothing is saved), and one common
+// per-point multiplier (or none) on the second-order terms.
+inline bool lap_eligible(int kind, int d, int m, const int* order, const int* aux_sel, const float* consts) {
+  if (kind != PINN_KIND_LINEAR || m != 1 || d < 2) return false;
+  int n2 = 0, sel = -2;
+  for (int j = 0; j < d; ++j) {
+    if (order[j] < 1 || order[j] > 2) return false;
+    if (order[j] == 2) ++n2;
+    if (order[j] < 2 && consts[LIN_C2 + j] != 0.f) return false;
+    if (consts[LIN_C2 + j] != 0.f) {
+      const int sj = aux_sel[LIN_SEL_C2 + j];
+      if (sel == -2) sel = sj;
+      else if (sel != sj) return false;
+    }
+  }
+  return n2 >= 2;
+}
 
 }  // namespace pinn

@@ -29,6 +29,7 @@ static const ConfigInfo* const* all_configs() {
 static thread_local std::string g_err;
 static thread_local int g_launches = 0;
 static int g_tc_pipelined = 0;
+static int g_no_lap = 0;   // pinn_set_laplacian_collapse(0)
 static int g_impl = 0;   // 0 = auto (tensor cores, pipelined where instantiated), 1 = FP32 FFMA kernel, 2 = tensor cores, one tile at a time
                          // (error if absent), 3 = pipelined tensor-core kernel (falls back to 2 where not instantiated)
 
@@ -60,9 +61,18 @@ static const ConfigInfo* find_config(const pinn_kind_desc* d, std::string* why) 
   for (int i = 0; i < PINN_MAX_AUXSEL; ++i)
     if (d->aux_sel[i] >= d->n_aux) { *why = "aux selector beyond n_aux"; return nullptr; }
   const ConfigInfo* const* tab = all_configs();
+  // forward-Laplacian signature first where the descriptor allows it (fewer channels for the same result);
+  // PINN_NO_LAPLACIAN=1 keeps the per-direction second-order jets (for A/B measurements)
+  static const bool no_lap = [] { const char* e = getenv("PINN_NO_LAPLACIAN"); return e != nullptr && e[0] == '1'; }();
+  if (!no_lap && !g_no_lap && lap_eligible(d->kind, d->d, d->m, d->order, d->aux_sel, d->consts)) {
+    for (int i = 0; i < PINN_NUM_CONFIGS; ++i) {
+      const ConfigInfo* c = tab[i];
+      if (c != nullptr && c->lap && c->H == d->H && c->m == d->m && c->d == d->d && c->valid_kind(d->kind)) return c;
+    }
+  }
   for (int i = 0; i < PINN_NUM_CONFIGS; ++i) {
     const ConfigInfo* c = tab[i];
-    if (c == nullptr || c->H != d->H || c->m != d->m || c->d != d->d) continue;
+    if (c == nullptr || c->lap || c->H != d->H || c->m != d->m || c->d != d->d) continue;
     bool same = true;
     for (int j = 0; j < d->d; ++j) same = same && (c->order[j] == d->order[j]);
     if (!same) continue;
@@ -311,6 +321,17 @@ int pinn_has_tensor_core_kernel(const pinn_kind_desc* desc) {
   std::string why;
   const ConfigInfo* c = find_config(desc, &why);
   return (c != nullptr && c->tc_T > 0) ? 1 : 0;
+}
+
+int pinn_set_laplacian_collapse(int enable) {
+  g_no_lap = enable ? 0 : 1;
+  return 0;
+}
+
+int pinn_effective_channels(const pinn_kind_desc* desc) {
+  std::string why;
+  const ConfigInfo* c = find_config(desc, &why);
+  return c == nullptr ? 0 : c->C;
 }
 
 int pinn_selected_impl(const pinn_kind_desc* desc) {

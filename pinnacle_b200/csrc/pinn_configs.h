@@ -14,6 +14,9 @@
 //  9  PoissonND                                    (2,2,2,2,2)
 // 10  HeatND                                       (2,2,2,2,2,1)
 // 11-18 value-type BC/IC/point-set terms (PINN_KIND_VALUE): jet-free signatures (0,..,0), d x m = 2x1 2x3 3x1 3x2 3x3 1x1 5x1 6x1
+// 21-24 forward-Laplacian signatures LapSig<d> (orders entry -d), d = 2, 3, 5, 6: C = d + 2 channels for LINEAR-kind
+//       residuals whose second derivatives enter through one weighted sum (Poisson*, Heat2D_{Multiscale,VaryingCoef,
+//       ComplexGeometry}, Wave*, Helmholtz2D, PoissonND, HeatND); chosen automatically (jet_math.cuh: lap_eligible)
 // 19-20 flux-type boundary terms (PINN_KIND_FLUX: Neumann / affine Robin): first-order signatures (1,1), (1,1,1), m = 1
 #pragma once
 
@@ -38,6 +41,10 @@
   X(17, 100, 1, 32, 4, 0, 0, 0, 0, 0, 0)   \
   X(18, 100, 1, 32, 4, 0, 0, 0, 0, 0, 0, 0) \
   X(19, 100, 1, 32, 4, 0, 1, 1)            \
-  X(20, 100, 1, 32, 4, 0, 1, 1, 1)
+  X(20, 100, 1, 32, 4, 0, 1, 1, 1)         \
+  X(21, 100, 1, 32, 4, 32, -2)             \
+  X(22, 100, 1, 32, 4, 32, -3)             \
+  X(23, 100, 1, 16, 2, 16, -5)             \
+  X(24, 100, 1, 16, 2, 16, -6)
 
-#define PINN_NUM_CONFIGS 21
+#define PINN_NUM_CONFIGS 25

@@ -3,12 +3,27 @@
 #include "pinn_configs.h"
 #include "pinn_dispatch.h"
 
+#include <type_traits>
+
 namespace pinn {
 namespace {
 
+// orders pack -> signature: (k_1, .., k_d) = per-direction Taylor orders; a single negative entry -d = the
+// forward-Laplacian signature LapSig<d> (value, d first derivatives, one weighted sum of second derivatives)
+template <int... KS>
+struct SigOf {
+  using type = JetSig<KS...>;
+  static constexpr int lap = 0;
+};
+template <int K0>
+struct SigOf<K0> {
+  using type = std::conditional_t<(K0 < 0), LapSig<(K0 < 0 ? -K0 : 1)>, JetSig<(K0 < 0 ? 0 : K0)>>;
+  static constexpr int lap = K0 < 0 ? 1 : 0;
+};
+
 template <int ID, int H, int M, int T, int TN, int TCT, int... KS>
 struct Inst {
-  using SIG = JetSig<KS...>;
+  using SIG = typename SigOf<KS...>::type;
   using CF = KCfg<SIG, M, H, T, TN, false>;
   using CB = KCfg<SIG, M, H, T, TN, true>;
 
@@ -76,7 +91,8 @@ struct Inst {
       ConfigInfo c{};
       c.id = ID; c.H = H; c.m = M; c.d = SIG::D; c.C = SIG::C;
       const int o[] = {KS...};
-      for (int j = 0; j < PINN_MAX_DIM; ++j) c.order[j] = j < SIG::D ? o[j] : 0;
+      c.lap = SigOf<KS...>::lap;
+      for (int j = 0; j < PINN_MAX_DIM; ++j) c.order[j] = j < SIG::D ? (c.lap ? 2 : o[j]) : 0;
       c.T = T; c.NT = CB::NT; c.NTP = CB::NTP; c.E4 = CB::E4;
       c.smem_fwd = CF::smem_bytes; c.smem_bwd = CB::smem_bytes;
       c.valid_kind = &valid_kind; c.prepare = &prepare; c.launch = &launch;

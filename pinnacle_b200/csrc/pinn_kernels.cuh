@@ -219,7 +219,7 @@ __device__ __forceinline__ void frag_store_stash(float4* st, const float (&acc)[
 }
 
 template <class CFG>
-__device__ __forceinline__ void frag_tanh_fwd(float (&acc)[CFG::C][4][CFG::TN]) {
+__device__ __forceinline__ void frag_tanh_fwd(float (&acc)[CFG::C][4][CFG::TN], const float* lw) {
 #pragma unroll
   for (int n = 0; n < CFG::TN; ++n)
 #pragma unroll
@@ -227,7 +227,7 @@ __device__ __forceinline__ void frag_tanh_fwd(float (&acc)[CFG::C][4][CFG::TN]) 
       float z[CFG::C], a[CFG::C];
 #pragma unroll
       for (int c = 0; c < CFG::C; ++c) z[c] = acc[c][p][n];
-      tanh_jet_fwd<typename CFG::SIG>(z, a);
+      tanh_jet_fwd<typename CFG::SIG>(z, a, lw);
 #pragma unroll
       for (int c = 0; c < CFG::C; ++c) acc[c][p][n] = a[c];
     }
@@ -235,7 +235,7 @@ __device__ __forceinline__ void frag_tanh_fwd(float (&acc)[CFG::C][4][CFG::TN]) 
 
 // reload z^l from the stash and turn it into a^l in registers
 template <class CFG>
-__device__ __forceinline__ void frag_load_tanh(const float4* st, float (&acc)[CFG::C][4][CFG::TN], int tid) {
+__device__ __forceinline__ void frag_load_tanh(const float4* st, float (&acc)[CFG::C][4][CFG::TN], int tid, const float* lw) {
 #pragma unroll
   for (int n = 0; n < CFG::TN; ++n) {
     float4 zv[CFG::C];
@@ -246,7 +246,7 @@ __device__ __forceinline__ void frag_load_tanh(const float4* st, float (&acc)[CF
       float z[CFG::C], a[CFG::C];
 #pragma unroll
       for (int c = 0; c < CFG::C; ++c) z[c] = (p == 0) ? zv[c].x : (p == 1) ? zv[c].y : (p == 2) ? zv[c].z : zv[c].w;
-      tanh_jet_fwd<typename CFG::SIG>(z, a);
+      tanh_jet_fwd<typename CFG::SIG>(z, a, lw);
 #pragma unroll
       for (int c = 0; c < CFG::C; ++c) acc[c][p][n] = a[c];
     }
@@ -255,7 +255,7 @@ __device__ __forceinline__ void frag_load_tanh(const float4* st, float (&acc)[CF
 
 // acc holds abar^l on entry and zbar^l on exit
 template <class CFG>
-__device__ __forceinline__ void frag_tanh_bwd(const float4* st, float (&acc)[CFG::C][4][CFG::TN], int tid) {
+__device__ __forceinline__ void frag_tanh_bwd(const float4* st, float (&acc)[CFG::C][4][CFG::TN], int tid, const float* lw) {
 #pragma unroll
   for (int n = 0; n < CFG::TN; ++n) {
     float4 zv[CFG::C];
@@ -270,7 +270,7 @@ __device__ __forceinline__ void frag_tanh_bwd(const float4* st, float (&acc)[CFG
         ab[c] = acc[c][p][n];
         zb[c] = 0.f;
       }
-      tanh_jet_bwd<typename CFG::SIG>(z, ab, zb);
+      tanh_jet_bwd<typename CFG::SIG>(z, ab, zb, lw);
 #pragma unroll
       for (int c = 0; c < CFG::C; ++c) acc[c][p][n] = zb[c];
     }
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(CFG::NTP, 1) pinn_fused_kernel(const LaunchPar
         }
       }
       if constexpr (BWD) frag_store_stash<CFG>(stash, acc, tid);
-      frag_tanh_fwd<CFG>(acc);
+      frag_tanh_fwd<CFG>(acc, kps->c + LIN_C2);
       frag_store_smem<CFG>(bufA, acc, pg, ng);
     }
     __syncthreads();
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(CFG::NTP, 1) pinn_fused_kernel(const LaunchPar
       }
       if (active) {
         if constexpr (BWD) frag_store_stash<CFG>(stash + (size_t)(l - 1) * kSlot, acc, tid);
-        frag_tanh_fwd<CFG>(acc);
+        frag_tanh_fwd<CFG>(acc, kps->c + LIN_C2);
         frag_store_smem<CFG>(bufA, acc, pg, ng);
       }
       __syncthreads();
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(CFG::NTP, 1) pinn_fused_kernel(const LaunchPar
         if (s > 0) {
           // bufA was consumed by the previous reverse sweep: rebuild a^L from the stash
           if (active) {
-            frag_load_tanh<CFG>(stash + (size_t)(L - 1) * kSlot, acc, tid);
+            frag_load_tanh<CFG>(stash + (size_t)(L - 1) * kSlot, acc, tid, kps->c + LIN_C2);
             frag_store_smem<CFG>(bufA, acc, pg, ng);
           }
         }
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(CFG::NTP, 1) pinn_fused_kernel(const LaunchPar
         // ---- hidden layers, top-down
         for (int l = L; l >= 1; --l) {
           if (active) {
-            frag_tanh_bwd<CFG>(stash + (size_t)(l - 1) * kSlot, acc, tid);     // acc: abar^l -> zbar^l
+            frag_tanh_bwd<CFG>(stash + (size_t)(l - 1) * kSlot, acc, tid, kps->c + LIN_C2);     // acc: abar^l -> zbar^l
             // bias gradient: sum over points of the value-channel adjoint
             float* gb = gs + ((l == 1) ? offB1 : offHid + (long long)(l - 2) * strideHid + (long long)H * H);
 #pragma unroll
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(CFG::NTP, 1) pinn_fused_kernel(const LaunchPar
               }
             } else {
               frag_store_smem<CFG>(bufB, acc, pg, ng);
-              frag_load_tanh<CFG>(stash + (size_t)(l - 2) * kSlot, acc, tid);   // a^{l-1}
+              frag_load_tanh<CFG>(stash + (size_t)(l - 2) * kSlot, acc, tid, kps->c + LIN_C2);   // a^{l-1}
               frag_store_smem<CFG>(bufA, acc, pg, ng);
             }
           }

@@ -5,6 +5,8 @@
 // the autograd oracle in the build container (no GPU).  Never linked into the product.
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "../../pinnacle_b200/csrc/jet_math.cuh"
@@ -46,7 +48,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
         if constexpr (SIG::order(j) >= 1) zz[SIG::base(j)] = params[offW[1] + nn * D + j];
       });
       float aa[C];
-      tanh_jet_fwd<SIG>(zz, aa);
+      tanh_jet_fwd<SIG>(zz, aa, kp.c + LIN_C2);
       for (int c = 0; c < C; ++c) { z[((size_t)1 * H + nn) * C + c] = zz[c]; a[((size_t)1 * H + nn) * C + c] = aa[c]; }
     }
     for (int l = 2; l <= L; ++l) {
@@ -59,7 +61,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
         }
         zz[0] += params[offB[l] + nn];
         float aa[C];
-        tanh_jet_fwd<SIG>(zz, aa);
+        tanh_jet_fwd<SIG>(zz, aa, kp.c + LIN_C2);
         for (int c = 0; c < C; ++c) { z[((size_t)l * H + nn) * C + c] = zz[c]; a[((size_t)l * H + nn) * C + c] = aa[c]; }
       }
     }
@@ -98,7 +100,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
         for (int nn = 0; nn < H; ++nn) {
           float zz[C], aa[C], zz_b[C];
           for (int c = 0; c < C; ++c) { zz[c] = z[((size_t)l * H + nn) * C + c]; aa[c] = ab[(size_t)nn * C + c]; zz_b[c] = 0.f; }
-          tanh_jet_bwd<SIG>(zz, aa, zz_b);
+          tanh_jet_bwd<SIG>(zz, aa, zz_b, kp.c + LIN_C2);
           for (int c = 0; c < C; ++c) zb[(size_t)nn * C + c] = zz_b[c];
           g[offB[l] + nn] += zz_b[0];
         }
@@ -132,14 +134,26 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
   for (int k = 0; k < PINN_MAX_PDE; ++k) loss[k] *= inv_n;
 }
 
+template <int... KS>
+struct SigOfH {
+  using type = JetSig<KS...>;
+};
+template <int K0>
+struct SigOfH<K0> {
+  using type = std::conditional_t<(K0 < 0), LapSig<(K0 < 0 ? -K0 : 1)>, JetSig<(K0 < 0 ? 0 : K0)>>;
+};
+
 extern "C" int harness_run(const pinn_kind_desc* d, const float* params, const float* x, const float* aux, long long n, double inv_n,
                            const float* seeds, int S, double* grad, double* loss, float* resid) {
+  // same selection rule as the library (pinn_api.cu find_config): forward-Laplacian signature where eligible
+  const char* nl = getenv("PINN_NO_LAPLACIAN");
+  const bool want_lap = !(nl != nullptr && nl[0] == '1') && lap_eligible(d->kind, d->d, d->m, d->order, d->aux_sel, d->consts);
 #define TRY(ID, H_, M_, T_, TN_, TCT_, ...)                                                                \
   {                                                                                                    \
-    using SIG = JetSig<__VA_ARGS__>;                                                                   \
+    using SIG = typename SigOfH<__VA_ARGS__>::type;                                                    \
     const int o[] = {__VA_ARGS__};                                                                     \
-    bool same = (SIG::D == d->d) && (M_ == d->m);                                                      \
-    for (int j = 0; same && j < SIG::D; ++j) same = (o[j] == d->order[j]);                             \
+    bool same = (SIG::D == d->d) && (M_ == d->m) && (SIG::kLap == want_lap);                           \
+    for (int j = 0; same && !SIG::kLap && j < SIG::D; ++j) same = (o[j] == d->order[j]);               \
     if (same && Residual<SIG, M_>::valid(d->kind)) {                                                   \
       run_cfg<SIG, M_>(d, params, x, aux, n, inv_n, seeds, S, grad, loss, resid);                      \
       return 0;                                                                                        \
