@@ -243,6 +243,7 @@ struct KindParams {
   int kind;
   int aux_sel[PINN_MAX_AUXSEL];
   float c[PINN_MAX_CONSTS];
+  float lapw[PINN_MAX_DIM];   // direction weights of the forward-Laplacian channel (set_kind_params; unused by JetSig signatures)
 };
 
 enum : int { LIN_CU = 0, LIN_C1 = 1, LIN_C2 = 1 + PINN_MAX_DIM, LIN_SEL_SRC = 0, LIN_SEL_CU = 1, LIN_SEL_C2 = 2 };
@@ -255,10 +256,30 @@ struct Residual {
   static constexpr int D = SIG::D;
 
   // true when (SIG, M) can host the kind
-  PINN_HD static constexpr bool sig22() { return D >= 2 && SIG::order(0) >= 2 && SIG::order(1) >= 2; }
+  PINN_HD static constexpr bool sig22() { return D >= 2 && (SIG::kLap || (SIG::order(0) >= 2 && SIG::order(1) >= 2)); }
+  // u_xx + u_yy of output row Uo, and its adjoint: two second-order Taylor coefficients, or the forward-Laplacian channel
+  // (whose direction weights the host sets to (1, 1, 0..) for the kinds below)
+  PINN_HD static float lap_xy(const float (&Uo)[C]) {
+    if constexpr (SIG::kLap) return Uo[SIG::lap];
+    else return 2.0f * Uo[SIG::chan(0, 2)] + 2.0f * Uo[SIG::chan(1, 2)];
+  }
+  PINN_HD static void lap_xy_adj(float (&Ubo)[C], float g) {
+    if constexpr (SIG::kLap) Ubo[SIG::lap] = g;
+    else Ubo[SIG::chan(0, 2)] = Ubo[SIG::chan(1, 2)] = 2.0f * g;
+  }
 
   PINN_HD static bool valid(int kind) {
-    if constexpr (SIG::kLap) return kind == PINN_KIND_LINEAR && M == 1;   // the forward-Laplacian channel only serves weighted-sum residuals
+    if constexpr (SIG::kLap) {   // the forward-Laplacian channel only serves residuals that use one weighted sum of second derivatives
+      switch (kind) {
+        case PINN_KIND_LINEAR: return M == 1;
+        case PINN_KIND_NS2D: return M == 3 && D == 2;
+        case PINN_KIND_NS2D_UNSTEADY: return M == 3 && D == 3;
+        case PINN_KIND_BURGERS2D: return M == 2 && D == 3;
+        case PINN_KIND_GRAYSCOTT: return M == 2 && D == 3;
+        case PINN_KIND_HEAT_NLSRC: return M == 1 && D == 3;
+        default: return false;
+      }
+    }
     switch (kind) {
       case PINN_KIND_LINEAR: return M == 1;
       case PINN_KIND_BURGERS1D: return M == 1 && D == 2 && SIG::order(0) >= 2 && SIG::order(1) >= 1;
@@ -321,10 +342,10 @@ struct Residual {
       case PINN_KIND_BURGERS2D: {
         if constexpr (M == 2 && D == 3) {
           if constexpr (sig22() && SIG::order(2) >= 1) {
-            constexpr int X1 = SIG::chan(0, 1), X2 = SIG::chan(0, 2), Y1 = SIG::chan(1, 1), Y2 = SIG::chan(1, 2), T1 = SIG::chan(2, 1);
+            constexpr int X1 = SIG::chan(0, 1), Y1 = SIG::chan(1, 1), T1 = SIG::chan(2, 1);
             const float u1 = U[0][0], u2 = U[1][0];
-            r[0] = U[0][T1] + u1 * U[0][X1] + u2 * U[0][Y1] - c[0] * (2.0f * U[0][X2] + 2.0f * U[0][Y2]);
-            r[1] = U[1][T1] + u1 * U[1][X1] + u2 * U[1][Y1] - c[0] * (2.0f * U[1][X2] + 2.0f * U[1][Y2]);
+            r[0] = U[0][T1] + u1 * U[0][X1] + u2 * U[0][Y1] - c[0] * lap_xy(U[0]);
+            r[1] = U[1][T1] + u1 * U[1][X1] + u2 * U[1][Y1] - c[0] * lap_xy(U[1]);
           }
         }
       } break;
@@ -332,10 +353,10 @@ struct Residual {
       case PINN_KIND_NS2D_UNSTEADY: {
         if constexpr (M == 3 && (D == 2 || D == 3)) {
           if constexpr (sig22()) {
-            constexpr int X1 = SIG::chan(0, 1), X2 = SIG::chan(0, 2), Y1 = SIG::chan(1, 1), Y2 = SIG::chan(1, 2);
+            constexpr int X1 = SIG::chan(0, 1), Y1 = SIG::chan(1, 1);
             const float u = U[0][0], v = U[1][0];
-            float mx = u * U[0][X1] + v * U[0][Y1] + U[2][X1] - c[0] * (2.0f * U[0][X2] + 2.0f * U[0][Y2]);
-            float my = u * U[1][X1] + v * U[1][Y1] + U[2][Y1] - c[0] * (2.0f * U[1][X2] + 2.0f * U[1][Y2]);
+            float mx = u * U[0][X1] + v * U[0][Y1] + U[2][X1] - c[0] * lap_xy(U[0]);
+            float my = u * U[1][X1] + v * U[1][Y1] + U[2][Y1] - c[0] * lap_xy(U[1]);
             if constexpr (D == 3) {
               if constexpr (SIG::order(2) >= 1) {
                 if (kp.kind == PINN_KIND_NS2D_UNSTEADY) {
@@ -355,7 +376,7 @@ struct Residual {
         if constexpr (M == 1 && D == 3) {
           if constexpr (sig22() && SIG::order(2) >= 1) {
             const float u = U[0][0];
-            const float lap = 2.0f * U[0][SIG::chan(0, 2)] + 2.0f * U[0][SIG::chan(1, 2)];
+            const float lap = lap_xy(U[0]);
             r[0] = U[0][SIG::chan(2, 1)] - c[0] * lap - c[1] * sinf(c[2] * u * u) * aux[kp.aux_sel[0]];
           }
         }
@@ -363,9 +384,9 @@ struct Residual {
       case PINN_KIND_GRAYSCOTT: {
         if constexpr (M == 2 && D == 3) {
           if constexpr (sig22() && SIG::order(2) >= 1) {
-            constexpr int X2 = SIG::chan(0, 2), Y2 = SIG::chan(1, 2), T1 = SIG::chan(2, 1);
+            constexpr int T1 = SIG::chan(2, 1);
             const float u = U[0][0], v = U[1][0];
-            const float lapu = 2.0f * U[0][X2] + 2.0f * U[0][Y2], lapv = 2.0f * U[1][X2] + 2.0f * U[1][Y2];
+            const float lapu = lap_xy(U[0]), lapv = lap_xy(U[1]);
             r[0] = U[0][T1] - (c[0] * lapu + c[2] * (1.0f - u) - u * v * v);
             r[1] = U[1][T1] - (c[1] * lapv - c[3] * v + u * v * v);
           }
@@ -452,7 +473,7 @@ struct Residual {
       case PINN_KIND_BURGERS2D: {
         if constexpr (M == 2 && D == 3) {
           if constexpr (sig22() && SIG::order(2) >= 1) {
-            constexpr int X1 = SIG::chan(0, 1), X2 = SIG::chan(0, 2), Y1 = SIG::chan(1, 1), Y2 = SIG::chan(1, 2), T1 = SIG::chan(2, 1);
+            constexpr int X1 = SIG::chan(0, 1), Y1 = SIG::chan(1, 1), T1 = SIG::chan(2, 1);
             const float u1 = U[0][0], u2 = U[1][0];
             Ub[0][0] = rb[0] * U[0][X1] + rb[1] * U[1][X1];
             Ub[1][0] = rb[0] * U[0][Y1] + rb[1] * U[1][Y1];
@@ -460,8 +481,7 @@ struct Residual {
             for (int o = 0; o < 2; ++o) {
               Ub[o][X1] = rb[o] * u1;
               Ub[o][Y1] = rb[o] * u2;
-              Ub[o][X2] = -2.0f * c[0] * rb[o];
-              Ub[o][Y2] = -2.0f * c[0] * rb[o];
+              lap_xy_adj(Ub[o], -c[0] * rb[o]);
               Ub[o][T1] = rb[o];
             }
           }
@@ -471,7 +491,7 @@ struct Residual {
       case PINN_KIND_NS2D_UNSTEADY: {
         if constexpr (M == 3 && (D == 2 || D == 3)) {
           if constexpr (sig22()) {
-            constexpr int X1 = SIG::chan(0, 1), X2 = SIG::chan(0, 2), Y1 = SIG::chan(1, 1), Y2 = SIG::chan(1, 2);
+            constexpr int X1 = SIG::chan(0, 1), Y1 = SIG::chan(1, 1);
             const float u = U[0][0], v = U[1][0];
             const float gx = rb[0], gy = rb[1], gc = rb[2];
             Ub[0][0] = gx * U[0][X1] + gy * U[1][X1];
@@ -482,8 +502,8 @@ struct Residual {
             Ub[1][Y1] = gy * v + gc;
             Ub[2][X1] = gx;
             Ub[2][Y1] = gy;
-            Ub[0][X2] = Ub[0][Y2] = -2.0f * c[0] * gx;
-            Ub[1][X2] = Ub[1][Y2] = -2.0f * c[0] * gy;
+            lap_xy_adj(Ub[0], -c[0] * gx);
+            lap_xy_adj(Ub[1], -c[0] * gy);
             if constexpr (D == 3) {
               if constexpr (SIG::order(2) >= 1) {
                 if (kp.kind == PINN_KIND_NS2D_UNSTEADY) {
@@ -501,8 +521,7 @@ struct Residual {
           if constexpr (sig22() && SIG::order(2) >= 1) {
             const float u = U[0][0], g = rb[0];
             Ub[0][0] = -c[1] * cosf(c[2] * u * u) * 2.0f * c[2] * u * aux[kp.aux_sel[0]] * g;
-            Ub[0][SIG::chan(0, 2)] = -2.0f * c[0] * g;
-            Ub[0][SIG::chan(1, 2)] = -2.0f * c[0] * g;
+            lap_xy_adj(Ub[0], -c[0] * g);
             Ub[0][SIG::chan(2, 1)] = g;
           }
         }
@@ -510,14 +529,14 @@ struct Residual {
       case PINN_KIND_GRAYSCOTT: {
         if constexpr (M == 2 && D == 3) {
           if constexpr (sig22() && SIG::order(2) >= 1) {
-            constexpr int X2 = SIG::chan(0, 2), Y2 = SIG::chan(1, 2), T1 = SIG::chan(2, 1);
+            constexpr int T1 = SIG::chan(2, 1);
             const float u = U[0][0], v = U[1][0];
             Ub[0][0] = rb[0] * (c[2] + v * v) - rb[1] * v * v;
             Ub[1][0] = rb[0] * 2.0f * u * v + rb[1] * (c[3] - 2.0f * u * v);
             Ub[0][T1] = rb[0];
             Ub[1][T1] = rb[1];
-            Ub[0][X2] = Ub[0][Y2] = -2.0f * c[0] * rb[0];
-            Ub[1][X2] = Ub[1][Y2] = -2.0f * c[1] * rb[1];
+            lap_xy_adj(Ub[0], -c[0] * rb[0]);
+            lap_xy_adj(Ub[1], -c[1] * rb[1]);
           }
         }
       } break;
@@ -556,10 +575,15 @@ struct Residual {
   }
 };
 
-// Host-side: can this descriptor run on the forward-Laplacian signature LapSig<d>?  LINEAR kind, one output, no
-// direction beyond second order, at least two second-order directions (else nothing is saved), and one common
-// per-point multiplier (or none) on the second-order terms.
+// Host-side: can this descriptor run on the forward-Laplacian signature LapSig<d>?
+//  * LINEAR kind, one output: no direction beyond second order, at least two second-order directions (else nothing is
+//    saved), one common per-point multiplier (or none) on the second-order terms; weights = c2_j;
+//  * the kinds whose only second derivatives are u_xx + u_yy (NS2D, NS2D_UNSTEADY, BURGERS2D, GRAYSCOTT, HEAT_NLSRC)
+//    with their canonical orders (2,2) / (2,2,1); weights = (1, 1, 0).
 inline bool lap_eligible(int kind, int d, int m, const int* order, const int* aux_sel, const float* consts) {
+  if (kind == PINN_KIND_NS2D) return d == 2 && m == 3 && order[0] == 2 && order[1] == 2;
+  if (kind == PINN_KIND_NS2D_UNSTEADY || kind == PINN_KIND_BURGERS2D || kind == PINN_KIND_GRAYSCOTT || kind == PINN_KIND_HEAT_NLSRC)
+    return d == 3 && order[0] == 2 && order[1] == 2 && order[2] == 1;
   if (kind != PINN_KIND_LINEAR || m != 1 || d < 2) return false;
   int n2 = 0, sel = -2;
   for (int j = 0; j < d; ++j) {
@@ -573,6 +597,14 @@ inline bool lap_eligible(int kind, int d, int m, const int* order, const int* au
     }
   }
   return n2 >= 2;
+}
+
+// descriptor -> KindParams (the kernels' copy of kind, selectors, constants and Laplacian weights)
+inline void set_kind_params(KindParams& kp, int kind, int d, const int* aux_sel, const float* consts) {
+  kp.kind = kind;
+  for (int i = 0; i < PINN_MAX_AUXSEL; ++i) kp.aux_sel[i] = aux_sel[i];
+  for (int i = 0; i < PINN_MAX_CONSTS; ++i) kp.c[i] = consts[i];
+  for (int j = 0; j < PINN_MAX_DIM; ++j) kp.lapw[j] = (kind == PINN_KIND_LINEAR) ? (j < d ? consts[LIN_C2 + j] : 0.f) : (j < 2 ? 1.0f : 0.f);
 }
 
 }  // namespace pinn

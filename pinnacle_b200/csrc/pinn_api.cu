@@ -217,9 +217,7 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
     pinn_pack_weights_tc<<<(total + 255) / 256, 256, 0, st>>>(params, wperm, desc->H, desc->d, desc->L, desc->m);
     ++g_launches;
     TcLaunchParams lp{};
-    lp.kp.kind = desc->kind;
-    for (int i = 0; i < PINN_MAX_AUXSEL; ++i) lp.kp.aux_sel[i] = desc->aux_sel[i];
-    for (int i = 0; i < PINN_MAX_CONSTS; ++i) lp.kp.c[i] = desc->consts[i];
+    set_kind_params(lp.kp, desc->kind, desc->d, desc->aux_sel, desc->consts);
     lp.L = desc->L; lp.n_aux = desc->n_aux; lp.n_pde = desc->n_pde; lp.n_seeds = n_seeds;
     lp.n_rows = n_rows; lp.P = P; lp.Ppad = ws.pstride; lp.inv_n = (float)inv_n;
     lp.params = params; lp.wn = wn; lp.wt = wt; lp.w6p = w6p; lp.x = x; lp.aux = aux; lp.seeds = seeds;
@@ -235,9 +233,7 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
     ++g_launches;
 
     LaunchParams lp{};
-    lp.kp.kind = desc->kind;
-    for (int i = 0; i < PINN_MAX_AUXSEL; ++i) lp.kp.aux_sel[i] = desc->aux_sel[i];
-    for (int i = 0; i < PINN_MAX_CONSTS; ++i) lp.kp.c[i] = desc->consts[i];
+    set_kind_params(lp.kp, desc->kind, desc->d, desc->aux_sel, desc->consts);
     lp.L = desc->L;
     lp.n_aux = desc->n_aux;
     lp.n_pde = desc->n_pde;

@@ -17,6 +17,8 @@
 // 21-24 forward-Laplacian signatures LapSig<d> (orders entry -d), d = 2, 3, 5, 6: C = d + 2 channels for LINEAR-kind
 //       residuals whose second derivatives enter through one weighted sum (Poisson*, Heat2D_{Multiscale,VaryingCoef,
 //       ComplexGeometry}, Wave*, Helmholtz2D, PoissonND, HeatND); chosen automatically (jet_math.cuh: lap_eligible)
+// 25-27 the same for the kinds whose only second derivatives are u_xx + u_yy: NS2D (d=2, m=3), Burgers2D / Gray-Scott
+//       (d=3, m=2), NS2D_LongTime (d=3, m=3); Heat2D_LongTime uses 22
 // 19-20 flux-type boundary terms (PINN_KIND_FLUX: Neumann / affine Robin): first-order signatures (1,1), (1,1,1), m = 1
 #pragma once
 
@@ -45,6 +47,9 @@
   X(21, 100, 1, 32, 4, 32, -2)             \
   X(22, 100, 1, 32, 4, 32, -3)             \
   X(23, 100, 1, 16, 2, 16, -5)             \
-  X(24, 100, 1, 16, 2, 16, -6)
+  X(24, 100, 1, 16, 2, 16, -6)             \
+  X(25, 100, 3, 32, 4, 32, -2)             \
+  X(26, 100, 2, 32, 4, 32, -3)             \
+  X(27, 100, 3, 32, 4, 32, -3)
 
-#define PINN_NUM_CONFIGS 25
+#define PINN_NUM_CONFIGS 28

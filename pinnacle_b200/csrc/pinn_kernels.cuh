@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(CFG::NTP, 1) pinn_fused_kernel(const LaunchPar
         }
       }
       if constexpr (BWD) frag_store_stash<CFG>(stash, acc, tid);
-      frag_tanh_fwd<CFG>(acc, kps->c + LIN_C2);
+      frag_tanh_fwd<CFG>(acc, kps->lapw);
       frag_store_smem<CFG>(bufA, acc, pg, ng);
     }
     __syncthreads();
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(CFG::NTP, 1) pinn_fused_kernel(const LaunchPar
       }
       if (active) {
         if constexpr (BWD) frag_store_stash<CFG>(stash + (size_t)(l - 1) * kSlot, acc, tid);
-        frag_tanh_fwd<CFG>(acc, kps->c + LIN_C2);
+        frag_tanh_fwd<CFG>(acc, kps->lapw);
         frag_store_smem<CFG>(bufA, acc, pg, ng);
       }
       __syncthreads();
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(CFG::NTP, 1) pinn_fused_kernel(const LaunchPar
         if (s > 0) {
           // bufA was consumed by the previous reverse sweep: rebuild a^L from the stash
           if (active) {
-            frag_load_tanh<CFG>(stash + (size_t)(L - 1) * kSlot, acc, tid, kps->c + LIN_C2);
+            frag_load_tanh<CFG>(stash + (size_t)(L - 1) * kSlot, acc, tid, kps->lapw);
             frag_store_smem<CFG>(bufA, acc, pg, ng);
           }
         }
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(CFG::NTP, 1) pinn_fused_kernel(const LaunchPar
         // ---- hidden layers, top-down
         for (int l = L; l >= 1; --l) {
           if (active) {
-            frag_tanh_bwd<CFG>(stash + (size_t)(l - 1) * kSlot, acc, tid, kps->c + LIN_C2);     // acc: abar^l -> zbar^l
+            frag_tanh_bwd<CFG>(stash + (size_t)(l - 1) * kSlot, acc, tid, kps->lapw);     // acc: abar^l -> zbar^l
             // bias gradient: sum over points of the value-channel adjoint
             float* gb = gs + ((l == 1) ? offB1 : offHid + (long long)(l - 2) * strideHid + (long long)H * H);
 #pragma unroll
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(CFG::NTP, 1) pinn_fused_kernel(const LaunchPar
               }
             } else {
               frag_store_smem<CFG>(bufB, acc, pg, ng);
-              frag_load_tanh<CFG>(stash + (size_t)(l - 2) * kSlot, acc, tid, kps->c + LIN_C2);   // a^{l-1}
+              frag_load_tanh<CFG>(stash + (size_t)(l - 2) * kSlot, acc, tid, kps->lapw);   // a^{l-1}
               frag_store_smem<CFG>(bufA, acc, pg, ng);
             }
           }

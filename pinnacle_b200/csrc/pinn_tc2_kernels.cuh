@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         float z[C], av[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) z[c] = a[c][pp];
-        tanh_jet_fwd<SIG>(z, av, kps->c + LIN_C2);
+        tanh_jet_fwd<SIG>(z, av, kps->lapw);
 #pragma unroll
         for (int c = 0; c < C; ++c) a[c][pp] = av[c];
       }
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         float z[C], av[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-        tanh_jet_fwd<SIG>(z, av, kps->c + LIN_C2);
+        tanh_jet_fwd<SIG>(z, av, kps->lapw);
 #pragma unroll
         for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
       }
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                     float z[C], av[C];
 #pragma unroll
                     for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-                    tanh_jet_fwd<SIG>(z, av, kps->c + LIN_C2);
+                    tanh_jet_fwd<SIG>(z, av, kps->lapw);
 #pragma unroll
                     for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
                   }
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                     float z[C], av[C];
 #pragma unroll
                     for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-                    tanh_jet_fwd<SIG>(z, av, kps->c + LIN_C2);
+                    tanh_jet_fwd<SIG>(z, av, kps->lapw);
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                       float v = 0.f;
@@ -750,7 +750,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                     a_[c] = ab[c][pp];
                     zb[c] = 0.f;
                   }
-                  tanh_jet_bwd<SIG>(z, a_, zb, kps->c + LIN_C2);
+                  tanh_jet_bwd<SIG>(z, a_, zb, kps->lapw);
                   dbias += zb[0];
                   if (IS_BOTTOM) {
                     static_for<D>([&](auto J) {

@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
           float z[C], av[C];
 #pragma unroll
           for (int c = 0; c < C; ++c) z[c] = a[c][pp];
-          tanh_jet_fwd_t0<SIG>(z, tanh_tc(z[0]), av, kps->c + LIN_C2);
+          tanh_jet_fwd_t0<SIG>(z, tanh_tc(z[0]), av, kps->lapw);
 #pragma unroll
           for (int c = 0; c < C; ++c) a[c][pp] = av[c];
         }
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
               float z[C], av[C];
 #pragma unroll
               for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-              tanh_jet_fwd_t0<SIG>(z, tanh_tc(z[0]), av, kps->c + LIN_C2);
+              tanh_jet_fwd_t0<SIG>(z, tanh_tc(z[0]), av, kps->lapw);
 #pragma unroll
               for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
             }
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
                   float z[C], av[C];
 #pragma unroll
                   for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-                  tanh_jet_fwd_t0<SIG>(z, tanh_tc(z[0]), av, kps->c + LIN_C2);
+                  tanh_jet_fwd_t0<SIG>(z, tanh_tc(z[0]), av, kps->lapw);
 #pragma unroll
                   for (int c = 0; c < C; ++c) {
                     float v = 0.f;
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
                   a_[c] = ab[c][pp];
                   zb[c] = 0.f;
                 }
-                tanh_jet_bwd_t0<SIG>(z, tanh_tc(z[0]), a_, zb, kps->c + LIN_C2);
+                tanh_jet_bwd_t0<SIG>(z, tanh_tc(z[0]), a_, zb, kps->lapw);
                 dbias += zb[0];
                 if (l == 1) {
                   static_for<D>([&](auto J) {
@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
                   float z[C], av[C];
 #pragma unroll
                   for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-                  tanh_jet_fwd_t0<SIG>(z, tanh_tc(z[0]), av, kps->c + LIN_C2);
+                  tanh_jet_fwd_t0<SIG>(z, tanh_tc(z[0]), av, kps->lapw);
 #pragma unroll
                   for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
                 }

@@ -25,9 +25,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
   for (int l = 2; l <= L; ++l) { offW[l] = (long long)H * D + H + (long long)(l - 2) * ((long long)H * H + H); offB[l] = offW[l] + (long long)H * H; }
   offW[L + 1] = (long long)H * D + H + (long long)(L - 1) * ((long long)H * H + H); offB[L + 1] = offW[L + 1] + (long long)M * H;
   KindParams kp;
-  kp.kind = d->kind;
-  for (int i = 0; i < PINN_MAX_AUXSEL; ++i) kp.aux_sel[i] = d->aux_sel[i];
-  for (int i = 0; i < PINN_MAX_CONSTS; ++i) kp.c[i] = d->consts[i];
+  set_kind_params(kp, d->kind, d->d, d->aux_sel, d->consts);
   for (int k = 0; k < PINN_MAX_PDE; ++k) loss[k] = 0.0;
   for (long long i = 0; i < (long long)S * P; ++i) grad[i] = 0.0;
 
@@ -48,7 +46,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
         if constexpr (SIG::order(j) >= 1) zz[SIG::base(j)] = params[offW[1] + nn * D + j];
       });
       float aa[C];
-      tanh_jet_fwd<SIG>(zz, aa, kp.c + LIN_C2);
+      tanh_jet_fwd<SIG>(zz, aa, kp.lapw);
       for (int c = 0; c < C; ++c) { z[((size_t)1 * H + nn) * C + c] = zz[c]; a[((size_t)1 * H + nn) * C + c] = aa[c]; }
     }
     for (int l = 2; l <= L; ++l) {
@@ -61,7 +59,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
         }
         zz[0] += params[offB[l] + nn];
         float aa[C];
-        tanh_jet_fwd<SIG>(zz, aa, kp.c + LIN_C2);
+        tanh_jet_fwd<SIG>(zz, aa, kp.lapw);
         for (int c = 0; c < C; ++c) { z[((size_t)l * H + nn) * C + c] = zz[c]; a[((size_t)l * H + nn) * C + c] = aa[c]; }
       }
     }
@@ -100,7 +98,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
         for (int nn = 0; nn < H; ++nn) {
           float zz[C], aa[C], zz_b[C];
           for (int c = 0; c < C; ++c) { zz[c] = z[((size_t)l * H + nn) * C + c]; aa[c] = ab[(size_t)nn * C + c]; zz_b[c] = 0.f; }
-          tanh_jet_bwd<SIG>(zz, aa, zz_b, kp.c + LIN_C2);
+          tanh_jet_bwd<SIG>(zz, aa, zz_b, kp.lapw);
           for (int c = 0; c < C; ++c) zb[(size_t)nn * C + c] = zz_b[c];
           g[offB[l] + nn] += zz_b[0];
         }
