@@ -37,7 +37,11 @@ import torch
 
 METRIC = "train-step collocation pts/sec"
 UNIT = "points/s"
-WORKLOAD_PROBLEMS = ("Poisson2D_Classic", "Heat2D_Multiscale")
+WORKLOADS = {   # BASELINE.json configs[1] (default, the config `metric` is quoted on) and configs[4] (scaling study)
+    "c2": ("Poisson2D_Classic", "Heat2D_Multiscale"),
+    "c5": ("Poisson3D_ComplexGeometry", "Heat2D_LongTime"),
+}
+WORKLOAD_PROBLEMS = WORKLOADS["c2"]
 
 
 def _peaks():
@@ -213,7 +217,8 @@ def run_fused(args):
     capi.load()
     capi.set_impl({"auto": capi.IMPL_AUTO, "ffma": capi.IMPL_FFMA, "tc": capi.IMPL_TC, "tc2": capi.IMPL_TC_PIPELINED}[args.kernel])
 
-    n_per = args.points                      # per problem, per GPU (weak scaling)
+    # weak scaling (default, the driver's contract): --points per problem PER GPU; strong: --points per problem in TOTAL
+    n_per = args.points if args.scaling == "weak" else args.points // world
     specs = [problems.make(n) for n in WORKLOAD_PROBLEMS]
     ops, params, seeds, outs = [], [], [], []
     for i, spec in enumerate(specs):
@@ -344,12 +349,15 @@ def run_fused(args):
         out = {"problem": specs[i].name, "kernel": capi.IMPL_NAMES.get(capi.selected_impl(d), "?"),
                "launch_ms": kern_ms[i], "achieved_tflops": d.flops_step_per_point() * n_per / t / 1e12,
                "hbm_gbs_algorithmic": d.bytes_per_point() * n_per / t / 1e9}
+        out["jet_channels"] = {"canonical": d.n_chan, "propagated": capi.effective_channels(d)}
         if tc_i:
-            out["executed_tensor_tflops"] = d.tc_executed_flops_per_point(1) * n_per / t / 1e12
+            out["executed_tensor_tflops"] = d.tc_executed_flops_per_point(1, capi.effective_channels(d)) * n_per / t / 1e12
         return out
 
     if on_tc:
-        exe = desc.tc_executed_flops_per_point(1) * n_per / (kern_ms[dom] * 1e-3) / 1e12
+        c_eff = capi.effective_channels(ops[dom].desc)
+        exe_pp = desc.tc_executed_flops_per_point(1, c_eff)
+        exe = exe_pp * n_per / (kern_ms[dom] * 1e-3) / 1e12
         roofline = {
             "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak if tensor_peak else None,
             "traffic": None,
@@ -357,10 +365,13 @@ def run_fused(args):
                       "(tcgen05 kind::f16, bf16x3 split precision, TMEM accumulators)",
             "launch_ms": kern_ms[dom], "algorithmic_flops_per_point": desc.flops_step_per_point(), "points_per_launch": n_per,
             "peak_source": peak_src + " bf16 dense, sustained",
-            "executed_tensor_flops_per_point": desc.tc_executed_flops_per_point(1), "executed_tensor_tflops": exe,
+            "executed_tensor_flops_per_point": exe_pp, "executed_tensor_tflops": exe,
+            "jet_channels": {"canonical": desc.n_chan, "propagated": c_eff},
             "tensor_pipe_frac_executed": exe / tensor_peak if tensor_peak else None,
-            "note": "fp32-accuracy contraction = 6 bf16 MMAs per k-step on a 128x112-padded 100x100 layer: executed/algorithmic = "
-                    f"{desc.tc_executed_flops_per_point(1) / desc.flops_step_per_point():.2f}x",
+            "note": "algorithmic flops use the canonical per-direction jet count C = 1 + sum(order) (SURVEY 8d); the kernel propagates "
+                    f"{c_eff} channels (forward-Laplacian collapse where the residual allows it) and runs each fp32-accuracy contraction as "
+                    "6 bf16 MMAs per k-step on a 128x112-padded 100x100 layer: executed/algorithmic = "
+                    f"{exe_pp / desc.flops_step_per_point():.2f}x",
             "ffma_peak_tflops": ffma_peak, "frac_of_ffma_peak": ach / ffma_peak if ffma_peak else None,
             "per_kernel": [kinfo(i) for i in range(len(ops))],
         }
@@ -394,9 +405,9 @@ def run_fused(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"Poisson2D_Classic + Heat2D_Multiscale, {n_per} synthetic collocation points each per GPU, 5x100 tanh MLP, "
+        "config": {"workload": f"{' + '.join(WORKLOAD_PROBLEMS)}, {n_per} synthetic collocation points each per GPU, 5x100 tanh MLP, "
                                "losses + flat parameter gradient (+ NCCL all-reduce when N>1)",
                    "points_per_step": pts_step, "l2": "flushed between timed iterations (256 MiB write outside the event pair)",
                    "parallelism": f"dp{world} over collocation points", "wall_s_timed_region": t_wall, "kernel": args.kernel},
@@ -420,7 +431,11 @@ def main():
                     help="fused arm only: tcgen05 tensor-core kernel (auto/tc) or the FP32 FFMA kernel")
     ap.add_argument("--gpu-ref-points", type=int, default=131072, help="points per problem of the stock-PyTorch-on-GPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU and stock-PyTorch-GPU baselines")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2", help="c2 = BASELINE configs[1] (default); c5 = configs[4]")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak", help="strong: --points is the TOTAL per problem, split over ranks")
     args = ap.parse_args()
+    global WORKLOAD_PROBLEMS
+    WORKLOAD_PROBLEMS = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args)
     else:

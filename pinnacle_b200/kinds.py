@@ -139,10 +139,12 @@ class KindDesc:
         C, H, L, d, m = self.n_chan, self.H, self.L, self.d, self.m
         return 4.0 * d * H + 6.0 * C * ((L - 1) * H * H + H * m)
 
-    def tc_executed_flops_per_point(self, n_seeds: int = 1) -> float:
+    def tc_executed_flops_per_point(self, n_seeds: int = 1, n_chan: int | None = None) -> float:
         """Tensor-core flops the tcgen05 kernel EXECUTES per point (bf16x3: 6 split products, neurons padded to
-        128 x 112): L forward batches (layers 2..L and the zero-padded output layer) + per seed (L-1) x (dW + Abar)."""
-        per_batch = 6.0 * (112 / 16) * 2.0 * 128 * 16 * self.n_chan      # = C * 172032
+        128 x 112): L forward batches (layers 2..L and the zero-padded output layer) + per seed (L-1) x (dW + Abar).
+        `n_chan`: channels the library actually propagates (capi.effective_channels: d+2 under the forward-Laplacian
+        collapse) -- defaults to the canonical C = 1 + sum(order)."""
+        per_batch = 6.0 * (112 / 16) * 2.0 * 128 * 16 * (self.n_chan if n_chan is None else n_chan)      # = C * 172032
         return per_batch * (self.L + 2.0 * (self.L - 1) * n_seeds)
 
     def bytes_per_point(self) -> int:
