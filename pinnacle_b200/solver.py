@@ -45,6 +45,22 @@ def _flux_aux(f: "FluxBC") -> np.ndarray:
     return np.concatenate(cols + [nrm], axis=1)
 
 
+def _apply_loss_weights(losses: torch.Tensor, loss_weights) -> torch.Tensor:
+    """``losses *= torch.as_tensor(loss_weights)`` exactly as deepxde/model.py:274-276 does it: in place, and WITHOUT a dtype
+    conversion of the weights.  On CPU ``as_tensor`` of the live float64 numpy array aliases it, and autograd keeps that
+    alias for the backward of the product -- LR_Adaptor / LR_Adaptor_NTK mutate the array between the closure call and
+    their last ``backward()`` (lr_adaptor.py:33-62) and rely on the product's backward seeing the NEW weights there (their
+    own ``self.losses / as_tensor(loss_weight)`` aliases the same array, so the two factors cancel).  A converted copy
+    would freeze the old weights into the graph and change the optimizer's trajectory."""
+    if loss_weights is None:
+        return losses
+    w = torch.as_tensor(loss_weights)
+    if w.device != losses.device:
+        w = w.to(losses.device)
+    losses *= w
+    return losses
+
+
 def _mse(err: torch.Tensor) -> torch.Tensor:
     # deepxde/losses.py:16-23 with y_true = zeros
     return torch.mean(torch.square(err))
@@ -182,8 +198,7 @@ class FusedPDESolver:
                 else:
                     terms.append(_mse(f(x_bc, y_bc)).reshape(1))
         losses = torch.cat(terms)
-        if self.loss_weights is not None:
-            losses = losses * torch.as_tensor(self.loss_weights, dtype=losses.dtype, device=losses.device)
+        losses = _apply_loss_weights(losses, self.loss_weights)
         return outputs_, losses
 
     def outputs_losses_train(self, inputs=None, targets=None):
@@ -324,8 +339,7 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
             with torch.no_grad():
                 outputs_ = net(torch.as_tensor(inputs, dtype=torch.float32).to(core.op.device))
         losses = torch.cat(terms)
-        if loss_weights is not None:
-            losses = losses * torch.as_tensor(loss_weights, dtype=losses.dtype, device=losses.device)
+        losses = _apply_loss_weights(losses, loss_weights)
         _clear_dde_grad_cache()
         return outputs_, losses
 

@@ -1,0 +1,96 @@
+"""The reference's own optimizer classes (src/optimizer/{lr_adaptor,multiadam,adam_lbfgs,ntk}.py, unmodified) driving a
+patched dde.Model, against the same optimizer driving the unpatched model: same weights, same points, a few steps.
+BASELINE.json configs[2] (NS2D_LidDriven + LRA) and configs[3] (Kuramoto-Sivashinsky, Adam then L-BFGS) at test size.
+
+CPU, reference tree mounted only (the oracle stands in for the C ABI as the compute backend of the host logic)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import refshim
+from util import oracle_backend
+
+needs_ref = pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted")
+
+
+def _build(name, method, seed=0):
+    dde, _ = refshim.load()
+    from src.optimizer import MultiAdam, LR_Adaptor, LR_Adaptor_NTK, Adam_LBFGS   # the reference's classes
+    torch.manual_seed(seed)
+    dde.config.set_random_seed(seed)
+    pde = refshim.construct(name)
+    pde.training_points(domain=128, boundary=48, **({"initial": 48} if hasattr(pde, "num_initial_points") else {}))
+    pde.num_test_points = 64
+    net = dde.nn.FNN([pde.input_dim] + [100] * 5 + [pde.output_dim], "tanh", "Glorot normal").float()
+    with torch.no_grad():
+        for lin in net.linears:
+            lin.bias.normal_(0, 0.1)       # zero biases make a BC gradient mean of exactly 0 -> inf in LRA
+    loss_weights = np.ones(pde.num_loss)
+    opt = torch.optim.Adam(net.parameters(), 1e-3)                                      # benchmark.py:107-115
+    if method == "multiadam":
+        opt = MultiAdam(net.parameters(), lr=1e-3, betas=(0.99, 0.99), loss_group_idx=[pde.num_pde])
+    elif method == "lra":
+        opt = LR_Adaptor(opt, loss_weights, pde.num_pde)
+    elif method == "ntk":
+        opt = LR_Adaptor_NTK(opt, loss_weights, pde)
+    elif method == "lbfgs":
+        opt = Adam_LBFGS(net.parameters(), switch_epoch=3, adam_param={"lr": 1e-3})
+    model = pde.create_model(net)
+    model.compile(opt, loss_weights=loss_weights)
+    net.auxiliary_vars = None
+    return model, net, loss_weights
+
+
+def _run(model, steps):
+    hist = []
+    x = model.data.train_x
+    for _ in range(steps):
+        model._train_step(x, None, None)
+        hist.append(model.opt.losses.detach().cpu().numpy().astype(np.float64).copy())
+    return np.array(hist)
+
+
+@needs_ref
+@pytest.mark.parametrize("name,method,steps", [
+    ("NS2D_LidDriven", "lra", 4),                       # configs[2]
+    ("KuramotoSivashinskyEquation", "lbfgs", 4),        # configs[3]: 2 Adam steps, then 2 L-BFGS steps (<= 20 closure calls each)
+    ("Burgers1D", "multiadam", 4),
+    ("Poisson2D_Classic", "ntk", 3),
+    ("Heat2D_Multiscale", "lra", 3),
+])
+def test_reference_optimizer_on_patched_model_follows_unpatched(name, method, steps):
+    from pinnacle_b200 import fused
+    from pinnacle_b200.solver import enable_fused
+    ref_model, ref_net, ref_w = _build(name, method)
+    new_model, new_net, new_w = _build(name, method)
+    for a, b in zip(ref_net.parameters(), new_net.parameters()):
+        assert torch.equal(a, b)
+    assert np.array_equal(ref_model.data.train_x, new_model.data.train_x)
+    ref_hist = _run(ref_model, steps)
+
+    orig = fused.FusedPDEResidual.__init__
+
+    def init_cpu(self, spec, H=100, L=5, policy="auto", device=None, group=None, check_library=True):
+        orig(self, spec, H, L, policy, "cpu", group, False)
+
+    fused.FusedPDEResidual.__init__ = init_cpu
+    try:
+        with oracle_backend():
+            enable_fused(new_model)
+            new_hist = _run(new_model, steps)
+    finally:
+        fused.FusedPDEResidual.__init__ = orig
+
+    assert np.all(np.isfinite(ref_hist)) and np.all(np.isfinite(new_hist)), (ref_hist, new_hist)
+    # step 1 sees identical weights: per-term (weighted) losses to parity tolerance; later steps compound the optimizer's
+    # sensitivity to 1e-7-level gradient differences (L-BFGS line search, LRA's max|g| / mean|g| ratio)
+    np.testing.assert_allclose(new_hist[0], ref_hist[0], rtol=5e-5)
+    np.testing.assert_allclose(new_hist, ref_hist, rtol=2e-2 if method == "lbfgs" else 5e-3)
+    if method in ("lra", "ntk"):
+        # the adapted loss weights (mutated in place by the optimizer, read live by outputs_losses) follow too
+        np.testing.assert_allclose(np.asarray(new_w, dtype=np.float64), np.asarray(ref_w, dtype=np.float64), rtol=5e-3)
+        assert not np.allclose(np.asarray(ref_w, dtype=np.float64), 1.0)
+    for a, b in zip(ref_net.parameters(), new_net.parameters()):
+        assert (a - b).norm() <= (2e-2 if method == "lbfgs" else 2e-3) * a.norm().clamp_min(1e-6)
