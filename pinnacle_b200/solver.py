@@ -366,9 +366,47 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
             else:
                 model.lr_scheduler.step()
 
+    # ---- model.predict(x, operator=pde) -> fused forward-only residual service (RAR: src/utils/rar.py:20-21) --------
+    orig_predict = model.predict
+    pde_fn = getattr(data, "pde", None)
+    predict_state = {"op": None, "as_list": None}
+
+    def predict(x, operator=None, callbacks=None):
+        """deepxde/model.py:801-885.  With ``operator`` = the problem's own pde function the residual comes from the fused
+        forward-only kernel (same return structure: an array, or a list of [N,1] arrays when pde() returns a list); any
+        other operator, and plain prediction, run the reference's code unchanged."""
+        if operator is None or pde_fn is None or not (operator is pde_fn or operator == pde_fn):
+            return orig_predict(x, operator=operator, callbacks=callbacks)
+        x = np.asarray(x, dtype=np.float32)
+        if predict_state["as_list"] is None:
+            probe = orig_predict(x[:2], operator=operator)          # learn the return structure from the reference itself
+            predict_state["as_list"] = isinstance(probe, (list, tuple))
+        if predict_state["op"] is None:
+            d, H, L, m = core._shape
+            op = FusedPDEResidual(spec, H, L, policy="lazy", device=core.op.device, group=None)
+            op.world, op.rank = 1, 0                                # every rank evaluates the rows it was handed
+            predict_state["op"] = op
+        cbs = None
+        if callbacks is not None:
+            import sys
+            dde = sys.modules.get("deepxde")
+            cbs = dde.callbacks.CallbackList(callbacks=callbacks)
+            cbs.set_model(model)
+            cbs.on_predict_begin()
+        net.eval()
+        op = predict_state["op"]
+        op.set_points(x, shard=False)
+        res = op.residual(core.params).cpu().numpy()                # [N, n_pde]
+        if cbs is not None:
+            cbs.on_predict_end()
+        if predict_state["as_list"]:
+            return [res[:, k:k + 1] for k in range(res.shape[1])]
+        return res
+
     model.outputs_losses_train = outputs_losses_train
     model.outputs_losses_test = outputs_losses_test
     model.train_step = train_step
+    model.predict = predict
     model.fused_core = core
     return model
 

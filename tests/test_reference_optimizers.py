@@ -94,3 +94,43 @@ def test_reference_optimizer_on_patched_model_follows_unpatched(name, method, st
         assert not np.allclose(np.asarray(ref_w, dtype=np.float64), 1.0)
     for a, b in zip(ref_net.parameters(), new_net.parameters()):
         assert (a - b).norm() <= (2e-2 if method == "lbfgs" else 2e-3) * a.norm().clamp_min(1e-6)
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["Burgers1D", "NS2D_LidDriven", "Poisson2D_ManyArea"])
+def test_predict_operator_pde_and_rar_wrapper_on_patched_model(name):
+    """model.predict(X, operator=pde.pde) -- the residual query of RAR (src/utils/rar.py:20-21) -- is served by the fused
+    forward-only path with the reference's return structure, and the reference's rar_wrapper picks the same anchor."""
+    from pinnacle_b200 import fused
+    from pinnacle_b200.solver import enable_fused
+    model, net, _ = _build(name, "adam")       # loads the reference (sys.path) first
+    from src.utils.rar import rar_wrapper
+    pde = model.pde
+    X = model.data.train_x
+    ref = model.predict(X, operator=pde.pde)
+    orig = fused.FusedPDEResidual.__init__
+
+    def init_cpu(self, spec, H=100, L=5, policy="auto", device=None, group=None, check_library=True):
+        orig(self, spec, H, L, policy, "cpu", group, False)
+
+    fused.FusedPDEResidual.__init__ = init_cpu
+    try:
+        with oracle_backend():
+            enable_fused(model)
+            new = model.predict(X, operator=pde.pde)
+            assert isinstance(new, list) == isinstance(ref, list)
+            r, n = np.asarray(ref, dtype=np.float64), np.asarray(new, dtype=np.float64)
+            assert r.shape == n.shape
+            assert np.linalg.norm(r - n) <= 2e-5 * np.linalg.norm(r)
+            # plain prediction and foreign operators keep the reference's code path
+            np.testing.assert_array_equal(model.predict(X[:5]), net(torch.as_tensor(X[:5])).detach().numpy())
+            other = model.predict(X[:5], operator=lambda x, y: y * 2.0)
+            np.testing.assert_allclose(other, 2.0 * model.predict(X[:5]), rtol=1e-6)
+            # the reference's RAR loop on the patched model: train, query residuals, add the worst point as an anchor, train
+            n_before = model.data.train_x_all.shape[0]
+            model.train = rar_wrapper(pde, model, {"interval": 2, "count": 1})
+            model.train(iterations=4, display_every=2)
+            assert model.data.train_x_all.shape[0] == n_before + 1
+            assert np.all(np.isfinite(model.opt.losses.detach().numpy()))
+    finally:
+        fused.FusedPDEResidual.__init__ = orig
