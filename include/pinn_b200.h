@@ -138,6 +138,27 @@ double pinn_ffma_peak_tflops(int iters);
  * memory, K-major.  variant bit 0 swaps the descriptor LBO/SBO fields (diagnostic).  K % 8 == 0, N % 16 == 0. */
 int pinn_debug_umma_gemm(int mode, int variant, int K, int N, const float* A, const float* B, float* D, void* stream);
 
+/* ---- optimizer-side kernels over the flat parameter / gradient buffers (one launch each, no host synchronisation) ----
+ *
+ * pinn_adam_step: torch.optim.Adam's update (amsgrad off; weight_decay = L2 term added to the gradient), the optimizer
+ * benchmark.py:107 constructs, over the flat buffers instead of 12 tensors.  step_dev: device float[2] = {updates applied
+ * so far, 0}; the kernel reads it for the bias corrections and increments it, so a captured CUDA graph can replay it. */
+int pinn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float* step_dev,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
+/* Floats of device scratch pinn_grad_stats / pinn_lra_combine need. */
+size_t pinn_optim_scratch_floats(void);
+/* out3 = { max|g|, sum|g|, sum g^2 } of a flat vector: the statistics src/optimizer/lr_adaptor.py:37-41,50-53 and
+ * ntk.py:38-58 compute with one torch reduction + .item() per parameter tensor. */
+int pinn_grad_stats(const float* g, int64_t n, float* out3, float* scratch, void* stream);
+/* One learning-rate-annealing update (src/optimizer/lr_adaptor.py:33-62, mode "max") from the per-term gradient rows
+ * G[n_terms][ldg] of the UNWEIGHTED loss terms (PDE terms first):
+ *   m_r = max_i |sum_{k<n_pde} G[k][i]|;   for t >= n_pde:  w_t <- (1-alpha) w_t + alpha m_r / (sum_i|G[t][i]| / counts[t] * w_t)
+ *   grad_out[i] = sum_t w_t G[t][i]        (the gradient lr_adaptor.py:59-62 back-propagates, with the new weights)
+ * w_in / w_out: device [n_terms] (may not alias); counts: device [n_terms], the element count the reference's mean
+ * runs over (parameters whose gradient is not None).  At most 15 boundary terms. */
+int pinn_lra_combine(const float* G, int n_terms, int n_pde, int64_t P, int64_t ldg, const float* w_in, const float* counts,
+                     float alpha, float* w_out, float* grad_out, float* scratch, void* stream);
+
 const char* pinn_last_error(void);
 const char* pinn_build_info(void);
 

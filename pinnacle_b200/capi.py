@@ -21,6 +21,7 @@ EXPORTS = (
     "pinn_param_count", "pinn_supported", "pinn_workspace_bytes", "pinn_fwd", "pinn_fwd_bwd",
     "pinn_last_launch_count", "pinn_ffma_peak_tflops", "pinn_last_error", "pinn_build_info", "pinn_debug_umma_gemm", "pinn_set_impl", "pinn_has_tensor_core_kernel",
     "pinn_selected_impl", "pinn_effective_channels", "pinn_set_laplacian_collapse",
+    "pinn_adam_step", "pinn_optim_scratch_floats", "pinn_grad_stats", "pinn_lra_combine",
 )
 
 
@@ -70,6 +71,15 @@ def load() -> ctypes.CDLL:
     lib.pinn_effective_channels.restype = ctypes.c_int
     lib.pinn_set_laplacian_collapse.argtypes = [ctypes.c_int]
     lib.pinn_set_laplacian_collapse.restype = ctypes.c_int
+    V, F, I64 = ctypes.c_void_p, ctypes.c_float, ctypes.c_int64
+    lib.pinn_adam_step.argtypes = [V, V, V, V, I64, V, F, F, F, F, F, V]
+    lib.pinn_adam_step.restype = ctypes.c_int
+    lib.pinn_optim_scratch_floats.argtypes = []
+    lib.pinn_optim_scratch_floats.restype = ctypes.c_size_t
+    lib.pinn_grad_stats.argtypes = [V, I64, V, V, V]
+    lib.pinn_grad_stats.restype = ctypes.c_int
+    lib.pinn_lra_combine.argtypes = [V, ctypes.c_int, ctypes.c_int, I64, I64, V, V, F, V, V, V, V]
+    lib.pinn_lra_combine.restype = ctypes.c_int
     lib.pinn_selected_impl.argtypes = [P]
     lib.pinn_selected_impl.restype = ctypes.c_int
     lib.pinn_last_error.argtypes = []
@@ -246,3 +256,57 @@ def ffma_peak_tflops(iters: int = 4096) -> float:
 
 def build_info() -> str:
     return load().pinn_build_info().decode()
+
+
+# ---- optimizer-side kernels over the flat buffers -------------------------------------------------------
+_optim_scratch = {}
+
+
+def _scratch(device) -> torch.Tensor:
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    b = _optim_scratch.get(key)
+    if b is None:
+        b = torch.empty(int(load().pinn_optim_scratch_floats()), dtype=torch.float32, device=device)
+        _optim_scratch[key] = b
+    return b
+
+
+def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step_dev: torch.Tensor,
+              lr: float, beta1: float, beta2: float, eps: float, weight_decay: float = 0.0):
+    """pinn_adam_step: one launch of torch.optim.Adam's update over flat fp32 buffers; `step_dev` = device float[2]."""
+    for t, nm in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq"), (step_dev, "step_dev")):
+        _req(t, nm)
+    n = params.numel()
+    if grads.numel() != n or exp_avg.numel() != n or exp_avg_sq.numel() != n or step_dev.numel() < 2:
+        raise FusedOpError("adam_step: buffer sizes differ")
+    with torch.cuda.device(params.device):
+        rc = load().pinn_adam_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), n, _ptr(step_dev), float(lr), float(beta1),
+                                   float(beta2), float(eps), float(weight_decay), _stream_ptr(params.device))
+    _check(rc, "pinn_adam_step")
+
+
+def grad_stats(g: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """pinn_grad_stats: device tensor [max|g|, sum|g|, sum g^2] of a flat vector, no host synchronisation."""
+    _req(g, "g")
+    if out is None:
+        out = torch.empty(3, dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        rc = load().pinn_grad_stats(_ptr(g), g.numel(), _ptr(out), _ptr(_scratch(g.device)), _stream_ptr(g.device))
+    _check(rc, "pinn_grad_stats")
+    return out
+
+
+def lra_combine(G: torch.Tensor, n_pde: int, w_in: torch.Tensor, counts: torch.Tensor, alpha: float, w_out: torch.Tensor,
+                grad_out: torch.Tensor):
+    """pinn_lra_combine: G [n_terms, P] rows of the unweighted terms -> new weights (w_out) and grad_out = sum_t w_t G[t]."""
+    for t, nm in ((G, "G"), (w_in, "w_in"), (counts, "counts"), (w_out, "w_out"), (grad_out, "grad_out")):
+        _req(t, nm)
+    if G.dim() != 2:
+        raise FusedOpError("lra_combine: G must be [n_terms, P]")
+    T, P = G.shape
+    if w_in.numel() != T or w_out.numel() != T or counts.numel() != T or grad_out.numel() != P or w_in.data_ptr() == w_out.data_ptr():
+        raise FusedOpError("lra_combine: buffer sizes differ or w_in aliases w_out")
+    with torch.cuda.device(G.device):
+        rc = load().pinn_lra_combine(_ptr(G), int(T), int(n_pde), int(P), int(G.stride(0)), _ptr(w_in), _ptr(counts), float(alpha), _ptr(w_out),
+                                     _ptr(grad_out), _ptr(_scratch(G.device)), _stream_ptr(G.device))
+    _check(rc, "pinn_lra_combine")

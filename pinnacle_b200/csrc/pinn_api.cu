@@ -52,6 +52,8 @@ static int fail(const std::string& msg) {
   return 1;
 }
 
+void set_error_string(const std::string& s) { g_err = s; }   // for the other translation units of the library (pinn_optim.cu)
+
 static const ConfigInfo* find_config(const pinn_kind_desc* d, std::string* why) {
   if (d == nullptr) { *why = "null descriptor"; return nullptr; }
   if (d->d < 1 || d->d > PINN_MAX_DIM) { *why = "input dimension out of range"; return nullptr; }

@@ -1,0 +1,195 @@
+"""Optimizers over ONE flat parameter buffer.
+
+The fused op already produces the gradient as a flat vector; the reference then spreads it over 12 ``nn.Linear`` tensors
+and updates them with the foreach ``torch.optim.Adam`` (benchmark.py:107), and its learning-rate-annealing wrapper
+(src/optimizer/lr_adaptor.py) runs one extra backward pass plus ``.item()`` synchronisations per boundary term.  Here:
+
+* ``FlatAdam``   -- ``torch.optim.Adam`` semantics (same hyper-parameters, same update) as one kernel launch
+  (``pinn_adam_step``) over a flat buffer the network's parameters are views of.  Works as a plain
+  ``torch.optim.Optimizer`` (closure protocol, ``opt.losses``) with any loss; with a ``FusedPDESolver`` whose terms are all
+  fused it also skips autograd: the solver writes the weighted gradient straight into ``flat_grad``.
+* ``FusedLRA``   -- the ``LR_Adaptor`` algorithm (mode "max") on the per-term gradient ROWS of the fused op: one fused
+  pass per term, then ``pinn_lra_combine`` computes max|g_r|, mean|g_t|, the new weights and the re-weighted total
+  gradient in two launches with every scalar on the device -- no per-term backward passes, no host synchronisation.
+
+Both need the CUDA library; there is no CPU implementation.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import capi
+
+
+class FlatAdam(torch.optim.Optimizer):
+    """Adam (amsgrad off) over a flat fp32 buffer; ``p.data`` / ``p.grad`` of every parameter become views of
+    ``self.flat`` / ``self.flat_grad``.  ``zero_grad()`` zeroes the flat gradient in one memset and keeps the views
+    attached (``set_to_none`` is ignored: a parameter no loss term reaches sees a zero gradient instead of being
+    skipped, which is the same update as long as it has never received a gradient)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        params = list(params)
+        if not params:
+            raise ValueError("FlatAdam got an empty parameter list")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        if len(self.param_groups) != 1:
+            raise ValueError("FlatAdam supports one parameter group")
+        dev = params[0].device
+        for p in params:
+            if p.device != dev or p.dtype != torch.float32 or not p.is_cuda:
+                raise capi.FusedOpError("FlatAdam needs fp32 CUDA parameters on one device (no CPU implementation)")
+        self._params = params
+        n = sum(p.numel() for p in params)
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros(2, dtype=torch.float32, device=dev)     # {updates applied, ticket}: see pinn_adam_step
+        self._slices = []
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                k = p.numel()
+                self.flat[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat[off:off + k].view(p.shape)
+                self._slices.append((off, k))
+                off += k
+        self._attach_grads()
+
+    def _attach_grads(self):
+        for p, (off, k) in zip(self._params, self._slices):
+            want = self.flat_grad[off:off + k]
+            if p.grad is None or p.grad.data_ptr() != want.data_ptr():
+                p.grad = want.view(p.shape)
+
+    def zero_grad(self, set_to_none: bool = True):
+        self.flat_grad.zero_()
+        self._attach_grads()
+
+    def _gather_grads(self):
+        """Bring gradients that autograd re-pointed (p.grad replaced instead of accumulated into) back into flat_grad."""
+        for p, (off, k) in zip(self._params, self._slices):
+            want = self.flat_grad[off:off + k]
+            if p.grad is None:
+                want.zero_()
+            elif p.grad.data_ptr() != want.data_ptr():
+                want.copy_(p.grad.reshape(-1))
+        self._attach_grads()
+
+    def apply_update(self):
+        """One Adam update of ``flat`` from ``flat_grad`` (one kernel launch)."""
+        g = self.param_groups[0]
+        capi.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_dev, g["lr"], g["betas"][0], g["betas"][1],
+                       g["eps"], g["weight_decay"])
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        self._gather_grads()
+        self.apply_update()
+        return loss
+
+    def fused_step(self, solver):
+        """One training step of a ``FusedPDESolver`` whose loss terms are all fused, without autograd: every term's fused
+        pass writes its gradient row, ``flat_grad = sum_t w_t G_t`` (one matrix-vector product), one Adam launch.
+        Sets ``self.losses`` to the weighted per-term losses like the reference closure (deepxde/model.py:311)."""
+        n_pde = solver.spec.desc.n_pde
+        T = solver.num_loss
+        dev = self.flat.device
+        w = solver.loss_weights
+        w_dev = getattr(self, "_w_dev", None)
+        w_host = None if w is None else np.asarray(w, dtype=np.float32).copy()
+        if w_dev is None or w_dev.numel() != T or (w_host is not None and not np.array_equal(w_host, self._w_host)) or (w_host is None) != (self._w_host is None):
+            self._w_host = w_host
+            self._w_dev = w_dev = torch.ones(T, dtype=torch.float32, device=dev) if w_host is None else torch.as_tensor(w_host).to(dev)
+            self._comb = torch.ones(1 + T - n_pde, dtype=torch.float32, device=dev)
+            self._comb[1:] = w_dev[n_pde:]
+        G, losses = solver.term_gradient_rows(self.flat, w_dev[:n_pde].view(1, n_pde))
+        torch.mv(G.t(), self._comb, out=self.flat_grad)
+        self.apply_update()
+        self.losses = losses * w_dev
+        return self.losses.sum()
+
+
+class FusedLRA(torch.optim.Optimizer):
+    """Learning-rate annealing (src/optimizer/lr_adaptor.py:4-64, mode "max") driven by the fused op's per-term gradient
+    rows.  Same constructor protocol as the reference class -- ``FusedLRA(inner, loss_weight, num_pde, alpha)`` -- with
+    ``inner`` a ``FlatAdam``; ``attach(solver)`` names the ``FusedPDESolver`` whose terms it balances.  The live weights
+    stay on the device (``self.weights``); ``loss_weight`` (the host array the reference mutates) is refreshed lazily by
+    ``sync_loss_weight()`` so a step never waits for the GPU."""
+
+    def __init__(self, optimizer: FlatAdam, loss_weight, num_pde: int, alpha: float = 0.1, mode: str = "max"):
+        if mode != "max":
+            raise ValueError("FusedLRA implements mode='max' (the only one the reference accepts, lr_adaptor.py:16)")
+        if not isinstance(optimizer, FlatAdam):
+            raise capi.FusedOpError("FusedLRA wraps a FlatAdam")
+        super().__init__(optimizer.param_groups, dict(alpha=alpha, mode=mode))
+        self.optimizer = optimizer
+        self.loss_weight = loss_weight
+        self.num_pde = int(num_pde)
+        self.alpha = float(alpha)
+        self.iter = 0
+        self.solver = None
+        dev = optimizer.flat.device
+        w = np.asarray(loss_weight, dtype=np.float32)
+        self.weights = torch.as_tensor(w.copy()).to(dev)
+        self._w_next = torch.empty_like(self.weights)
+        self.counts = torch.full((w.shape[0],), float(optimizer.flat.numel()), dtype=torch.float32, device=dev)
+        self._rows_w = None
+
+    def attach(self, solver):
+        if solver.spec.desc.n_pde != self.num_pde or solver.num_loss != self.weights.numel():
+            raise capi.FusedOpError("FusedLRA: loss_weight / num_pde do not match the solver's loss terms")
+        self.solver = solver
+        return self
+
+    def zero_grad(self, set_to_none: bool = True):
+        self.optimizer.zero_grad(set_to_none)
+
+    def sync_loss_weight(self):
+        """Copy the device weights into the host ``loss_weight`` array (one D2H; call when logging)."""
+        self.loss_weight[:] = self.weights.detach().cpu().numpy()
+        return self.loss_weight
+
+    def step(self, closure=None):
+        if self.solver is None:
+            raise capi.FusedOpError("FusedLRA.step(): attach(solver) first")
+        self.iter += 1
+        opt, n_pde = self.optimizer, self.num_pde
+        w = self.weights
+        T = w.numel()
+        pde_w = w[:n_pde]
+        # the PDE terms keep their (constant) weights; with equal weights c one row  sum_k G_k  serves both the statistic
+        # max|grad sum_k L_k| and the combination c * row; unequal weights need the individual rows
+        if self._rows_w is None:
+            hw = np.asarray(self.loss_weight, dtype=np.float32)[:n_pde]
+            self._pde_equal = bool(np.all(hw == hw[0]))
+            if self._pde_equal:
+                self._seeds = torch.ones(1, n_pde, dtype=torch.float32, device=w.device)
+                self._rows_w = torch.empty(1 + T - n_pde, dtype=torch.float32, device=w.device)
+                self._rows_w_next = torch.empty_like(self._rows_w)
+                self._rows_counts = torch.cat([self.counts[:1], self.counts[n_pde:]]).contiguous()
+            else:
+                self._seeds = torch.eye(n_pde, dtype=torch.float32, device=w.device)
+                self._rows_w = torch.empty(T, dtype=torch.float32, device=w.device)
+                self._rows_w_next = torch.empty_like(self._rows_w)
+                self._rows_counts = self.counts
+        G, losses = self.solver.term_gradient_rows(opt.flat, self._seeds)
+        if self._pde_equal:
+            self._rows_w[:1] = pde_w[:1]
+            self._rows_w[1:] = w[n_pde:]
+            n_rows_pde = 1
+        else:
+            self._rows_w.copy_(w)
+            n_rows_pde = n_pde
+        self.losses = losses * w                       # what the closure reports: weighted with the weights of this step
+        capi.lra_combine(G, n_rows_pde, self._rows_w, self._rows_counts, self.alpha, self._rows_w_next, opt.flat_grad)
+        w[n_pde:] = self._rows_w_next[n_rows_pde:]
+        opt.apply_update()
+        return torch.sum(losses * w)                   # lr_adaptor.py:60: total loss under the NEW weights

@@ -90,6 +90,10 @@ class _StepCore:
         """Mean-square of one boundary / initial / point-set term over the staged BC rows [beg, end) through the fused
         op.  `desc` is the term's kind descriptor (VALUE or FLUX); `aux_fn()` is called once per staged point set and
         returns its aux columns, broadcastable to [n, desc.n_aux]."""
+        return self.term_op(idx, beg, end, desc, aux_fn).losses(self.params)
+
+    def term_op(self, idx: int, beg: int, end: int, desc, aux_fn) -> FusedPDEResidual:
+        """The fused op (rows + term data device-resident) of boundary term `idx`; rebuilt when new rows were staged."""
         d, H, L, m = self._shape
         ent = self._value_ops.get(idx)
         if ent is None or ent[1] != self.generation:
@@ -105,7 +109,7 @@ class _StepCore:
             op.set_rows(self._x_bc[beg:end], aux.contiguous(), n)
             self._value_ops[idx] = (op, self.generation)
             ent = self._value_ops[idx]
-        return ent[0].losses(self.params)
+        return ent[0]
 
     def value_term_loss(self, idx: int, beg: int, end: int, component: int, values_fn):
         """u[beg:end, component] - values (DirichletBC / IC / PointSetBC)."""
@@ -207,6 +211,52 @@ class FusedPDESolver:
     def outputs_losses_test(self, inputs=None, targets=None):
         return self.outputs_losses(False, self.train_x if inputs is None else inputs, targets)
 
+    # ---- per-term gradient rows without autograd (optimizers of pinnacle_b200.optim) ----------------------
+    def term_gradient_rows(self, flat: torch.Tensor, pde_seeds: torch.Tensor):
+        """Gradient of every loss term w.r.t. the flat parameter vector as rows of one device matrix, and the unweighted
+        per-term losses -- what ``losses[i].backward(retain_graph=True)`` per term yields in the reference
+        (src/optimizer/lr_adaptor.py:36,49), from ONE fused pass per term and no autograd graph.
+
+        ``pde_seeds`` [S, n_pde]: row s is d(sum_k seeds[s,k] L_k)/dtheta of the PDE terms.  Returns (G [S + n_bc, P],
+        losses [n_pde + n_bc]); the buffers are reused by the next call.  Needs every boundary term on the fused path."""
+        from . import fused as _fused
+        core = self.core
+        core.stage(self.train_x, self.n_bc)
+        for f in self.bc_terms:
+            if not isinstance(f, (ValueBC, FluxBC)):
+                raise capi.FusedOpError("term_gradient_rows() needs every boundary term on the fused path (ValueBC / FluxBC)")
+            if f.end - f.beg == 0:
+                raise capi.FusedOpError("term_gradient_rows(): boundary term without rows")
+        op = core.op
+        desc = op.desc
+        P, n_pde, S, n_bc = desc.n_params, desc.n_pde, int(pde_seeds.shape[0]), len(self.bc_terms)
+        T = S + n_bc
+        need = T * P + max(n_pde, 1) + 1
+        buf = getattr(self, "_rows_buf", None)
+        if buf is None or buf.numel() < need or buf.device != flat.device:
+            buf = self._rows_buf = torch.empty(need, dtype=torch.float32, device=flat.device)
+            self._rows_losses = torch.empty(n_pde + n_bc, dtype=torch.float32, device=flat.device)
+            self._one_seed = torch.ones(1, 1, dtype=torch.float32, device=flat.device)
+        losses = self._rows_losses
+        out = buf[:S * P + n_pde]
+        _fused._backend_fwd_bwd(desc, flat, op.x, op.aux, op.inv_n_global, pde_seeds, out=out)
+        op.stats["fwd_bwd_calls"] += 1
+        if op.world > 1:
+            _fused._all_reduce(out, op.group)
+            op.stats["allreduce_calls"] += 1
+        losses[:n_pde].copy_(out[S * P:])
+        d, m = core._shape[0], core._shape[3]
+        for i, f in enumerate(self.bc_terms):
+            if isinstance(f, ValueBC):
+                bop = core.term_op(i, f.beg, f.end, value_desc(d, m, int(f.component)), lambda f=f: f.values)
+            else:
+                bop = core.term_op(i, f.beg, f.end, flux_desc(d, m, int(f.component), f.beta is not None), lambda f=f: _flux_aux(f))
+            o = buf[(S + i) * P:(S + i) * P + P + 1]
+            _fused._backend_fwd_bwd(bop.desc, flat, bop.x, bop.aux, bop.inv_n_global, self._one_seed, out=o)
+            bop.stats["fwd_bwd_calls"] += 1
+            losses[n_pde + i:n_pde + i + 1].copy_(o[P:])
+        return buf[:T * P].view(T, P), losses
+
     # ---- whole-step CUDA graph -----------------------------------------------------------------------
     def capture_step(self, warmup: int = 3):
         """Capture one full training step (fused PDE op, BC terms, backward, optimizer update) into a CUDA graph.
@@ -222,13 +272,17 @@ class FusedPDESolver:
             raise capi.FusedOpError("capture_step() does not support lr schedulers")
         if not self.core.cache_points:
             raise capi.FusedOpError("capture_step() needs device-resident points (cache_points=True)")
+        from .optim import FlatAdam, FusedLRA
+        flat_opt = isinstance(self.opt, (FlatAdam, FusedLRA))
         for grp in self.opt.param_groups:
-            if not grp.get("capturable", False):
-                raise capi.FusedOpError("capture_step() needs an optimizer constructed with capturable=True")
+            if not flat_opt and not grp.get("capturable", False):
+                raise capi.FusedOpError("capture_step() needs an optimizer constructed with capturable=True (or a FlatAdam / FusedLRA)")
         dev = self.core.op.device
         self.core.stage(self.train_x, self.n_bc)           # upload outside the graph
 
         def body():
+            if flat_opt and self._flat_optimizer_step() is not None:
+                return self.opt.losses
             losses = self.outputs_losses_train(self.train_x, None)[1]
             total = torch.sum(losses)
             self.opt.zero_grad(set_to_none=False)
@@ -249,10 +303,25 @@ class FusedPDESolver:
         self.opt.losses = self._graph_losses
         return self
 
+    def _flat_optimizer_step(self):
+        """Autograd-free step for the optimizers of pinnacle_b200.optim (None when the configuration needs autograd)."""
+        from .optim import FlatAdam, FusedLRA
+        if isinstance(self.opt, FusedLRA):
+            if self.opt.solver is None:
+                self.opt.attach(self)
+            return self.opt.step()
+        if isinstance(self.opt, FlatAdam) and all(isinstance(f, (ValueBC, FluxBC)) and f.end > f.beg for f in self.bc_terms):
+            return self.opt.fused_step(self)
+        return None
+
     def train_step(self, inputs=None, targets=None):
         if getattr(self, "_graph", None) is not None and inputs is None:
             self._graph.replay()
             return self._graph_losses.sum()
+        if inputs is None and self.lr_scheduler is None:
+            loss = self._flat_optimizer_step()
+            if loss is not None:
+                return loss
         inputs = self.train_x if inputs is None else inputs
 
         def closure(*, skip_backward=False):

@@ -1,0 +1,165 @@
+"""Optimizer-side kernels over the flat buffers on the GPU: FlatAdam against torch.optim.Adam,
+FusedLRA against a line-by-line restatement of the reference's LR_Adaptor driven through autograd, the statistics kernel
+against torch reductions, and CUDA-graph replay of the autograd-free step."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _net(desc, dev, seed=0):
+    from pinnacle_b200.nn import FNN
+    torch.manual_seed(seed)
+    net = FNN([desc.d] + [100] * 5 + [desc.m])
+    with torch.no_grad():
+        for lin in net.linears:
+            lin.bias.normal_(0, 0.1)
+    return net.to(dev)
+
+
+def _flat(net):
+    return torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+
+
+def _ns_problem(dev, n=4096, nb=256, seed=0):
+    """NS2D_LidDriven residual rows + four value-type boundary terms (u, v on two walls), BASELINE configs[2] at test size."""
+    from pinnacle_b200 import problems
+    from pinnacle_b200.solver import ValueBC
+    spec = problems.make("NS2D_LidDriven")
+    x = spec.sample(n, seed=seed + 1)
+    rs = np.random.RandomState(seed + 2)
+    xb = rs.uniform(0, 1, (4 * nb, 2)).astype(np.float32)
+    xb[:nb, 1] = 1.0
+    xb[nb:2 * nb, 1] = 0.0
+    xb[2 * nb:3 * nb, 0] = 0.0
+    xb[3 * nb:, 0] = 1.0
+    lid = (4.0 * xb[:nb, :1] * (1.0 - xb[:nb, :1])).astype(np.float32)
+    terms = [ValueBC(0, nb, 0, lid), ValueBC(0, nb, 1, np.zeros((nb, 1), np.float32)),
+             ValueBC(nb, 4 * nb, 0, np.zeros((3 * nb, 1), np.float32)), ValueBC(nb, 4 * nb, 1, np.zeros((3 * nb, 1), np.float32)),
+             ValueBC(4 * nb - 1, 4 * nb, 2, np.zeros((1, 1), np.float32))]       # one-point pressure pin (ns.py PointSetBC)
+    return spec, x, xb, terms
+
+
+def test_grad_stats_matches_torch():
+    from pinnacle_b200 import capi
+    dev = torch.device("cuda:0")
+    g = torch.randn(41003, device=dev) * 3.0
+    out = capi.grad_stats(g).cpu().double().numpy()
+    ref = np.array([g.abs().max().item(), g.abs().double().sum().item(), (g.double() ** 2).sum().item()])
+    np.testing.assert_allclose(out, ref, rtol=2e-6)
+
+
+@pytest.mark.parametrize("wd", [0.0, 1e-2])
+def test_flat_adam_follows_torch_adam(wd):
+    """Same gradients in, same parameters out: 25 updates on the fused Poisson loss, generic closure protocol."""
+    from pinnacle_b200 import problems
+    from pinnacle_b200.optim import FlatAdam
+    from pinnacle_b200.solver import FusedPDESolver
+    dev = torch.device("cuda:0")
+    spec = problems.make("Poisson2D_Classic")
+    x = spec.sample(2048, seed=3)
+    net_a, net_b = _net(spec.desc, dev, 5), _net(spec.desc, dev, 5)
+    sa = FusedPDESolver(spec, net_a, x).compile(FlatAdam(net_a.parameters(), lr=1e-3, weight_decay=wd))
+    sb = FusedPDESolver(spec, net_b, x).compile(torch.optim.Adam(net_b.parameters(), lr=1e-3, weight_decay=wd))
+    assert sa.opt.flat.data_ptr() == next(net_a.parameters()).data_ptr()
+    for _ in range(25):
+        sa.train_step()
+        sb.train_step()
+    la, lb = sa.opt.losses.detach().cpu().numpy(), sb.opt.losses.detach().cpu().numpy()
+    np.testing.assert_allclose(la, lb, rtol=2e-4)
+    pa, pb = _flat(net_a), _flat(net_b)
+    assert float((pa - pb).norm() / pb.norm()) < 2e-5
+    assert float(sa.opt.step_dev[0]) == 25.0
+
+
+def test_autograd_free_step_matches_autograd_step_and_replays_as_graph():
+    from pinnacle_b200.optim import FlatAdam
+    from pinnacle_b200.solver import FusedPDESolver
+    dev = torch.device("cuda:0")
+    spec, x, xb, terms = _ns_problem(dev)
+    w = np.array([1.0, 1.0, 1.0, 2.0, 3.0, 0.5, 1.5, 10.0])
+    nets = [_net(spec.desc, dev, 7) for _ in range(3)]
+    sa = FusedPDESolver(spec, nets[0], x, xb, terms).compile(FlatAdam(nets[0].parameters(), lr=1e-3), loss_weights=w)
+    sb = FusedPDESolver(spec, nets[1], x, xb, terms).compile(torch.optim.Adam(nets[1].parameters(), lr=1e-3), loss_weights=w.copy())
+    sc = FusedPDESolver(spec, nets[2], x, xb, terms).compile(FlatAdam(nets[2].parameters(), lr=1e-3), loss_weights=w.copy())
+    sc.capture_step()            # 3 warm-up steps inside, then every train_step() is a graph replay
+    for _ in range(3):
+        sa.train_step()
+        sb.train_step()
+    for k in range(6):
+        sa.train_step()
+        sb.train_step()
+        sc.train_step()
+        la, lb = sa.opt.losses.detach().cpu().numpy(), sb.opt.losses.detach().cpu().numpy()
+        np.testing.assert_allclose(la, lb, rtol=5e-4)
+    # the captured solver has made the same number of updates (capture itself executes nothing): 3 warm-up + 6 replays
+    assert float(sc.opt.step_dev[0]) == float(sa.opt.step_dev[0]) == 9.0
+    np.testing.assert_allclose(sc.opt.losses.detach().cpu().numpy(), sa.opt.losses.detach().cpu().numpy(), rtol=5e-4)
+    pa, pb, pc = _flat(nets[0]), _flat(nets[1]), _flat(nets[2])
+    assert float((pa - pc).norm() / pa.norm()) < 1e-4
+    assert sa.core.op.stats["fwd_calls"] == 0         # no autograd forward: one fwd_bwd per term per step
+
+
+class _LRAdaptorPort(torch.optim.Optimizer):
+    """Test-side restatement of the reference's LR_Adaptor.step (src/optimizer/lr_adaptor.py:27-64) on torch tensors
+    (device-agnostic: the reference's `torch.as_tensor(self.loss_weight)` of a host array becomes an explicit device copy)."""
+
+    def __init__(self, optimizer, loss_weight, num_pde, alpha=0.1):
+        super().__init__(optimizer.param_groups, dict(alpha=alpha))
+        self.optimizer, self.loss_weight, self.num_pde, self.alpha = optimizer, loss_weight, num_pde, alpha
+
+    @torch.no_grad()
+    def step(self, closure):
+        with torch.enable_grad():
+            closure(skip_backward=True)
+            dev = self.losses.device
+            losses = self.losses / torch.as_tensor(self.loss_weight, dtype=torch.float32).to(dev)
+            pde_loss = torch.sum(losses[:self.num_pde])
+        self.zero_grad()
+        pde_loss.backward(retain_graph=True)
+        m_grad_r = max(torch.max(torch.abs(p.grad)).item() for g in self.param_groups for p in g["params"] if p.grad is not None)
+        for i in range(self.num_pde, len(self.loss_weight)):
+            with torch.enable_grad():
+                self.zero_grad()
+                losses[i].backward(retain_graph=True)
+            s, c = 0.0, 0
+            for g in self.param_groups:
+                for p in g["params"]:
+                    if p.grad is not None:
+                        s += torch.sum(torch.abs(p.grad)).item()
+                        c += p.grad.numel()
+            lambda_hat = m_grad_r / ((s / c) * self.loss_weight[i])
+            self.loss_weight[i] = (1 - self.alpha) * self.loss_weight[i] + self.alpha * lambda_hat
+        with torch.enable_grad():
+            self.zero_grad()
+            total = torch.sum(losses * torch.as_tensor(self.loss_weight, dtype=torch.float32).to(dev))
+            total.backward()
+        self.optimizer.step()
+        return total
+
+
+@pytest.mark.parametrize("pde_w", [1.0, None])
+def test_fused_lra_follows_reference_algorithm(pde_w):
+    """NS2D_LidDriven + learning-rate annealing (BASELINE configs[2]): the row-based FusedLRA against the reference's
+    algorithm run through autograd (one backward per term, host-side statistics) on the same fused losses."""
+    from pinnacle_b200.optim import FlatAdam, FusedLRA
+    from pinnacle_b200.solver import FusedPDESolver
+    dev = torch.device("cuda:0")
+    spec, x, xb, terms = _ns_problem(dev)
+    w0 = np.ones(8) if pde_w is not None else np.array([1.0, 2.0, 0.5, 1.0, 1.0, 1.0, 1.0, 1.0])
+    net_a, net_b = _net(spec.desc, dev, 9), _net(spec.desc, dev, 9)
+    wa, wb = w0.copy(), w0.copy()
+    sa = FusedPDESolver(spec, net_a, x, xb, terms)
+    sa.compile(FusedLRA(FlatAdam(net_a.parameters(), lr=1e-3), wa, 3), loss_weights=wa)
+    sb = FusedPDESolver(spec, net_b, x, xb, terms)
+    sb.compile(_LRAdaptorPort(torch.optim.Adam(net_b.parameters(), lr=1e-3), wb, 3), loss_weights=wb)
+    for k in range(6):
+        ta = sa.train_step()
+        tb = sb.train_step()
+        assert abs(float(ta) - float(tb)) <= 2e-3 * abs(float(tb)), (k, float(ta), float(tb))
+        np.testing.assert_allclose(sa.opt.sync_loss_weight(), wb, rtol=2e-3)
+    assert not np.allclose(wb[3:], 1.0)
+    np.testing.assert_array_equal(wa[:3], w0[:3])
+    pa, pb = _flat(net_a), _flat(net_b)
+    assert float((pa - pb).norm() / pb.norm()) < 2e-3

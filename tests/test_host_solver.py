@@ -201,3 +201,39 @@ def test_flux_boundary_terms_take_the_fused_path(name, n_flux):
         fused.FusedPDEResidual.__init__ = orig
     assert made.count(kinds.KIND_FLUX) == n_flux
     np.testing.assert_allclose(losses.detach().numpy(), ref_losses.detach().numpy(), rtol=2e-5)
+
+
+def test_term_gradient_rows_equal_per_term_autograd_backward():
+    """FusedPDESolver.term_gradient_rows (host logic of the autograd-free optimizers, oracle as compute backend): row t is
+    what losses[t].backward() leaves in p.grad, the loss vector is the unweighted one."""
+    from pinnacle_b200 import fused, problems
+    from pinnacle_b200.solver import FusedPDESolver, ValueBC
+    spec = problems.make("NS2D_LidDriven")
+    x = spec.sample(160, seed=1)
+    xb = spec.sample(48, seed=2)
+    terms = [ValueBC(0, 32, 0, np.ones((32, 1), np.float32)), ValueBC(32, 48, 2, np.zeros((16, 1), np.float32))]
+    net = _net(spec.desc)
+    orig = fused.FusedPDEResidual.__init__
+
+    def init_cpu(self, spec, H=100, L=5, policy="auto", device=None, group=None, check_library=True):
+        orig(self, spec, H, L, policy, "cpu", group, False)
+
+    fused.FusedPDEResidual.__init__ = init_cpu
+    try:
+        with oracle_backend():
+            s = FusedPDESolver(spec, net, x, xb, terms, device="cpu").compile(torch.optim.Adam(net.parameters(), 1e-3))
+            flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+            G, L = s.term_gradient_rows(flat, torch.eye(3))
+            G, L = G.clone(), L.clone()
+            _, losses = s.outputs_losses_train()
+            np.testing.assert_allclose(L.numpy(), losses.detach().numpy(), rtol=1e-5)
+            assert G.shape == (5, spec.desc.n_params)
+            for t in range(5):
+                net.zero_grad()
+                losses[t].backward(retain_graph=True)
+                g = torch.cat([(torch.zeros_like(p) if p.grad is None else p.grad).reshape(-1) for p in net.parameters()])
+                assert (G[t] - g).norm() <= 2e-5 * g.norm()
+            G1, _ = s.term_gradient_rows(flat, torch.tensor([[1.0, 2.0, 0.5]]))
+            assert (G1[0] - (G[0] + 2 * G[1] + 0.5 * G[2])).norm() <= 2e-5 * G1[0].norm()
+    finally:
+        fused.FusedPDEResidual.__init__ = orig

@@ -70,7 +70,11 @@ def oracle_fwd_bwd(desc, params, x, aux, inv_n_global, seeds, out=None):
     from oracle import autograd_ref as O
     with torch.enable_grad():
         losses, grads, _ = O.losses_and_grads(desc, params.detach(), x, aux, seeds=seeds, inv_n=inv_n_global)
-    return torch.cat([grads.reshape(-1), losses]).to(torch.float32)
+    res = torch.cat([grads.reshape(-1), losses]).to(torch.float32)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
 
 
 class oracle_backend:
