@@ -20,6 +20,7 @@
 // 25-27 the same for the kinds whose only second derivatives are u_xx + u_yy: NS2D (d=2, m=3), Burgers2D / Gray-Scott
 //       (d=3, m=2), NS2D_LongTime (d=3, m=3); Heat2D_LongTime uses 22
 // 19-20 flux-type boundary terms (PINN_KIND_FLUX: Neumann / affine Robin): first-order signatures (1,1), (1,1,1), m = 1
+// 28    the same for the 6-dimensional Neumann term of HeatND (heat.py:296-301): (1,1,1,1,1,1)
 #pragma once
 
 #define PINN_FOR_EACH_CONFIG(X)        \
@@ -50,6 +51,7 @@
   X(24, 100, 1, 16, 2, 16, -6)             \
   X(25, 100, 3, 32, 4, 32, -2)             \
   X(26, 100, 2, 32, 4, 32, -3)             \
-  X(27, 100, 3, 32, 4, 32, -3)
+  X(27, 100, 3, 32, 4, 32, -3)             \
+  X(28, 100, 1, 16, 2, 0, 1, 1, 1, 1, 1, 1)
 
-#define PINN_NUM_CONFIGS 28
+#define PINN_NUM_CONFIGS 29

@@ -35,6 +35,66 @@ ValueBC = namedtuple("ValueBC", ["beg", "end", "component", "values"])
 FluxBC = namedtuple("FluxBC", ["beg", "end", "component", "normals", "values", "beta"], defaults=[None])
 
 
+# A periodic boundary term on BC rows [beg, end): rows [beg, mid) are the boundary points, rows [mid, end) their periodic
+# images, error = u[beg:mid, component] - u[mid:end, component] (PeriodicBC.error with derivative_order = 0,
+# deepxde/icbc/boundary_conditions.py:108-134).  Fused through the VALUE kind, see _PeriodicLossFn.
+PeriodicPairBC = namedtuple("PeriodicPairBC", ["beg", "end", "component"])
+
+
+class _PeriodicLossFn(torch.autograd.Function):
+    """mean_i (u(xl_i) - u(xr_i))^2 through the VALUE kernels, which only know r = u - g with a given target g.
+
+    Pass 1 (forward only, zero targets, residual matrix out) yields u at all 2n rows.  Pass 2 runs the VALUE term on the
+    2n rows with every row's target set to the (frozen) value at its partner row: its loss is
+    (1/2n) [sum (ul - ur)^2 + sum (ur - ul)^2] = the periodic loss, and its gradient with frozen targets is
+    (1/n) sum (ul - ur)(grad ul - grad ur) = HALF the true gradient -- hence the seed 2."""
+
+    @staticmethod
+    def forward(ctx, op: FusedPDEResidual, *params: torch.Tensor):
+        from . import fused as _fused
+        flat = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
+        need_grad = any(ctx.needs_input_grad[1:])
+        ctx.shapes = [p.shape for p in params]
+        ctx.g = None
+        loss, row = _periodic_eval(op, flat, need_grad, None)
+        ctx.g = row
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.g is None:
+            return (None,) + tuple(None for _ in ctx.shapes)
+        flat_grad = ctx.g * g.detach().to(torch.float32).reshape(())
+        grads, off = [], 0
+        for i, shp in enumerate(ctx.shapes):
+            n = int(np.prod(shp))
+            grads.append(flat_grad[off:off + n].view(shp) if ctx.needs_input_grad[1 + i] else None)
+            off += n
+        return (None,) + tuple(grads)
+
+
+def _periodic_eval(op: FusedPDEResidual, flat: torch.Tensor, want_grad: bool, out: Optional[torch.Tensor]):
+    """(loss [1], gradient row [P] or None) of a periodic term whose 2n rows (left block, right block) live in `op`."""
+    from . import fused as _fused
+    n2 = op.x.shape[0]
+    n = n2 // 2
+    zero = getattr(op, "_zero_targets", None)
+    if zero is None or zero.shape[0] != n2:
+        zero = op._zero_targets = torch.zeros(n2, 1, dtype=torch.float32, device=op.x.device)
+        op._two = torch.full((1, 1), 2.0, dtype=torch.float32, device=op.x.device)
+    _, u = _fused._backend_fwd(op.desc, flat, op.x, zero, op.inv_n_global, True)
+    op.stats["fwd_calls"] += 1
+    targets = torch.cat([u[n:], u[:n]]).contiguous()
+    if not want_grad:
+        loss, _ = _fused._backend_fwd(op.desc, flat, op.x, targets, op.inv_n_global)
+        op.stats["fwd_calls"] += 1
+        return loss, None
+    res = _fused._backend_fwd_bwd(op.desc, flat, op.x, targets, op.inv_n_global, op._two, out=out)
+    op.stats["fwd_bwd_calls"] += 1
+    P = op.desc.n_params
+    return res[P:].clone() if out is None else res[P:], res[:P]
+
+
 def _flux_aux(f: "FluxBC") -> np.ndarray:
     """aux columns of a FLUX term: [g, beta (optional), n_0 .. n_{d-1}]."""
     n = f.end - f.beg
@@ -111,6 +171,16 @@ class _StepCore:
             ent = self._value_ops[idx]
         return ent[0]
 
+    def periodic_op(self, idx: int, beg: int, end: int, component: int) -> FusedPDEResidual:
+        if (end - beg) % 2:
+            raise capi.FusedOpError(f"periodic term {idx}: odd number of rows ({end - beg}); rows must come as (points, images)")
+        d, H, L, m = self._shape
+        return self.term_op(idx, beg, end, value_desc(d, m, int(component)), lambda: np.zeros((end - beg, 1), np.float32))
+
+    def periodic_term_loss(self, idx: int, beg: int, end: int, component: int):
+        """mean (u[beg:mid, c] - u[mid:end, c])^2 (PeriodicBC, derivative_order 0) through the fused VALUE kernels."""
+        return _PeriodicLossFn.apply(self.periodic_op(idx, beg, end, component), *self.params)
+
     def value_term_loss(self, idx: int, beg: int, end: int, component: int, values_fn):
         """u[beg:end, component] - values (DirichletBC / IC / PointSetBC)."""
         d, H, L, m = self._shape
@@ -181,7 +251,7 @@ class FusedPDESolver:
         terms = [pde_losses]
         outputs_ = None
         if self.n_bc > 0:
-            need_torch = any(not isinstance(f, (ValueBC, FluxBC)) for f in self.bc_terms) or not self.bc_terms
+            need_torch = any(not isinstance(f, (ValueBC, FluxBC, PeriodicPairBC)) for f in self.bc_terms) or not self.bc_terms
             x_bc = y_bc = None
             if need_torch:
                 x_bc = core._x_bc.detach().requires_grad_(True)
@@ -199,6 +269,11 @@ class FusedPDESolver:
                     else:
                         terms.append(core.fused_term_loss(i, f.beg, f.end, flux_desc(core._shape[0], core._shape[3], int(f.component), f.beta is not None),
                                                           lambda f=f: _flux_aux(f)))
+                elif isinstance(f, PeriodicPairBC):
+                    if f.end - f.beg == 0:
+                        terms.append(torch.full((1,), float("nan"), device=pde_losses.device))
+                    else:
+                        terms.append(core.periodic_term_loss(i, f.beg, f.end, f.component))
                 else:
                     terms.append(_mse(f(x_bc, y_bc)).reshape(1))
         losses = torch.cat(terms)
@@ -223,8 +298,8 @@ class FusedPDESolver:
         core = self.core
         core.stage(self.train_x, self.n_bc)
         for f in self.bc_terms:
-            if not isinstance(f, (ValueBC, FluxBC)):
-                raise capi.FusedOpError("term_gradient_rows() needs every boundary term on the fused path (ValueBC / FluxBC)")
+            if not isinstance(f, (ValueBC, FluxBC, PeriodicPairBC)):
+                raise capi.FusedOpError("term_gradient_rows() needs every boundary term on the fused path (ValueBC / FluxBC / PeriodicPairBC)")
             if f.end - f.beg == 0:
                 raise capi.FusedOpError("term_gradient_rows(): boundary term without rows")
         op = core.op
@@ -247,11 +322,15 @@ class FusedPDESolver:
         losses[:n_pde].copy_(out[S * P:])
         d, m = core._shape[0], core._shape[3]
         for i, f in enumerate(self.bc_terms):
+            o = buf[(S + i) * P:(S + i) * P + P + 1]
+            if isinstance(f, PeriodicPairBC):
+                _periodic_eval(core.periodic_op(i, f.beg, f.end, f.component), flat, True, o)
+                losses[n_pde + i:n_pde + i + 1].copy_(o[P:])
+                continue
             if isinstance(f, ValueBC):
                 bop = core.term_op(i, f.beg, f.end, value_desc(d, m, int(f.component)), lambda f=f: f.values)
             else:
                 bop = core.term_op(i, f.beg, f.end, flux_desc(d, m, int(f.component), f.beta is not None), lambda f=f: _flux_aux(f))
-            o = buf[(S + i) * P:(S + i) * P + P + 1]
             _fused._backend_fwd_bwd(bop.desc, flat, bop.x, bop.aux, bop.inv_n_global, self._one_seed, out=o)
             bop.stats["fwd_bwd_calls"] += 1
             losses[n_pde + i:n_pde + i + 1].copy_(o[P:])
@@ -310,7 +389,7 @@ class FusedPDESolver:
             if self.opt.solver is None:
                 self.opt.attach(self)
             return self.opt.step()
-        if isinstance(self.opt, FlatAdam) and all(isinstance(f, (ValueBC, FluxBC)) and f.end > f.beg for f in self.bc_terms):
+        if isinstance(self.opt, FlatAdam) and all(isinstance(f, (ValueBC, FluxBC, PeriodicPairBC)) and f.end > f.beg for f in self.bc_terms):
             return self.opt.fused_step(self)
         return None
 
@@ -379,7 +458,8 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
         if n_bc > 0:
             bcs_start = np.cumsum([0] + list(data.num_bcs))
             flux = [(_flux_bc_info(bc, core) if fuse_bcs else None) for bc in data.bcs]
-            fused_ok = [fuse_bcs and (_value_bc_info(bc) is not None or flux[i] is not None) for i, bc in enumerate(data.bcs)]
+            periodic = [fuse_bcs and _periodic_bc_component(bc) is not None for bc in data.bcs]
+            fused_ok = [fuse_bcs and (_value_bc_info(bc) is not None or flux[i] is not None or periodic[i]) for i, bc in enumerate(data.bcs)]
             x_bc = y_bc = None
             if not all(fused_ok):
                 x_bc = core._x_bc.detach().requires_grad_(True)
@@ -387,7 +467,13 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
                 outputs_ = y_bc
             for i, bc in enumerate(data.bcs):
                 beg, end = int(bcs_start[i]), int(bcs_start[i + 1])
-                if fused_ok[i] and flux[i] is not None:
+                if fused_ok[i] and periodic[i]:
+                    # PeriodicBC (derivative_order 0): u_c(points) - u_c(images), rows come as (points, images)
+                    if end == beg:
+                        terms.append(torch.full((1,), float("nan"), device=pde_losses.device))
+                    else:
+                        terms.append(core.periodic_term_loss(i, beg, end, _periodic_bc_component(bc)))
+                elif fused_ok[i] and flux[i] is not None:
                     # NeumannBC / affine RobinBC: n.grad u_c + beta u_c - g, term data evaluated once per point set
                     fdesc, aux_fn = flux[i]
                     if end == beg:
@@ -506,6 +592,14 @@ def _value_bc_info(bc):
     return None
 
 
+def _periodic_bc_component(bc):
+    """Output component of a PeriodicBC with derivative_order 0 (icbc/boundary_conditions.py:108-134), else None."""
+    if type(bc).__name__ != "PeriodicBC" or getattr(bc, "derivative_order", None) != 0:
+        return None
+    comp = getattr(bc, "component", None)
+    return int(comp) if isinstance(comp, (int, np.integer)) else None
+
+
 def _flux_bc_info(bc, core):
     """(descriptor, aux_fn(X, beg, end)) when `bc` is a flux-type term the FLUX kind covers, else None:
     NeumannBC.error = n.grad u_c - func(x) and RobinBC.error = n.grad u_c - func(x, u) with func affine in u
@@ -514,7 +608,7 @@ def _flux_bc_info(bc, core):
     name = type(bc).__name__
     comp = getattr(bc, "component", None)
     d, H, L, m = core._shape
-    if name not in ("NeumannBC", "RobinBC") or not isinstance(comp, (int, np.integer)) or m != 1 or d not in (2, 3):
+    if name not in ("NeumannBC", "RobinBC") or not isinstance(comp, (int, np.integer)) or m != 1:
         return None
     if not capi.supported(flux_desc(d, m, int(comp), True)):
         return None

@@ -206,7 +206,7 @@ def test_value_bc_kind_matches_oracle(d, m, comp, n):
     assert_parity(out[:desc.n_params].cpu().numpy(), og[0].numpy(), "grad")
 
 
-@pytest.mark.parametrize("d,with_beta,n", [(2, False, 129), (2, True, 1), (2, True, 2049), (3, False, 513), (3, True, 8193)])
+@pytest.mark.parametrize("d,with_beta,n", [(2, False, 129), (2, True, 1), (2, True, 2049), (3, False, 513), (3, True, 8193), (6, False, 2049), (6, True, 33)])
 def test_flux_bc_kind_matches_oracle(d, with_beta, n):
     """Fused flux-type boundary term (kind FLUX: NeumannBC.error / affine RobinBC.error) vs the oracle."""
     from oracle import autograd_ref as O

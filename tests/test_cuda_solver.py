@@ -157,3 +157,37 @@ def test_flux_term_steps_match_stock_autograd():
     pa = torch.cat([p.detach().reshape(-1) for p in net_a.parameters()])
     pb = torch.cat([p.detach().reshape(-1) for p in net_b.parameters()])
     assert float((pa - pb).norm() / pb.norm()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_periodic_term_matches_stock_autograd():
+    """PeriodicBC (derivative_order 0): u_c(points) - u_c(images) through the fused VALUE kernels (PeriodicPairBC) vs the same
+    term written on the network outputs (icbc/boundary_conditions.py:125-134): losses, gradients, three Adam steps."""
+    from pinnacle_b200 import problems
+    from pinnacle_b200.solver import FusedPDESolver, PeriodicPairBC
+    dev = torch.device("cuda:0")
+    spec = problems.make("Burgers2D")
+    x = spec.sample(1024, seed=3)
+    nb = 257
+    left = spec.sample(nb, seed=4)
+    right = left.copy()
+    left[:, 0], right[:, 0] = 0.0, 4.0
+    xb = np.vstack([left, right]).astype(np.float32)
+    net_a, net_b = _net(spec.desc, dev, 13), _net(spec.desc, dev, 13)
+    sa = FusedPDESolver(spec, net_a, x, xb, [PeriodicPairBC(0, 2 * nb, 0), PeriodicPairBC(0, 2 * nb, 1)]).compile(
+        torch.optim.Adam(net_a.parameters(), 1e-3))
+    sb = FusedPDESolver(spec, net_b, x, xb, [lambda xbt, ybt: ybt[:nb, 0:1] - ybt[nb:, 0:1], lambda xbt, ybt: ybt[:nb, 1:2] - ybt[nb:, 1:2]]).compile(
+        torch.optim.Adam(net_b.parameters(), 1e-3))
+    _, la = sa.outputs_losses_train()
+    _, lb = sb.outputs_losses_train()
+    np.testing.assert_allclose(la.detach().cpu().numpy(), lb.detach().cpu().numpy(), rtol=2e-5)
+    for k in (2, 3):
+        net_a.zero_grad(); net_b.zero_grad()
+        la[k].backward(retain_graph=True); lb[k].backward(retain_graph=True)
+        ga = torch.cat([p.grad.reshape(-1) for p in net_a.parameters()])
+        gb = torch.cat([p.grad.reshape(-1) for p in net_b.parameters()])
+        assert float((ga - gb).norm() / gb.norm()) < 2e-5
+    for _ in range(3):
+        sa.train_step()
+        sb.train_step()
+        np.testing.assert_allclose(sa.opt.losses.detach().cpu().numpy(), sb.opt.losses.detach().cpu().numpy(), rtol=5e-4)

@@ -91,7 +91,7 @@ def _flux_case(d, with_beta, seed, n=61):
 def test_flux_kind_matches_oracle(harness_lib):
     """Flux-type boundary term (Neumann / affine Robin: kind FLUX, first-order jets) of the device math vs the oracle."""
     from oracle import autograd_ref as O
-    for d, with_beta in ((2, False), (2, True), (3, False), (3, True)):
+    for d, with_beta in ((2, False), (2, True), (3, False), (3, True), (6, False), (6, True)):
         desc, flat, x, aux = _flux_case(d, with_beta, 7 * d + with_beta)
         ol, og, orr = O.losses_and_grads(desc, torch.as_tensor(flat).double(), torch.as_tensor(x).double(), torch.as_tensor(aux).double())
         n, P = x.shape[0], desc.n_params

@@ -97,7 +97,7 @@ def test_solver_adam_steps_follow_oracle_training():
 
 @needs_ref
 @pytest.mark.parametrize("name", ["Burgers1D", "Poisson2D_Classic", "NS2D_LidDriven", "Wave1D", "Heat2D_ComplexGeometry", "Poisson2D_ManyArea",
-                                  "Wave2D_LongTime"])
+                                  "Wave2D_LongTime", "Burgers2D", "HeatND"])
 def test_patched_dde_model_matches_unpatched_reference_step(name):
     """Same weights, same points: losses and p.grad of the reference closure vs the patched closure."""
     import copy
@@ -170,10 +170,10 @@ def test_unsupported_problems_raise():
 
 
 @needs_ref
-@pytest.mark.parametrize("name,n_flux", [("Wave1D", 1), ("Heat2D_ComplexGeometry", 3), ("Poisson2D_ManyArea", 1), ("HeatND", 0)])
+@pytest.mark.parametrize("name,n_flux", [("Wave1D", 1), ("Heat2D_ComplexGeometry", 3), ("Poisson2D_ManyArea", 1), ("HeatND", 1)])
 def test_flux_boundary_terms_take_the_fused_path(name, n_flux):
-    """NeumannBC and affine RobinBC terms (d <= 3, m = 1) are evaluated by the fused op (kind FLUX), not by stock autograd;
-    the 6-dimensional Neumann term of HeatND stays on the stock path."""
+    """NeumannBC and affine RobinBC terms (m = 1) are evaluated by the fused op (kind FLUX), not by stock autograd --
+    including the 6-dimensional Neumann term of HeatND."""
     dde, _ = refshim.load()
     from pinnacle_b200 import fused, kinds
     from pinnacle_b200.solver import enable_fused
@@ -235,5 +235,40 @@ def test_term_gradient_rows_equal_per_term_autograd_backward():
                 assert (G[t] - g).norm() <= 2e-5 * g.norm()
             G1, _ = s.term_gradient_rows(flat, torch.tensor([[1.0, 2.0, 0.5]]))
             assert (G1[0] - (G[0] + 2 * G[1] + 0.5 * G[2])).norm() <= 2e-5 * G1[0].norm()
+    finally:
+        fused.FusedPDEResidual.__init__ = orig
+
+
+@needs_ref
+def test_every_boundary_term_of_burgers2d_and_heatnd_is_fused():
+    """Burgers2D: 2 IC + 4 PeriodicBC terms; HeatND: IC + 6-dimensional NeumannBC -- no stock-autograd BC evaluation is left
+    (the net is never called on the BC rows in training mode)."""
+    dde, _ = refshim.load()
+    from pinnacle_b200 import fused
+    from pinnacle_b200.solver import enable_fused
+    orig = fused.FusedPDEResidual.__init__
+
+    def init_cpu(self, spec, H=100, L=5, policy="auto", device=None, group=None, check_library=True):
+        orig(self, spec, H, L, policy, "cpu", group, False)
+
+    fused.FusedPDEResidual.__init__ = init_cpu
+    try:
+        for name in ("Burgers2D", "HeatND"):
+            torch.manual_seed(0)
+            pde = refshim.construct(name)
+            pde.training_points(domain=64, boundary=48, initial=32)
+            net = dde.nn.FNN([pde.input_dim] + [100] * 5 + [pde.output_dim], "tanh", "Glorot normal").float()
+            model = pde.create_model(net)
+            model.compile(torch.optim.Adam(net.parameters(), 1e-3), loss_weights=np.ones(pde.num_loss))
+            net.auxiliary_vars = None
+            calls = []
+            fwd = net.forward
+            net.forward = lambda x, fwd=fwd: (calls.append(x.shape), fwd(x))[1]
+            with oracle_backend():
+                enable_fused(model)
+                _, losses = model.outputs_losses_train(model.data.train_x, None)
+                losses.sum().backward()
+            assert calls == [], (name, calls)
+            assert losses.shape[0] == pde.num_loss and torch.isfinite(losses).all()
     finally:
         fused.FusedPDEResidual.__init__ = orig
