@@ -196,6 +196,42 @@ class FusedPDEResidual:
         return res
 
 
+def _is_adaptive_activation_net(net) -> bool:
+    """DNN_LAAF / DNN_GAAF of src/model/laaf.py (benchmark.py --method laaf / gaaf): Sequential of LAAFlayer(fc, n, a) + Linear."""
+    layers = getattr(net, "layers", None)
+    if layers is None or not isinstance(getattr(net, "a", None), torch.Tensor) or len(layers) < 3:
+        return False
+    return all(hasattr(l, "fc") and hasattr(l, "a") and hasattr(l, "n") for l in list(layers)[:-1]) and isinstance(layers[-1], torch.nn.Linear)
+
+
+def adaptive_activation_params(net) -> List[torch.Tensor]:
+    """Effective FNN parameters of a layer-wise / global adaptive-activation net (src/model/laaf.py:5-80).
+
+    LAAFlayer computes tanh(n * a * (W x + b)) with a trainable slope a (per neuron: DNN_LAAF, per layer: DNN_GAAF) and
+    the constant n = 10.  That IS a plain tanh layer with W' = diag(n a) W, b' = n a * b, so the fused kernels run
+    unchanged on (W', b') and autograd carries their gradient rows back to W, b and a through these few element-wise
+    products (dL/da = n * (sum_i dL/dW'_ji W_ji + dL/db'_j b_j), summed over neurons for the global variant)."""
+    out = []
+    layers = list(net.layers)
+    for lay in layers[:-1]:
+        if not isinstance(lay.activation, torch.nn.Tanh):
+            raise capi.FusedOpError(f"fused path supports the tanh activation only (got {lay.activation!r})")
+        s = (lay.n * lay.a).reshape(-1)                    # [H] (LAAF) or [1] (GAAF)
+        out += [s.reshape(-1, 1) * lay.fc.weight, s * lay.fc.bias]
+    out += [layers[-1].weight, layers[-1].bias]
+    return out
+
+
+def net_param_provider(net):
+    """(fn, dynamic): ``fn()`` returns the 2(L+1) effective ``nn.Linear``-order tensors the fused op differentiates with
+    respect to.  Plain FNN: the parameters themselves (static list).  Adaptive-activation nets: recomputed from the live
+    W, b, a on every call (dynamic)."""
+    if _is_adaptive_activation_net(net):
+        return (lambda: adaptive_activation_params(net)), True
+    params = net_linear_params(net)
+    return (lambda: params), False
+
+
 def net_linear_params(net) -> List[torch.Tensor]:
     """The 2(L+1) nn.Linear tensors of a dde.nn.FNN-style net, in net.parameters() order
     (deepxde/nn/pytorch/fnn.py:25-33), after checking the net is one the fused path supports."""
@@ -216,8 +252,8 @@ def net_linear_params(net) -> List[torch.Tensor]:
 
 
 def net_shape(net):
-    """(d, H, L, m) of an FNN; raises when hidden widths differ."""
-    lins = list(net.linears)
+    """(d, H, L, m) of an FNN (or of the FNN an adaptive-activation net is equivalent to); raises when hidden widths differ."""
+    lins = [l.fc for l in list(net.layers)[:-1]] + [net.layers[-1]] if _is_adaptive_activation_net(net) else list(net.linears)
     d = lins[0].in_features
     H = lins[0].out_features
     m = lins[-1].out_features

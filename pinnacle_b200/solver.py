@@ -23,7 +23,7 @@ import torch
 from collections import namedtuple
 
 from . import capi
-from .fused import FusedPDEResidual, net_linear_params, net_shape
+from .fused import FusedPDEResidual, net_linear_params, net_param_provider, net_shape
 from .kinds import flux_desc, value_desc
 from .problems import ProblemSpec, describe_reference
 
@@ -133,7 +133,8 @@ class _StepCore:
         d, H, L, m = net_shape(net)
         if d != spec.desc.d or m != spec.desc.m:
             raise capi.FusedOpError(f"net maps {d}->{m} but problem {spec.name} needs {spec.desc.d}->{spec.desc.m}")
-        self.params = net_linear_params(net)
+        self._param_fn, self.dynamic_params = net_param_provider(net)
+        self.params = self._param_fn()
         self.net = net
         dev = self.params[0].device if device is None else torch.device(device)
         self.op = FusedPDEResidual(spec, H, L, policy=policy, device=dev, group=group)
@@ -170,6 +171,11 @@ class _StepCore:
             self._value_ops[idx] = (op, self.generation)
             ent = self._value_ops[idx]
         return ent[0]
+
+    def refresh_params(self):
+        """Adaptive-activation nets: rebuild the effective (W', b') from the live W, b, a (once per loss evaluation)."""
+        if self.dynamic_params:
+            self.params = self._param_fn()
 
     def periodic_op(self, idx: int, beg: int, end: int, component: int) -> FusedPDEResidual:
         if (end - beg) % 2:
@@ -247,6 +253,7 @@ class FusedPDESolver:
         self.net.train(mode=training)
         core = self.core
         core.stage(inputs, self.n_bc)
+        core.refresh_params()
         pde_losses = core.op.losses(core.params)
         terms = [pde_losses]
         outputs_ = None
@@ -385,6 +392,10 @@ class FusedPDESolver:
     def _flat_optimizer_step(self):
         """Autograd-free step for the optimizers of pinnacle_b200.optim (None when the configuration needs autograd)."""
         from .optim import FlatAdam, FusedLRA
+        if self.core.dynamic_params:
+            if isinstance(self.opt, FusedLRA):
+                raise capi.FusedOpError("FusedLRA works on the flat parameter vector of a plain FNN; adaptive-activation nets need an autograd optimizer")
+            return None        # the flat buffer is not the vector the kernels differentiate with respect to
         if isinstance(self.opt, FusedLRA):
             if self.opt.solver is None:
                 self.opt.attach(self)
@@ -451,9 +462,10 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
         net.train(mode=training)
         n_bc = int(np.sum(data.num_bcs))
         core.stage(inputs, n_bc)
+        core.refresh_params()
         pde_losses = core.op.losses(core.params)
         terms = [pde_losses]
-        training_graph = any(p.requires_grad for p in core.params)
+        training_graph = any(p.requires_grad for p in net.parameters())     # _test() freezes the net (model.py:483-485)
         outputs_ = None
         if n_bc > 0:
             bcs_start = np.cumsum([0] + list(data.num_bcs))
@@ -551,6 +563,7 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
         net.eval()
         op = predict_state["op"]
         op.set_points(x, shard=False)
+        core.refresh_params()
         res = op.residual(core.params).cpu().numpy()                # [N, n_pde]
         if cbs is not None:
             cbs.on_predict_end()

@@ -191,3 +191,41 @@ def test_periodic_term_matches_stock_autograd():
         sa.train_step()
         sb.train_step()
         np.testing.assert_allclose(sa.opt.losses.detach().cpu().numpy(), sb.opt.losses.detach().cpu().numpy(), rtol=5e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["laaf", "gaaf"])
+def test_adaptive_activation_net_gradients_reach_slopes(kind):
+    """DNN_LAAF / DNN_GAAF (src/model/laaf.py): the fused op on the equivalent FNN, gradients w.r.t. W, b and the slopes a
+    against the reference algorithm in fp64 on the CPU."""
+    from oracle import autograd_ref as O
+    from pinnacle_b200 import problems
+    from pinnacle_b200.fused import adaptive_activation_params
+    from pinnacle_b200.nn import DNN_GAAF, DNN_LAAF
+    from pinnacle_b200.solver import FusedPDESolver
+    dev = torch.device("cuda:0")
+    spec = problems.make("Burgers1D")
+    cls = DNN_LAAF if kind == "laaf" else DNN_GAAF
+    torch.manual_seed(4)
+    net = cls(5, 100, 2, 1)
+    with torch.no_grad():
+        net.a.mul_(0.3)
+    net64 = cls(5, 100, 2, 1)
+    net64.load_state_dict(net.state_dict())
+    net64 = net64.double()
+    net = net.to(dev)
+    x = spec.sample(2000, seed=6)
+    solver = FusedPDESolver(spec, net, x).compile(torch.optim.Adam(net.parameters(), 1e-3))
+    _, losses = solver.outputs_losses_train()
+    net.zero_grad()
+    losses.sum().backward()
+    flat = torch.cat([p.reshape(-1) for p in adaptive_activation_params(net64)])
+    ol, _, _ = O.pde_losses(spec.desc, flat, torch.as_tensor(x).double(), None)
+    ol.sum().backward()
+    np.testing.assert_allclose(losses.detach().cpu().numpy(), ol.detach().numpy(), rtol=1e-5)
+    for (n, p), (_, q) in zip(net.named_parameters(), net64.named_parameters()):
+        assert p.grad is not None, n
+        assert float((p.grad.cpu().double() - q.grad).norm()) <= 1e-5 * float(q.grad.norm()), n
+    for _ in range(3):
+        solver.train_step()
+    assert torch.isfinite(solver.opt.losses).all()

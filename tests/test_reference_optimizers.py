@@ -134,3 +134,64 @@ def test_predict_operator_pde_and_rar_wrapper_on_patched_model(name):
             assert np.all(np.isfinite(model.opt.losses.detach().numpy()))
     finally:
         fused.FusedPDEResidual.__init__ = orig
+
+
+@needs_ref
+@pytest.mark.parametrize("name,kind", [("Burgers1D", "laaf"), ("Poisson2D_Classic", "gaaf"), ("NS2D_LidDriven", "laaf")])
+def test_adaptive_activation_nets_on_patched_model(name, kind):
+    """benchmark.py --method laaf / gaaf: the reference's DNN_LAAF / DNN_GAAF (src/model/laaf.py, unmodified) under a patched
+    model -- the fused op runs on the equivalent FNN (W' = diag(10 a) W, b' = 10 a b) and autograd carries the gradient
+    back to W, b AND the slopes a.  Losses, every parameter gradient, the _test() path and three Adam steps."""
+    from pinnacle_b200 import fused
+    from pinnacle_b200.solver import enable_fused
+    dde, _ = refshim.load()
+    from src.model.laaf import DNN_GAAF, DNN_LAAF
+
+    def build():
+        torch.manual_seed(3)
+        dde.config.set_random_seed(3)
+        pde = refshim.construct(name)
+        pde.training_points(domain=128, boundary=48, **({"initial": 48} if hasattr(pde, "num_initial_points") else {}))
+        pde.num_test_points = 64
+        net = (DNN_LAAF if kind == "laaf" else DNN_GAAF)(5, 100, pde.input_dim, pde.output_dim).float()
+        with torch.no_grad():
+            net.a.mul_(0.3)            # slopes 10*a of order one (the xavier init gives |10 a| up to ~3: saturated tanh everywhere)
+        model = pde.create_model(net)
+        model.compile(torch.optim.Adam(net.parameters(), 1e-3), loss_weights=np.ones(pde.num_loss))
+        net.auxiliary_vars = None
+        return model, net
+
+    ref_model, ref_net = build()
+    new_model, new_net = build()
+    x = ref_model.data.train_x
+    _, ref_losses = ref_model.outputs_losses_train(x, None)
+    ref_net.zero_grad()
+    ref_losses.sum().backward()
+    ref_test = ref_model._outputs_losses(False, ref_model.data.test_x, None, None)
+    orig = fused.FusedPDEResidual.__init__
+
+    def init_cpu(self, spec, H=100, L=5, policy="auto", device=None, group=None, check_library=True):
+        orig(self, spec, H, L, policy, "cpu", group, False)
+
+    fused.FusedPDEResidual.__init__ = init_cpu
+    try:
+        with oracle_backend():
+            enable_fused(new_model)
+            assert new_model.fused_core.dynamic_params
+            _, new_losses = new_model.outputs_losses_train(x, None)
+            new_net.zero_grad()
+            new_losses.sum().backward()
+            np.testing.assert_allclose(new_losses.detach().numpy(), ref_losses.detach().numpy(), rtol=5e-5)
+            names = [n for n, _ in ref_net.named_parameters()]
+            assert "a" in names
+            for (n, p), (_, q) in zip(ref_net.named_parameters(), new_net.named_parameters()):
+                rg = torch.zeros_like(p) if p.grad is None else p.grad
+                ng = torch.zeros_like(q) if q.grad is None else q.grad
+                assert (ng - rg).norm() <= 5e-5 * max(float(rg.norm()), 1e-12), (n, float((ng - rg).norm()), float(rg.norm()))
+            new_test = new_model._outputs_losses(False, new_model.data.test_x, None, None)
+            np.testing.assert_allclose(new_test[1], ref_test[1], rtol=5e-5)
+            np.testing.assert_allclose(new_test[0], ref_test[0], rtol=1e-5, atol=1e-6)
+            ref_hist, new_hist = _run(ref_model, 3), _run(new_model, 3)
+            np.testing.assert_allclose(new_hist, ref_hist, rtol=5e-3)
+    finally:
+        fused.FusedPDEResidual.__init__ = orig
