@@ -53,6 +53,18 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_traffic(problem: str):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the fused kernel of `problem`, from the
+    committed `ncu --set full` capture of this same command (profiles/ncu_traffic.json names the capture)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        d = json.load(f)
+    ent = d.get("kernels", {}).get(problem)
+    return (ent["dram_bytes"], d.get("source")) if ent else (None, None)
+
+
 def _seeded_params(desc, seed=0):
     """Glorot-normal weights + N(0,0.1^2) biases ("trained-like" variant), flat fp32."""
     g = torch.Generator().manual_seed(seed)
@@ -78,7 +90,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -354,13 +366,14 @@ def run_fused(args):
             out["executed_tensor_tflops"] = d.tc_executed_flops_per_point(1, capi.effective_channels(d)) * n_per / t / 1e12
         return out
 
+    traffic, traffic_src = _ncu_traffic(specs[dom].name) if n_per == (1 << 20) else (None, None)
     if on_tc:
         c_eff = capi.effective_channels(ops[dom].desc)
         exe_pp = desc.tc_executed_flops_per_point(1, c_eff)
         exe = exe_pp * n_per / (kern_ms[dom] * 1e-3) / 1e12
         roofline = {
             "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak if tensor_peak else None,
-            "traffic": None,
+            "traffic": traffic, "traffic_source": traffic_src, "algorithmic_hbm_bytes": desc.bytes_per_point() * n_per,
             "kernel": f"{'pinn_tc2_kernel' if capi.selected_impl(desc) == 3 else 'pinn_tc_kernel'}<{specs[dom].name}, fwd+reverse> "
                       "(tcgen05 kind::f16, bf16x3 split precision, TMEM accumulators)",
             "launch_ms": kern_ms[dom], "algorithmic_flops_per_point": desc.flops_step_per_point(), "points_per_launch": n_per,
@@ -422,7 +435,7 @@ def run_fused(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--points", type=int, default=1 << 20, help="collocation points per problem per GPU")
     ap.add_argument("--cpu-points", type=int, default=16384, help="points per problem of the bounded CPU sample")

@@ -460,6 +460,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
     // =====================================================================================================
     float4* stash = reinterpret_cast<float4*>(p.stash) + (size_t)blockIdx.x * L * NSUB * C * NEW;
     auto stash_at = [&](int l, int h, int c) -> float4* { return stash + ((size_t)((l - 1) * NSUB + h) * C + c) * NEW + tid; };
+    const bool stash_discard = (reinterpret_cast<uintptr_t>(p.stash) & 127) == 0;
     uint32_t ph[2] = {0, 0}, dph[2] = {0, 0};
     bool dwp[2] = {false, false};          // a dW contraction that reads sub-tile h's arrays may still be running
 
@@ -762,6 +763,15 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
 #pragma unroll
                   for (int c = 0; c < C; ++c) ab[c][pp] = zb[c];
                 }
+#ifndef PINN_NO_STASH_DISCARD
+                // That was the last read of z^l of this tile: drop its (dirty) L2 lines instead of letting L2 write them back
+                // to HBM -- the stash is scratch, rewritten by the next tile.  One 128-byte line per 8 consecutive threads;
+                // the loaded values have been consumed above, so every lane's read of the line has completed.
+                if (stash_discard && s == S - 1 && (lane & 7) == 0) {     // (the other seeds' reverse sweeps still read it)
+#pragma unroll
+                  for (int c = 0; c < C; ++c) asm volatile("discard.global.L2 [%0], 128;" ::"l"(stash_at(l, h, c)) : "memory");
+                }
+#endif
               }
               if (!IS_BOTTOM) {
                 if constexpr (CFG::SHZ) {
