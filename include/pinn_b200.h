@@ -63,7 +63,11 @@ enum pinn_kind {
    * aux_sel[0] = g column, aux_sel[1] = beta column (-1: none), aux_sel[2+j] = column of the outward normal component
    * n_j (deepxde/icbc/boundary_conditions.py:44-57,83-105: NeumannBC.error, RobinBC.error with func affine in u).
    * First-order jets in every direction: signature (1,..,1). */
-  PINN_KIND_FLUX = 9
+  PINN_KIND_FLUX = 9,
+  /* inverse problems with an unknown diffusion field (src/pde/inverse.py:19-24 PoissonInv, 129-136 HeatInv), outputs (u, a):
+   *   r = c0 u_t + c1 div(a grad u) + c2 aux[aux_sel[0]],   div(a grad u) = a (u_xx + u_yy) + a_x u_x + a_y u_y
+   * (the reference differentiates the products a u_x, a u_y).  d = 2 (c0 = 0) or 3 (x, y, t); m = 2; orders (2,2[,1]). */
+  PINN_KIND_DIV_AGRAD = 10
 };
 
 typedef struct pinn_kind_desc {

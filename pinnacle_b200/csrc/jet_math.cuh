@@ -277,6 +277,7 @@ struct Residual {
         case PINN_KIND_BURGERS2D: return M == 2 && D == 3;
         case PINN_KIND_GRAYSCOTT: return M == 2 && D == 3;
         case PINN_KIND_HEAT_NLSRC: return M == 1 && D == 3;
+        case PINN_KIND_DIV_AGRAD: return M == 2 && (D == 2 || D == 3);
         default: return false;
       }
     }
@@ -291,6 +292,7 @@ struct Residual {
       case PINN_KIND_KS: return M == 1 && D == 2 && SIG::order(0) >= 4 && SIG::order(1) >= 1;
       case PINN_KIND_VALUE: return C == 1;
       case PINN_KIND_FLUX: return C == 1 + D && SIG::order(0) == 1;
+      case PINN_KIND_DIV_AGRAD: return M == 2 && sig22() && (D == 2 || (D == 3 && SIG::order(D - 1) >= 1));
       default: return false;
     }
   }
@@ -389,6 +391,17 @@ struct Residual {
             const float lapu = lap_xy(U[0]), lapv = lap_xy(U[1]);
             r[0] = U[0][T1] - (c[0] * lapu + c[2] * (1.0f - u) - u * v * v);
             r[1] = U[1][T1] - (c[1] * lapv - c[3] * v + u * v * v);
+          }
+        }
+      } break;
+      case PINN_KIND_DIV_AGRAD: {
+        if constexpr (M == 2 && (D == 2 || D == 3)) {
+          if constexpr (sig22()) {
+            constexpr int X1 = SIG::chan(0, 1), Y1 = SIG::chan(1, 1);
+            const float a = U[1][0];
+            float acc = c[1] * (a * lap_xy(U[0]) + U[1][X1] * U[0][X1] + U[1][Y1] * U[0][Y1]) + c[2] * aux[kp.aux_sel[0]];
+            if constexpr (D == 3) acc = fmaf(c[0], U[0][SIG::chan(2, 1)], acc);
+            r[0] = acc;
           }
         }
       } break;
@@ -540,6 +553,21 @@ struct Residual {
           }
         }
       } break;
+      case PINN_KIND_DIV_AGRAD: {
+        if constexpr (M == 2 && (D == 2 || D == 3)) {
+          if constexpr (sig22()) {
+            constexpr int X1 = SIG::chan(0, 1), Y1 = SIG::chan(1, 1);
+            const float g = c[1] * rb[0];
+            lap_xy_adj(Ub[0], g * U[1][0]);
+            Ub[0][X1] = g * U[1][X1];
+            Ub[0][Y1] = g * U[1][Y1];
+            Ub[1][0] = g * lap_xy(U[0]);
+            Ub[1][X1] = g * U[0][X1];
+            Ub[1][Y1] = g * U[0][Y1];
+            if constexpr (D == 3) Ub[0][SIG::chan(2, 1)] = c[0] * rb[0];
+          }
+        }
+      } break;
       case PINN_KIND_KS: {
         if constexpr (M == 1 && D == 2) {
           if constexpr (SIG::order(0) >= 4 && SIG::order(1) >= 1) {
@@ -579,11 +607,13 @@ struct Residual {
 //  * LINEAR kind, one output: no direction beyond second order, at least two second-order directions (else nothing is
 //    saved), one common per-point multiplier (or none) on the second-order terms; weights = c2_j;
 //  * the kinds whose only second derivatives are u_xx + u_yy (NS2D, NS2D_UNSTEADY, BURGERS2D, GRAYSCOTT, HEAT_NLSRC)
-//    with their canonical orders (2,2) / (2,2,1); weights = (1, 1, 0).
+//    and DIV_AGRAD (outputs u, a) with their canonical orders (2,2) / (2,2,1); weights = (1, 1, 0).
 inline bool lap_eligible(int kind, int d, int m, const int* order, const int* aux_sel, const float* consts) {
   if (kind == PINN_KIND_NS2D) return d == 2 && m == 3 && order[0] == 2 && order[1] == 2;
   if (kind == PINN_KIND_NS2D_UNSTEADY || kind == PINN_KIND_BURGERS2D || kind == PINN_KIND_GRAYSCOTT || kind == PINN_KIND_HEAT_NLSRC)
     return d == 3 && order[0] == 2 && order[1] == 2 && order[2] == 1;
+  if (kind == PINN_KIND_DIV_AGRAD)
+    return m == 2 && order[0] == 2 && order[1] == 2 && (d == 2 || (d == 3 && order[2] == 1));
   if (kind != PINN_KIND_LINEAR || m != 1 || d < 2) return false;
   int n2 = 0, sel = -2;
   for (int j = 0; j < d; ++j) {

@@ -20,6 +20,7 @@
 // 25-27 the same for the kinds whose only second derivatives are u_xx + u_yy: NS2D (d=2, m=3), Burgers2D / Gray-Scott
 //       (d=3, m=2), NS2D_LongTime (d=3, m=3); Heat2D_LongTime uses 22
 // 19-20 flux-type boundary terms (PINN_KIND_FLUX: Neumann / affine Robin): first-order signatures (1,1), (1,1,1), m = 1
+// 29-30 PoissonInv (inverse.py:19-24; outputs u, a): (2,2) m=2 and its forward-Laplacian form LapSig<2> m=2 (HeatInv uses 5 / 26)
 // 28    the same for the 6-dimensional Neumann term of HeatND (heat.py:296-301): (1,1,1,1,1,1)
 #pragma once
 
@@ -52,6 +53,8 @@
   X(25, 100, 3, 32, 4, 32, -2)             \
   X(26, 100, 2, 32, 4, 32, -3)             \
   X(27, 100, 3, 32, 4, 32, -3)             \
-  X(28, 100, 1, 16, 2, 0, 1, 1, 1, 1, 1, 1)
+  X(28, 100, 1, 16, 2, 0, 1, 1, 1, 1, 1, 1) \
+  X(29, 100, 2, 32, 4, 32, 2, 2)           \
+  X(30, 100, 2, 32, 4, 32, -2)
 
-#define PINN_NUM_CONFIGS 29
+#define PINN_NUM_CONFIGS 31

@@ -32,6 +32,7 @@ KIND_GRAYSCOTT = 6       # src/pde/chaotic.py:21-31
 KIND_KS = 7              # src/pde/chaotic.py:77-83
 KIND_VALUE = 8           # value-type BC/IC/point-set term: u_c - g(x)  (icbc/boundary_conditions.py:73-80,214-241)
 KIND_FLUX = 9            # flux-type BC term: n(x).grad u_c + beta(x) u_c - g(x)  (icbc/boundary_conditions.py:44-57,83-105)
+KIND_DIV_AGRAD = 10      # inverse problems, outputs (u, a): c0 u_t + c1 div(a grad u) + c2 src   (inverse.py:19-24, 129-136)
 
 KIND_NAMES = {
     KIND_LINEAR: "linear",
@@ -44,6 +45,7 @@ KIND_NAMES = {
     KIND_KS: "ks",
     KIND_VALUE: "value",
     KIND_FLUX: "flux",
+    KIND_DIV_AGRAD: "div_agrad",
 }
 
 # LINEAR kind constant layout

@@ -286,6 +286,33 @@ def helmholtz2d(scale=1, A=(4, 4), k=1) -> ProblemSpec:
     return ProblemSpec("Helmholtz2D", d, [0, scale, 0, scale], aux)
 
 
+def poisson_inv(bbox=(0, 1, 0, 1)) -> ProblemSpec:
+    # src/pde/inverse.py:19-24   (a u_x)_x + (a u_y)_y + f_src(x),  outputs (u, a);  f_src: inverse.py:69-79
+    def a_ref(x, y):
+        return 1 / (1 + x ** 2 + y ** 2 + (x - 1) ** 2 + (y - 1) ** 2)
+
+    def aux(xy):
+        x, y = _col(xy, 0), _col(xy, 1)
+        return (2 * np.pi ** 2 * torch.sin(np.pi * x) * torch.sin(np.pi * y) * a_ref(x, y)
+                + 2 * np.pi * ((2 * x + 1) * torch.cos(np.pi * x) * torch.sin(np.pi * y)
+                               + (2 * y + 1) * torch.sin(np.pi * x) * torch.cos(np.pi * y)) * a_ref(x, y) ** 2)
+
+    d = KindDesc(K.KIND_DIV_AGRAD, 2, 2, (2, 2), n_pde=1, n_aux=1, consts=[0.0, 1.0, 1.0], aux_sel=[0], name="PoissonInv")
+    return ProblemSpec("PoissonInv", d, list(bbox), aux)
+
+
+def heat_inv(bbox=(-1, 1, -1, 1, 0, 1)) -> ProblemSpec:
+    # src/pde/inverse.py:129-136   u_t - [(a u_x)_x + (a u_y)_y] - f(x),  outputs (u, a);  f: inverse.py:101-113
+    def aux(xyt):
+        x, y, t = _col(xyt, 0), _col(xyt, 1), _col(xyt, 2)
+        s, c, p = torch.sin, torch.cos, np.pi
+        return torch.exp(-t) * ((4 * p ** 2 - 1) * s(p * x) * s(p * y)
+                                + p ** 2 * (2 * s(p * x) ** 2 * s(p * y) ** 2 - c(p * x) ** 2 * s(p * y) ** 2 - s(p * x) ** 2 * c(p * y) ** 2))
+
+    d = KindDesc(K.KIND_DIV_AGRAD, 3, 2, (2, 2, 1), n_pde=1, n_aux=1, consts=[1.0, -1.0, -1.0], aux_sel=[0], name="HeatInv")
+    return ProblemSpec("HeatInv", d, list(bbox), aux)
+
+
 BUILDERS: Dict[str, Callable[..., ProblemSpec]] = {
     "Burgers1D": burgers1d,
     "Burgers2D": burgers2d,
@@ -310,6 +337,8 @@ BUILDERS: Dict[str, Callable[..., ProblemSpec]] = {
     "GrayScottEquation": grayscott,
     "KuramotoSivashinskyEquation": kuramoto_sivashinsky,
     "Helmholtz2D": helmholtz2d,
+    "PoissonInv": poisson_inv,
+    "HeatInv": heat_inv,
 }
 
 
@@ -398,6 +427,10 @@ def describe_reference(pde_obj) -> ProblemSpec:
         spec = kuramoto_sivashinsky(bbox, cv["alpha"], cv["beta"], cv["gamma"])
     elif name == "Helmholtz2D":
         spec = helmholtz2d(cv["scale"], cv["A"], cv["k"])
+    elif name == "PoissonInv":
+        spec = poisson_inv(bbox)
+    elif name == "HeatInv":
+        spec = heat_inv(bbox)
     else:  # pragma: no cover
         raise UnsupportedProblem(name)
     if spec.desc.d != pde_obj.input_dim or spec.desc.m != pde_obj.output_dim or spec.desc.n_pde != pde_obj.num_pde:

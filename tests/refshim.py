@@ -80,8 +80,8 @@ def load():
     import deepxde as dde
     torch.set_default_dtype(torch.float32)
     dde.config.set_default_float("float32")
-    from src.pde import baseclass, burgers, chaotic, heat, helmholtz, ns, poisson, wave
-    _loaded = (dde, dict(baseclass=baseclass, burgers=burgers, chaotic=chaotic, heat=heat, helmholtz=helmholtz, ns=ns,
+    from src.pde import baseclass, burgers, chaotic, heat, helmholtz, inverse, ns, poisson, wave
+    _loaded = (dde, dict(baseclass=baseclass, burgers=burgers, chaotic=chaotic, heat=heat, helmholtz=helmholtz, inverse=inverse, ns=ns,
                          poisson=poisson, wave=wave))
     return _loaded
 
@@ -120,6 +120,7 @@ CLASS_MODULE = {
     "Wave1D": "wave", "Wave2D_Heterogeneous": "wave", "Wave2D_LongTime": "wave",
     "GrayScottEquation": "chaotic", "KuramotoSivashinskyEquation": "chaotic",
     "Helmholtz2D": "helmholtz",
+    "PoissonInv": "inverse", "HeatInv": "inverse",
 }
 
 

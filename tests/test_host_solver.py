@@ -97,7 +97,7 @@ def test_solver_adam_steps_follow_oracle_training():
 
 @needs_ref
 @pytest.mark.parametrize("name", ["Burgers1D", "Poisson2D_Classic", "NS2D_LidDriven", "Wave1D", "Heat2D_ComplexGeometry", "Poisson2D_ManyArea",
-                                  "Wave2D_LongTime", "Burgers2D", "HeatND"])
+                                  "Wave2D_LongTime", "Burgers2D", "HeatND", "PoissonInv", "HeatInv"])
 def test_patched_dde_model_matches_unpatched_reference_step(name):
     """Same weights, same points: losses and p.grad of the reference closure vs the patched closure."""
     import copy
