@@ -519,6 +519,10 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
           if constexpr (SIG::order(jj) >= 1) a[SIG::base(jj)][pp] = w[jj];
         });
       }
+      // The stash keeps t0 = tanh(z_0) in channel 0 instead of z_0: nothing downstream needs z_0 itself (tanh_jet_*_t0),
+      // and the reverse sweep then recomputes a^{l-1} and the adjoint without a transcendental.
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) a[0][pp] = tanh_tc(a[0][pp]);
       if constexpr (BWD) {
 #pragma unroll
         for (int c = 0; c < C; ++c) *stash_at(1, h, c) = make_float4(a[c][0], a[c][1], a[c][2], a[c][3]);
@@ -528,7 +532,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         float z[C], av[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) z[c] = a[c][pp];
-        tanh_jet_fwd<SIG>(z, av, kps->lapw);
+        tanh_jet_fwd_t0<SIG>(z, z[0], av, kps->lapw);
 #pragma unroll
         for (int c = 0; c < C; ++c) a[c][pp] = av[c];
       }
@@ -543,7 +547,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       if (!act) return;
       const float b = bs[(l - 1) * H + j];
 #pragma unroll
-      for (int pp = 0; pp < 4; ++pp) zq[0][pp] += b;
+      for (int pp = 0; pp < 4; ++pp) zq[0][pp] = tanh_tc(zq[0][pp] + b);      // channel 0 holds t0 from here on (see epi_layer1)
       if constexpr (BWD) {
 #pragma unroll
         for (int c = 0; c < C; ++c) *stash_at(l, h, c) = make_float4(zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         float z[C], av[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-        tanh_jet_fwd<SIG>(z, av, kps->lapw);
+        tanh_jet_fwd_t0<SIG>(z, z[0], av, kps->lapw);
 #pragma unroll
         for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
       }
@@ -697,7 +701,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                     float z[C], av[C];
 #pragma unroll
                     for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-                    tanh_jet_fwd<SIG>(z, av, kps->lapw);
+                    tanh_jet_fwd_t0<SIG>(z, z[0], av, kps->lapw);       // z[0] is the stashed t0
 #pragma unroll
                     for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
                   }
@@ -728,7 +732,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                     float z[C], av[C];
 #pragma unroll
                     for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-                    tanh_jet_fwd<SIG>(z, av, kps->lapw);
+                    tanh_jet_fwd_t0<SIG>(z, z[0], av, kps->lapw);       // z[0] is the stashed t0
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                       float v = 0.f;
@@ -751,7 +755,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                     a_[c] = ab[c][pp];
                     zb[c] = 0.f;
                   }
-                  tanh_jet_bwd<SIG>(z, a_, zb, kps->lapw);
+                  tanh_jet_bwd_t0<SIG>(z, z[0], a_, zb, kps->lapw);  // z[0] is the stashed t0
                   dbias += zb[0];
                   if (IS_BOTTOM) {
                     static_for<D>([&](auto J) {

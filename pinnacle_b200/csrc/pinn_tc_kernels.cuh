@@ -405,6 +405,9 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
             if constexpr (SIG::order(jj) >= 1) a[SIG::base(jj)][pp] = w[jj];
           });
         }
+        // the stash keeps t0 = tanh(z_0) in channel 0 instead of z_0 (nothing downstream needs z_0 itself)
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) a[0][pp] = tanh_tc(a[0][pp]);
         if constexpr (BWD) {
 #pragma unroll
           for (int c = 0; c < C; ++c) *stash_at(1, qi, c) = make_float4(a[c][0], a[c][1], a[c][2], a[c][3]);
@@ -414,7 +417,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
           float z[C], av[C];
 #pragma unroll
           for (int c = 0; c < C; ++c) z[c] = a[c][pp];
-          tanh_jet_fwd_t0<SIG>(z, tanh_tc(z[0]), av, kps->lapw);
+          tanh_jet_fwd_t0<SIG>(z, z[0], av, kps->lapw);
 #pragma unroll
           for (int c = 0; c < C; ++c) a[c][pp] = av[c];
         }
@@ -453,7 +456,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
           umma::wait_ld();
           if (act) {
 #pragma unroll
-            for (int pp = 0; pp < 4; ++pp) zq[0][pp] += b;
+            for (int pp = 0; pp < 4; ++pp) zq[0][pp] = tanh_tc(zq[0][pp] + b);      // channel 0 holds t0 from here on
             if constexpr (BWD) {
 #pragma unroll
               for (int c = 0; c < C; ++c) *stash_at(l, qi, c) = make_float4(zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
@@ -463,7 +466,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
               float z[C], av[C];
 #pragma unroll
               for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-              tanh_jet_fwd_t0<SIG>(z, tanh_tc(z[0]), av, kps->lapw);
+              tanh_jet_fwd_t0<SIG>(z, z[0], av, kps->lapw);
 #pragma unroll
               for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
             }
@@ -572,7 +575,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
                   float z[C], av[C];
 #pragma unroll
                   for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-                  tanh_jet_fwd_t0<SIG>(z, tanh_tc(z[0]), av, kps->lapw);
+                  tanh_jet_fwd_t0<SIG>(z, z[0], av, kps->lapw);       // z[0] is the stashed t0
 #pragma unroll
                   for (int c = 0; c < C; ++c) {
                     float v = 0.f;
@@ -595,7 +598,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
                   a_[c] = ab[c][pp];
                   zb[c] = 0.f;
                 }
-                tanh_jet_bwd_t0<SIG>(z, tanh_tc(z[0]), a_, zb, kps->lapw);
+                tanh_jet_bwd_t0<SIG>(z, z[0], a_, zb, kps->lapw);  // z[0] is the stashed t0
                 dbias += zb[0];
                 if (l == 1) {
                   static_for<D>([&](auto J) {
@@ -621,7 +624,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
                   float z[C], av[C];
 #pragma unroll
                   for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-                  tanh_jet_fwd_t0<SIG>(z, tanh_tc(z[0]), av, kps->lapw);
+                  tanh_jet_fwd_t0<SIG>(z, z[0], av, kps->lapw);       // z[0] is the stashed t0
 #pragma unroll
                   for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
                 }
