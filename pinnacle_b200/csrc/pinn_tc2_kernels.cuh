@@ -55,6 +55,14 @@ struct TC2fg {
   static constexpr bool PEEL = (M > 1) || (C <= 5);
   // sub-tile loop of a reverse stage: unrolled for C <= 5, rolled for C = 6 (measured: Poisson2D 11.4 vs 11.8 ms, Burgers2D 16.4 vs 15.7 ms)
   static constexpr int REV_UNROLL = (C <= 5) ? NSUB : 1;
+  // Reverse-sweep schedule.  Joint (default): per sub-tile a^{l-1}, zbar^l, then the issuer runs rows(h) + dW(h).
+  // Split (what-if, private zbar arrays only): the element-wise warps first turn BOTH sub-tiles' abar^l into zbar^l (the
+  // operand of the rows MMAs), then rebuild both a^{l-1} (second operand of the dW contraction); the issuer runs
+  // rows(A) rows(B) dW(A) dW(B).  Measured on B200 (1 Mi points, fwd+reverse): Poisson2D 8.82 -> 9.17 ms, Heat2D_Multiscale
+  // 10.53 -> 11.51 ms -- the stage no longer waits for the previous dW contraction at its start, but zbar^l(h) cannot be
+  // stored before dW(h) of the previous stage has read the arrays, and that contraction is now issued after both rows
+  // batches, so the wait moves into the middle of the stage and grows (event trace: profiles/r1_lap_summary.md).
+  static constexpr bool SPLIT_REV = false;
   static constexpr int NARR = 3 * NSUB + (BWD ? (SHZ ? 3 : 3 * NSUB) : 0);
   // TMEM columns: D_A | D_B | dW (112) | stub (4) | four weight-split slots at a 52-column stride (the last one 48 wide)
   static constexpr int tcD = 0, tcDstride = R, tcDW = 2 * R, tcStub = 2 * R + 112, tcW = tcStub + 4, tcWStride = 52, tcTotal = 512;
@@ -71,8 +79,8 @@ struct TC2fg {
   static constexpr int oRs = oUb + NSUB * M * R * 4;
   static constexpr int oRed = oRs + PINN_MAX_PDE * T * 4;
   static constexpr int oLred = (oRed + 4 * 128 * 4 + 7) / 8 * 8;
-  static constexpr int oBar = oLred + PINN_MAX_PDE * T * 8;    // 15 mbarriers + tmem slot
-  static constexpr int oKp = oBar + 128;
+  static constexpr int oBar = oLred + PINN_MAX_PDE * T * 8;    // 17 mbarriers + tmem slot
+  static constexpr int oKp = oBar + 160;
   static constexpr int nBytes = oKp + (int)((sizeof(KindParams) + 15) / 16 * 16);
   static constexpr size_t smem_bytes = (size_t)nBytes;
 
@@ -137,7 +145,9 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
   uint64_t* wf2 = bars + 11;                                          // ... and with w3 (after group G1)
   uint64_t* dwd = bars + 12;                                          // [h] dW MMAs of sub-tile h complete: its arrays may be rewritten
   uint64_t* dwfree = bars + 14;                                       // dW flushed out of TMEM (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  // rdy2[h]: reverse sweep, split schedule (CFG::SPLIT_REV): the dW operand a^{l-1} of sub-tile h is in place (512 arrivals)
+  uint64_t* rdy2 = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
   KindParams* kps = reinterpret_cast<KindParams*>(smraw + CFG::oKp);
   // a = 0..2: splits of a^{l} / a^{l-1} of sub-tile h; a = 3..5: splits of zbar^{l}
   auto arr_ptr = [&](int h, int a) -> unsigned char* {
@@ -181,6 +191,8 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
     mbar_init_n(&bars[1], 1);
     mbar_init_n(&rdy[0], NEW);
     mbar_init_n(&rdy[1], NEW);
+    mbar_init_n(&rdy2[0], NEW);
+    mbar_init_n(&rdy2[1], NEW);
     for (int i = 0; i < 4; ++i) mbar_init_n(&wr[i], CFG::NPR);
     mbar_init_n(&wfree[0], 1);
     mbar_init_n(&wfree[1], 1);
@@ -427,6 +439,35 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         PINN_TR(68 + h);
       }
     };
+    // split reverse schedule (CFG::SPLIT_REV): rows(A) rows(B) dW(A) dW(B)
+    uint32_t r2ph[2] = {0, 0};
+    auto issue_rows_only = [&](int h) {
+      PINN_TR(60 + h);
+      mbar_wait(&rdy[h], rph[h]);
+      rph[h] ^= 1;
+      umma::fence_after_sync();
+      PINN_TR(62 + h);
+      const uint32_t el = umma::elect_one();
+      issue_rows(h, arr_ptr(h, 3), el, h == 0, h == NSUB - 1);
+      umma::commit_e(&bars[h], el);
+      if (h == NSUB - 1) umma::commit_e(&wfree[nstep & 1], el);
+      PINN_TR(64 + h);
+    };
+    auto issue_dw_only = [&](int h) {
+      if (h == 0 && flush_pending) {
+        mbar_wait(dwfree, fph);            // the previous reverse step's dW has left TMEM
+        fph ^= 1;
+        umma::fence_after_sync();
+      }
+      mbar_wait(&rdy2[h], r2ph[h]);
+      r2ph[h] ^= 1;
+      umma::fence_after_sync();
+      PINN_TR(66 + h);
+      const uint32_t el = umma::elect_one();
+      issue_dw(h, h == 0 ? 0u : 1u, el);
+      umma::commit_e(&dwd[h], el);
+      PINN_TR(68 + h);
+    };
     auto step = [&](const uint4* Wp, bool reverse, int s, int l) {
       if (do_prod) {
         producer_stage(Wp);
@@ -437,8 +478,15 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         }
       } else {
         PINN_TR(58);
-        issue_sub(0, reverse);
-        issue_sub(1, reverse);
+        if (reverse && CFG::SPLIT_REV) {
+          issue_rows_only(0);
+          issue_rows_only(1);
+          issue_dw_only(0);
+          issue_dw_only(1);
+        } else {
+          issue_sub(0, reverse);
+          issue_sub(1, reverse);
+        }
         if (reverse) flush_pending = true;
       }
       ++nstep;
@@ -477,6 +525,11 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       umma::fence_async_smem();
       umma::fence_before_sync();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(&rdy[h])) : "memory");
+    };
+    auto signal_ready2 = [&](int h) {
+      umma::fence_async_smem();
+      umma::fence_before_sync();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(&rdy2[h])) : "memory");
     };
     auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NEW) : "memory"); };
     auto wait_bar = [&](int h) {
@@ -682,8 +735,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
             float dw1[D];
 #pragma unroll
             for (int i = 0; i < D; ++i) dw1[i] = 0.f;
-#pragma unroll(CFG::REV_UNROLL)
-            for (int h = 0; h < NSUB; ++h) {
+            auto part1 = [&](int h) {
               // ---- part 1, independent of the tensor core: splits of a^{l-1} (operand of the dW contraction)
               PINN_TR(20 + h);
               if (!IS_BOTTOM) {
@@ -709,6 +761,8 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                   for (int c = 0; c < C; ++c) store_quad(arr_ptr(h, 0), c * TS + pb, zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
                 }
               }
+            };
+            auto part2 = [&](int h) {
               // ---- part 2: abar^l (from D_h, written by the rows MMAs of layer l+1) -> zbar^l
               PINN_TR(24 + h);
               if (!IS_TOP) wait_bar(h);
@@ -782,14 +836,40 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                   // shared zbar arrays: the other sub-tile's MMAs (its pending dwd phase) must be done reading them
                   if (dwp[1 - h]) mbar_wait(&dwd[1 - h], dph[1 - h]);
                 }
+                // split schedule: zbar(h) was last read by the previous stage's dW(h) contraction (so were the a arrays part1
+                // rewrites afterwards); in the joint schedule part1 has waited for it already
+                if constexpr (CFG::SPLIT_REV) guard_arrays(h);
                 if (act) {
 #pragma unroll
                   for (int c = 0; c < C; ++c) store_quad(arr_ptr(h, 3), c * TS + pb, ab[c][0], ab[c][1], ab[c][2], ab[c][3]);
                 }
-                signal_ready(h);
-                dwp[h] = true;
               }
               PINN_TR(28 + h);
+            };
+            if constexpr (CFG::SPLIT_REV) {
+#pragma unroll
+              for (int h = 0; h < NSUB; ++h) {
+                part2(h);
+                if (!IS_BOTTOM) signal_ready(h);
+              }
+              if (!IS_BOTTOM) {
+#pragma unroll
+                for (int h = 0; h < NSUB; ++h) {
+                  part1(h);
+                  signal_ready2(h);
+                  dwp[h] = true;
+                }
+              }
+            } else {
+#pragma unroll(CFG::REV_UNROLL)
+              for (int h = 0; h < NSUB; ++h) {
+                part1(h);
+                part2(h);
+                if (!IS_BOTTOM) {
+                  signal_ready(h);
+                  dwp[h] = true;
+                }
+              }
             }
             float* gb = gs + (IS_BOTTOM ? offB1 : offHid + (l - 2) * strideHid + H * H);
             reduce_groups_red(dbias, gb + j);
