@@ -225,6 +225,7 @@ def run_fused(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
         dist.init_process_group("nccl", device_id=dev)
     capi.load()
     capi.set_impl({"auto": capi.IMPL_AUTO, "ffma": capi.IMPL_FFMA, "tc": capi.IMPL_TC, "tc2": capi.IMPL_TC_PIPELINED}[args.kernel])
