@@ -46,6 +46,7 @@ PINN_HD void static_for(F&& f) {
 template <int... KS>
 struct JetSig {
   static constexpr bool kLap = false;
+  static constexpr bool kLapPW = false;
   static constexpr int D = sizeof...(KS);
   static constexpr int C = 1 + (0 + ... + KS);
   PINN_HD static constexpr int order(int j) {
@@ -66,9 +67,12 @@ struct JetSig {
 // Helmholtz), carry per neuron  [value, du/dx_1 .. du/dx_D, s]  instead of separate second-order coefficients per
 // direction.  Linear layers act per channel as before; tanh couples them:
 //   a_0 = t,  a_j = t' z_j,  a_s = t' z_s + t'' sum_j w_j z_j^2      (t = tanh z_0, t' = 1 - t^2, t'' = -2 t t').
-template <int D_>
+// PW_: the direction weights carry a per-point factor (lap_point_weights) -- a separate instantiation, so that the
+// constant-weight kernels keep their loop-invariant weight loads.
+template <int D_, bool PW_ = false>
 struct LapSig {
   static constexpr bool kLap = true;
+  static constexpr bool kLapPW = PW_;
   static constexpr int D = D_;
   static constexpr int C = D_ + 2;
   static constexpr int lap = D_ + 1;                        // channel of s
@@ -244,11 +248,19 @@ struct KindParams {
   int aux_sel[PINN_MAX_AUXSEL];
   float c[PINN_MAX_CONSTS];
   float lapw[PINN_MAX_DIM];   // direction weights of the forward-Laplacian channel (set_kind_params; unused by JetSig signatures)
+  int lap_pw;                 // 1: the weights carry a per-point factor (aux column aux_sel[LIN_SEL_C2 + j]), see lap_point_weights
 };
 
 enum : int { LIN_CU = 0, LIN_C1 = 1, LIN_C2 = 1 + PINN_MAX_DIM, LIN_SEL_SRC = 0, LIN_SEL_CU = 1, LIN_SEL_C2 = 2 };
 
 PINN_HD float aux_or_one(const float* aux, int sel) { return sel >= 0 ? aux[sel] : 1.0f; }
+
+// Direction weights of the forward-Laplacian channel AT ONE POINT: the descriptor's constants, times the per-point
+// multiplier of each second-order term when the terms do not share one (Wave2D_Heterogeneous: u_xx + u_yy - u_tt / c(x),
+// wave.py:85-89).  A per-point weight is constant through the layers, so the tanh rule is unchanged.
+PINN_HD void lap_point_weights(const KindParams& kp, const float* aux, int D, float* out) {
+  for (int j = 0; j < D; ++j) out[j] = kp.lap_pw ? kp.lapw[j] * aux_or_one(aux, kp.aux_sel[LIN_SEL_C2 + j]) : kp.lapw[j];
+}
 
 template <class SIG, int M>
 struct Residual {
@@ -304,11 +316,12 @@ struct Residual {
     switch (kp.kind) {
       case PINN_KIND_LINEAR: {
         if constexpr (M == 1 && SIG::kLap) {
-          // U[0][lap] = sum_j c2_j d2u/dx_j^2 already; the c2 terms share one per-point multiplier (host-checked)
+          // U[0][lap] = sum_j c2_j d2u/dx_j^2 already; the c2 terms share one per-point multiplier (host-checked), or each
+          // carries its own inside the weights (lap_pw)
           float mul = 1.0f;
 #pragma unroll
           for (int j = 0; j < D; ++j)
-            if (c[LIN_C2 + j] != 0.f && kp.aux_sel[LIN_SEL_C2 + j] >= 0) mul = aux[kp.aux_sel[LIN_SEL_C2 + j]];
+            if (!kp.lap_pw && c[LIN_C2 + j] != 0.f && kp.aux_sel[LIN_SEL_C2 + j] >= 0) mul = aux[kp.aux_sel[LIN_SEL_C2 + j]];
           float acc = mul * U[0][SIG::lap];
 #pragma unroll
           for (int j = 0; j < D; ++j) acc = fmaf(c[LIN_C1 + j], U[0][1 + j], acc);
@@ -454,7 +467,7 @@ struct Residual {
           float mul = 1.0f;
 #pragma unroll
           for (int j = 0; j < D; ++j)
-            if (c[LIN_C2 + j] != 0.f && kp.aux_sel[LIN_SEL_C2 + j] >= 0) mul = aux[kp.aux_sel[LIN_SEL_C2 + j]];
+            if (!kp.lap_pw && c[LIN_C2 + j] != 0.f && kp.aux_sel[LIN_SEL_C2 + j] >= 0) mul = aux[kp.aux_sel[LIN_SEL_C2 + j]];
           Ub[0][SIG::lap] = mul * g;
 #pragma unroll
           for (int j = 0; j < D; ++j) Ub[0][1 + j] = c[LIN_C1 + j] * g;
@@ -605,33 +618,37 @@ struct Residual {
 
 // Host-side: can this descriptor run on the forward-Laplacian signature LapSig<d>?
 //  * LINEAR kind, one output: no direction beyond second order, at least two second-order directions (else nothing is
-//    saved), one common per-point multiplier (or none) on the second-order terms; weights = c2_j;
+//    saved); weights = c2_j, times each term's own per-point multiplier when the terms do not share one;
 //  * the kinds whose only second derivatives are u_xx + u_yy (NS2D, NS2D_UNSTEADY, BURGERS2D, GRAYSCOTT, HEAT_NLSRC)
 //    and DIV_AGRAD (outputs u, a) with their canonical orders (2,2) / (2,2,1); weights = (1, 1, 0).
-inline bool lap_eligible(int kind, int d, int m, const int* order, const int* aux_sel, const float* consts) {
+// returns 0 (no), 1 (yes, constant direction weights) or 2 (yes, per-point direction weights: lap_point_weights)
+inline int lap_eligible(int kind, int d, int m, const int* order, const int* aux_sel, const float* consts) {
   if (kind == PINN_KIND_NS2D) return d == 2 && m == 3 && order[0] == 2 && order[1] == 2;
   if (kind == PINN_KIND_NS2D_UNSTEADY || kind == PINN_KIND_BURGERS2D || kind == PINN_KIND_GRAYSCOTT || kind == PINN_KIND_HEAT_NLSRC)
     return d == 3 && order[0] == 2 && order[1] == 2 && order[2] == 1;
   if (kind == PINN_KIND_DIV_AGRAD)
     return m == 2 && order[0] == 2 && order[1] == 2 && (d == 2 || (d == 3 && order[2] == 1));
-  if (kind != PINN_KIND_LINEAR || m != 1 || d < 2) return false;
+  if (kind != PINN_KIND_LINEAR || m != 1 || d < 2) return 0;
   int n2 = 0, sel = -2;
+  bool common = true;
   for (int j = 0; j < d; ++j) {
-    if (order[j] < 1 || order[j] > 2) return false;
+    if (order[j] < 1 || order[j] > 2) return 0;
     if (order[j] == 2) ++n2;
-    if (order[j] < 2 && consts[LIN_C2 + j] != 0.f) return false;
+    if (order[j] < 2 && consts[LIN_C2 + j] != 0.f) return 0;
     if (consts[LIN_C2 + j] != 0.f) {
       const int sj = aux_sel[LIN_SEL_C2 + j];
       if (sel == -2) sel = sj;
-      else if (sel != sj) return false;
+      else if (sel != sj) common = false;
     }
   }
-  return n2 >= 2;
+  if (n2 < 2) return 0;
+  return common ? 1 : 2;
 }
 
 // descriptor -> KindParams (the kernels' copy of kind, selectors, constants and Laplacian weights)
-inline void set_kind_params(KindParams& kp, int kind, int d, const int* aux_sel, const float* consts) {
+inline void set_kind_params(KindParams& kp, int kind, int d, const int* aux_sel, const float* consts, int lap_mode = 0) {
   kp.kind = kind;
+  kp.lap_pw = (lap_mode == 2) ? 1 : 0;
   for (int i = 0; i < PINN_MAX_AUXSEL; ++i) kp.aux_sel[i] = aux_sel[i];
   for (int i = 0; i < PINN_MAX_CONSTS; ++i) kp.c[i] = consts[i];
   for (int j = 0; j < PINN_MAX_DIM; ++j) kp.lapw[j] = (kind == PINN_KIND_LINEAR) ? (j < d ? consts[LIN_C2 + j] : 0.f) : (j < 2 ? 1.0f : 0.f);

@@ -66,10 +66,12 @@ static const ConfigInfo* find_config(const pinn_kind_desc* d, std::string* why) 
   // forward-Laplacian signature first where the descriptor allows it (fewer channels for the same result);
   // PINN_NO_LAPLACIAN=1 keeps the per-direction second-order jets (for A/B measurements)
   static const bool no_lap = [] { const char* e = getenv("PINN_NO_LAPLACIAN"); return e != nullptr && e[0] == '1'; }();
-  if (!no_lap && !g_no_lap && lap_eligible(d->kind, d->d, d->m, d->order, d->aux_sel, d->consts)) {
+  // (per-point direction weights -- lap_eligible() == 2 -- exist in the tensor-core kernels only)
+  const int lap_mode = lap_eligible(d->kind, d->d, d->m, d->order, d->aux_sel, d->consts);
+  if (!no_lap && !g_no_lap && (lap_mode == 1 || (lap_mode == 2 && effective_impl() != 1))) {
     for (int i = 0; i < PINN_NUM_CONFIGS; ++i) {
       const ConfigInfo* c = tab[i];
-      if (c != nullptr && c->lap && c->H == d->H && c->m == d->m && c->d == d->d && c->valid_kind(d->kind)) return c;
+      if (c != nullptr && c->lap == lap_mode && c->H == d->H && c->m == d->m && c->d == d->d && c->valid_kind(d->kind)) return c;
     }
   }
   for (int i = 0; i < PINN_NUM_CONFIGS; ++i) {
@@ -219,7 +221,7 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
     pinn_pack_weights_tc<<<(total + 255) / 256, 256, 0, st>>>(params, wperm, desc->H, desc->d, desc->L, desc->m);
     ++g_launches;
     TcLaunchParams lp{};
-    set_kind_params(lp.kp, desc->kind, desc->d, desc->aux_sel, desc->consts);
+    set_kind_params(lp.kp, desc->kind, desc->d, desc->aux_sel, desc->consts, c->lap);
     lp.L = desc->L; lp.n_aux = desc->n_aux; lp.n_pde = desc->n_pde; lp.n_seeds = n_seeds;
     lp.n_rows = n_rows; lp.P = P; lp.Ppad = ws.pstride; lp.inv_n = (float)inv_n;
     lp.params = params; lp.wn = wn; lp.wt = wt; lp.w6p = w6p; lp.x = x; lp.aux = aux; lp.seeds = seeds;
@@ -235,7 +237,7 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
     ++g_launches;
 
     LaunchParams lp{};
-    set_kind_params(lp.kp, desc->kind, desc->d, desc->aux_sel, desc->consts);
+    set_kind_params(lp.kp, desc->kind, desc->d, desc->aux_sel, desc->consts, c->lap);
     lp.L = desc->L;
     lp.n_aux = desc->n_aux;
     lp.n_pde = desc->n_pde;

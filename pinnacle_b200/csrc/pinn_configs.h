@@ -21,6 +21,7 @@
 //       (d=3, m=2), NS2D_LongTime (d=3, m=3); Heat2D_LongTime uses 22
 // 19-20 flux-type boundary terms (PINN_KIND_FLUX: Neumann / affine Robin): first-order signatures (1,1), (1,1,1), m = 1
 // 29-30 PoissonInv (inverse.py:19-24; outputs u, a): (2,2) m=2 and its forward-Laplacian form LapSig<2> m=2 (HeatInv uses 5 / 26)
+// 31    LapSig<3> with per-point direction weights (orders entry -(10+d)): Wave2D_Heterogeneous, u_xx + u_yy - u_tt / c(x,y)
 // 28    the same for the 6-dimensional Neumann term of HeatND (heat.py:296-301): (1,1,1,1,1,1)
 #pragma once
 
@@ -55,6 +56,7 @@
   X(27, 100, 3, 32, 4, 32, -3)             \
   X(28, 100, 1, 16, 2, 0, 1, 1, 1, 1, 1, 1) \
   X(29, 100, 2, 32, 4, 32, 2, 2)           \
-  X(30, 100, 2, 32, 4, 32, -2)
+  X(30, 100, 2, 32, 4, 32, -2)             \
+  X(31, 100, 1, 32, 4, 32, -13)
 
-#define PINN_NUM_CONFIGS 31
+#define PINN_NUM_CONFIGS 32

@@ -10,7 +10,7 @@ namespace pinn {
 
 struct ConfigInfo {
   int id, H, m, d, C;
-  int lap;   // 1: forward-Laplacian signature LapSig<d> (serves eligible LINEAR-kind descriptors whatever their order[])
+  int lap;   // 1: forward-Laplacian signature LapSig<d> (serves eligible LINEAR-kind descriptors whatever their order[]); 2: with per-point direction weights
   int order[PINN_MAX_DIM];
   int T, NT, NTP, E4;
   size_t smem_fwd, smem_bwd;

@@ -15,10 +15,12 @@ struct SigOf {
   using type = JetSig<KS...>;
   static constexpr int lap = 0;
 };
+// -d: LapSig<d> with constant direction weights; -(10 + d): LapSig<d, true>, per-point direction weights
 template <int K0>
 struct SigOf<K0> {
-  using type = std::conditional_t<(K0 < 0), LapSig<(K0 < 0 ? -K0 : 1)>, JetSig<(K0 < 0 ? 0 : K0)>>;
-  static constexpr int lap = K0 < 0 ? 1 : 0;
+  using type = std::conditional_t<(K0 < -10), LapSig<(K0 < -10 ? -K0 - 10 : 1), true>,
+                                  std::conditional_t<(K0 < 0), LapSig<(K0 < 0 ? -K0 : 1)>, JetSig<(K0 < 0 ? 0 : K0)>>>;
+  static constexpr int lap = K0 < -10 ? 2 : (K0 < 0 ? 1 : 0);
 };
 
 template <int ID, int H, int M, int T, int TN, int TCT, int... KS>

@@ -74,7 +74,8 @@ struct TC2fg {
   static constexpr int oB6 = oW6 + M * H * 4;
   static constexpr int oX = oB6 + 16;
   static constexpr int oAux = oX + T * D * 4;
-  static constexpr int oUo = oAux + T * PINN_MAX_AUX * 4;
+  static constexpr int oLw = oAux + T * PINN_MAX_AUX * 4;      // per-point direction weights of the Laplacian channel [T][PINN_MAX_DIM]
+  static constexpr int oUo = oLw + (SIG::kLapPW ? T * PINN_MAX_DIM * 4 : 0);
   static constexpr int oUb = oUo + NSUB * M * R * 4;
   static constexpr int oRs = oUb + NSUB * M * R * 4;
   static constexpr int oRed = oRs + PINN_MAX_PDE * T * 4;
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
   float* b6s = reinterpret_cast<float*>(smraw + CFG::oB6);
   float* xs = reinterpret_cast<float*>(smraw + CFG::oX);
   float* auxs = reinterpret_cast<float*>(smraw + CFG::oAux);
+  float* lws = reinterpret_cast<float*>(smraw + CFG::oLw);
   float* uo = reinterpret_cast<float*>(smraw + CFG::oUo);
   float* ub = reinterpret_cast<float*>(smraw + CFG::oUb);
   float* rs = reinterpret_cast<float*>(smraw + CFG::oRs);
@@ -149,6 +151,11 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
   uint64_t* rdy2 = bars + 15;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
   KindParams* kps = reinterpret_cast<KindParams*>(smraw + CFG::oKp);
+  // direction weights of the Laplacian channel at tile point `pt`: per point (LapSig<D, true>) or the descriptor's constants
+  auto lw_at = [&](int pt) -> const float* {
+    if constexpr (SIG::kLapPW) return lws + pt * PINN_MAX_DIM;
+    else return kps->lapw;
+  };
   // a = 0..2: splits of a^{l} / a^{l-1} of sub-tile h; a = 3..5: splits of zbar^{l}
   auto arr_ptr = [&](int h, int a) -> unsigned char* {
     return smraw + (size_t)(a < 3 ? h * 3 + a : 3 * NSUB + (CFG::SHZ ? 0 : h * 3) + (a - 3)) * ARR;
@@ -585,7 +592,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         float z[C], av[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) z[c] = a[c][pp];
-        tanh_jet_fwd_t0<SIG>(z, z[0], av, kps->lapw);
+        tanh_jet_fwd_t0<SIG>(z, z[0], av, lw_at(h * TS + pb + pp));
 #pragma unroll
         for (int c = 0; c < C; ++c) a[c][pp] = av[c];
       }
@@ -610,7 +617,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         float z[C], av[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-        tanh_jet_fwd_t0<SIG>(z, z[0], av, kps->lapw);
+        tanh_jet_fwd_t0<SIG>(z, z[0], av, lw_at(h * TS + pb + pp));
 #pragma unroll
         for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
       }
@@ -645,6 +652,10 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
           const long long r = row0 + pt;
           auxs[pt * PINN_MAX_AUX + a] = (r < p.n_rows) ? p.aux[r * p.n_aux + a] : 0.f;
         }
+      }
+      if constexpr (SIG::kLapPW) {
+        epi_sync();                        // the weights read this tile's aux columns
+        if (tid < T) lap_point_weights(*kps, auxs + tid * PINN_MAX_AUX, D, lws + tid * PINN_MAX_DIM);
       }
       epi_sync();
 
@@ -753,7 +764,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                     float z[C], av[C];
 #pragma unroll
                     for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-                    tanh_jet_fwd_t0<SIG>(z, z[0], av, kps->lapw);       // z[0] is the stashed t0
+                    tanh_jet_fwd_t0<SIG>(z, z[0], av, lw_at(h * TS + pb + pp));       // z[0] is the stashed t0
 #pragma unroll
                     for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
                   }
@@ -786,7 +797,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                     float z[C], av[C];
 #pragma unroll
                     for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-                    tanh_jet_fwd_t0<SIG>(z, z[0], av, kps->lapw);       // z[0] is the stashed t0
+                    tanh_jet_fwd_t0<SIG>(z, z[0], av, lw_at(h * TS + pb + pp));       // z[0] is the stashed t0
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                       float v = 0.f;
@@ -809,7 +820,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                     a_[c] = ab[c][pp];
                     zb[c] = 0.f;
                   }
-                  tanh_jet_bwd_t0<SIG>(z, z[0], a_, zb, kps->lapw);  // z[0] is the stashed t0
+                  tanh_jet_bwd_t0<SIG>(z, z[0], a_, zb, lw_at(h * TS + pb + pp));  // z[0] is the stashed t0
                   dbias += zb[0];
                   if (IS_BOTTOM) {
                     static_for<D>([&](auto J) {

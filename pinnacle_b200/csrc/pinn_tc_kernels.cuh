@@ -78,7 +78,8 @@ struct TCfg {
   static constexpr int oB6 = oW6 + M * H * 4;                  // float [4]
   static constexpr int oX = oB6 + 16;                          // float [T*D]
   static constexpr int oAux = oX + T * D * 4;                  // float [T*4]
-  static constexpr int oUo = oAux + T * PINN_MAX_AUX * 4;      // float [M*R]
+  static constexpr int oLw = oAux + T * PINN_MAX_AUX * 4;      // per-point direction weights of the Laplacian channel [T][PINN_MAX_DIM]
+  static constexpr int oUo = oLw + (SIG::kLapPW ? T * PINN_MAX_DIM * 4 : 0);       // float [M*R]
   static constexpr int oUb = oUo + M * R * 4;                  // float [M*R]
   static constexpr int oRs = oUb + M * R * 4;                  // float [3*T]
   static constexpr int oRed = oRs + PINN_MAX_PDE * T * 4;      // float [4*128]
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
   float* b6s = reinterpret_cast<float*>(smraw + CFG::oB6);
   float* xs = reinterpret_cast<float*>(smraw + CFG::oX);
   float* auxs = reinterpret_cast<float*>(smraw + CFG::oAux);
+  float* lws = reinterpret_cast<float*>(smraw + CFG::oLw);
   float* uo = reinterpret_cast<float*>(smraw + CFG::oUo);
   float* ub = reinterpret_cast<float*>(smraw + CFG::oUb);
   float* rs = reinterpret_cast<float*>(smraw + CFG::oRs);
@@ -178,6 +180,11 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
   uint64_t* bar1 = bar0 + 1;                                              // dW MMAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar0 + 2);
   KindParams* kps = reinterpret_cast<KindParams*>(smraw + CFG::oKp);
+  // direction weights of the Laplacian channel at tile point `pt`: per point (LapSig<D, true>) or the descriptor's constants
+  auto lw_at = [&](int pt) -> const float* {
+    if constexpr (SIG::kLapPW) return lws + pt * PINN_MAX_DIM;
+    else return kps->lapw;
+  };
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -379,6 +386,10 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
         auxs[pt * PINN_MAX_AUX + a] = (r < p.n_rows) ? p.aux[r * p.n_aux + a] : 0.f;
       }
     }
+    if constexpr (SIG::kLapPW) {
+      __syncthreads();                        // the weights read this tile's aux columns
+      if (tid < T) lap_point_weights(*kps, auxs + tid * PINN_MAX_AUX, D, lws + tid * PINN_MAX_DIM);
+    }
     __syncthreads();
 
     // ================= layer 1 (d -> H), CUDA cores =================
@@ -417,7 +428,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
           float z[C], av[C];
 #pragma unroll
           for (int c = 0; c < C; ++c) z[c] = a[c][pp];
-          tanh_jet_fwd_t0<SIG>(z, z[0], av, kps->lapw);
+          tanh_jet_fwd_t0<SIG>(z, z[0], av, lw_at(pb + pp));
 #pragma unroll
           for (int c = 0; c < C; ++c) a[c][pp] = av[c];
         }
@@ -466,7 +477,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
               float z[C], av[C];
 #pragma unroll
               for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-              tanh_jet_fwd_t0<SIG>(z, z[0], av, kps->lapw);
+              tanh_jet_fwd_t0<SIG>(z, z[0], av, lw_at(pb + pp));
 #pragma unroll
               for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
             }
@@ -575,7 +586,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
                   float z[C], av[C];
 #pragma unroll
                   for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-                  tanh_jet_fwd_t0<SIG>(z, z[0], av, kps->lapw);       // z[0] is the stashed t0
+                  tanh_jet_fwd_t0<SIG>(z, z[0], av, lw_at(pb + pp));       // z[0] is the stashed t0
 #pragma unroll
                   for (int c = 0; c < C; ++c) {
                     float v = 0.f;
@@ -598,7 +609,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
                   a_[c] = ab[c][pp];
                   zb[c] = 0.f;
                 }
-                tanh_jet_bwd_t0<SIG>(z, z[0], a_, zb, kps->lapw);  // z[0] is the stashed t0
+                tanh_jet_bwd_t0<SIG>(z, z[0], a_, zb, lw_at(pb + pp));  // z[0] is the stashed t0
                 dbias += zb[0];
                 if (l == 1) {
                   static_for<D>([&](auto J) {
@@ -624,7 +635,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
                   float z[C], av[C];
 #pragma unroll
                   for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-                  tanh_jet_fwd_t0<SIG>(z, z[0], av, kps->lapw);       // z[0] is the stashed t0
+                  tanh_jet_fwd_t0<SIG>(z, z[0], av, lw_at(pb + pp));       // z[0] is the stashed t0
 #pragma unroll
                   for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
                 }

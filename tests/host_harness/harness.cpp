@@ -25,7 +25,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
   for (int l = 2; l <= L; ++l) { offW[l] = (long long)H * D + H + (long long)(l - 2) * ((long long)H * H + H); offB[l] = offW[l] + (long long)H * H; }
   offW[L + 1] = (long long)H * D + H + (long long)(L - 1) * ((long long)H * H + H); offB[L + 1] = offW[L + 1] + (long long)M * H;
   KindParams kp;
-  set_kind_params(kp, d->kind, d->d, d->aux_sel, d->consts);
+  set_kind_params(kp, d->kind, d->d, d->aux_sel, d->consts, SIG::kLap ? (SIG::kLapPW ? 2 : 1) : 0);
   for (int k = 0; k < PINN_MAX_PDE; ++k) loss[k] = 0.0;
   for (long long i = 0; i < (long long)S * P; ++i) grad[i] = 0.0;
 
@@ -34,6 +34,9 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
     const float* xp = x + pt * D;
     float auxv[PINN_MAX_AUX] = {};
     for (int q = 0; q < d->n_aux; ++q) auxv[q] = aux[pt * d->n_aux + q];
+    float lwp[PINN_MAX_DIM] = {};
+    if constexpr (SIG::kLapPW) lap_point_weights(kp, auxv, D, lwp);
+    else if constexpr (SIG::kLap) for (int j = 0; j < D; ++j) lwp[j] = kp.lapw[j];
     // ---- forward
     for (int nn = 0; nn < H; ++nn) {
       float zz[C];
@@ -46,7 +49,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
         if constexpr (SIG::order(j) >= 1) zz[SIG::base(j)] = params[offW[1] + nn * D + j];
       });
       float aa[C];
-      tanh_jet_fwd<SIG>(zz, aa, kp.lapw);
+      tanh_jet_fwd<SIG>(zz, aa, lwp);
       for (int c = 0; c < C; ++c) { z[((size_t)1 * H + nn) * C + c] = zz[c]; a[((size_t)1 * H + nn) * C + c] = aa[c]; }
     }
     for (int l = 2; l <= L; ++l) {
@@ -59,7 +62,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
         }
         zz[0] += params[offB[l] + nn];
         float aa[C];
-        tanh_jet_fwd<SIG>(zz, aa, kp.lapw);
+        tanh_jet_fwd<SIG>(zz, aa, lwp);
         for (int c = 0; c < C; ++c) { z[((size_t)l * H + nn) * C + c] = zz[c]; a[((size_t)l * H + nn) * C + c] = aa[c]; }
       }
     }
@@ -98,7 +101,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
         for (int nn = 0; nn < H; ++nn) {
           float zz[C], aa[C], zz_b[C];
           for (int c = 0; c < C; ++c) { zz[c] = z[((size_t)l * H + nn) * C + c]; aa[c] = ab[(size_t)nn * C + c]; zz_b[c] = 0.f; }
-          tanh_jet_bwd<SIG>(zz, aa, zz_b, kp.lapw);
+          tanh_jet_bwd<SIG>(zz, aa, zz_b, lwp);
           for (int c = 0; c < C; ++c) zb[(size_t)nn * C + c] = zz_b[c];
           g[offB[l] + nn] += zz_b[0];
         }
@@ -138,19 +141,20 @@ struct SigOfH {
 };
 template <int K0>
 struct SigOfH<K0> {
-  using type = std::conditional_t<(K0 < 0), LapSig<(K0 < 0 ? -K0 : 1)>, JetSig<(K0 < 0 ? 0 : K0)>>;
+  using type = std::conditional_t<(K0 < -10), LapSig<(K0 < -10 ? -K0 - 10 : 1), true>,
+                                  std::conditional_t<(K0 < 0), LapSig<(K0 < 0 ? -K0 : 1)>, JetSig<(K0 < 0 ? 0 : K0)>>>;
 };
 
 extern "C" int harness_run(const pinn_kind_desc* d, const float* params, const float* x, const float* aux, long long n, double inv_n,
                            const float* seeds, int S, double* grad, double* loss, float* resid) {
   // same selection rule as the library (pinn_api.cu find_config): forward-Laplacian signature where eligible
   const char* nl = getenv("PINN_NO_LAPLACIAN");
-  const bool want_lap = !(nl != nullptr && nl[0] == '1') && lap_eligible(d->kind, d->d, d->m, d->order, d->aux_sel, d->consts);
+  const int want_lap = (nl != nullptr && nl[0] == '1') ? 0 : lap_eligible(d->kind, d->d, d->m, d->order, d->aux_sel, d->consts);
 #define TRY(ID, H_, M_, T_, TN_, TCT_, ...)                                                                \
   {                                                                                                    \
     using SIG = typename SigOfH<__VA_ARGS__>::type;                                                    \
     const int o[] = {__VA_ARGS__};                                                                     \
-    bool same = (SIG::D == d->d) && (M_ == d->m) && (SIG::kLap == want_lap);                           \
+    bool same = (SIG::D == d->d) && (M_ == d->m) && ((SIG::kLap ? (SIG::kLapPW ? 2 : 1) : 0) == want_lap);                           \
     for (int j = 0; same && !SIG::kLap && j < SIG::D; ++j) same = (o[j] == d->order[j]);               \
     if (same && Residual<SIG, M_>::valid(d->kind)) {                                                   \
       run_cfg<SIG, M_>(d, params, x, aux, n, inv_n, seeds, S, grad, loss, resid);                      \
