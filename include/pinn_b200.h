@@ -149,6 +149,14 @@ int pinn_debug_umma_gemm(int mode, int variant, int K, int N, const float* A, co
  * so far, 0}; the kernel reads it for the bias corrections and increments it, so a captured CUDA graph can replay it. */
 int pinn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float* step_dev,
                    float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
+/* One MultiAdam update (src/optimizer/multiadam.py:54-122 `sadam`; amsgrad off, no aggregated momentum -- what
+ * benchmark.py:108 constructs) from gradient rows G[n_rows][ldg]: row t belongs to loss group row_group[t] (device int32)
+ * with factor row_weight[t] (its loss weight); per group k one Adam moment pair exp_avg / exp_avg_sq [n_groups][P]; the
+ * parameter update is  -lr/(1-beta1^t) * sum_k group_weights[k] * m_k / (sqrt(v_k)/sqrt(1-beta2^t) + eps).
+ * The reference runs one backward pass per group and a stack/copy of every moment tensor per parameter per step. */
+int pinn_multiadam_step(float* params, const float* G, int n_rows, int64_t P, int64_t ldg, const int32_t* row_group,
+                        const float* row_weight, int n_groups, const float* group_weights, float* exp_avg, float* exp_avg_sq,
+                        float* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
 /* Floats of device scratch pinn_grad_stats / pinn_lra_combine need. */
 size_t pinn_optim_scratch_floats(void);
 /* out3 = { max|g|, sum|g|, sum g^2 } of a flat vector: the statistics src/optimizer/lr_adaptor.py:37-41,50-53 and

@@ -21,7 +21,7 @@ EXPORTS = (
     "pinn_param_count", "pinn_supported", "pinn_workspace_bytes", "pinn_fwd", "pinn_fwd_bwd",
     "pinn_last_launch_count", "pinn_ffma_peak_tflops", "pinn_last_error", "pinn_build_info", "pinn_debug_umma_gemm", "pinn_set_impl", "pinn_has_tensor_core_kernel",
     "pinn_selected_impl", "pinn_effective_channels", "pinn_set_laplacian_collapse",
-    "pinn_adam_step", "pinn_optim_scratch_floats", "pinn_grad_stats", "pinn_lra_combine",
+    "pinn_adam_step", "pinn_optim_scratch_floats", "pinn_grad_stats", "pinn_lra_combine", "pinn_multiadam_step",
 )
 
 
@@ -74,6 +74,8 @@ def load() -> ctypes.CDLL:
     V, F, I64 = ctypes.c_void_p, ctypes.c_float, ctypes.c_int64
     lib.pinn_adam_step.argtypes = [V, V, V, V, I64, V, F, F, F, F, F, V]
     lib.pinn_adam_step.restype = ctypes.c_int
+    lib.pinn_multiadam_step.argtypes = [V, V, ctypes.c_int, I64, I64, V, V, ctypes.c_int, V, V, V, V, F, F, F, F, F, V]
+    lib.pinn_multiadam_step.restype = ctypes.c_int
     lib.pinn_optim_scratch_floats.argtypes = []
     lib.pinn_optim_scratch_floats.restype = ctypes.c_size_t
     lib.pinn_grad_stats.argtypes = [V, I64, V, V, V]
@@ -310,3 +312,22 @@ def lra_combine(G: torch.Tensor, n_pde: int, w_in: torch.Tensor, counts: torch.T
         rc = load().pinn_lra_combine(_ptr(G), int(T), int(n_pde), int(P), int(G.stride(0)), _ptr(w_in), _ptr(counts), float(alpha), _ptr(w_out),
                                      _ptr(grad_out), _ptr(_scratch(G.device)), _stream_ptr(G.device))
     _check(rc, "pinn_lra_combine")
+
+
+def multiadam_step(params: torch.Tensor, G: torch.Tensor, row_group: torch.Tensor, row_weight: torch.Tensor, group_weights: torch.Tensor,
+                   exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step_dev: torch.Tensor, lr: float, beta1: float, beta2: float, eps: float,
+                   weight_decay: float = 0.0):
+    """pinn_multiadam_step: one MultiAdam update from the gradient rows G [n_rows, P] (row t: group row_group[t], factor row_weight[t])."""
+    for t, nm in ((params, "params"), (G, "G"), (row_weight, "row_weight"), (group_weights, "group_weights"), (exp_avg, "exp_avg"),
+                  (exp_avg_sq, "exp_avg_sq"), (step_dev, "step_dev")):
+        _req(t, nm)
+    _req(row_group, "row_group", torch.int32)
+    T, P = G.shape
+    ng = group_weights.numel()
+    if params.numel() != P or row_group.numel() != T or row_weight.numel() != T or exp_avg.numel() != ng * P or exp_avg_sq.numel() != ng * P:
+        raise FusedOpError("multiadam_step: buffer sizes differ")
+    with torch.cuda.device(params.device):
+        rc = load().pinn_multiadam_step(_ptr(params), _ptr(G), int(T), int(P), int(G.stride(0)), _ptr(row_group), _ptr(row_weight), int(ng),
+                                        _ptr(group_weights), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(step_dev), float(lr), float(beta1), float(beta2),
+                                        float(eps), float(weight_decay), _stream_ptr(params.device))
+    _check(rc, "pinn_multiadam_step")

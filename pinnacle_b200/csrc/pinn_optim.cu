@@ -152,6 +152,60 @@ __global__ void lra_apply_kernel(const float* __restrict__ G, int n_terms, int n
   }
 }
 
+// ---- MultiAdam (src/optimizer/multiadam.py:54-122 `sadam`, amsgrad off, no aggregated momentum) ----------------------
+// One Adam moment pair PER LOSS GROUP; the update is the group-weighted sum of the groups' normalised first moments.
+// G: [n_rows][ldg] gradient rows; row t belongs to group gid[t] with factor rw[t] (its loss weight), so the group gradient
+// g_k = sum_{gid[t] = k} rw[t] G[t] is formed on the fly.  m, v: [n_groups][P].
+constexpr int kMaxGroups = 4;
+__global__ void multiadam_kernel(float* __restrict__ p, const float* __restrict__ G, int n_rows, int64_t P, int64_t ldg, const int* __restrict__ gid,
+                                 const float* __restrict__ rw, int n_groups, const float* __restrict__ gw, float* __restrict__ m, float* __restrict__ v,
+                                 float* step_dev, float lr, float b1, float b2, float eps, float wd) {
+  const float t = step_dev[0] + 1.0f;
+  const float bc1 = 1.0f - powf(b1, t);
+  const float rs_bc2 = sqrtf(1.0f - powf(b2, t));
+  const float step_size = lr / bc1;
+  __shared__ int s_gid[kMaxTerms + PINN_MAX_PDE];
+  __shared__ float s_rw[kMaxTerms + PINN_MAX_PDE], s_gw[kMaxGroups];
+  if (threadIdx.x < n_rows) { s_gid[threadIdx.x] = gid[threadIdx.x]; s_rw[threadIdx.x] = rw[threadIdx.x]; }
+  if (threadIdx.x < n_groups) s_gw[threadIdx.x] = gw[threadIdx.x];
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+    float g[kMaxGroups];
+#pragma unroll
+    for (int k = 0; k < kMaxGroups; ++k) g[k] = 0.f;
+    for (int r = 0; r < n_rows; ++r) {
+      const float x = s_rw[r] * G[(int64_t)r * ldg + i];
+#pragma unroll
+      for (int k = 0; k < kMaxGroups; ++k)
+        if (s_gid[r] == k) g[k] += x;
+    }
+    const float pi = p[i];
+    float upd = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxGroups; ++k) {
+      if (k < n_groups) {
+        float gk = g[k];
+        if (wd != 0.0f) gk = fmaf(wd, pi, gk);
+        const float mk = b1 * m[(int64_t)k * P + i] + (1.0f - b1) * gk;
+        const float vk = b2 * v[(int64_t)k * P + i] + (1.0f - b2) * gk * gk;
+        m[(int64_t)k * P + i] = mk;
+        v[(int64_t)k * P + i] = vk;
+        upd = fmaf(s_gw[k], mk / (sqrtf(vk) / rs_bc2 + eps), upd);
+      }
+    }
+    p[i] = pi - step_size * upd;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned* ticket = reinterpret_cast<unsigned*>(step_dev + 1);
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      *ticket = 0u;
+      step_dev[0] = t;
+    }
+  }
+}
+
 int fail(const char* what, cudaError_t e) {
   pinn::set_error_string(std::string(what) + ": " + cudaGetErrorString(e));
   return 1;
@@ -172,6 +226,25 @@ int pinn_adam_step(float* params, const float* grads, float* exp_avg, float* exp
   adam_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, step_dev, lr, beta1, beta2, eps, weight_decay);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : fail("pinn_adam_step", e);
+}
+
+int pinn_multiadam_step(float* params, const float* G, int n_rows, int64_t P, int64_t ldg, const int* row_group, const float* row_weight,
+                        int n_groups, const float* group_weights, float* exp_avg, float* exp_avg_sq, float* step_dev, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, void* stream) {
+  if (!params || !G || !row_group || !row_weight || !group_weights || !exp_avg || !exp_avg_sq || !step_dev || P <= 0 || ldg < P) {
+    pinn::set_error_string("pinn_multiadam_step: null buffer, P <= 0 or ldg < P");
+    return 1;
+  }
+  if (n_groups < 1 || n_groups > kMaxGroups || n_rows < 1 || n_rows > kMaxTerms + PINN_MAX_PDE) {
+    pinn::set_error_string("pinn_multiadam_step: 1..4 loss groups and 1..19 gradient rows");
+    return 1;
+  }
+  const int threads = 256;
+  const int blocks = (int)((P + threads - 1) / threads < 148 ? (P + threads - 1) / threads : 148);
+  multiadam_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(params, G, n_rows, P, ldg, row_group, row_weight, n_groups, group_weights, exp_avg,
+                                                                exp_avg_sq, step_dev, lr, beta1, beta2, eps, weight_decay);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : fail("pinn_multiadam_step", e);
 }
 
 size_t pinn_optim_scratch_floats(void) { return (size_t)kStatBlocks * kMaxTerms; }

@@ -193,3 +193,75 @@ class FusedLRA(torch.optim.Optimizer):
         w[n_pde:] = self._rows_w_next[n_rows_pde:]
         opt.apply_update()
         return torch.sum(losses * w)                   # lr_adaptor.py:60: total loss under the NEW weights
+
+
+class FlatMultiAdam(torch.optim.Optimizer):
+    """MultiAdam (src/optimizer/multiadam.py:125-330 with its defaults: amsgrad off, no aggregated momentum, no parameter
+    scheduler) on the fused op's gradient rows: one Adam moment pair per loss group, update = group-weighted sum of the
+    groups' normalised first moments -- ONE kernel launch (``pinn_multiadam_step``) after one fused pass per term, where the
+    reference runs one backward pass per group and stacks / copies every moment tensor of every parameter each step.
+
+    Same constructor protocol: ``FlatMultiAdam(params, lr, betas, eps, weight_decay, loss_group_idx=[num_pde], group_weights)``
+    (benchmark.py:108); ``attach(solver)`` names the ``FusedPDESolver``.  The loss weights of the terms are read from
+    ``solver.loss_weights`` (constant, as in the reference where MultiAdam differentiates the weighted losses)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.99, 0.99), eps=1e-8, weight_decay=0.0, loss_group_idx=None, group_weights=None):
+        params = list(params)
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._flat = FlatAdam(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)     # owns the flat buffers / views
+        self.flat = self._flat.flat
+        self.loss_group_idx = list(loss_group_idx or [])
+        self.n_groups = len(self.loss_group_idx) + 1
+        dev = self.flat.device
+        gw = torch.full((self.n_groups,), 1.0 / self.n_groups) if group_weights is None else torch.as_tensor(group_weights, dtype=torch.float32)
+        self.group_weights = gw.to(dev).contiguous()
+        n = self.flat.numel()
+        self.exp_avg = torch.zeros(self.n_groups * n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.n_groups * n, dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.solver = None
+        self._rows = None
+
+    def attach(self, solver):
+        self.solver = solver
+        self._rows = None
+        return self
+
+    def zero_grad(self, set_to_none: bool = True):
+        self._flat.zero_grad(set_to_none)
+
+    def step(self, closure=None):
+        if self.solver is None:
+            raise capi.FusedOpError("FlatMultiAdam.step(): attach(solver) first")
+        solver = self.solver
+        n_pde, T = solver.spec.desc.n_pde, solver.num_loss
+        dev = self.flat.device
+        if self._rows is None:
+            w = np.ones(T, dtype=np.float32) if solver.loss_weights is None else np.asarray(solver.loss_weights, dtype=np.float32)
+            bounds = [0] + self.loss_group_idx + [T]
+            group_of = np.zeros(T, dtype=np.int32)
+            for k in range(len(bounds) - 1):
+                group_of[bounds[k]:bounds[k + 1]] = k
+            # PDE terms of one group share a fused pass (seed row = their loss weights); a group boundary inside the PDE terms
+            # needs one seed row per piece
+            pieces = sorted(set([0, n_pde] + [b for b in self.loss_group_idx if 0 < b < n_pde]))
+            seeds = np.zeros((len(pieces) - 1, n_pde), dtype=np.float32)
+            row_group, row_weight = [], []
+            for r in range(len(pieces) - 1):
+                seeds[r, pieces[r]:pieces[r + 1]] = w[pieces[r]:pieces[r + 1]]
+                row_group.append(group_of[pieces[r]])
+                row_weight.append(1.0)
+            for t in range(n_pde, T):
+                row_group.append(group_of[t])
+                row_weight.append(float(w[t]))
+            self._seeds = torch.as_tensor(seeds).to(dev)
+            self._row_group = torch.as_tensor(np.asarray(row_group, dtype=np.int32)).to(dev)
+            self._row_weight = torch.as_tensor(np.asarray(row_weight, dtype=np.float32)).to(dev)
+            self._w_dev = torch.as_tensor(w).to(dev)
+            self._rows = True
+        G, losses = solver.term_gradient_rows(self.flat, self._seeds)
+        g = self.param_groups[0]
+        capi.multiadam_step(self.flat, G, self._row_group, self._row_weight, self.group_weights, self.exp_avg, self.exp_avg_sq, self.step_dev,
+                            g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"])
+        self.losses = losses * self._w_dev
+        return self.losses.sum()

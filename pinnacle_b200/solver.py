@@ -358,8 +358,8 @@ class FusedPDESolver:
             raise capi.FusedOpError("capture_step() does not support lr schedulers")
         if not self.core.cache_points:
             raise capi.FusedOpError("capture_step() needs device-resident points (cache_points=True)")
-        from .optim import FlatAdam, FusedLRA
-        flat_opt = isinstance(self.opt, (FlatAdam, FusedLRA))
+        from .optim import FlatAdam, FlatMultiAdam, FusedLRA
+        flat_opt = isinstance(self.opt, (FlatAdam, FusedLRA, FlatMultiAdam))
         for grp in self.opt.param_groups:
             if not flat_opt and not grp.get("capturable", False):
                 raise capi.FusedOpError("capture_step() needs an optimizer constructed with capturable=True (or a FlatAdam / FusedLRA)")
@@ -391,12 +391,12 @@ class FusedPDESolver:
 
     def _flat_optimizer_step(self):
         """Autograd-free step for the optimizers of pinnacle_b200.optim (None when the configuration needs autograd)."""
-        from .optim import FlatAdam, FusedLRA
+        from .optim import FlatAdam, FlatMultiAdam, FusedLRA
         if self.core.dynamic_params:
-            if isinstance(self.opt, FusedLRA):
-                raise capi.FusedOpError("FusedLRA works on the flat parameter vector of a plain FNN; adaptive-activation nets need an autograd optimizer")
+            if isinstance(self.opt, (FusedLRA, FlatMultiAdam)):
+                raise capi.FusedOpError("FusedLRA / FlatMultiAdam work on the flat parameter vector of a plain FNN; adaptive-activation nets need an autograd optimizer")
             return None        # the flat buffer is not the vector the kernels differentiate with respect to
-        if isinstance(self.opt, FusedLRA):
+        if isinstance(self.opt, (FusedLRA, FlatMultiAdam)):
             if self.opt.solver is None:
                 self.opt.attach(self)
             return self.opt.step()

@@ -163,3 +163,76 @@ def test_fused_lra_follows_reference_algorithm(pde_w):
     np.testing.assert_array_equal(wa[:3], w0[:3])
     pa, pb = _flat(net_a), _flat(net_b)
     assert float((pa - pb).norm() / pb.norm()) < 2e-3
+
+
+class _MultiAdamPort(torch.optim.Optimizer):
+    """Test-side restatement of the reference's MultiAdam.step + sadam (src/optimizer/multiadam.py:54-122, 216-330) with its
+    benchmark.py:108 configuration (amsgrad off, no aggregated momentum, no parameter scheduler), flat over all parameters."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.99, 0.99), eps=1e-8, loss_group_idx=None, group_weights=None):
+        params = list(params)
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self.loss_group_idx = list(loss_group_idx or [])
+        self.n_groups = len(self.loss_group_idx) + 1
+        self.gw = [1.0 / self.n_groups] * self.n_groups if group_weights is None else list(group_weights)
+        self.m = [[torch.zeros_like(p) for p in params] for _ in range(self.n_groups)]
+        self.v = [[torch.zeros_like(p) for p in params] for _ in range(self.n_groups)]
+        self.t = 0
+
+    @torch.no_grad()
+    def step(self, closure):
+        with torch.enable_grad():
+            closure(skip_backward=True)
+            losses = self.losses
+            idx = [0] + self.loss_group_idx + [len(losses)]
+            grouped = [torch.sum(losses[idx[i]:idx[i + 1]]) for i in range(len(idx) - 1)]
+        params = self.param_groups[0]["params"]
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        grads = []
+        for loss in grouped:
+            self.zero_grad()
+            with torch.enable_grad():
+                loss.backward(retain_graph=True)
+            grads.append([torch.zeros_like(p) if p.grad is None else p.grad.clone() for p in params])
+        self.t += 1
+        bc1, bc2 = 1 - b1 ** self.t, 1 - b2 ** self.t
+        for j, p in enumerate(params):
+            upd = torch.zeros_like(p)
+            for k in range(self.n_groups):
+                self.m[k][j].mul_(b1).add_(grads[k][j], alpha=1 - b1)
+                self.v[k][j].mul_(b2).addcmul_(grads[k][j], grads[k][j], value=1 - b2)
+                upd += self.gw[k] * self.m[k][j] / ((self.v[k][j].sqrt() / bc2 ** 0.5) + g["eps"])
+            p -= (g["lr"] / bc1) * upd
+        return sum(grouped)
+
+
+@pytest.mark.parametrize("groups", [[3], [1, 3]])
+def test_flat_multiadam_follows_reference_algorithm(groups):
+    """benchmark.py --method multiadam (loss_group_idx = [num_pde], betas (0.99, 0.99)): the one-launch FlatMultiAdam on the
+    gradient rows against the reference algorithm run through autograd; also with a group boundary inside the PDE terms."""
+    from pinnacle_b200.optim import FlatMultiAdam
+    from pinnacle_b200.solver import FusedPDESolver
+    dev = torch.device("cuda:0")
+    spec, x, xb, terms = _ns_problem(dev)
+    w = np.array([1.0, 2.0, 0.5, 1.0, 3.0, 1.0, 0.25, 10.0])
+    net_a, net_b = _net(spec.desc, dev, 21), _net(spec.desc, dev, 21)
+    sa = FusedPDESolver(spec, net_a, x, xb, terms).compile(
+        FlatMultiAdam(net_a.parameters(), lr=1e-3, betas=(0.99, 0.99), loss_group_idx=groups), loss_weights=w)
+    sb = FusedPDESolver(spec, net_b, x, xb, terms).compile(
+        _MultiAdamPort(net_b.parameters(), lr=1e-3, betas=(0.99, 0.99), loss_group_idx=groups), loss_weights=w.copy())
+    for k in range(8):
+        sa.train_step()
+        sb.train_step()
+        np.testing.assert_allclose(sa.opt.losses.detach().cpu().numpy(), sb.opt.losses.detach().cpu().numpy(), rtol=1e-3)
+    pa, pb = _flat(net_a), _flat(net_b)
+    assert float((pa - pb).norm() / pb.norm()) < 1e-4
+    assert float(sa.opt.step_dev[0]) == 8.0
+    # graph replay of the same step
+    net_c = _net(spec.desc, dev, 21)
+    sc = FusedPDESolver(spec, net_c, x, xb, terms).compile(
+        FlatMultiAdam(net_c.parameters(), lr=1e-3, betas=(0.99, 0.99), loss_group_idx=groups), loss_weights=w.copy())
+    sc.capture_step(warmup=3)
+    for _ in range(5):
+        sc.train_step()
+    assert float((_flat(net_c) - pa).norm() / pa.norm()) < 1e-4
