@@ -1,2 +1,2 @@
 set -x
-timeout -s KILL 400 python -m pytest tests/test_cuda_optim.py -x -q 2>&1 | tail -12
+timeout -s KILL 400 python -m pytest tests/test_cuda_solver.py -x -q 2>&1 | tail -25

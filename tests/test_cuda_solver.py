@@ -229,3 +229,84 @@ def test_adaptive_activation_net_gradients_reach_slopes(kind):
     for _ in range(3):
         solver.train_step()
     assert torch.isfinite(solver.opt.losses).all()
+
+
+class DirichletBC:          # the patch recognises boundary-term classes by name (deepxde/icbc/boundary_conditions.py:66-80)
+    def __init__(self, component, values):
+        self.component, self._values = component, values
+
+    def func(self, X, beg, end, aux_var):
+        return self._values[beg:end]
+
+    def error(self, X, inputs, outputs, beg, end, aux_var=None):
+        return outputs[beg:end, self.component:self.component + 1] - torch.as_tensor(self._values[beg:end], device=outputs.device)
+
+
+class OperatorBC:           # stays on the stock path: evaluated with torch on the BC rows (boundary_conditions.py:137-160)
+    def __init__(self, fn):
+        self.fn = fn
+
+    def error(self, X, inputs, outputs, beg, end, aux_var=None):
+        return self.fn(inputs, outputs, X)[beg:end]
+
+
+class _StubData:
+    def __init__(self, pde_fn, bcs, num_bcs, train_x):
+        self.pde, self.bcs, self.num_bcs, self.train_x = pde_fn, bcs, num_bcs, train_x
+        self.auxiliary_var_fn = None
+
+
+class _StubModel:
+    """The attributes of a compiled dde.Model that enable_fused reads and re-assigns (deepxde/model.py:243-329)."""
+
+    def __init__(self, data, net, opt, loss_weights):
+        self.data, self.net, self.opt, self.lr_scheduler = data, net, opt, None
+        self.losshistory = type("LH", (), {"loss_weights": loss_weights})()
+        self.external_trainable_variables = []
+        self.train_step = self.outputs_losses_train = self.outputs_losses_test = None
+
+    def predict(self, x, operator=None, callbacks=None):
+        with torch.no_grad():
+            return self.net(torch.as_tensor(x, dtype=torch.float32, device=next(self.net.parameters()).device)).cpu().numpy()
+
+
+@pytest.mark.gpu
+def test_enable_fused_patch_on_a_model_like_object_on_the_gpu():
+    """enable_fused() -- the dde.Model patch -- with the CUDA kernels underneath (the reference package is not on the GPU box,
+    so a stand-in object with the attributes the patch touches plays the compiled model): fused Dirichlet term + a stock
+    operator term, live loss weights, closure(skip_backward) protocol, frozen-net test path, against FusedPDESolver."""
+    from pinnacle_b200 import problems
+    from pinnacle_b200.solver import FusedPDESolver, ValueBC, enable_fused
+    dev = torch.device("cuda:0")
+    spec = problems.make("Poisson2D_Classic")
+    x = spec.sample(1500, seed=3)
+    nb = 200
+    xb = spec.sample(2 * nb, seed=4)
+    vals = np.random.RandomState(1).standard_normal((2 * nb, 1)).astype(np.float32)
+    train_x = np.vstack([xb, x]).astype(np.float32)
+    op_term = lambda inputs, outputs, X: outputs[:, 0:1] ** 2 - 0.25
+    net_a, net_b = _net(spec.desc, dev, 17), _net(spec.desc, dev, 17)
+    w = np.array([1.0, 2.0, 0.5])
+    data = _StubData(lambda x_, u_: None, [DirichletBC(0, vals), OperatorBC(op_term)], [nb, nb], train_x)
+    model = _StubModel(data, net_a, torch.optim.Adam(net_a.parameters(), 1e-3), w)
+    enable_fused(model, spec=spec)
+    # the same problem through the reference-free front end
+    sb = FusedPDESolver(spec, net_b, x, xb, [ValueBC(0, nb, 0, vals[:nb]), lambda xbt, ybt: (ybt[:, 0:1] ** 2 - 0.25)[nb:]]).compile(
+        torch.optim.Adam(net_b.parameters(), 1e-3), loss_weights=w.copy())
+    out_a, la = model.outputs_losses_train(train_x, None)
+    _, lb = sb.outputs_losses_train()
+    np.testing.assert_allclose(la.detach().cpu().numpy(), lb.detach().cpu().numpy(), rtol=2e-5)
+    for _ in range(3):
+        model.train_step(train_x, None)
+        sb.train_step()
+        np.testing.assert_allclose(model.opt.losses.detach().cpu().numpy(), sb.opt.losses.detach().cpu().numpy(), rtol=5e-4)
+    w[1] = 7.0                                  # the live array: the next evaluation sees the new weight
+    _, la2 = model.outputs_losses_train(train_x, None)
+    _, la1 = model.outputs_losses_train(train_x, None)
+    assert abs(float(la2[1]) / 7.0 - float(sb.outputs_losses_train()[1][1]) / 2.0) <= 1e-4 * abs(float(la2[1]) / 7.0)
+    # _test(): frozen net -> losses on the rows handed in, outputs for every row
+    net_a.requires_grad_(False)
+    out_t, lt = model.outputs_losses_test(train_x, None)
+    net_a.requires_grad_(True)
+    assert out_t.shape == (train_x.shape[0], 1) and lt.shape == (3,) and torch.isfinite(lt).all()
+    assert float((_flat(net_a) - _flat(net_b)).norm() / _flat(net_b).norm()) < 1e-4
