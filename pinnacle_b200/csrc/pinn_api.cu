@@ -370,6 +370,10 @@ double pinn_ffma_peak_tflops(int iters) {
 
 const char* pinn_last_error(void) { return g_err.c_str(); }
 
-const char* pinn_build_info(void) { return "libpinn_b200 sm_100a fp32-ffma + tcgen05 bf16x3 jets; configs=" "19" "; built " __DATE__ " " __TIME__; }
+#define PINN_STR2(x) #x
+#define PINN_STR(x) PINN_STR2(x)
+const char* pinn_build_info(void) {
+  return "libpinn_b200 sm_100a fp32-ffma + tcgen05 bf16x3 jets; configs=" PINN_STR(PINN_NUM_CONFIGS) "; built " __DATE__ " " __TIME__;
+}
 
 }  // extern "C"
