@@ -192,6 +192,42 @@ class _StepCore:
         d, H, L, m = self._shape
         return self.fused_term_loss(idx, beg, end, value_desc(d, m, int(component)), values_fn)
 
+    def gradient_rows(self, flat: torch.Tensor, pde_seeds: torch.Tensor, terms):
+        """Gradient rows of the staged point set without autograd.  ``terms``: resolved boundary terms, each
+        ``("op", idx, beg, end, desc, aux_fn)`` (VALUE / FLUX) or ``("periodic", idx, beg, end, component)``.
+        Returns (G [S + len(terms), P], unweighted losses [n_pde + len(terms)]); buffers are reused by the next call."""
+        from . import fused as _fused
+        op = self.op
+        desc = op.desc
+        P, n_pde, S, n_bc = desc.n_params, desc.n_pde, int(pde_seeds.shape[0]), len(terms)
+        T = S + n_bc
+        need = T * P + max(n_pde, 1) + 1
+        buf = getattr(self, "_rows_buf", None)
+        if buf is None or buf.numel() < need or buf.device != flat.device or self._rows_losses.numel() != n_pde + n_bc:
+            buf = self._rows_buf = torch.empty(need, dtype=torch.float32, device=flat.device)
+            self._rows_losses = torch.empty(n_pde + n_bc, dtype=torch.float32, device=flat.device)
+            self._one_seed = torch.ones(1, 1, dtype=torch.float32, device=flat.device)
+        losses = self._rows_losses
+        out = buf[:S * P + n_pde]
+        _fused._backend_fwd_bwd(desc, flat, op.x, op.aux, op.inv_n_global, pde_seeds, out=out)
+        op.stats["fwd_bwd_calls"] += 1
+        if op.world > 1:
+            _fused._all_reduce(out, op.group)
+            op.stats["allreduce_calls"] += 1
+        losses[:n_pde].copy_(out[S * P:])
+        for i, t in enumerate(terms):
+            o = buf[(S + i) * P:(S + i) * P + P + 1]
+            if t[3] - t[2] == 0:
+                raise capi.FusedOpError("gradient rows: boundary term without rows")
+            if t[0] == "periodic":
+                _periodic_eval(self.periodic_op(t[1], t[2], t[3], t[4]), flat, True, o)
+            else:
+                bop = self.term_op(t[1], t[2], t[3], t[4], t[5])
+                _fused._backend_fwd_bwd(bop.desc, flat, bop.x, bop.aux, bop.inv_n_global, self._one_seed, out=o)
+                bop.stats["fwd_bwd_calls"] += 1
+            losses[n_pde + i:n_pde + i + 1].copy_(o[P:])
+        return buf[:T * P].view(T, P), losses
+
     def stage(self, inputs, n_bc: int):
         """Make the rows of ``inputs`` device-resident: BC rows -> self._x_bc, residual rows -> fused op.
         Keyed on the identity of the host array, as the reference keeps one array per (re)sample
@@ -301,47 +337,20 @@ class FusedPDESolver:
 
         ``pde_seeds`` [S, n_pde]: row s is d(sum_k seeds[s,k] L_k)/dtheta of the PDE terms.  Returns (G [S + n_bc, P],
         losses [n_pde + n_bc]); the buffers are reused by the next call.  Needs every boundary term on the fused path."""
-        from . import fused as _fused
         core = self.core
         core.stage(self.train_x, self.n_bc)
-        for f in self.bc_terms:
-            if not isinstance(f, (ValueBC, FluxBC, PeriodicPairBC)):
-                raise capi.FusedOpError("term_gradient_rows() needs every boundary term on the fused path (ValueBC / FluxBC / PeriodicPairBC)")
-            if f.end - f.beg == 0:
-                raise capi.FusedOpError("term_gradient_rows(): boundary term without rows")
-        op = core.op
-        desc = op.desc
-        P, n_pde, S, n_bc = desc.n_params, desc.n_pde, int(pde_seeds.shape[0]), len(self.bc_terms)
-        T = S + n_bc
-        need = T * P + max(n_pde, 1) + 1
-        buf = getattr(self, "_rows_buf", None)
-        if buf is None or buf.numel() < need or buf.device != flat.device:
-            buf = self._rows_buf = torch.empty(need, dtype=torch.float32, device=flat.device)
-            self._rows_losses = torch.empty(n_pde + n_bc, dtype=torch.float32, device=flat.device)
-            self._one_seed = torch.ones(1, 1, dtype=torch.float32, device=flat.device)
-        losses = self._rows_losses
-        out = buf[:S * P + n_pde]
-        _fused._backend_fwd_bwd(desc, flat, op.x, op.aux, op.inv_n_global, pde_seeds, out=out)
-        op.stats["fwd_bwd_calls"] += 1
-        if op.world > 1:
-            _fused._all_reduce(out, op.group)
-            op.stats["allreduce_calls"] += 1
-        losses[:n_pde].copy_(out[S * P:])
         d, m = core._shape[0], core._shape[3]
+        terms = []
         for i, f in enumerate(self.bc_terms):
-            o = buf[(S + i) * P:(S + i) * P + P + 1]
             if isinstance(f, PeriodicPairBC):
-                _periodic_eval(core.periodic_op(i, f.beg, f.end, f.component), flat, True, o)
-                losses[n_pde + i:n_pde + i + 1].copy_(o[P:])
-                continue
-            if isinstance(f, ValueBC):
-                bop = core.term_op(i, f.beg, f.end, value_desc(d, m, int(f.component)), lambda f=f: f.values)
+                terms.append(("periodic", i, f.beg, f.end, f.component))
+            elif isinstance(f, ValueBC):
+                terms.append(("op", i, f.beg, f.end, value_desc(d, m, int(f.component)), lambda f=f: f.values))
+            elif isinstance(f, FluxBC):
+                terms.append(("op", i, f.beg, f.end, flux_desc(d, m, int(f.component), f.beta is not None), lambda f=f: _flux_aux(f)))
             else:
-                bop = core.term_op(i, f.beg, f.end, flux_desc(d, m, int(f.component), f.beta is not None), lambda f=f: _flux_aux(f))
-            _fused._backend_fwd_bwd(bop.desc, flat, bop.x, bop.aux, bop.inv_n_global, self._one_seed, out=o)
-            bop.stats["fwd_bwd_calls"] += 1
-            losses[n_pde + i:n_pde + i + 1].copy_(o[P:])
-        return buf[:T * P].view(T, P), losses
+                raise capi.FusedOpError("term_gradient_rows() needs every boundary term on the fused path (ValueBC / FluxBC / PeriodicPairBC)")
+        return core.gradient_rows(flat, pde_seeds, terms)
 
     # ---- whole-step CUDA graph -----------------------------------------------------------------------
     def capture_step(self, warmup: int = 3):
@@ -433,12 +442,18 @@ class FusedPDESolver:
 
 
 def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto", cache_points: bool = True, group=None,
-                 fuse_bcs: bool = True):
+                 fuse_bcs: bool = True, fuse_optimizer: bool = False):
     """Swap a COMPILED reference ``dde.Model`` onto the fused path (call after ``model.compile``).
 
     Raises (never falls back) when the problem class, the net or the data object is outside what
-    the fused path covers.  With ``fuse_bcs`` (default) value-type boundary terms (DirichletBC, IC, PointSetBC) also run
-    through the fused op (kind VALUE); Neumann / Robin / Periodic / Operator terms stay stock PyTorch on the BC rows."""
+    the fused path covers.  With ``fuse_bcs`` (default) value-type (DirichletBC, IC, PointSetBC), flux-type (NeumannBC, affine
+    RobinBC) and periodic boundary terms also run through the fused op; Operator terms stay stock PyTorch on the BC rows.
+
+    ``fuse_optimizer=True`` additionally replaces ``model.opt`` by its flat-buffer equivalent when there is one and every
+    loss term is fused: ``torch.optim.Adam`` -> ``optim.FlatAdam``, the reference's ``LR_Adaptor`` (around Adam) ->
+    ``optim.FusedLRA``, ``MultiAdam`` -> ``optim.FlatMultiAdam`` (same hyper-parameters; see ``_swap_optimizer``).  The
+    training step then needs no autograd graph at all.  Any other optimizer (L-BFGS, NTK, a scheduler attached) is left
+    alone and keeps driving the fused losses through autograd."""
     if getattr(model, "opt", None) is None or not hasattr(model, "train_step"):
         raise capi.FusedOpError("enable_fused() must be called after model.compile()")
     data, net = model.data, model.net
@@ -514,9 +529,58 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
         return outputs_losses(True, inputs, targets)
 
     def outputs_losses_test(inputs, targets):
+        if hasattr(model.opt, "sync_loss_weight"):
+            model.opt.sync_loss_weight()         # FusedLRA keeps the live weights on the device; refresh the host array for logging
         return outputs_losses(False, inputs, targets)
 
+    class _Rows:
+        """What the flat-buffer optimizers need from a solver (see FusedPDESolver): the loss-term layout and gradient rows."""
+
+        def __init__(self):
+            self.spec = spec
+            self.loss_weights = loss_weights
+            self.inputs = None
+
+        @property
+        def num_loss(self):
+            return n_pde + len(data.bcs)
+
+        def term_gradient_rows(self, flat, pde_seeds):
+            inputs = data.train_x if self.inputs is None else self.inputs
+            n_bc = int(np.sum(data.num_bcs))
+            core.stage(inputs, n_bc)
+            bcs_start = np.cumsum([0] + list(data.num_bcs))
+            d, H, L, m = core._shape
+            terms = []
+            for i, bc in enumerate(data.bcs):
+                beg, end = int(bcs_start[i]), int(bcs_start[i + 1])
+                comp = _periodic_bc_component(bc)
+                flux = _flux_bc_info(bc, core)
+                val = _value_bc_info(bc)
+                if comp is not None:
+                    terms.append(("periodic", i, beg, end, comp))
+                elif flux is not None:
+                    terms.append(("op", i, beg, end, flux[0], lambda af=flux[1], b=beg, e=end: af(data.train_x, b, e)))
+                elif val is not None:
+                    terms.append(("op", i, beg, end, value_desc(d, m, val[0]), lambda vf=val[1], b=beg, e=end: vf(data.train_x, b, e)))
+                else:
+                    raise capi.FusedOpError(f"boundary term {i} ({type(bc).__name__}) is not on the fused path")
+            return core.gradient_rows(flat, pde_seeds, terms)
+
+    rows = _Rows()
+
     def train_step(inputs, targets):
+        from .optim import FlatAdam, FlatMultiAdam, FusedLRA
+        if isinstance(model.opt, (FlatAdam, FlatMultiAdam, FusedLRA)) and model.lr_scheduler is None and not core.dynamic_params:
+            rows.inputs = inputs
+            if isinstance(model.opt, FlatAdam):
+                model.opt.fused_step(rows)
+            else:
+                if model.opt.solver is None:
+                    model.opt.attach(rows)
+                model.opt.step()
+            return
+
         def closure(*, skip_backward=False):
             losses = outputs_losses_train(inputs, targets)[1]
             model.opt.losses = losses
@@ -576,7 +640,58 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
     model.train_step = train_step
     model.predict = predict
     model.fused_core = core
+    if fuse_optimizer:
+        all_fused = fuse_bcs and not core.dynamic_params and all(
+            _periodic_bc_component(bc) is not None or _flux_bc_info(bc, core) is not None or _value_bc_info(bc) is not None for bc in data.bcs)
+        if all_fused and model.lr_scheduler is None:
+            new_opt = _swap_optimizer(model.opt, net, loss_weights, n_pde)
+            if new_opt is not None:
+                model.opt = new_opt
     return model
+
+
+def _swap_optimizer(opt, net, loss_weights, n_pde):
+    """The flat-buffer equivalent of a reference-side optimizer, or None when there is none.
+
+    * ``torch.optim.Adam`` (benchmark.py:107; amsgrad / maximize / capturable variants excluded) -> ``FlatAdam``
+    * ``LR_Adaptor(Adam, loss_weight, num_pde, alpha)`` (src/optimizer/lr_adaptor.py:10-25)       -> ``FusedLRA(FlatAdam, ...)``
+    * ``MultiAdam(params, lr, betas, ..., loss_group_idx, group_weights)`` without amsgrad, aggregated momentum or a custom
+      parameter scheduler (src/optimizer/multiadam.py:127-190)                                      -> ``FlatMultiAdam``
+    Optimizers that have already stepped are left alone (their state would be lost)."""
+    from .optim import FlatAdam, FlatMultiAdam, FusedLRA
+
+    def plain_adam(o):
+        if type(o) is not torch.optim.Adam or len(o.param_groups) != 1 or len(o.state) != 0:
+            return None
+        g = o.param_groups[0]
+        if g.get("amsgrad") or g.get("maximize") or g.get("capturable") or g.get("differentiable"):
+            return None
+        if [id(p) for p in g["params"]] != [id(p) for p in net.parameters()]:
+            return None
+        return g
+
+    name = type(opt).__name__
+    g = plain_adam(opt)
+    if g is not None:
+        return FlatAdam(net.parameters(), lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"])
+    if name == "LR_Adaptor" and getattr(opt, "mode", "max") == "max" and getattr(opt, "iter", 0) == 0:
+        g = plain_adam(getattr(opt, "optimizer", None))
+        if g is None or int(opt.num_pde) != n_pde:
+            return None
+        inner = FlatAdam(net.parameters(), lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"])
+        return FusedLRA(inner, opt.loss_weight, opt.num_pde, alpha=opt.alpha)
+    if name == "MultiAdam" and getattr(opt, "is_init_state", True):
+        g = opt.param_groups[0]
+        sched = getattr(opt, "param_scheduler", None)
+        custom = sched is not None and any(getattr(sched, a, None) is not None for a in ("lr_scheduler", "betas_scheduler", "group_weights_scheduler"))
+        if len(opt.param_groups) != 1 or g.get("amsgrad") or g.get("maximize") or g.get("agg_momentum") or custom:
+            return None
+        if [id(p) for p in g["params"]] != [id(p) for p in net.parameters()]:
+            return None
+        gw = getattr(opt, "group_weights", None)
+        return FlatMultiAdam(net.parameters(), lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"],
+                             loss_group_idx=list(opt.loss_group_idx), group_weights=None if gw is None else [float(v) for v in gw])
+    return None
 
 
 def _value_bc_info(bc):

@@ -310,3 +310,69 @@ def test_enable_fused_patch_on_a_model_like_object_on_the_gpu():
     net_a.requires_grad_(True)
     assert out_t.shape == (train_x.shape[0], 1) and lt.shape == (3,) and torch.isfinite(lt).all()
     assert float((_flat(net_a) - _flat(net_b)).norm() / _flat(net_b).norm()) < 1e-4
+
+
+class LR_Adaptor:           # attribute layout of src/optimizer/lr_adaptor.py:10-25 (the patch recognises it by name)
+    def __init__(self, optimizer, loss_weight, num_pde, alpha=0.1, mode="max"):
+        self.optimizer, self.loss_weight, self.num_pde, self.alpha, self.mode, self.iter = optimizer, loss_weight, num_pde, alpha, mode, 0
+        self.param_groups = optimizer.param_groups
+
+
+class MultiAdam:            # attribute layout of src/optimizer/multiadam.py:127-190
+    def __init__(self, params, lr=1e-3, betas=(0.99, 0.99), eps=1e-8, loss_group_idx=None):
+        self.param_groups = [dict(params=list(params), lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False, agg_momentum=False)]
+        self.loss_group_idx, self.is_init_state, self.param_scheduler = loss_group_idx, True, None
+        self.group_weights = torch.ones(len(loss_group_idx) + 1) / (len(loss_group_idx) + 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["adam", "lra", "multiadam"])
+def test_enable_fused_swaps_in_the_flat_optimizers(method):
+    """enable_fused(model, fuse_optimizer=True): torch Adam -> FlatAdam, LR_Adaptor -> FusedLRA, MultiAdam -> FlatMultiAdam when every
+    loss term is fused; the patched train_step then runs without an autograd graph and follows the reference-free solver
+    driven by the same flat optimizer.  An optimizer the patch does not know (L-BFGS) is left alone."""
+    from pinnacle_b200 import problems
+    from pinnacle_b200.optim import FlatAdam, FlatMultiAdam, FusedLRA
+    from pinnacle_b200.solver import FusedPDESolver, ValueBC, enable_fused
+    dev = torch.device("cuda:0")
+    spec = problems.make("NS2D_LidDriven")
+    x = spec.sample(2000, seed=3)
+    nb = 128
+    xb = spec.sample(2 * nb, seed=4)
+    vals = np.random.RandomState(1).standard_normal((2 * nb, 1)).astype(np.float32)
+    train_x = np.vstack([xb, x]).astype(np.float32)
+    net_a, net_b = _net(spec.desc, dev, 19), _net(spec.desc, dev, 19)
+    wa, wb = np.array([1.0, 1.0, 1.0, 2.0, 0.5]), np.array([1.0, 1.0, 1.0, 2.0, 0.5])
+    data = _StubData(lambda x_, u_: None, [DirichletBC(0, vals), DirichletBC(1, vals)], [nb, nb], train_x)
+    terms = [ValueBC(0, nb, 0, vals[:nb]), ValueBC(nb, 2 * nb, 1, vals[nb:])]
+    if method == "adam":
+        opt_a, want = torch.optim.Adam(net_a.parameters(), 2e-3, betas=(0.8, 0.99)), FlatAdam
+        opt_b = FlatAdam(net_b.parameters(), 2e-3, betas=(0.8, 0.99))
+    elif method == "lra":
+        opt_a, want = LR_Adaptor(torch.optim.Adam(net_a.parameters(), 1e-3), wa, 3, alpha=0.2), FusedLRA
+        opt_b = FusedLRA(FlatAdam(net_b.parameters(), 1e-3), wb, 3, alpha=0.2)
+    else:
+        opt_a, want = MultiAdam(net_a.parameters(), lr=1e-3, loss_group_idx=[3]), FlatMultiAdam
+        opt_b = FlatMultiAdam(net_b.parameters(), lr=1e-3, betas=(0.99, 0.99), loss_group_idx=[3])
+    model = _StubModel(data, net_a, opt_a, wa)
+    enable_fused(model, spec=spec, fuse_optimizer=True)
+    assert type(model.opt) is want
+    sb = FusedPDESolver(spec, net_b, x, xb, terms).compile(opt_b, loss_weights=wb)
+    for _ in range(5):
+        model.train_step(train_x, None)
+        sb.train_step()
+        np.testing.assert_allclose(model.opt.losses.detach().cpu().numpy(), sb.opt.losses.detach().cpu().numpy(), rtol=1e-5)
+    assert model.fused_core.op.stats["fwd_calls"] == 0          # no autograd forward was ever run
+    assert float((_flat(net_a) - _flat(net_b)).norm() / _flat(net_b).norm()) < 1e-6
+    if method == "lra":
+        model.outputs_losses_test(train_x, None)                 # refreshes the host array the reference logs
+        np.testing.assert_allclose(wa, sb.opt.sync_loss_weight(), rtol=1e-6)
+        assert not np.allclose(wa[3:], [2.0, 0.5])
+    # unknown optimizer: untouched
+    net_c = _net(spec.desc, dev, 19)
+    lb = torch.optim.LBFGS(net_c.parameters(), max_iter=3)
+    m2 = _StubModel(_StubData(lambda x_, u_: None, data.bcs, [nb, nb], train_x), net_c, lb, np.ones(5))
+    enable_fused(m2, spec=spec, fuse_optimizer=True)
+    assert m2.opt is lb
+    m2.train_step(train_x, None)
+    assert torch.isfinite(m2.opt.losses).all()

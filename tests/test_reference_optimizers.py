@@ -195,3 +195,37 @@ def test_adaptive_activation_nets_on_patched_model(name, kind):
             np.testing.assert_allclose(new_hist, ref_hist, rtol=5e-3)
     finally:
         fused.FusedPDEResidual.__init__ = orig
+
+
+@needs_ref
+def test_swap_optimizer_reads_the_reference_classes_correctly(monkeypatch):
+    """enable_fused(fuse_optimizer=True) maps the reference's own optimizer objects (benchmark.py:107-115) to their flat-buffer
+    equivalents with the same hyper-parameters.  The flat optimizers need CUDA, so recorders stand in for them here; the
+    GPU side of the swap is tests/test_cuda_solver.py::test_enable_fused_swaps_in_the_flat_optimizers."""
+    from pinnacle_b200 import optim, solver
+    dde, _ = refshim.load()
+    from src.optimizer import MultiAdam, LR_Adaptor, LR_Adaptor_NTK, Adam_LBFGS
+    made = []
+
+    class Rec:
+        def __init__(self, *a, **k):
+            made.append((type(self).__name__, a, k))
+
+    for nm in ("FlatAdam", "FlatMultiAdam", "FusedLRA"):
+        monkeypatch.setattr(optim, nm, type(nm, (Rec,), {}))
+    net = dde.nn.FNN([2] + [100] * 5 + [1], "tanh", "Glorot normal").float()
+    w = np.ones(4)
+    adam = torch.optim.Adam(net.parameters(), 3e-3, betas=(0.8, 0.95), eps=1e-7, weight_decay=1e-4)
+    out = solver._swap_optimizer(adam, net, w, 1)
+    assert type(out).__name__ == "FlatAdam" and made[-1][2] == dict(lr=3e-3, betas=(0.8, 0.95), eps=1e-7, weight_decay=1e-4)
+    out = solver._swap_optimizer(LR_Adaptor(torch.optim.Adam(net.parameters(), 1e-3), w, 1, alpha=0.3), net, w, 1)
+    assert type(out).__name__ == "FusedLRA"
+    assert made[-1][1][1] is w and made[-1][1][2] == 1 and made[-1][2] == dict(alpha=0.3)
+    out = solver._swap_optimizer(MultiAdam(net.parameters(), lr=1e-3, betas=(0.99, 0.99), loss_group_idx=[1]), net, w, 1)
+    assert type(out).__name__ == "FlatMultiAdam"
+    assert made[-1][2]["loss_group_idx"] == [1] and made[-1][2]["betas"] == (0.99, 0.99) and made[-1][2]["group_weights"] == [0.5, 0.5]
+    # no flat equivalent: left alone
+    assert solver._swap_optimizer(Adam_LBFGS(net.parameters(), switch_epoch=5), net, w, 1) is None
+    assert solver._swap_optimizer(torch.optim.Adam(net.parameters(), 1e-3, amsgrad=True), net, w, 1) is None
+    assert solver._swap_optimizer(MultiAdam(net.parameters(), loss_group_idx=[1], agg_momentum=True, agg_betas=(0.9, 0.9)), net, w, 1) is None
+    assert solver._swap_optimizer(LR_Adaptor(torch.optim.Adam(net.parameters(), 1e-3), w, 2), net, w, 1) is None      # num_pde mismatch
