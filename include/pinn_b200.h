@@ -110,6 +110,12 @@ int pinn_fwd_bwd(const pinn_kind_desc* desc, const float* params, const float* x
                  int64_t n_rows, double inv_n_global, const float* seeds, int n_seeds, float* out,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same pass with LINEAR seeds:  out[s*P + i] = d( sum_k seeds[s][k] * sum_rows r_k ) / d params[i]  -- the gradient of the
+ * residual SUMS, which src/optimizer/ntk.py:24-58 builds with loss_fn = (y - x).sum() for its NTK-trace statistics.
+ * out[n_seeds*P + k] still holds sum_rows r_k^2 (inv_n_global = 1). */
+int pinn_fwd_bwd_linear(const pinn_kind_desc* desc, const float* params, const float* x, const float* aux, int64_t n_rows,
+                        const float* seeds, int n_seeds, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Kernel selection: 0 = automatic (tcgen05 tensor-core kernel where one is instantiated -- its pipelined variant
  * where that exists -- else the FP32 FFMA kernel), 1 = FP32 FFMA kernel, 2 = tensor-core kernel, one tile at a time
  * (calls fail where none exists), 3 = pipelined tensor-core kernel (two sub-tiles in flight, warp-specialised;

@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libpinn_b200.so")
 
 EXPORTS = (
-    "pinn_param_count", "pinn_supported", "pinn_workspace_bytes", "pinn_fwd", "pinn_fwd_bwd",
+    "pinn_param_count", "pinn_supported", "pinn_workspace_bytes", "pinn_fwd", "pinn_fwd_bwd", "pinn_fwd_bwd_linear",
     "pinn_last_launch_count", "pinn_ffma_peak_tflops", "pinn_last_error", "pinn_build_info", "pinn_debug_umma_gemm", "pinn_set_impl", "pinn_has_tensor_core_kernel",
     "pinn_selected_impl", "pinn_effective_channels", "pinn_set_laplacian_collapse",
     "pinn_adam_step", "pinn_optim_scratch_floats", "pinn_grad_stats", "pinn_lra_combine", "pinn_multiadam_step",
@@ -76,6 +76,8 @@ def load() -> ctypes.CDLL:
     lib.pinn_adam_step.restype = ctypes.c_int
     lib.pinn_multiadam_step.argtypes = [V, V, ctypes.c_int, I64, I64, V, V, ctypes.c_int, V, V, V, V, F, F, F, F, F, V]
     lib.pinn_multiadam_step.restype = ctypes.c_int
+    lib.pinn_fwd_bwd_linear.argtypes = [P, V, V, V, I64, V, ctypes.c_int, V, V, ctypes.c_size_t, V]
+    lib.pinn_fwd_bwd_linear.restype = ctypes.c_int
     lib.pinn_optim_scratch_floats.argtypes = []
     lib.pinn_optim_scratch_floats.restype = ctypes.c_size_t
     lib.pinn_grad_stats.argtypes = [V, I64, V, V, V]
@@ -331,3 +333,34 @@ def multiadam_step(params: torch.Tensor, G: torch.Tensor, row_group: torch.Tenso
                                         _ptr(group_weights), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(step_dev), float(lr), float(beta1), float(beta2),
                                         float(eps), float(weight_decay), _stream_ptr(params.device))
     _check(rc, "pinn_multiadam_step")
+
+
+def fwd_bwd_linear(desc: KindDesc, params: torch.Tensor, x: torch.Tensor, aux: Optional[torch.Tensor], seeds: torch.Tensor,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """pinn_fwd_bwd_linear: rows d(sum_k seeds[s,k] * sum_rows r_k)/dtheta (gradient of the residual SUMS, ntk.py:24-58);
+    returns the flat device buffer [S*P | sum_rows r_k^2]."""
+    lib = load()
+    _req(params, "params"); _req(x, "x"); _req(seeds, "seeds")
+    if aux is not None:
+        _req(aux, "aux")
+    n = x.shape[0]
+    if params.numel() != desc.n_params or x.dim() != 2 or x.shape[1] != desc.d:
+        raise FusedOpError("fwd_bwd_linear: params / x do not match the descriptor")
+    if desc.n_aux and (aux is None or tuple(aux.shape) != (n, desc.n_aux)):
+        raise FusedOpError(f"aux must be [N,{desc.n_aux}]")
+    if seeds.dim() != 2 or seeds.shape[1] != desc.n_pde:
+        raise FusedOpError(f"seeds must be [S,{desc.n_pde}]")
+    S = seeds.shape[0]
+    c = desc.to_c()
+    with torch.cuda.device(x.device):
+        ws = _WS.get(x.device, workspace_bytes(desc, S))
+        if out is None:
+            out = torch.empty(S * desc.n_params + desc.n_pde, dtype=torch.float32, device=x.device)
+        else:
+            _req(out, "out")
+            if out.numel() != S * desc.n_params + desc.n_pde:
+                raise FusedOpError("out has the wrong size")
+        rc = lib.pinn_fwd_bwd_linear(ctypes.byref(c), _ptr(params), _ptr(x), _ptr(aux), n, _ptr(seeds), S, _ptr(out), _ptr(ws), ws.numel(),
+                                     _stream_ptr(x.device))
+    _check(rc, "pinn_fwd_bwd_linear")
+    return out

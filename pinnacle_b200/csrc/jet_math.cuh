@@ -249,6 +249,7 @@ struct KindParams {
   float c[PINN_MAX_CONSTS];
   float lapw[PINN_MAX_DIM];   // direction weights of the forward-Laplacian channel (set_kind_params; unused by JetSig signatures)
   int lap_pw;                 // 1: the weights carry a per-point factor (aux column aux_sel[LIN_SEL_C2 + j]), see lap_point_weights
+  int lin_seed;               // 1: reverse seeds multiply sum_rows r_k (pinn_fwd_bwd_linear) instead of the mean-square loss
 };
 
 enum : int { LIN_CU = 0, LIN_C1 = 1, LIN_C2 = 1 + PINN_MAX_DIM, LIN_SEL_SRC = 0, LIN_SEL_CU = 1, LIN_SEL_C2 = 2 };
@@ -649,6 +650,7 @@ inline int lap_eligible(int kind, int d, int m, const int* order, const int* aux
 inline void set_kind_params(KindParams& kp, int kind, int d, const int* aux_sel, const float* consts, int lap_mode = 0) {
   kp.kind = kind;
   kp.lap_pw = (lap_mode == 2) ? 1 : 0;
+  kp.lin_seed = 0;
   for (int i = 0; i < PINN_MAX_AUXSEL; ++i) kp.aux_sel[i] = aux_sel[i];
   for (int i = 0; i < PINN_MAX_CONSTS; ++i) kp.c[i] = consts[i];
   for (int j = 0; j < PINN_MAX_DIM; ++j) kp.lapw[j] = (kind == PINN_KIND_LINEAR) ? (j < d ? consts[LIN_C2 + j] : 0.f) : (j < 2 ? 1.0f : 0.f);

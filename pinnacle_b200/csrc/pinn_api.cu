@@ -171,7 +171,7 @@ static bool want_tc(const ConfigInfo* c, std::string* why) {
 
 static int run(const pinn_kind_desc* desc, const float* params, const float* x, const float* aux, int64_t n_rows, double inv_n,
                const float* seeds, int n_seeds, float* grad_out, float* loss_out, float* resid_out, void* workspace,
-               size_t workspace_bytes, void* stream_v) {
+               size_t workspace_bytes, void* stream_v, int lin_seed = 0) {
   g_launches = 0;
   std::string why;
   const ConfigInfo* c = find_config(desc, &why);
@@ -222,6 +222,7 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
     ++g_launches;
     TcLaunchParams lp{};
     set_kind_params(lp.kp, desc->kind, desc->d, desc->aux_sel, desc->consts, c->lap);
+    lp.kp.lin_seed = lin_seed;
     lp.L = desc->L; lp.n_aux = desc->n_aux; lp.n_pde = desc->n_pde; lp.n_seeds = n_seeds;
     lp.n_rows = n_rows; lp.P = P; lp.Ppad = ws.pstride; lp.inv_n = (float)inv_n;
     lp.params = params; lp.wn = wn; lp.wt = wt; lp.w6p = w6p; lp.x = x; lp.aux = aux; lp.seeds = seeds;
@@ -238,6 +239,7 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
 
     LaunchParams lp{};
     set_kind_params(lp.kp, desc->kind, desc->d, desc->aux_sel, desc->consts, c->lap);
+    lp.kp.lin_seed = lin_seed;
     lp.L = desc->L;
     lp.n_aux = desc->n_aux;
     lp.n_pde = desc->n_pde;
@@ -307,6 +309,14 @@ int pinn_fwd_bwd(const pinn_kind_desc* desc, const float* params, const float* x
   const long long P = param_count(desc);
   return run(desc, params, x, aux, n_rows, inv_n_global, seeds, n_seeds, out, out + (size_t)n_seeds * P, nullptr, workspace,
              workspace_bytes, stream);
+}
+
+int pinn_fwd_bwd_linear(const pinn_kind_desc* desc, const float* params, const float* x, const float* aux, int64_t n_rows,
+                        const float* seeds, int n_seeds, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n_seeds < 1) return fail("n_seeds must be >= 1");
+  if (desc == nullptr || out == nullptr) return fail("null pointer argument");
+  const long long P = param_count(desc);
+  return run(desc, params, x, aux, n_rows, 1.0, seeds, n_seeds, out, out + (size_t)n_seeds * P, nullptr, workspace, workspace_bytes, stream, 1);
 }
 
 int pinn_last_launch_count(void) { return g_launches; }

@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(CFG::NTP, 1) pinn_fused_kernel(const LaunchPar
           float rb[PINN_MAX_PDE];
 #pragma unroll
           for (int k = 0; k < PINN_MAX_PDE; ++k)
-            rb[k] = (k < p.n_pde) ? p.seeds[s * p.n_pde + k] * 2.0f * rs[k * T + tid] * p.inv_n : 0.f;
+            rb[k] = (k < p.n_pde) ? p.seeds[s * p.n_pde + k] * (kps->lin_seed ? (row0 + tid < p.n_rows ? 1.0f : 0.f) : 2.0f * rs[k * T + tid] * p.inv_n) : 0.f;
           Residual<SIG, M>::adjoint(*kps, auxs + tid * PINN_MAX_AUX, U, rb, Ub);
 #pragma unroll
           for (int o = 0; o < M; ++o)

@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
             for (int c = 0; c < C; ++c) U[o][c] = uo[o * R + c * T + tid];
           float rb[PINN_MAX_PDE];
 #pragma unroll
-          for (int k = 0; k < PINN_MAX_PDE; ++k) rb[k] = (k < p.n_pde) ? p.seeds[s * p.n_pde + k] * 2.0f * rs[k * T + tid] * p.inv_n : 0.f;
+          for (int k = 0; k < PINN_MAX_PDE; ++k) rb[k] = (k < p.n_pde) ? p.seeds[s * p.n_pde + k] * (kps->lin_seed ? (row0 + tid < p.n_rows ? 1.0f : 0.f) : 2.0f * rs[k * T + tid] * p.inv_n) : 0.f;
           Residual<SIG, M>::adjoint(*kps, auxs + tid * PINN_MAX_AUX, U, rb, Ub);
 #pragma unroll
           for (int o = 0; o < M; ++o)

@@ -36,6 +36,7 @@ from .problems import ProblemSpec
 # sharding + all-reduce plumbing can substitute a checker explicitly; nothing in the product does.
 _backend_fwd = capi.fwd
 _backend_fwd_bwd = capi.fwd_bwd
+_backend_fwd_bwd_linear = capi.fwd_bwd_linear      # gradient of the residual SUMS (NTK statistics); no CPU stand-in
 
 
 def shard_bounds(n_rows: int, rank: int, world: int):

@@ -95,21 +95,27 @@ class FlatAdam(torch.optim.Optimizer):
         self.apply_update()
         return loss
 
-    def fused_step(self, solver):
+    def fused_step(self, solver, w_dev: Optional[torch.Tensor] = None):
         """One training step of a ``FusedPDESolver`` whose loss terms are all fused, without autograd: every term's fused
         pass writes its gradient row, ``flat_grad = sum_t w_t G_t`` (one matrix-vector product), one Adam launch.
         Sets ``self.losses`` to the weighted per-term losses like the reference closure (deepxde/model.py:311)."""
         n_pde = solver.spec.desc.n_pde
         T = solver.num_loss
         dev = self.flat.device
-        w = solver.loss_weights
-        w_dev = getattr(self, "_w_dev", None)
-        w_host = None if w is None else np.asarray(w, dtype=np.float32).copy()
-        if w_dev is None or w_dev.numel() != T or (w_host is not None and not np.array_equal(w_host, self._w_host)) or (w_host is None) != (self._w_host is None):
-            self._w_host = w_host
-            self._w_dev = w_dev = torch.ones(T, dtype=torch.float32, device=dev) if w_host is None else torch.as_tensor(w_host).to(dev)
-            self._comb = torch.ones(1 + T - n_pde, dtype=torch.float32, device=dev)
+        if w_dev is not None:            # live weights already on the device (FusedNTK): no host round trip
+            if getattr(self, "_comb", None) is None or self._comb.numel() != 1 + T - n_pde:
+                self._comb = torch.ones(1 + T - n_pde, dtype=torch.float32, device=dev)
             self._comb[1:] = w_dev[n_pde:]
+            self._w_dev, self._w_host = None, None
+        else:
+            w = solver.loss_weights
+            w_dev = getattr(self, "_w_dev", None)
+            w_host = None if w is None else np.asarray(w, dtype=np.float32).copy()
+            if w_dev is None or w_dev.numel() != T or (w_host is not None and not np.array_equal(w_host, self._w_host)) or (w_host is None) != (self._w_host is None):
+                self._w_host = w_host
+                self._w_dev = w_dev = torch.ones(T, dtype=torch.float32, device=dev) if w_host is None else torch.as_tensor(w_host).to(dev)
+                self._comb = torch.ones(1 + T - n_pde, dtype=torch.float32, device=dev)
+                self._comb[1:] = w_dev[n_pde:]
         G, losses = solver.term_gradient_rows(self.flat, w_dev[:n_pde].view(1, n_pde))
         torch.mv(G.t(), self._comb, out=self.flat_grad)
         self.apply_update()
@@ -265,3 +271,55 @@ class FlatMultiAdam(torch.optim.Optimizer):
                             g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"])
         self.losses = losses * self._w_dev
         return self.losses.sum()
+
+
+class FusedNTK(torch.optim.Optimizer):
+    """NTK-based loss balancing (src/optimizer/ntk.py:6-66) on the fused op's LINEAR gradient rows.
+
+    The reference evaluates, every step, the gradient of the SUM of all PDE residuals and of the sum of all boundary errors
+    with stock autograd (``data.losses`` with ``loss_fn = (y - x).sum()``), takes m_r = |g_r|^2, m_b = |g_b|^2, sets the PDE
+    weights to (m_r + m_b) / m_r and the boundary weights to (m_r + m_b) / m_b, then lets the inner optimizer take a normal
+    step under the new weights.  Here the two gradients come from one ``pinn_fwd_bwd_linear`` pass per term, the norms from
+    ``pinn_grad_stats``, the weights never leave the device, and the inner ``FlatAdam`` step is the autograd-free one.
+    Same constructor protocol as ``FusedLRA``; ``sync_loss_weight()`` refreshes the host array."""
+
+    def __init__(self, optimizer: FlatAdam, loss_weight, num_pde: int):
+        if not isinstance(optimizer, FlatAdam):
+            raise capi.FusedOpError("FusedNTK wraps a FlatAdam")
+        super().__init__(optimizer.param_groups, {})
+        self.optimizer, self.loss_weight, self.num_pde, self.iter, self.solver = optimizer, loss_weight, int(num_pde), 0, None
+        dev = optimizer.flat.device
+        self.weights = torch.as_tensor(np.asarray(loss_weight, dtype=np.float32).copy()).to(dev)
+        self._seeds = torch.ones(1, self.num_pde, dtype=torch.float32, device=dev)
+        self._sr = torch.empty(3, dtype=torch.float32, device=dev)
+        self._sb = torch.empty(3, dtype=torch.float32, device=dev)
+
+    def attach(self, solver):
+        if solver.spec.desc.n_pde != self.num_pde or solver.num_loss != self.weights.numel():
+            raise capi.FusedOpError("FusedNTK: loss_weight / num_pde do not match the solver's loss terms")
+        self.solver = solver
+        return self
+
+    def zero_grad(self, set_to_none: bool = True):
+        self.optimizer.zero_grad(set_to_none)
+
+    def sync_loss_weight(self):
+        self.loss_weight[:] = self.weights.detach().cpu().numpy()
+        return self.loss_weight
+
+    def step(self, closure=None):
+        if self.solver is None:
+            raise capi.FusedOpError("FusedNTK.step(): attach(solver) first")
+        self.iter += 1
+        opt = self.optimizer
+        G, _ = self.solver.term_gradient_rows(opt.flat, self._seeds, linear=True)
+        capi.grad_stats(G[0], out=self._sr)
+        g_b = G[1:].sum(dim=0) if G.shape[0] > 2 else G[1]
+        capi.grad_stats(g_b.contiguous(), out=self._sb)
+        m_r, m_b = self._sr[2], self._sb[2]
+        tot = m_r + m_b
+        self.weights[:self.num_pde] = tot / m_r            # ntk.py:60-63
+        self.weights[self.num_pde:] = tot / m_b
+        loss = opt.fused_step(self.solver, w_dev=self.weights)
+        self.losses = opt.losses
+        return loss

@@ -29,6 +29,7 @@ from .problems import ProblemSpec, describe_reference
 
 # A value-type boundary / initial / point-set term on BC rows [beg, end):  u[:, component] - values
 # (DirichletBC / IC / PointSetBC of deepxde/icbc).  Evaluated by the fused op (kind VALUE) instead of stock autograd.
+PINN_ROW_SLACK = 8       # room behind the last gradient row for the loss entries the kernels append
 ValueBC = namedtuple("ValueBC", ["beg", "end", "component", "values"])
 # A flux-type boundary term on BC rows [beg, end):  normals . grad u[:, component] + beta * u[:, component] - values
 # (NeumannBC: beta = None; RobinBC dy/dn = a - b*y: values = a, beta = b).  Fused op, kind FLUX (d <= 3, one output).
@@ -192,11 +193,16 @@ class _StepCore:
         d, H, L, m = self._shape
         return self.fused_term_loss(idx, beg, end, value_desc(d, m, int(component)), values_fn)
 
-    def gradient_rows(self, flat: torch.Tensor, pde_seeds: torch.Tensor, terms):
+    def gradient_rows(self, flat: torch.Tensor, pde_seeds: torch.Tensor, terms, linear: bool = False):
         """Gradient rows of the staged point set without autograd.  ``terms``: resolved boundary terms, each
         ``("op", idx, beg, end, desc, aux_fn)`` (VALUE / FLUX) or ``("periodic", idx, beg, end, component)``.
-        Returns (G [S + len(terms), P], unweighted losses [n_pde + len(terms)]); buffers are reused by the next call."""
+        Returns (G [S + len(terms), P], unweighted losses [n_pde + len(terms)]); buffers are reused by the next call.
+
+        ``linear``: rows are gradients of the residual SUMS sum_rows r (``pinn_fwd_bwd_linear``; the statistics of
+        src/optimizer/ntk.py:24-58) into a second buffer; the loss vector is then meaningless.  Single process only."""
         from . import fused as _fused
+        if linear:
+            return self._linear_rows(flat, pde_seeds, terms)
         op = self.op
         desc = op.desc
         P, n_pde, S, n_bc = desc.n_params, desc.n_pde, int(pde_seeds.shape[0]), len(terms)
@@ -227,6 +233,27 @@ class _StepCore:
                 bop.stats["fwd_bwd_calls"] += 1
             losses[n_pde + i:n_pde + i + 1].copy_(o[P:])
         return buf[:T * P].view(T, P), losses
+
+    def _linear_rows(self, flat, pde_seeds, terms):
+        from . import fused as _fused
+        op = self.op
+        if op.world > 1:
+            raise capi.FusedOpError("linear gradient rows are not sharded yet (NTK statistics): run single-process")
+        desc = op.desc
+        P, S = desc.n_params, int(pde_seeds.shape[0])
+        T = S + len(terms)
+        need = T * P + PINN_ROW_SLACK
+        buf = getattr(self, "_lin_buf", None)
+        if buf is None or buf.numel() < need or buf.device != flat.device:
+            buf = self._lin_buf = torch.empty(need, dtype=torch.float32, device=flat.device)
+            self._lin_one = torch.ones(1, 1, dtype=torch.float32, device=flat.device)
+        _fused._backend_fwd_bwd_linear(desc, flat, op.x, op.aux, pde_seeds, out=buf[:S * P + desc.n_pde])
+        for i, t in enumerate(terms):
+            if t[0] == "periodic":
+                raise capi.FusedOpError("periodic terms have no linear gradient row (NTK statistics): use the autograd optimizer")
+            bop = self.term_op(t[1], t[2], t[3], t[4], t[5])
+            _fused._backend_fwd_bwd_linear(bop.desc, flat, bop.x, bop.aux, self._lin_one, out=buf[(S + i) * P:(S + i) * P + P + 1])
+        return buf[:T * P].view(T, P), None
 
     def stage(self, inputs, n_bc: int):
         """Make the rows of ``inputs`` device-resident: BC rows -> self._x_bc, residual rows -> fused op.
@@ -330,7 +357,7 @@ class FusedPDESolver:
         return self.outputs_losses(False, self.train_x if inputs is None else inputs, targets)
 
     # ---- per-term gradient rows without autograd (optimizers of pinnacle_b200.optim) ----------------------
-    def term_gradient_rows(self, flat: torch.Tensor, pde_seeds: torch.Tensor):
+    def term_gradient_rows(self, flat: torch.Tensor, pde_seeds: torch.Tensor, linear: bool = False):
         """Gradient of every loss term w.r.t. the flat parameter vector as rows of one device matrix, and the unweighted
         per-term losses -- what ``losses[i].backward(retain_graph=True)`` per term yields in the reference
         (src/optimizer/lr_adaptor.py:36,49), from ONE fused pass per term and no autograd graph.
@@ -350,7 +377,7 @@ class FusedPDESolver:
                 terms.append(("op", i, f.beg, f.end, flux_desc(d, m, int(f.component), f.beta is not None), lambda f=f: _flux_aux(f)))
             else:
                 raise capi.FusedOpError("term_gradient_rows() needs every boundary term on the fused path (ValueBC / FluxBC / PeriodicPairBC)")
-        return core.gradient_rows(flat, pde_seeds, terms)
+        return core.gradient_rows(flat, pde_seeds, terms, linear)
 
     # ---- whole-step CUDA graph -----------------------------------------------------------------------
     def capture_step(self, warmup: int = 3):
@@ -367,8 +394,8 @@ class FusedPDESolver:
             raise capi.FusedOpError("capture_step() does not support lr schedulers")
         if not self.core.cache_points:
             raise capi.FusedOpError("capture_step() needs device-resident points (cache_points=True)")
-        from .optim import FlatAdam, FlatMultiAdam, FusedLRA
-        flat_opt = isinstance(self.opt, (FlatAdam, FusedLRA, FlatMultiAdam))
+        from .optim import FlatAdam, FlatMultiAdam, FusedLRA, FusedNTK
+        flat_opt = isinstance(self.opt, (FlatAdam, FusedLRA, FlatMultiAdam, FusedNTK))
         for grp in self.opt.param_groups:
             if not flat_opt and not grp.get("capturable", False):
                 raise capi.FusedOpError("capture_step() needs an optimizer constructed with capturable=True (or a FlatAdam / FusedLRA)")
@@ -400,12 +427,12 @@ class FusedPDESolver:
 
     def _flat_optimizer_step(self):
         """Autograd-free step for the optimizers of pinnacle_b200.optim (None when the configuration needs autograd)."""
-        from .optim import FlatAdam, FlatMultiAdam, FusedLRA
+        from .optim import FlatAdam, FlatMultiAdam, FusedLRA, FusedNTK
         if self.core.dynamic_params:
-            if isinstance(self.opt, (FusedLRA, FlatMultiAdam)):
+            if isinstance(self.opt, (FusedLRA, FlatMultiAdam, FusedNTK)):
                 raise capi.FusedOpError("FusedLRA / FlatMultiAdam work on the flat parameter vector of a plain FNN; adaptive-activation nets need an autograd optimizer")
             return None        # the flat buffer is not the vector the kernels differentiate with respect to
-        if isinstance(self.opt, (FusedLRA, FlatMultiAdam)):
+        if isinstance(self.opt, (FusedLRA, FlatMultiAdam, FusedNTK)):
             if self.opt.solver is None:
                 self.opt.attach(self)
             return self.opt.step()
@@ -545,7 +572,7 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
         def num_loss(self):
             return n_pde + len(data.bcs)
 
-        def term_gradient_rows(self, flat, pde_seeds):
+        def term_gradient_rows(self, flat, pde_seeds, linear=False):
             inputs = data.train_x if self.inputs is None else self.inputs
             n_bc = int(np.sum(data.num_bcs))
             core.stage(inputs, n_bc)
@@ -565,13 +592,13 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
                     terms.append(("op", i, beg, end, value_desc(d, m, val[0]), lambda vf=val[1], b=beg, e=end: vf(data.train_x, b, e)))
                 else:
                     raise capi.FusedOpError(f"boundary term {i} ({type(bc).__name__}) is not on the fused path")
-            return core.gradient_rows(flat, pde_seeds, terms)
+            return core.gradient_rows(flat, pde_seeds, terms, linear)
 
     rows = _Rows()
 
     def train_step(inputs, targets):
-        from .optim import FlatAdam, FlatMultiAdam, FusedLRA
-        if isinstance(model.opt, (FlatAdam, FlatMultiAdam, FusedLRA)) and model.lr_scheduler is None and not core.dynamic_params:
+        from .optim import FlatAdam, FlatMultiAdam, FusedLRA, FusedNTK
+        if isinstance(model.opt, (FlatAdam, FlatMultiAdam, FusedLRA, FusedNTK)) and model.lr_scheduler is None and not core.dynamic_params:
             rows.inputs = inputs
             if isinstance(model.opt, FlatAdam):
                 model.opt.fused_step(rows)
@@ -655,10 +682,11 @@ def _swap_optimizer(opt, net, loss_weights, n_pde):
 
     * ``torch.optim.Adam`` (benchmark.py:107; amsgrad / maximize / capturable variants excluded) -> ``FlatAdam``
     * ``LR_Adaptor(Adam, loss_weight, num_pde, alpha)`` (src/optimizer/lr_adaptor.py:10-25)       -> ``FusedLRA(FlatAdam, ...)``
+    * ``LR_Adaptor_NTK(Adam, loss_weight, pde)`` (src/optimizer/ntk.py:10-21), no periodic terms      -> ``FusedNTK(FlatAdam, ...)``
     * ``MultiAdam(params, lr, betas, ..., loss_group_idx, group_weights)`` without amsgrad, aggregated momentum or a custom
       parameter scheduler (src/optimizer/multiadam.py:127-190)                                      -> ``FlatMultiAdam``
     Optimizers that have already stepped are left alone (their state would be lost)."""
-    from .optim import FlatAdam, FlatMultiAdam, FusedLRA
+    from .optim import FlatAdam, FlatMultiAdam, FusedLRA, FusedNTK
 
     def plain_adam(o):
         if type(o) is not torch.optim.Adam or len(o.param_groups) != 1 or len(o.state) != 0:
@@ -680,6 +708,12 @@ def _swap_optimizer(opt, net, loss_weights, n_pde):
             return None
         inner = FlatAdam(net.parameters(), lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"])
         return FusedLRA(inner, opt.loss_weight, opt.num_pde, alpha=opt.alpha)
+    if name == "LR_Adaptor_NTK" and getattr(opt, "iter", 0) == 0:
+        g = plain_adam(getattr(opt, "optimizer", None))
+        if g is None or any(type(bc).__name__ == "PeriodicBC" for bc in getattr(getattr(opt.pde, "data", None), "bcs", [])):
+            return None
+        inner = FlatAdam(net.parameters(), lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"])
+        return FusedNTK(inner, opt.loss_weight, n_pde)
     if name == "MultiAdam" and getattr(opt, "is_init_state", True):
         g = opt.param_groups[0]
         sched = getattr(opt, "param_scheduler", None)

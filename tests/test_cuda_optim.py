@@ -236,3 +236,58 @@ def test_flat_multiadam_follows_reference_algorithm(groups):
     for _ in range(5):
         sc.train_step()
     assert float((_flat(net_c) - pa).norm() / pa.norm()) < 1e-4
+
+
+class _NTKPort(torch.optim.Optimizer):
+    """Test-side restatement of LR_Adaptor_NTK.step (src/optimizer/ntk.py:22-66): `sums_fn()` returns the differentiable sums of
+    all PDE residuals and of all boundary errors (data.losses with loss_fn = (y - x).sum())."""
+
+    def __init__(self, optimizer, loss_weight, num_pde, sums_fn):
+        super().__init__(optimizer.param_groups, {})
+        self.optimizer, self.loss_weight, self.num_pde, self.sums_fn = optimizer, loss_weight, num_pde, sums_fn
+
+    @torch.no_grad()
+    def step(self, closure):
+        with torch.enable_grad():
+            loss_r, loss_b = self.sums_fn()
+        sq = []
+        for loss in (loss_r, loss_b):
+            self.zero_grad()
+            with torch.enable_grad():
+                loss.backward(retain_graph=True)
+            sq.append(sum(float((p.grad ** 2).sum()) for g in self.param_groups for p in g["params"] if p.grad is not None))
+        m_r, m_b = sq
+        for i in range(len(self.loss_weight)):
+            self.loss_weight[i] = (m_r + m_b) / (m_r if i < self.num_pde else m_b)
+        return self.optimizer.step(closure)          # the solver's closure reports its losses to `self` (solver.opt)
+
+
+def test_fused_ntk_follows_reference_algorithm():
+    """benchmark.py --method ntk: FusedNTK (linear gradient rows from pinn_fwd_bwd_linear, weights on the device) against the
+    reference algorithm with stock autograd statistics (oracle residuals on the GPU + net forward on the BC rows)."""
+    from oracle import autograd_ref as O
+    from pinnacle_b200.optim import FlatAdam, FusedNTK
+    from pinnacle_b200.solver import FusedPDESolver
+    dev = torch.device("cuda:0")
+    spec, x, xb, terms = _ns_problem(dev, n=1024, nb=64)
+    net_a, net_b = _net(spec.desc, dev, 23), _net(spec.desc, dev, 23)
+    wa, wb = np.ones(8), np.ones(8)
+    xt, xbt = torch.as_tensor(x).to(dev), torch.as_tensor(xb).to(dev)
+
+    def sums():
+        flat = torch.cat([p.reshape(-1) for p in net_b.parameters()])
+        _, res, _ = O.pde_losses(spec.desc, flat, xt, None)
+        yb = net_b(xbt)
+        lb = sum((yb[t.beg:t.end, t.component:t.component + 1] - torch.as_tensor(t.values, device=dev)).sum() for t in terms)
+        return res.sum(), lb
+
+    sa = FusedPDESolver(spec, net_a, x, xb, terms).compile(FusedNTK(FlatAdam(net_a.parameters(), lr=1e-3), wa, 3), loss_weights=wa)
+    inner_b = torch.optim.Adam(net_b.parameters(), lr=1e-3)
+    sb = FusedPDESolver(spec, net_b, x, xb, terms).compile(_NTKPort(inner_b, wb, 3, sums), loss_weights=wb)
+    for k in range(4):
+        sa.train_step()
+        sb.train_step()
+        np.testing.assert_allclose(sa.opt.sync_loss_weight(), wb, rtol=2e-3)
+        np.testing.assert_allclose(sa.opt.losses.detach().cpu().numpy(), sb.opt.losses.detach().cpu().numpy(), rtol=2e-3)
+    assert wb[0] != 1.0 and wb[3] != 1.0
+    assert float((_flat(net_a) - _flat(net_b)).norm() / _flat(net_b).norm()) < 1e-3

@@ -237,3 +237,31 @@ def test_errors_are_loud():
         capi.check_supported(G.desc.with_net(64, 5))
     with pytest.raises(capi.FusedOpError):
         capi.fwd(G.desc, flat.to(dev)[:-1].contiguous(), x.to(dev), None, 1.0)
+
+
+@pytest.mark.parametrize("name", ["Poisson2D_Classic", "NS2D_LidDriven", "KuramotoSivashinskyEquation", "Heat2D_Multiscale", "PoissonND"])
+@pytest.mark.parametrize("impl", ["ffma", "tc", "tc2"])
+def test_linear_seed_rows_match_the_gradient_of_the_residual_sums(name, impl):
+    """pinn_fwd_bwd_linear: row s = d(sum_k seeds[s,k] sum_rows r_k)/dtheta (the NTK statistics of src/optimizer/ntk.py:24-58)
+    against the reference algorithm's autograd gradient of the same sums, on the golden points and weights (fp64 oracle)."""
+    from oracle import autograd_ref as O
+    from pinnacle_b200 import capi
+    dev = _cuda()
+    G = Golden(name)
+    flat, x, aux = G.inputs(torch.float64)
+    p = flat.clone().requires_grad_(True)
+    _, res, _ = O.pde_losses(G.desc, p, x, aux)
+    rs = np.random.RandomState(3)
+    seeds = np.vstack([np.ones(G.desc.n_pde), rs.standard_normal(G.desc.n_pde)])
+    refs = [torch.autograd.grad((res * torch.as_tensor(sd)).sum(), p, retain_graph=True)[0].numpy() for sd in seeds]
+    capi.set_impl({"ffma": capi.IMPL_FFMA, "tc": capi.IMPL_TC, "tc2": capi.IMPL_TC_PIPELINED}[impl])
+    try:
+        if impl != "ffma" and not capi.has_tensor_core_kernel(G.desc):
+            pytest.skip("no tensor-core kernel for this configuration")
+        out = capi.fwd_bwd_linear(G.desc, flat.float().to(dev), x.float().to(dev), None if aux is None else aux.float().to(dev),
+                                  torch.as_tensor(seeds, dtype=torch.float32).to(dev))
+    finally:
+        capi.set_impl(capi.IMPL_AUTO)
+    P = G.desc.n_params
+    for s, ref in enumerate(refs):
+        assert_parity(out[s * P:(s + 1) * P].cpu().numpy(), ref, f"linear row {s}")

@@ -211,7 +211,7 @@ def test_swap_optimizer_reads_the_reference_classes_correctly(monkeypatch):
         def __init__(self, *a, **k):
             made.append((type(self).__name__, a, k))
 
-    for nm in ("FlatAdam", "FlatMultiAdam", "FusedLRA"):
+    for nm in ("FlatAdam", "FlatMultiAdam", "FusedLRA", "FusedNTK"):
         monkeypatch.setattr(optim, nm, type(nm, (Rec,), {}))
     net = dde.nn.FNN([2] + [100] * 5 + [1], "tanh", "Glorot normal").float()
     w = np.ones(4)
@@ -224,6 +224,11 @@ def test_swap_optimizer_reads_the_reference_classes_correctly(monkeypatch):
     out = solver._swap_optimizer(MultiAdam(net.parameters(), lr=1e-3, betas=(0.99, 0.99), loss_group_idx=[1]), net, w, 1)
     assert type(out).__name__ == "FlatMultiAdam"
     assert made[-1][2]["loss_group_idx"] == [1] and made[-1][2]["betas"] == (0.99, 0.99) and made[-1][2]["group_weights"] == [0.5, 0.5]
+    pde = refshim.construct("Poisson2D_Classic")
+    pde.training_points(domain=32, boundary=16)
+    pde.create_model(net)
+    out = solver._swap_optimizer(LR_Adaptor_NTK(torch.optim.Adam(net.parameters(), 1e-3), w, pde), net, w, 1)
+    assert type(out).__name__ == "FusedNTK" and made[-1][1][1] is w and made[-1][1][2] == 1
     # no flat equivalent: left alone
     assert solver._swap_optimizer(Adam_LBFGS(net.parameters(), switch_epoch=5), net, w, 1) is None
     assert solver._swap_optimizer(torch.optim.Adam(net.parameters(), 1e-3, amsgrad=True), net, w, 1) is None
