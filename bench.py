@@ -40,6 +40,7 @@ UNIT = "points/s"
 WORKLOADS = {   # BASELINE.json configs[1] (default, the config `metric` is quoted on) and configs[4] (scaling study)
     "c2": ("Poisson2D_Classic", "Heat2D_Multiscale"),
     "c5": ("Poisson3D_ComplexGeometry", "Heat2D_LongTime"),
+    "c3": ("NS2D_LidDriven",),      # + LRA, see run_c3
 }
 WORKLOAD_PROBLEMS = WORKLOADS["c2"]
 
@@ -433,6 +434,82 @@ def run_fused(args):
         dist.destroy_process_group()
 
 
+def run_c3(args):
+    """BASELINE.json configs[2]: NS2D_LidDriven (u, v, p; 3 coupled residuals + 5 boundary terms incl. a one-point pressure pin)
+    with learning-rate-annealing loss re-weighting, `--points` residual rows IN TOTAL sharded over the ranks (strong scaling),
+    through the public API: FusedPDESolver + optim.FusedLRA(FlatAdam).  One step = per-term gradient rows (one NCCL
+    all-reduce of the PDE rows), the LRA statistics / re-weighting kernel, the Adam kernel.  Not the driver's default line."""
+    import torch.distributed as dist
+    from pinnacle_b200 import capi, problems
+    from pinnacle_b200.fused import shard_bounds
+    from pinnacle_b200.nn import FNN
+    from pinnacle_b200.optim import FlatAdam, FusedLRA
+    from pinnacle_b200.solver import FusedPDESolver, ValueBC
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    capi.load()
+    spec = problems.make("NS2D_LidDriven")
+    N, nb = args.points, 1024
+    beg, end = shard_bounds(N, rank, world)
+    x_local = spec.sample(N, seed=7)[beg:end]                     # every rank draws the same set and keeps its block
+    rs = np.random.RandomState(11)
+    xb = rs.uniform(0, 1, (4 * nb, 2)).astype(np.float32)
+    xb[:nb, 1], xb[nb:2 * nb, 1], xb[2 * nb:3 * nb, 0], xb[3 * nb:, 0] = 1.0, 0.0, 0.0, 1.0
+    lid = (4.0 * xb[:nb, :1] * (1.0 - xb[:nb, :1])).astype(np.float32)       # ns.py lid profile a*x*(1-x), a = 4
+    zero = lambda n: np.zeros((n, 1), np.float32)
+    terms = [ValueBC(0, nb, 0, lid), ValueBC(0, nb, 1, zero(nb)), ValueBC(nb, 4 * nb, 0, zero(3 * nb)), ValueBC(nb, 4 * nb, 1, zero(3 * nb)),
+             ValueBC(4 * nb - 1, 4 * nb, 2, zero(1))]
+    torch.manual_seed(0)
+    net = FNN([2] + [100] * 5 + [3]).to(dev)
+    with torch.no_grad():
+        for lin in net.linears:
+            lin.bias.normal_(0, 0.1)
+    w = np.ones(8)
+    solver = FusedPDESolver(spec, net, x_local, xb, terms, n_global=N)
+    solver.compile(FusedLRA(FlatAdam(net.parameters(), 1e-3), w, 3), loss_weights=w)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        solver.train_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    K = args.steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        solver.train_step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / K
+    losses = solver.opt.losses.detach().cpu().tolist()
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": N / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"NS2D_LidDriven + learning-rate annealing (FusedLRA over FlatAdam), {N} residual rows in total + {4 * nb} boundary "
+                                   "rows (replicated), 3 PDE + 5 boundary terms, 5x100 tanh MLP; optimizer update included",
+                       "parallelism": f"dp{world} over collocation points", "l2": "inputs larger than L2 at 1 GPU; no flush between steps"},
+            "clocks": clocks, "loss_weights_after": solver.opt.sync_loss_weight().tolist(), "losses_after": losses}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -445,13 +522,15 @@ def main():
                     help="fused arm only: tcgen05 tensor-core kernel (auto/tc) or the FP32 FFMA kernel")
     ap.add_argument("--gpu-ref-points", type=int, default=131072, help="points per problem of the stock-PyTorch-on-GPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU and stock-PyTorch-GPU baselines")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2", help="c2 = BASELINE configs[1] (default); c5 = configs[4]")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2", help="c2 = BASELINE configs[1] (default); c5 = configs[4]; c3 = configs[2] (NS2D_LidDriven + LRA, strong scaling)")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak", help="strong: --points is the TOTAL per problem, split over ranks")
     args = ap.parse_args()
     global WORKLOAD_PROBLEMS
     WORKLOAD_PROBLEMS = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c3":
+        run_c3(args)
     else:
         run_fused(args)
 
