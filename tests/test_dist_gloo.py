@@ -114,3 +114,89 @@ def test_shard_bounds_cover_all_rows():
             assert all(segs[i][1] == segs[i + 1][0] for i in range(world - 1))
             sizes = [e - b for b, e in segs]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _rows_worker(rank, world, port, n, q):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pinnacle_b200 import fused, problems
+        from pinnacle_b200.fused import shard_bounds
+        from pinnacle_b200.nn import FNN
+        from pinnacle_b200.solver import FusedPDESolver, ValueBC
+        from util import oracle_backend
+        torch.manual_seed(0)
+        torch.set_num_threads(2)
+        spec = problems.make("NS2D_LidDriven")
+        net = FNN([2] + [100] * 5 + [3])
+        with torch.no_grad():
+            for lin in net.linears:
+                lin.bias.normal_(0, 0.1)
+        x = spec.sample(n, seed=4)
+        xb = spec.sample(40, seed=5)
+        terms = [ValueBC(0, 24, 0, np.ones((24, 1), np.float32)), ValueBC(24, 40, 2, np.zeros((16, 1), np.float32))]
+        beg, end = shard_bounds(n, rank, world)
+        orig = fused.FusedPDEResidual.__init__
+
+        def init_cpu(self, spec, H=100, L=5, policy="auto", device=None, group=None, check_library=True):
+            orig(self, spec, H, L, policy, "cpu", group, False)
+
+        fused.FusedPDEResidual.__init__ = init_cpu
+        with oracle_backend():
+            s = FusedPDESolver(spec, net, x[beg:end], xb, terms, device="cpu", n_global=n).compile(torch.optim.Adam(net.parameters(), 1e-3))
+            flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+            G, L = s.term_gradient_rows(flat, torch.eye(3))
+            q.put((rank, G.clone().numpy(), L.clone().numpy(), dict(s.core.op.stats)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gradient_rows_match_single_process():
+    """The autograd-free row builder of the flat optimizers (FusedPDESolver.term_gradient_rows) under sharding: PDE rows are
+    all-reduced once, boundary rows are replicated; every rank ends with the same global rows as a single process."""
+    from pinnacle_b200 import fused, problems
+    from pinnacle_b200.nn import FNN
+    from pinnacle_b200.solver import FusedPDESolver, ValueBC
+    from util import oracle_backend
+    n, world = 150, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rows_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    spec = problems.make("NS2D_LidDriven")
+    net = FNN([2] + [100] * 5 + [3])
+    with torch.no_grad():
+        for lin in net.linears:
+            lin.bias.normal_(0, 0.1)
+    x, xb = spec.sample(n, seed=4), spec.sample(40, seed=5)
+    terms = [ValueBC(0, 24, 0, np.ones((24, 1), np.float32)), ValueBC(24, 40, 2, np.zeros((16, 1), np.float32))]
+    orig = fused.FusedPDEResidual.__init__
+
+    def init_cpu(self, spec, H=100, L=5, policy="auto", device=None, group=None, check_library=True):
+        orig(self, spec, H, L, policy, "cpu", group, False)
+
+    fused.FusedPDEResidual.__init__ = init_cpu
+    try:
+        with oracle_backend():
+            s = FusedPDESolver(spec, net, x, xb, terms, device="cpu").compile(torch.optim.Adam(net.parameters(), 1e-3))
+            flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+            G, L = s.term_gradient_rows(flat, torch.eye(3))
+    finally:
+        fused.FusedPDEResidual.__init__ = orig
+    for rank, Gr, Lr, stats in res:
+        np.testing.assert_allclose(Lr, L.numpy(), rtol=2e-5)
+        for t in range(5):
+            assert np.linalg.norm(Gr[t] - G[t].numpy()) <= 2e-5 * np.linalg.norm(G[t].numpy()), t
+        assert stats["allreduce_calls"] == 1
+    assert np.array_equal(res[0][1], res[1][1])
