@@ -223,12 +223,59 @@ def adaptive_activation_params(net) -> List[torch.Tensor]:
     return out
 
 
+def _is_pfnn(net) -> bool:
+    """dde.nn.PFNN (deepxde/nn/pytorch/fnn.py:50-150) / src.model.fnn.PFNN (with split_mask): every layer a ModuleList of one
+    Linear per output -- the `recommend_net` of the inverse problems (src/pde/inverse.py:30-32, 143-148)."""
+    layers = getattr(net, "layers", None)
+    return (isinstance(layers, torch.nn.ModuleList) and len(layers) >= 3
+            and all(isinstance(l, torch.nn.ModuleList) and all(isinstance(f, torch.nn.Linear) for f in l) for l in layers)
+            and len({len(l) for l in layers}) == 1)
+
+
+def pfnn_params(net) -> List[torch.Tensor]:
+    """Effective FNN parameters of a fully parallel PFNN: independent sub-networks are ONE dense net whose hidden weight
+    matrices are block diagonal (W' = blockdiag(W_0, .., W_{m-1}), b' = cat(b_j)), whose first layer stacks the branches
+    (times each branch's input mask, ``split_mask``, when the net has one) and whose output layer puts branch j's
+    Linear(h_j -> 1) in row j.  The fused kernels run unchanged on the dense form; autograd carries the gradient of the
+    blocks back to the branch parameters (the off-diagonal zeros are constants)."""
+    act = getattr(net, "activation", None)
+    if getattr(act, "__name__", "") != "tanh" and not isinstance(act, torch.nn.Tanh):
+        raise capi.FusedOpError(f"fused path supports the tanh activation only (got {act!r})")
+    if getattr(net, "_input_transform", None) is not None or getattr(net, "_output_transform", None) is not None:
+        raise capi.FusedOpError("fused path does not support input/output transforms (deepxde/nn/pytorch/nn.py:13-23)")
+    layers = list(net.layers)
+    m = len(layers[0])
+    mask = getattr(net, "split_mask", None)
+    out = []
+    first = []
+    for j, f in enumerate(layers[0]):
+        w = f.weight
+        if mask is not None:
+            w = w * torch.as_tensor(mask[j], dtype=w.dtype, device=w.device).reshape(1, -1)
+        first.append(w)
+    out += [torch.cat(first, dim=0), torch.cat([f.bias for f in layers[0]])]
+    for lay in layers[1:-1]:
+        out += [torch.block_diag(*[f.weight for f in lay]), torch.cat([f.bias for f in lay])]
+    last = layers[-1]
+    if any(f.out_features != 1 for f in last):
+        raise capi.FusedOpError("PFNN output sub-layers must map to one output each")
+    rows = []
+    widths = [f.in_features for f in last]
+    for j, f in enumerate(last):
+        left, right = sum(widths[:j]), sum(widths[j + 1:])
+        rows.append(torch.nn.functional.pad(f.weight, (left, right)))
+    out += [torch.cat(rows, dim=0), torch.cat([f.bias for f in last])]
+    return out
+
+
 def net_param_provider(net):
     """(fn, dynamic): ``fn()`` returns the 2(L+1) effective ``nn.Linear``-order tensors the fused op differentiates with
     respect to.  Plain FNN: the parameters themselves (static list).  Adaptive-activation nets: recomputed from the live
     W, b, a on every call (dynamic)."""
     if _is_adaptive_activation_net(net):
         return (lambda: adaptive_activation_params(net)), True
+    if _is_pfnn(net):
+        return (lambda: pfnn_params(net)), True
     params = net_linear_params(net)
     return (lambda: params), False
 
@@ -254,6 +301,16 @@ def net_linear_params(net) -> List[torch.Tensor]:
 
 def net_shape(net):
     """(d, H, L, m) of an FNN (or of the FNN an adaptive-activation net is equivalent to); raises when hidden widths differ."""
+    if _is_pfnn(net):
+        layers = list(net.layers)
+        d = layers[0][0].in_features
+        widths = [sum(f.out_features for f in lay) for lay in layers[:-1]]
+        if len(set(widths)) != 1:
+            raise capi.FusedOpError("fused path needs equal hidden widths")
+        for a, b in zip(layers[:-1], layers[1:]):
+            if [f.out_features for f in a] != [f.in_features for f in b]:
+                raise capi.FusedOpError("PFNN branches must keep their widths from layer to layer")
+        return d, widths[0], len(layers) - 1, len(layers[0])
     lins = [l.fc for l in list(net.layers)[:-1]] + [net.layers[-1]] if _is_adaptive_activation_net(net) else list(net.linears)
     d = lins[0].in_features
     H = lins[0].out_features

@@ -234,3 +234,63 @@ def test_swap_optimizer_reads_the_reference_classes_correctly(monkeypatch):
     assert solver._swap_optimizer(torch.optim.Adam(net.parameters(), 1e-3, amsgrad=True), net, w, 1) is None
     assert solver._swap_optimizer(MultiAdam(net.parameters(), loss_group_idx=[1], agg_momentum=True, agg_betas=(0.9, 0.9)), net, w, 1) is None
     assert solver._swap_optimizer(LR_Adaptor(torch.optim.Adam(net.parameters(), 1e-3), w, 2), net, w, 1) is None      # num_pde mismatch
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["PoissonInv", "HeatInv"])
+def test_inverse_problems_with_their_recommended_pfnn(name):
+    """The inverse problems with the net their class recommends (src/pde/inverse.py:30-32,143-148: a parallel FNN of two
+    50-wide sub-networks, HeatInv's with an input mask): the fused op runs on the equivalent dense 100-wide FNN (block-diagonal
+    weights), autograd returns the gradient of the blocks to the branch parameters."""
+    from pinnacle_b200 import fused
+    from pinnacle_b200.solver import enable_fused
+    dde, _ = refshim.load()
+
+    def build():
+        torch.manual_seed(5)
+        np.random.seed(5)
+        dde.config.set_random_seed(5)
+        pde = refshim.construct(name)
+        pde.training_points(domain=96, boundary=32, **({"initial": 32} if hasattr(pde, "num_initial_points") else {}))
+        pde.num_test_points = 48
+        net = pde.recommend_net.float()
+        with torch.no_grad():
+            for lay in net.layers:
+                for f in lay:
+                    f.bias.normal_(0, 0.1)
+        model = pde.create_model(net)
+        model.compile(torch.optim.Adam(net.parameters(), 1e-3), loss_weights=np.ones(pde.num_loss))
+        net.auxiliary_vars = None
+        return model, net
+
+    ref_model, ref_net = build()
+    new_model, new_net = build()
+    for a, b in zip(ref_net.parameters(), new_net.parameters()):
+        assert torch.equal(a, b)
+    x = ref_model.data.train_x
+    assert np.array_equal(x, new_model.data.train_x)
+    _, ref_losses = ref_model.outputs_losses_train(x, None)
+    ref_net.zero_grad()
+    ref_losses.sum().backward()
+    orig = fused.FusedPDEResidual.__init__
+
+    def init_cpu(self, spec, H=100, L=5, policy="auto", device=None, group=None, check_library=True):
+        orig(self, spec, H, L, policy, "cpu", group, False)
+
+    fused.FusedPDEResidual.__init__ = init_cpu
+    try:
+        with oracle_backend():
+            enable_fused(new_model)
+            assert new_model.fused_core._shape == (new_net.layers[0][0].in_features, 100, 5, 2)
+            _, new_losses = new_model.outputs_losses_train(x, None)
+            new_net.zero_grad()
+            new_losses.sum().backward()
+            np.testing.assert_allclose(new_losses.detach().numpy(), ref_losses.detach().numpy(), rtol=5e-5)
+            for (n, p), (_, q) in zip(ref_net.named_parameters(), new_net.named_parameters()):
+                rg = torch.zeros_like(p) if p.grad is None else p.grad
+                ng = torch.zeros_like(q) if q.grad is None else q.grad
+                assert (ng - rg).norm() <= 5e-5 * max(float(rg.norm()), 1e-9), (n, float((ng - rg).norm()), float(rg.norm()))
+            ref_hist, new_hist = _run(ref_model, 3), _run(new_model, 3)
+            np.testing.assert_allclose(new_hist, ref_hist, rtol=5e-3)
+    finally:
+        fused.FusedPDEResidual.__init__ = orig
