@@ -51,7 +51,7 @@ enum pinn_kind {
   PINN_KIND_LINEAR = 0,
   PINN_KIND_BURGERS1D = 1,     /* burgers.py:21-25   u_t + u u_x - c0 u_xx                      */
   PINN_KIND_BURGERS2D = 2,     /* burgers.py:66-80   2 outputs, 2 residuals, c0 = nu            */
-  PINN_KIND_NS2D = 3,          /* ns.py:141-160      (u,v,p): momentum x/y + continuity, c0 = nu */
+  PINN_KIND_NS2D = 3,          /* ns.py:141-160      (u,v,p): momentum x/y + continuity, c0 = nu; c1 = 1 drops the convective terms (ns.py:51-67) */
   PINN_KIND_NS2D_UNSTEADY = 4, /* ns.py:330-352      + u_t, v_t, aux[aux_sel[0]] added to mom-y  */
   PINN_KIND_HEAT_NLSRC = 5,    /* heat.py:214-222    u_t - c0 lap u - c1 sin(c2 u^2) aux          */
   PINN_KIND_GRAYSCOTT = 6,     /* chaotic.py:21-31   c0,c1 = eps; c2 = b; c3 = d                  */

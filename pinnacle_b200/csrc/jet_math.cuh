@@ -371,8 +371,9 @@ struct Residual {
           if constexpr (sig22()) {
             constexpr int X1 = SIG::chan(0, 1), Y1 = SIG::chan(1, 1);
             const float u = U[0][0], v = U[1][0];
-            float mx = u * U[0][X1] + v * U[0][Y1] + U[2][X1] - c[0] * lap_xy(U[0]);
-            float my = u * U[1][X1] + v * U[1][Y1] + U[2][Y1] - c[0] * lap_xy(U[1]);
+            const float cv = 1.0f - c[1];        // c[1] = 1: Stokes form without the convective terms (ns.py:51-67, linear=True)
+            float mx = cv * (u * U[0][X1] + v * U[0][Y1]) + U[2][X1] - c[0] * lap_xy(U[0]);
+            float my = cv * (u * U[1][X1] + v * U[1][Y1]) + U[2][Y1] - c[0] * lap_xy(U[1]);
             if constexpr (D == 3) {
               if constexpr (SIG::order(2) >= 1) {
                 if (kp.kind == PINN_KIND_NS2D_UNSTEADY) {
@@ -520,13 +521,15 @@ struct Residual {
           if constexpr (sig22()) {
             constexpr int X1 = SIG::chan(0, 1), Y1 = SIG::chan(1, 1);
             const float u = U[0][0], v = U[1][0];
+            const float cv = 1.0f - c[1];
             const float gx = rb[0], gy = rb[1], gc = rb[2];
-            Ub[0][0] = gx * U[0][X1] + gy * U[1][X1];
-            Ub[1][0] = gx * U[0][Y1] + gy * U[1][Y1];
-            Ub[0][X1] = gx * u + gc;
-            Ub[0][Y1] = gx * v;
-            Ub[1][X1] = gy * u;
-            Ub[1][Y1] = gy * v + gc;
+            const float cx = cv * gx, cy = cv * gy;
+            Ub[0][0] = cx * U[0][X1] + cy * U[1][X1];
+            Ub[1][0] = cx * U[0][Y1] + cy * U[1][Y1];
+            Ub[0][X1] = cx * u + gc;
+            Ub[0][Y1] = cx * v;
+            Ub[1][X1] = cy * u;
+            Ub[1][Y1] = cy * v + gc;
             Ub[2][X1] = gx;
             Ub[2][Y1] = gy;
             lap_xy_adj(Ub[0], -c[0] * gx);

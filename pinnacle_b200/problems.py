@@ -209,14 +209,14 @@ def heat_nd(dim=5, T=1) -> ProblemSpec:
     return ProblemSpec("HeatND", d, [-1, 1] * dim + [0, T], aux)
 
 
-def _ns2d(name, nu, bbox) -> ProblemSpec:
-    # src/pde/ns.py:30-49 / 141-160 / 240-259   momentum_x, momentum_y, continuity
-    d = KindDesc(K.KIND_NS2D, 2, 3, (2, 2), n_pde=3, consts=[nu], name=name)
+def _ns2d(name, nu, bbox, linear=False) -> ProblemSpec:
+    # src/pde/ns.py:30-49 / 141-160 / 240-259   momentum_x, momentum_y, continuity;  linear: ns.py:51-67 (no convective terms)
+    d = KindDesc(K.KIND_NS2D, 2, 3, (2, 2), n_pde=3, consts=[nu, 1.0 if linear else 0.0], name=name)
     return ProblemSpec(name, d, list(bbox))
 
 
-def ns2d_classic(nu=1, bbox=(0, 8, 0, 8)) -> ProblemSpec:
-    return _ns2d("NS2D_Classic", nu, bbox)
+def ns2d_classic(nu=1, bbox=(0, 8, 0, 8), linear=False) -> ProblemSpec:
+    return _ns2d("NS2D_Classic", nu, bbox, linear)
 
 
 def ns2d_liddriven(nu=1 / 100, bbox=(0, 1, 0, 1)) -> ProblemSpec:
@@ -406,9 +406,7 @@ def describe_reference(pde_obj) -> ProblemSpec:
     elif name == "HeatND":
         spec = heat_nd(cv["dim"], bbox[-1])
     elif name == "NS2D_Classic":
-        if pde_obj.pde.__name__ != "ns_pde":
-            raise UnsupportedProblem("NS2D_Classic(linear=True) is not supported by the fused path")
-        spec = ns2d_classic(pde_obj.nu, bbox)
+        spec = ns2d_classic(pde_obj.nu, bbox, linear=(pde_obj.pde.__name__ == "ns_pde_linear"))
     elif name == "NS2D_LidDriven":
         spec = ns2d_liddriven(cv["nu"], bbox)
     elif name == "NS2D_BackStep":

@@ -9,7 +9,7 @@ from util import GOLDEN_NAMES, Golden, assert_parity, rel_l2
 
 
 def test_fixture_inventory():
-    assert len(GOLDEN_NAMES) == 25
+    assert len(GOLDEN_NAMES) == 26
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.skipif(not refshim.available(), reason="reference tree 
 
 CLASSES = ["Burgers1D", "Poisson2D_Classic", "PoissonBoltzmann2D", "Poisson3D_ComplexGeometry", "Heat2D_Multiscale",
            "Heat2D_LongTime", "NS2D_LidDriven", "NS2D_LongTime", "KuramotoSivashinskyEquation", "GrayScottEquation",
-           "Burgers2D", "Poisson2D_ManyArea", "Heat2D_VaryingCoef", "Wave2D_Heterogeneous", "HeatND", "Helmholtz2D"]
+           "Burgers2D", "Poisson2D_ManyArea", "Heat2D_VaryingCoef", "Wave2D_Heterogeneous", "HeatND", "Helmholtz2D",
+           "PoissonInv", "HeatInv", "NS2D_Classic_linear"]
 
 
 @pytest.mark.parametrize("name", CLASSES)
