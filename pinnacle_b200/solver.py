@@ -272,6 +272,9 @@ class _StepCore:
         if n_bc > 0 and xt.device != self.op.device:
             self.op.stats["h2d_bytes"] += n_bc * xt.shape[1] * 4
         self._key = key
+        # keep the staged host buffer alive: its address is the cache key, and a resampled array of the same shape
+        # (PDEPointResampler, deepxde/callbacks.py:563-568) could otherwise be allocated at the address of a freed one
+        self._key_ref = inputs if self.cache_points else None
         self.generation += 1
 
 

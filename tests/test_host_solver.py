@@ -272,3 +272,37 @@ def test_every_boundary_term_of_burgers2d_and_heatnd_is_fused():
             assert losses.shape[0] == pde.num_loss and torch.isfinite(losses).all()
     finally:
         fused.FusedPDEResidual.__init__ = orig
+
+
+def test_resampled_points_of_the_same_shape_are_restaged():
+    """The point cache is keyed on the host array's address; the staged array is kept alive so that a freshly resampled
+    array of the same shape (PDEPointResampler) can never alias a freed one and be mistaken for the staged set."""
+    import gc
+    from pinnacle_b200 import fused, problems
+    from pinnacle_b200.solver import FusedPDESolver
+    spec = problems.make("Poisson2D_Classic")
+    net = _net(spec.desc)
+    orig = fused.FusedPDEResidual.__init__
+
+    def init_cpu(self, spec, H=100, L=5, policy="auto", device=None, group=None, check_library=True):
+        orig(self, spec, H, L, policy, "cpu", group, False)
+
+    fused.FusedPDEResidual.__init__ = init_cpu
+    try:
+        with oracle_backend():
+            s = FusedPDESolver(spec, net, spec.sample(64, seed=1), device="cpu").compile(torch.optim.Adam(net.parameters(), 1e-3))
+            seen = set()
+            for k in range(6):
+                x = spec.sample(64, seed=10 + k)           # same shape every time, previous array unreferenced by the caller
+                _, losses = s.outputs_losses_train(x)
+                ref = float(losses[0])
+                gen = s.core.generation
+                _, again = s.outputs_losses_train(x)       # same array: cache hit
+                assert s.core.generation == gen and float(again[0]) == ref
+                assert s.core._key_ref is x
+                seen.add(round(ref, 12))
+                del x
+                gc.collect()
+            assert len(seen) == 6                           # six different point sets gave six different losses
+    finally:
+        fused.FusedPDEResidual.__init__ = orig
