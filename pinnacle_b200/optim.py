@@ -95,6 +95,22 @@ class FlatAdam(torch.optim.Optimizer):
         self.apply_update()
         return loss
 
+    # ---- checkpointing (deepxde/model.py:945-948 saves opt.state_dict(); restore() loads it back) -------------------
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["flat_state"] = {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step_dev[:1].clone()}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        flat_state = state_dict.pop("flat_state", None)
+        super().load_state_dict(state_dict)
+        if flat_state is not None:
+            self.exp_avg.copy_(flat_state["exp_avg"])
+            self.exp_avg_sq.copy_(flat_state["exp_avg_sq"])
+            self.step_dev.zero_()
+            self.step_dev[:1].copy_(flat_state["step"])
+
     def fused_step(self, solver, w_dev: Optional[torch.Tensor] = None):
         """One training step of a ``FusedPDESolver`` whose loss terms are all fused, without autograd: every term's fused
         pass writes its gradient row, ``flat_grad = sum_t w_t G_t`` (one matrix-vector product), one Adam launch.
@@ -162,6 +178,15 @@ class FusedLRA(torch.optim.Optimizer):
         """Copy the device weights into the host ``loss_weight`` array (one D2H; call when logging)."""
         self.loss_weight[:] = self.weights.detach().cpu().numpy()
         return self.loss_weight
+
+    def state_dict(self):
+        return {"inner": self.optimizer.state_dict(), "weights": self.weights.clone(), "iter": self.iter}
+
+    def load_state_dict(self, state_dict):
+        self.optimizer.load_state_dict(state_dict["inner"])
+        self.weights.copy_(state_dict["weights"])
+        self.iter = int(state_dict["iter"])
+        self.sync_loss_weight()
 
     def step(self, closure=None):
         if self.solver is None:
@@ -236,6 +261,21 @@ class FlatMultiAdam(torch.optim.Optimizer):
     def zero_grad(self, set_to_none: bool = True):
         self._flat.zero_grad(set_to_none)
 
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["flat_state"] = {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step_dev[:1].clone()}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        flat_state = state_dict.pop("flat_state", None)
+        super().load_state_dict(state_dict)
+        if flat_state is not None:
+            self.exp_avg.copy_(flat_state["exp_avg"])
+            self.exp_avg_sq.copy_(flat_state["exp_avg_sq"])
+            self.step_dev.zero_()
+            self.step_dev[:1].copy_(flat_state["step"])
+
     def step(self, closure=None):
         if self.solver is None:
             raise capi.FusedOpError("FlatMultiAdam.step(): attach(solver) first")
@@ -306,6 +346,15 @@ class FusedNTK(torch.optim.Optimizer):
     def sync_loss_weight(self):
         self.loss_weight[:] = self.weights.detach().cpu().numpy()
         return self.loss_weight
+
+    def state_dict(self):
+        return {"inner": self.optimizer.state_dict(), "weights": self.weights.clone(), "iter": self.iter}
+
+    def load_state_dict(self, state_dict):
+        self.optimizer.load_state_dict(state_dict["inner"])
+        self.weights.copy_(state_dict["weights"])
+        self.iter = int(state_dict["iter"])
+        self.sync_loss_weight()
 
     def step(self, closure=None):
         if self.solver is None:

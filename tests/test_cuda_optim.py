@@ -291,3 +291,41 @@ def test_fused_ntk_follows_reference_algorithm():
         np.testing.assert_allclose(sa.opt.losses.detach().cpu().numpy(), sb.opt.losses.detach().cpu().numpy(), rtol=2e-3)
     assert wb[0] != 1.0 and wb[3] != 1.0
     assert float((_flat(net_a) - _flat(net_b)).norm() / _flat(net_b).norm()) < 1e-3
+
+
+@pytest.mark.parametrize("kind", ["adam", "lra", "multiadam"])
+def test_flat_optimizer_checkpoint_round_trip(kind, tmp_path):
+    """model.save / restore (deepxde/model.py:933-987) store net.state_dict() and opt.state_dict(): a run restored from a
+    checkpoint continues exactly like the uninterrupted one (moments, device step counter, device loss weights included)."""
+    from pinnacle_b200.optim import FlatAdam, FlatMultiAdam, FusedLRA
+    from pinnacle_b200.solver import FusedPDESolver
+    dev = torch.device("cuda:0")
+    spec, x, xb, terms = _ns_problem(dev, n=1024, nb=64)
+
+    def make(seed):
+        net = _net(spec.desc, dev, seed)
+        w = np.ones(8)
+        if kind == "adam":
+            opt = FlatAdam(net.parameters(), lr=1e-3)
+        elif kind == "lra":
+            opt = FusedLRA(FlatAdam(net.parameters(), lr=1e-3), w, 3)
+        else:
+            opt = FlatMultiAdam(net.parameters(), lr=1e-3, betas=(0.99, 0.99), loss_group_idx=[3])
+        return net, FusedPDESolver(spec, net, x, xb, terms).compile(opt, loss_weights=w)
+
+    net_a, sa = make(31)
+    for _ in range(4):
+        sa.train_step()
+    path = str(tmp_path / "ckpt.pt")
+    torch.save({"model_state_dict": net_a.state_dict(), "optimizer_state_dict": sa.opt.state_dict()}, path)
+    for _ in range(3):
+        sa.train_step()
+    net_b, sb = make(99)                         # different initial weights: everything must come from the checkpoint
+    ck = torch.load(path, weights_only=False)
+    net_b.load_state_dict(ck["model_state_dict"])
+    sb.opt.load_state_dict(ck["optimizer_state_dict"])
+    assert next(net_b.parameters()).data_ptr() == (sb.opt.optimizer if kind == "lra" else sb.opt).flat.data_ptr()   # still views of the flat buffer
+    for _ in range(3):
+        sb.train_step()
+    np.testing.assert_allclose(sb.opt.losses.detach().cpu().numpy(), sa.opt.losses.detach().cpu().numpy(), rtol=1e-6)
+    assert float((_flat(net_a) - _flat(net_b)).norm() / _flat(net_a).norm()) < 1e-7
