@@ -376,3 +376,47 @@ def test_enable_fused_swaps_in_the_flat_optimizers(method):
     assert m2.opt is lb
     m2.train_step(train_x, None)
     assert torch.isfinite(m2.opt.losses).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["Burgers1D", "Poisson2D_Classic", "KuramotoSivashinskyEquation"])
+def test_parity_holds_after_a_thousand_adam_steps(name):
+    """parity at initialisation AND after ~1k Adam steps (larger weights, saturating tanh).  Train with the fused
+    path, then compare residual-loss and gradient at the trained weights with the reference algorithm in fp64."""
+    from oracle import autograd_ref as O
+    from pinnacle_b200 import problems
+    from pinnacle_b200.optim import FlatAdam
+    from pinnacle_b200.solver import FusedPDESolver, ValueBC
+    dev = torch.device("cuda:0")
+    spec = problems.make(name)
+    net = _net(spec.desc, dev, 41)
+    x = spec.sample(2048, seed=5)
+    xb = spec.sample(256, seed=6)
+    tgt = np.sin(3.0 * xb[:, :1]).astype(np.float32)            # a boundary target that makes the net move away from u = 0
+    solver = FusedPDESolver(spec, net, x, xb, [ValueBC(0, 256, 0, tgt)]).compile(FlatAdam(net.parameters(), lr=2e-3))
+    flat0 = _flat(net).clone()
+    solver.train_step()
+    first = float(solver.opt.losses.sum())
+    for _ in range(999):
+        solver.train_step()
+    flat = _flat(net)
+    assert float((flat - flat0).norm() / flat0.norm()) > 5e-3 and np.isfinite(first) and torch.isfinite(solver.opt.losses).all()   # it moved
+    _, losses = solver.outputs_losses_train()
+    net.zero_grad()
+    losses[:spec.desc.n_pde].sum().backward()
+    got = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).cpu().double()
+    seeds = np.ones((1, spec.desc.n_pde))
+    ol, og, _ = O.losses_and_grads(spec.desc, flat.double(), torch.as_tensor(x).double(), None, seeds=seeds)
+    np.testing.assert_allclose(losses[:spec.desc.n_pde].detach().cpu().double().numpy(), ol.numpy(), rtol=1e-5)
+    err = float((got - og[0]).norm() / og[0].norm())
+    # Near a minimum the gradient is a small difference of large per-point terms (sum_i r_i dr_i/dtheta with r -> 0 and mixed
+    # signs), so ANY fp32 evaluation drifts from fp64 by more than at initialisation: the yard-stick is the reference
+    # algorithm itself in fp32 on the same weights and points.
+    _, og32, _ = O.losses_and_grads(spec.desc, flat.float(), torch.as_tensor(x), None, seeds=seeds)
+    err_ref32 = float((og32[0].double() - og[0]).norm() / og[0].norm())
+    print(f"{name}: |grad| {float(og[0].norm()):.3e}  fused-vs-fp64 {err:.2e}  reference-fp32-vs-fp64 {err_ref32:.2e}")
+    # Measured envelope (scripts/accuracy_after_training.py, DESIGN.md section 5): the split-precision tensor-core path sits at
+    # 2e-6 .. 2.5e-5 at trained weights where the reference's own fp32 evaluation sits at 3e-7 .. 1.4e-6; the 1e-5 bar of the
+    # north star holds at initialisation-like weights (tests/test_cuda_parity.py) and for the well-conditioned cases here, and
+    # is missed by 2.5x on the nearly converged Laplace problem (|grad| 5e-3 from terms four orders larger).
+    assert err < 5e-5 and err < max(1e-5, 25.0 * err_ref32), (err, err_ref32)
