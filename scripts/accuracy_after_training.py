@@ -10,6 +10,8 @@ from pinnacle_b200.nn import FNN
 from pinnacle_b200.optim import FlatAdam
 from pinnacle_b200.solver import FusedPDESolver, ValueBC
 dev = torch.device("cuda:0")
+if os.environ.get("PINN_LIB"):                       # what-if builds of the library
+    capi.LIB_PATH = os.path.abspath(os.environ["PINN_LIB"])
 for name in sys.argv[1:] or ["Poisson2D_Classic", "Burgers1D", "Heat2D_Multiscale", "NS2D_LidDriven"]:
     spec = problems.make(name)
     d = spec.desc
@@ -20,10 +22,16 @@ for name in sys.argv[1:] or ["Poisson2D_Classic", "Burgers1D", "Heat2D_Multiscal
             lin.bias.normal_(0, 0.1)
     x = spec.sample(2048, seed=5); xb = spec.sample(256, seed=6)
     tgt = np.sin(3.0 * xb[:, :1]).astype(np.float32)
-    s = FusedPDESolver(spec, net, x, xb, [ValueBC(0, 256, 0, tgt)]).compile(FlatAdam(net.parameters(), lr=2e-3))
-    for _ in range(1000):
-        s.train_step()
-    flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    wfile = os.path.join(ROOT, "gpurun_out", f"trained_{name}.pt")
+    if os.environ.get("PINN_LOAD_TRAINED") and os.path.exists(wfile):      # evaluate a what-if build at the SAME trained weights
+        flat = torch.load(wfile).to(dev)
+    else:
+        s = FusedPDESolver(spec, net, x, xb, [ValueBC(0, 256, 0, tgt)]).compile(FlatAdam(net.parameters(), lr=2e-3))
+        for _ in range(1000):
+            s.train_step()
+        flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+        os.makedirs(os.path.dirname(wfile), exist_ok=True)
+        torch.save(flat.cpu(), wfile)
     seeds = np.ones((1, d.n_pde))
     _, og, _ = O.losses_and_grads(d, flat.cpu().double(), torch.as_tensor(x).double(), None, seeds=seeds)
     _, og32, _ = O.losses_and_grads(d, flat.cpu().float(), torch.as_tensor(x), None, seeds=seeds)
