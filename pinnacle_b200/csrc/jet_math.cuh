@@ -110,12 +110,33 @@ PINN_HD void tanh_jet_fwd_t0(const float (&z)[SIG::C], float t0, float (&a)[SIG:
 template <class SIG>
 PINN_HD void tanh_jet_bwd_t0(const float (&z)[SIG::C], float t0, const float (&abar)[SIG::C], float (&zbar)[SIG::C], const float* lw = nullptr);
 
+// tanh of a pre-activation for the FP32 FFMA kernel (and the host build of this header): evaluated in double and rounded
+// once.  Near a minimum the parameter gradient is a sum of per-point terms orders of magnitude larger than the result, and
+// one or two ulp of (slightly biased) error in tanh then decide the last digits: on the nearly converged Laplace problem the
+// gradient's distance from the fp64 reference drops from 1.3e-5 (tanhf) to 5e-7 with this, below the reference's own fp32
+// evaluation (1.4e-6); profiles/r1_lap_summary.md.  Costs the FFMA kernel 19 %.  The tensor-core kernels keep tanhf
+// (tanh_tc): their error there is set by the tensor core's truncating accumulate, not by tanh.
+// -DPINN_TANH_MODE=0 restores tanhf, 2 = expm1f-based t/(t+2).
+#ifndef PINN_TANH_MODE
+#define PINN_TANH_MODE 1
+#endif
+PINN_HD float pinn_tanh(float z) {
+#if PINN_TANH_MODE == 1
+  return (float)tanh((double)z);
+#elif PINN_TANH_MODE == 2
+  const float t = expm1f(2.0f * z);
+  return (z > 9.0f) ? 1.0f : t / (t + 2.0f);
+#else
+  return tanhf(z);
+#endif
+}
+
 template <class SIG>
 PINN_HD void tanh_jet_fwd(const float (&z)[SIG::C], float (&a)[SIG::C], const float* lw = nullptr) {
 #ifdef PINN_EXP_NO_JET
   tanh_jet_fwd_t0<SIG>(z, z[0], a, lw);
 #else
-  tanh_jet_fwd_t0<SIG>(z, tanhf(z[0]), a, lw);
+  tanh_jet_fwd_t0<SIG>(z, pinn_tanh(z[0]), a, lw);
 #endif
 }
 
@@ -160,7 +181,7 @@ PINN_HD void tanh_jet_bwd(const float (&z)[SIG::C], const float (&abar)[SIG::C],
 #ifdef PINN_EXP_NO_JET
   for (int c = 0; c < SIG::C; ++c) zbar[c] = abar[c] * 0.5f + z[c] * 1e-9f;
 #else
-  tanh_jet_bwd_t0<SIG>(z, tanhf(z[0]), abar, zbar, lw);
+  tanh_jet_bwd_t0<SIG>(z, pinn_tanh(z[0]), abar, zbar, lw);
 #endif
 }
 
