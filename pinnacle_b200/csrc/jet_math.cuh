@@ -49,6 +49,9 @@ struct JetSig {
   static constexpr bool kLapPW = false;
   static constexpr int D = sizeof...(KS);
   static constexpr int C = 1 + (0 + ... + KS);
+  // residual signatures (some direction beyond first order) take the double-evaluated tanh in the FFMA kernel; the
+  // boundary-term signatures (VALUE: all 0, FLUX: all 1), which always run on the FFMA kernel, keep tanhf (see pinn_tanh)
+  static constexpr bool kAccTanh = ((KS >= 2) || ...);
   PINN_HD static constexpr int order(int j) {
     constexpr int o[sizeof...(KS)] = {KS...};
     return o[j];
@@ -73,6 +76,7 @@ template <int D_, bool PW_ = false>
 struct LapSig {
   static constexpr bool kLap = true;
   static constexpr bool kLapPW = PW_;
+  static constexpr bool kAccTanh = true;
   static constexpr int D = D_;
   static constexpr int C = D_ + 2;
   static constexpr int lap = D_ + 1;                        // channel of s
@@ -114,7 +118,8 @@ PINN_HD void tanh_jet_bwd_t0(const float (&z)[SIG::C], float t0, const float (&a
 // once.  Near a minimum the parameter gradient is a sum of per-point terms orders of magnitude larger than the result, and
 // one or two ulp of (slightly biased) error in tanh then decide the last digits: on the nearly converged Laplace problem the
 // gradient's distance from the fp64 reference drops from 1.3e-5 (tanhf) to 5e-7 with this, below the reference's own fp32
-// evaluation (1.4e-6); profiles/r1_lap_summary.md.  Costs the FFMA kernel 19 %.  The tensor-core kernels keep tanhf
+// evaluation (1.4e-6); profiles/r1_lap_summary.md.  Costs the FFMA kernel 19 %, so the boundary-term signatures (which
+// always run on it, inside the default path) stay on tanhf: SIG::kAccTanh.  The tensor-core kernels keep tanhf
 // (tanh_tc): their error there is set by the tensor core's truncating accumulate, not by tanh.
 // -DPINN_TANH_MODE=0 restores tanhf, 2 = expm1f-based t/(t+2).
 #ifndef PINN_TANH_MODE
@@ -136,7 +141,7 @@ PINN_HD void tanh_jet_fwd(const float (&z)[SIG::C], float (&a)[SIG::C], const fl
 #ifdef PINN_EXP_NO_JET
   tanh_jet_fwd_t0<SIG>(z, z[0], a, lw);
 #else
-  tanh_jet_fwd_t0<SIG>(z, pinn_tanh(z[0]), a, lw);
+  tanh_jet_fwd_t0<SIG>(z, SIG::kAccTanh ? pinn_tanh(z[0]) : tanhf(z[0]), a, lw);
 #endif
 }
 
@@ -181,7 +186,7 @@ PINN_HD void tanh_jet_bwd(const float (&z)[SIG::C], const float (&abar)[SIG::C],
 #ifdef PINN_EXP_NO_JET
   for (int c = 0; c < SIG::C; ++c) zbar[c] = abar[c] * 0.5f + z[c] * 1e-9f;
 #else
-  tanh_jet_bwd_t0<SIG>(z, pinn_tanh(z[0]), abar, zbar, lw);
+  tanh_jet_bwd_t0<SIG>(z, SIG::kAccTanh ? pinn_tanh(z[0]) : tanhf(z[0]), abar, zbar, lw);
 #endif
 }
 
