@@ -14,6 +14,30 @@
 
 using namespace pinn;
 
+
+// ---- emulation of the tensor-core contraction (bf16x3, 6 products, k-steps of 16, fp32 accumulate) for accuracy studies ----
+#include <cstring>
+#include <cstdlib>
+static inline float bf16_rn(float x) { uint32_t b; std::memcpy(&b, &x, 4); uint32_t r = b + 0x7FFFu + ((b >> 16) & 1u); r &= 0xFFFF0000u; float y; std::memcpy(&y, &r, 4); return y; }
+static inline void split3(float x, float (&s)[3]) { s[0] = bf16_rn(x); float r = x - s[0]; s[1] = bf16_rn(r); r -= s[1]; s[2] = bf16_rn(r); }
+static inline float trunc_f32(double v) { float f = (float)v; if (std::fabs((double)f) > std::fabs(v)) { uint32_t b; std::memcpy(&b, &f, 4); b -= 1; std::memcpy(&f, &b, 4); } return f; }
+static int g_tc_mode = -1;   // 0 off, 1 truncating accumulate, 2 round-to-nearest accumulate
+static inline int tc_mode() { if (g_tc_mode < 0) { const char* e = getenv("PINN_HARNESS_TC"); g_tc_mode = e ? atoi(e) : 0; } return g_tc_mode; }
+extern "C" void harness_set_tc_mode(int m) { g_tc_mode = m; }   // 0 plain fp32 FMA, 1 tensor-core model (truncating accumulate), 2 same with RN accumulate
+// dot(w[0..n), a[0..n)) as the kernels' rows contraction computes it
+static float tc_dot(const float* w, const float* a, int n, int astride) {
+  static const int wa[6] = {1, 1, 2, 0, 0, 0}, ab[6] = {1, 0, 0, 2, 1, 0};
+  float acc = 0.f;
+  for (int t = 0; t < 6; ++t)
+    for (int k0 = 0; k0 < n; k0 += 16) {
+      double s = 0.0;
+      for (int k = k0; k < k0 + 16 && k < n; ++k) { float ws[3], as[3]; split3(w[k], ws); split3(a[(size_t)k * astride], as); s += (double)ws[wa[t]] * (double)as[ab[t]]; }
+      const double v = (double)acc + s;
+      acc = (tc_mode() == 1) ? trunc_f32(v) : (float)v;
+    }
+  return acc;
+}
+
 template <class SIG, int M>
 static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x, const float* aux, long long n, double inv_n,
                     const float* seeds, int S, double* grad, double* loss, float* resid) {
@@ -56,6 +80,9 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
       for (int nn = 0; nn < H; ++nn) {
         float zz[C];
         for (int c = 0; c < C; ++c) zz[c] = 0.f;
+        if (tc_mode()) {
+          for (int c = 0; c < C; ++c) zz[c] = tc_dot(&params[offW[l] + (long long)nn * H], &a[((size_t)(l - 1) * H) * C + c], H, C);
+        } else
         for (int k = 0; k < H; ++k) {
           const float w = params[offW[l] + (long long)nn * H + k];
           for (int c = 0; c < C; ++c) zz[c] = fmaf(a[((size_t)(l - 1) * H + k) * C + c], w, zz[c]);
@@ -124,6 +151,11 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
           for (int k = 0; k < H; ++k)
             for (int c = 0; c < C; ++c) {
               float v = 0.f;
+              if (tc_mode()) {
+                float wcol[128];
+                for (int nn = 0; nn < H; ++nn) wcol[nn] = params[offW[l] + (long long)nn * H + k];
+                v = tc_dot(wcol, &zb[c], H, C);
+              } else
               for (int nn = 0; nn < H; ++nn) v = fmaf(zb[(size_t)nn * C + c], params[offW[l] + (long long)nn * H + k], v);
               abp[(size_t)k * C + c] = v;
             }

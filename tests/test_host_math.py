@@ -105,3 +105,26 @@ def test_flux_kind_matches_oracle(harness_lib):
         assert_parity(resid, orr.numpy(), "residual")
         assert_parity(loss[:1], ol.numpy(), "loss")
         assert_parity(grad, og.numpy(), "grad")
+
+
+@pytest.mark.parametrize("name", ["Poisson2D_Classic", "Burgers1D", "NS2D_LidDriven", "Heat2D_Multiscale", "KuramotoSivashinskyEquation"])
+def test_tensor_core_arithmetic_model_keeps_parity(harness_lib, name):
+    """The numerical scheme of the tcgen05 kernels, modelled on the host: every hidden-layer contraction as bf16x3 splits, six
+    products in the kernels' issue order, k-steps of 16, fp32 accumulate that TRUNCATES (mode 1) or rounds to nearest (mode 2).
+    Parity against the reference's golden vectors holds under the truncating model, and the comparison of the two modes shows
+    what the truncation costs (the model reproduces the GPU kernels' distance from fp64 at trained weights: DESIGN section 5)."""
+    G = Golden(name)
+    seeds = np.eye(G.desc.n_pde, dtype=np.float32)
+    err = {}
+    try:
+        for mode in (1, 2):
+            harness_lib.harness_set_tc_mode(mode)
+            loss, grad, resid = _run(harness_lib, G, seeds)
+            assert_parity(resid, G.g["resid64"], f"residual (mode {mode})")
+            assert_parity(loss, G.g["loss64"], f"loss (mode {mode})")
+            assert_parity(grad[:, G.idx], G.g["grad64"], f"grad (mode {mode})")
+            err[mode] = float(np.linalg.norm(grad[:, G.idx] - G.g["grad64"]) / np.linalg.norm(G.g["grad64"]))
+    finally:
+        harness_lib.harness_set_tc_mode(0)
+    assert err[2] < 1e-6 and err[1] < 1e-5
+    assert err[1] > err[2]            # the truncating accumulate is the less accurate one
