@@ -23,19 +23,20 @@ static inline void split3(float x, float (&s)[3]) { s[0] = bf16_rn(x); float r =
 static inline float trunc_f32(double v) { float f = (float)v; if (std::fabs((double)f) > std::fabs(v)) { uint32_t b; std::memcpy(&b, &f, 4); b -= 1; std::memcpy(&f, &b, 4); } return f; }
 static int g_tc_mode = -1;   // 0 off, 1 truncating accumulate, 2 round-to-nearest accumulate
 static inline int tc_mode() { if (g_tc_mode < 0) { const char* e = getenv("PINN_HARNESS_TC"); g_tc_mode = e ? atoi(e) : 0; } return g_tc_mode; }
-extern "C" void harness_set_tc_mode(int m) { g_tc_mode = m; }   // 0 plain fp32 FMA, 1 tensor-core model (truncating accumulate), 2 same with RN accumulate
+extern "C" void harness_set_tc_mode(int m) { g_tc_mode = m; }   // 0 plain fp32 FMA, 1 tensor-core model (truncating accumulate), 2 same with RN accumulate, 3 truncating, main term over two accumulators
 // dot(w[0..n), a[0..n)) as the kernels' rows contraction computes it
 static float tc_dot(const float* w, const float* a, int n, int astride) {
   static const int wa[6] = {1, 1, 2, 0, 0, 0}, ab[6] = {1, 0, 0, 2, 1, 0};
-  float acc = 0.f;
+  float acc = 0.f, acc2 = 0.f;     // acc2: mode 3 only -- odd k-steps of the main term go to a second (truncating) accumulator
   for (int t = 0; t < 6; ++t)
     for (int k0 = 0; k0 < n; k0 += 16) {
       double s = 0.0;
       for (int k = k0; k < k0 + 16 && k < n; ++k) { float ws[3], as[3]; split3(w[k], ws); split3(a[(size_t)k * astride], as); s += (double)ws[wa[t]] * (double)as[ab[t]]; }
+      if (tc_mode() == 3 && t == 5 && ((k0 / 16) & 1)) { acc2 = trunc_f32((double)acc2 + s); continue; }
       const double v = (double)acc + s;
-      acc = (tc_mode() == 1) ? trunc_f32(v) : (float)v;
+      acc = (tc_mode() == 1 || tc_mode() == 3) ? trunc_f32(v) : (float)v;
     }
-  return acc;
+  return acc + acc2;
 }
 
 template <class SIG, int M>
