@@ -135,19 +135,34 @@ def workspace_bytes(desc: KindDesc, n_seeds: int) -> int:
 
 
 class Workspace:
-    """Caller-owned device scratch (torch caching allocator), grown on demand, one per device."""
+    """Caller-owned device scratch (torch caching allocator), grown on demand.
+
+    One buffer per (device, stream): calls enqueued on one stream serialise, so they may share scratch; calls on different
+    streams (two ops running concurrently, a graph being captured on a side stream) get different buffers and cannot race
+    on the stash / partial accumulators.  A buffer whose pointer was handed out while its stream was capturing is baked
+    into a CUDA graph: it is kept alive for the life of the process and never replaced in its slot by regrowth, so a later
+    replay can never write into memory the caching allocator has given to someone else."""
 
     def __init__(self):
         self._buf = {}
+        self._captured = []            # buffers a CUDA graph may hold raw pointers to
 
     def get(self, device: torch.device, nbytes: int) -> torch.Tensor:
-        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        stream = torch.cuda.current_stream(device)
+        capturing = torch.cuda.is_current_stream_capturing()
+        key = (device.type, idx, int(stream.cuda_stream))
         b = self._buf.get(key)
-        if b is None or b.numel() < nbytes:
+        if b is None or b.numel() < nbytes + 256:
             b = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
             self._buf[key] = b
+        if capturing and not any(c is b for c in self._captured):
+            self._captured.append(b)
         off = (-b.data_ptr()) % 256
         return b[off:off + nbytes]
+
+    def n_buffers(self) -> int:
+        return len(self._buf)
 
 
 _WS = Workspace()

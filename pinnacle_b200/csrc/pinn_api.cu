@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
 
@@ -28,13 +29,15 @@ static const ConfigInfo* const* all_configs() {
 
 static thread_local std::string g_err;
 static thread_local int g_launches = 0;
-static int g_tc_pipelined = 0;
-static int g_no_lap = 0;   // pinn_set_laplacian_collapse(0)
-static int g_impl = 0;   // 0 = auto (tensor cores, pipelined where instantiated), 1 = FP32 FFMA kernel, 2 = tensor cores, one tile at a time
-                         // (error if absent), 3 = pipelined tensor-core kernel (falls back to 2 where not instantiated)
+// Process-wide configuration knobs (the programmatic form of the PINN_IMPL / PINN_NO_LAPLACIAN environment variables):
+// atomics that a call only READS.  They select among kernels that compute the same result, so a call racing with a
+// setter runs one kernel or the other, never a mixture; no call mutates library state.
+static std::atomic<int> g_no_lap{0};   // pinn_set_laplacian_collapse(0)
+static std::atomic<int> g_impl{0};     // 0 = auto (tensor cores, pipelined where instantiated), 1 = FP32 FFMA kernel, 2 = tensor cores, one tile at a
+                                       // time (error if absent), 3 = pipelined tensor-core kernel (falls back to 2 where not instantiated)
 
 static int effective_impl() {
-  int impl = g_impl;
+  int impl = g_impl.load(std::memory_order_relaxed);
   if (impl == 0) {
     const char* e = getenv("PINN_IMPL");
     if (e != nullptr) {
@@ -43,9 +46,10 @@ static int effective_impl() {
       if (strcmp(e, "tc2") == 0) impl = 3;
     }
   }
-  g_tc_pipelined = (impl == 3 || impl == 0) ? 1 : 0;   // auto prefers the pipelined kernel where it is instantiated
   return impl;
 }
+// auto prefers the pipelined kernel where it is instantiated
+static bool tc_pipelined() { const int impl = effective_impl(); return impl == 3 || impl == 0; }
 
 static int fail(const std::string& msg) {
   g_err = msg;
@@ -68,7 +72,7 @@ static const ConfigInfo* find_config(const pinn_kind_desc* d, std::string* why) 
   static const bool no_lap = [] { const char* e = getenv("PINN_NO_LAPLACIAN"); return e != nullptr && e[0] == '1'; }();
   // (per-point direction weights -- lap_eligible() == 2 -- exist in the tensor-core kernels only)
   const int lap_mode = lap_eligible(d->kind, d->d, d->m, d->order, d->aux_sel, d->consts);
-  if (!no_lap && !g_no_lap && (lap_mode == 1 || (lap_mode == 2 && effective_impl() != 1))) {
+  if (!no_lap && !g_no_lap.load(std::memory_order_relaxed) && (lap_mode == 1 || (lap_mode == 2 && effective_impl() != 1))) {
     for (int i = 0; i < PINN_NUM_CONFIGS; ++i) {
       const ConfigInfo* c = tab[i];
       if (c != nullptr && c->lap == lap_mode && c->H == d->H && c->m == d->m && c->d == d->d && c->valid_kind(d->kind)) return c;
@@ -95,6 +99,7 @@ static long long param_count(const pinn_kind_desc* d) {
 }
 
 struct DeviceInfo {
+  int dev = -1;
   int sms = 0;
   bool ok = false;
   std::string err;
@@ -124,6 +129,7 @@ static const DeviceInfo& device_info() {
       return di;
     }
     di.sms = prop.multiProcessorCount;
+    di.dev = dev;
     di.ok = true;
     cached_dev = dev;
   }
@@ -194,7 +200,11 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
   const Workspace ws = carve(desc, c, max_grid, n_seeds, tc);
   if (workspace_bytes < ws.total) return fail("workspace too small: need " + std::to_string(ws.total) + " bytes");
 
-  static thread_local bool prepared[PINN_NUM_CONFIGS] = {};
+  // cudaFuncSetAttribute (dynamic shared memory above 48 KB) is per device: one process may drive several
+  constexpr int kMaxDevices = 64;
+  static thread_local bool prepared_tab[kMaxDevices][PINN_NUM_CONFIGS] = {};
+  if (di.dev < 0 || di.dev >= kMaxDevices) return fail("device ordinal out of range");
+  bool* prepared = prepared_tab[di.dev];
   if (!prepared[c->id]) {
     cudaError_t e = c->prepare();
     if (e == cudaSuccess && c->tc_T > 0) e = c->tc_prepare();
@@ -203,7 +213,7 @@ static int run(const pinn_kind_desc* desc, const float* params, const float* x, 
   }
 
   const long long P = param_count(desc);
-  const bool pipe = tc && c->tc_pipe && g_tc_pipelined;
+  const bool pipe = tc && c->tc_pipe && tc_pipelined();
   const int tileT = tc ? (pipe ? 32 : c->tc_T) : c->T;
   const long long ntiles = (n_rows + tileT - 1) / tileT;
   int grid = (int)(ntiles < max_grid ? ntiles : max_grid);
@@ -323,7 +333,7 @@ int pinn_last_launch_count(void) { return g_launches; }
 
 int pinn_set_impl(int impl) {
   if (impl < 0 || impl > 3) return fail("impl must be 0 (auto), 1 (ffma), 2 (tensor cores) or 3 (pipelined tensor cores)");
-  g_impl = impl;
+  g_impl.store(impl, std::memory_order_relaxed);
   return 0;
 }
 
@@ -334,7 +344,7 @@ int pinn_has_tensor_core_kernel(const pinn_kind_desc* desc) {
 }
 
 int pinn_set_laplacian_collapse(int enable) {
-  g_no_lap = enable ? 0 : 1;
+  g_no_lap.store(enable ? 0 : 1, std::memory_order_relaxed);
   return 0;
 }
 
@@ -350,7 +360,7 @@ int pinn_selected_impl(const pinn_kind_desc* desc) {
   if (c == nullptr) return 0;
   std::string why_tc;
   if (!want_tc(c, &why_tc)) return why_tc.empty() ? 1 : 0;
-  return (c->tc_pipe && g_tc_pipelined) ? 3 : 2;
+  return (c->tc_pipe && tc_pipelined()) ? 3 : 2;
 }
 
 double pinn_ffma_peak_tflops(int iters) {

@@ -60,11 +60,36 @@ __global__ void pinn_pack_weights_tc(const float* __restrict__ params, uint4* __
       }
       v[i] = x;
     }
+    // Forward operands (W_l and the output layer): the leading split w1 keeps 8 significant bits but is never finer than 2^-14
+    // of the row's leading bit, so that all products w1 * a1 of a dot product sit on one coarse grid and the tensor core's
+    // accumulate of them is exact (pinn_tc2_kernels.cuh header).  w1 + w2 + w3 == w still holds bit for bit for every weight
+    // within 7 binades of the row maximum (below that the loss is < 2^-31 of the maximum).  Transposed operands keep the
+    // plain floating split.
+    float floor_grid = 0.f;
+    if (mat < L - 1 || mat == 2 * (L - 1)) {
+      unsigned mx = 0u;
+      if (mat < L - 1 ? row < H : row < M) {
+        const float* wr = (mat < L - 1) ? params + offHid + (long long)mat * strideHid + (long long)row * H : params + offW6 + (long long)row * H;
+        for (int k = 0; k < H; ++k) {
+          const unsigned b = __float_as_uint(wr[k]) & 0x7fffffffu;
+          mx = b > mx ? b : mx;
+        }
+      }
+      const int e = (int)(mx >> 23);                       // leading bit 2^(e - 127)
+      floor_grid = (e > 14) ? __uint_as_float((unsigned)(e - 14) << 23) : 0.f;
+    }
     uint32_t p1[4], p2[4], p3[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float x0 = v[2 * i], x1 = v[2 * i + 1];
-      p1[i] = pack_bf16x2_h(x0, x1);
+      if (floor_grid > 0.f) {
+        // grid of the 8-bit floating split of x: 2^(e_x - 7); the coarser of that and the floor
+        const float g0 = fmaxf(__uint_as_float((__float_as_uint(x0) & 0x7f800000u)) * 0.0078125f, floor_grid);
+        const float g1 = fmaxf(__uint_as_float((__float_as_uint(x1) & 0x7f800000u)) * 0.0078125f, floor_grid);
+        p1[i] = pack_bf16x2_h(rintf(x0 / g0) * g0, rintf(x1 / g1) * g1);       // exact: <= 8 significant bits
+      } else {
+        p1[i] = pack_bf16x2_h(x0, x1);
+      }
       float r0 = x0 - __uint_as_float(p1[i] << 16), r1 = x1 - __uint_as_float(p1[i] & 0xFFFF0000u);
       p2[i] = pack_bf16x2_h(r0, r1);
       r0 -= __uint_as_float(p2[i] << 16);

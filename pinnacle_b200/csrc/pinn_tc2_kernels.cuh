@@ -23,6 +23,23 @@
 // (any finite value will do); the last slot's k-step 6 lives in a 4-column stub in front of slot 0.
 //
 // The element-wise warps never touch weights, never issue MMAs and never flush dW.
+//
+// Forward contractions: exact main term (round 2).  The tensor core's fp32 accumulate truncates (scripts/umma_round_probe.py:
+// the 16 products and the accumulator are aligned to the largest exponent among them, each addend cut to a 26-bit window,
+// the sum cut to 24 bits, all toward zero), which biases every pre-activation toward zero by ~0.5 ulp per full-magnitude
+// k-step -- coherently over all points, i.e. like a relative weight perturbation of ~1e-7; near a minimum the gradient
+// amplifies that ~1000x (2.5e-5 on the nearly converged Laplace problem; host model: tests/host_harness, mode 4).  So in the
+// FORWARD sweep the leading product w1*a1 gets an accumulator of its own in which every sum is EXACT:
+//   * w1 = 8 significant bits of w but never finer than 2^-14 of its row's leading bit (pinn_pack_weights_tc; w1 + w2 + w3
+//     still equals w bit for bit for every weight within 7 binades of the row maximum),
+//   * a1 = a rounded to 7 bits below the leading bit of max |a| over the warp's 32 neurons, per (channel, point) column
+//     (store_quad_fwd; a2, a3 = floating bf16 splits of the remainder as before),
+//   so all products of a column sit on one grid and span < 24 bits: no truncation can occur.  That accumulator, Dm, is shared
+//   by the two sub-tiles and aliased onto the dW columns, which are idle in the forward sweep; the other five products
+//   accumulate in D_h as before, and the epilogue adds the two in round-to-nearest fp32.  The main term stays the LAST group of
+//   a batch: by then (~0.8 us after the batch started) the element-wise warps have long read the other sub-tile's main term
+//   out of Dm, so the wait (dsfree) is a formality and the two sub-tiles stay decoupled.  The reverse sweep keeps the one-
+//   accumulator scheme: its truncation is not coherent in the weights and costs nothing measurable (host model mode 0:4).
 #pragma once
 
 #include <cstdio>
@@ -80,7 +97,7 @@ struct TC2fg {
   static constexpr int oRs = oUb + NSUB * M * R * 4;
   static constexpr int oRed = oRs + PINN_MAX_PDE * T * 4;
   static constexpr int oLred = (oRed + 4 * 128 * 4 + 7) / 8 * 8;
-  static constexpr int oBar = oLred + PINN_MAX_PDE * T * 8;    // 17 mbarriers + tmem slot
+  static constexpr int oBar = oLred + PINN_MAX_PDE * T * 8;    // 18 mbarriers + tmem slot
   static constexpr int oKp = oBar + 160;
   static constexpr int nBytes = oKp + (int)((sizeof(KindParams) + 15) / 16 * 16);
   static constexpr size_t smem_bytes = (size_t)nBytes;
@@ -149,7 +166,8 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
   uint64_t* dwfree = bars + 14;                                       // dW flushed out of TMEM (128 arrivals)
   // rdy2[h]: reverse sweep, split schedule (CFG::SPLIT_REV): the dW operand a^{l-1} of sub-tile h is in place (512 arrivals)
   uint64_t* rdy2 = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* dsfree = bars + 17;                                       // forward: the shared main-term accumulator Dm has been read (16 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
   KindParams* kps = reinterpret_cast<KindParams*>(smraw + CFG::oKp);
   // direction weights of the Laplacian channel at tile point `pt`: per point (LapSig<D, true>) or the descriptor's constants
   auto lw_at = [&](int pt) -> const float* {
@@ -208,6 +226,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
     mbar_init_n(&dwd[0], 1);
     mbar_init_n(&dwd[1], 1);
     mbar_init_n(dwfree, CFG::NPR);
+    mbar_init_n(dsfree, NEW / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     *kps = p.kp;
   }
@@ -371,15 +390,19 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       pend_l = -1;
     };
     uint32_t rph[2] = {0, 0}, wrp[4] = {0, 0, 0, 0}, fph = 0;
-    bool flush_pending = false;
+    bool flush_pending = false;            // a reverse step's dW is still in TMEM (its flush has not been waited for)
     // rows MMAs of sub-tile h: D_h (+)= W[TMEM] * B[smem, MN-major], 7 k-steps x 6 split products in three groups.
     // first: this is the step's first batch (wait for each split as its group comes up); last: it is the step's last
     // batch (release w2 / w3 / everything as the groups retire).
-    auto issue_rows = [&](int h, unsigned char* bbase, uint32_t el, bool first, bool last) {
+    uint32_t dsph = 0;
+    bool dm_used = false;                  // a forward batch has written Dm: the next one may only once that has been read
+    auto issue_rows = [&](int h, unsigned char* bbase, uint32_t el, bool first, bool last, auto fwd_c) {
+      constexpr bool fwd = decltype(fwd_c)::value;          // compile-time: every operand address below folds to a constant offset
       constexpr uint32_t idesc = umma::make_idesc_bf16(kTcRows, R, 0, 1);
-      //                 G0    G1   G2
-      const int wa[6] = {1, 1, 2, 0, 0, 0};      // weight split     (w2 w2 | w3 | w1 w1 w1)
-      const int ab[6] = {1, 0, 0, 2, 1, 0};      // activation split (a2 a1 | a1 | a3 a2 a1): the main term goes last
+      // G0 = w2*(a2, a1) | G1 = w3*a1 | G2 = w1*(a3, a2, a1), the main term last.  Reverse: all into D_h.  Forward: the five
+      // small products into D_h, the main term w1*a1 into Dm (exact, see the header) -- Dm is shared by the two sub-tiles, but
+      // by the time a batch reaches its last group the element-wise warps have long read the other sub-tile's main term.
+      constexpr int wa[6] = {1, 1, 2, 0, 0, 0}, ab[6] = {1, 0, 0, 2, 1, 0};
       const uint32_t d = tD(h);
       const uint32_t s0 = (uint32_t)(CFG::tcWStride * slot_of(0, nstep));
       const uint32_t s0last = (nstep & 1) ? tStub : tW + s0 + 48;     // k-step 6 of w1 (slot 3 keeps it in the stub)
@@ -394,10 +417,27 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
           wrp[wb] ^= 1;
           umma::fence_after_sync();
         }
+        if (fwd && t == 5) {
+          // Dm: the element-wise warps must have read the previous forward batch's main term out of it, and the last
+          // reverse step's dW (same columns) must have been flushed
+          if (dm_used) {
+            mbar_wait(dsfree, dsph);
+            dsph ^= 1;
+          }
+          dm_used = true;
+          if (flush_pending) {
+            mbar_wait(dwfree, fph);
+            fph ^= 1;
+            flush_pending = false;
+          }
+          umma::fence_after_sync();
+          accum = 0;
+        }
+        const uint32_t dst = (fwd && t == 5) ? tDW : d;
 #pragma unroll
         for (int ks = 0; ks < kTcHP / 16; ++ks) {
           const uint32_t wad = (wa[t] == 0) ? (ks == 6 ? s0last : tW + s0 + (uint32_t)(ks * 8)) : tW + (uint32_t)(wa[t] * CFG::tcWStride + ks * 8);
-          umma::mma_bf16_ts_e2(d, wad, lo0 + (uint32_t)((ab[t] * ARR + ks * 2 * JB) >> 4), hi, idesc, accum, el);
+          umma::mma_bf16_ts_e2(dst, wad, lo0 + (uint32_t)((ab[t] * ARR + ks * 2 * JB) >> 4), hi, idesc, accum, el);
           accum = 1;
         }
         if (last && t == 1) umma::commit_e(wf1, el);
@@ -430,7 +470,8 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       umma::fence_after_sync();
       PINN_TR(62 + h);
       const uint32_t el = umma::elect_one();
-      issue_rows(h, reverse ? arr_ptr(h, 3) : arr_ptr(h, 0), el, h == 0, h == NSUB - 1);
+      if (reverse) issue_rows(h, arr_ptr(h, 3), el, h == 0, h == NSUB - 1, std::false_type{});
+      else issue_rows(h, arr_ptr(h, 0), el, h == 0, h == NSUB - 1, std::true_type{});
       umma::commit_e(&bars[h], el);
       if (h == NSUB - 1) umma::commit_e(&wfree[nstep & 1], el);
       PINN_TR(64 + h);
@@ -438,6 +479,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         if (h == 0 && flush_pending) {
           mbar_wait(dwfree, fph);          // the previous reverse step's dW has left TMEM
           fph ^= 1;
+          flush_pending = false;
           umma::fence_after_sync();
         }
         PINN_TR(66 + h);
@@ -455,7 +497,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       umma::fence_after_sync();
       PINN_TR(62 + h);
       const uint32_t el = umma::elect_one();
-      issue_rows(h, arr_ptr(h, 3), el, h == 0, h == NSUB - 1);
+      issue_rows(h, arr_ptr(h, 3), el, h == 0, h == NSUB - 1, std::false_type{});
       umma::commit_e(&bars[h], el);
       if (h == NSUB - 1) umma::commit_e(&wfree[nstep & 1], el);
       PINN_TR(64 + h);
@@ -464,6 +506,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       if (h == 0 && flush_pending) {
         mbar_wait(dwfree, fph);            // the previous reverse step's dW has left TMEM
         fph ^= 1;
+        flush_pending = false;
         umma::fence_after_sync();
       }
       mbar_wait(&rdy2[h], r2ph[h]);
@@ -482,6 +525,9 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         if (reverse) {
           pend_s = s;
           pend_l = l;
+          // The tile's last reverse step: flush its dW right away instead of one step late -- the next step is a forward
+          // one, whose small-term accumulator lives in the dW columns, and the tensor core idles at the tile boundary anyway.
+          if (l == 2 && s == S - 1) producer_flush();
         }
       } else {
         PINN_TR(58);
@@ -527,6 +573,64 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       *reinterpret_cast<uint2*>(base + off) = make_uint2(a1, b1);
       *reinterpret_cast<uint2*>(base + ARR + off) = make_uint2(a2, b2);
       *reinterpret_cast<uint2*>(base + 2 * ARR + off) = make_uint2(a3, b3);
+    };
+    // Forward operand of the next layer's rows contraction (see the header): a1 on the column's grid, a2 + a3 the remainder.
+    // `mg` = 1.5 * 2^23 * grid per point: (v + mg) - mg rounds v to a multiple of the grid (|v| < 2^22 grids always holds).
+    const unsigned wmask = (q == 3) ? ((1u << (H - 96)) - 1u) : 0xffffffffu;     // lanes of this warp that own a neuron
+    auto grid_magic = [&](float v) -> float {
+      // leading bit of max |v| over the warp's neurons -> grid 2^(e - 7) -> magic constant 1.5 * 2^(e + 16)
+      const unsigned mx = __reduce_max_sync(wmask, __float_as_uint(v) & 0x7fffffffu);
+      unsigned e = mx >> 23;
+      e = e > 230u ? 230u : e;
+      return __uint_as_float(((e + 17u) << 23) | 0x00400000u);
+    };
+    auto store_quad_fwd = [&](unsigned char* base, int c, int r0, float v0, float v1, float v2, float v3) {
+      float m0, m1, m2, m3;
+      if (c == 0) {
+        m0 = m1 = m2 = m3 = 1.5f * 65536.0f;                                    // tanh values: |v| < 1, grid 2^-7
+      } else {
+        m0 = grid_magic(v0); m1 = grid_magic(v1); m2 = grid_magic(v2); m3 = grid_magic(v3);
+      }
+      const float h0 = __fsub_rn(__fadd_rn(v0, m0), m0), h1 = __fsub_rn(__fadd_rn(v1, m1), m1);
+      const float h2 = __fsub_rn(__fadd_rn(v2, m2), m2), h3 = __fsub_rn(__fadd_rn(v3, m3), m3);
+      const uint32_t a1 = pack_bf16x2(h0, h1), b1 = pack_bf16x2(h2, h3);        // exact: at most 8 significant bits
+      uint32_t a2, a3, b2, b3;
+      split2_pair(v0 - h0, v1 - h1, a2, a3);
+      split2_pair(v2 - h2, v3 - h3, b2, b3);
+      const int off = (j >> 3) * JB + (r0 >> 3) * 128 + (j & 7) * 16 + (r0 & 7) * 2;
+      *reinterpret_cast<uint2*>(base + off) = make_uint2(a1, b1);
+      *reinterpret_cast<uint2*>(base + ARR + off) = make_uint2(a2, b2);
+      *reinterpret_cast<uint2*>(base + 2 * ARR + off) = make_uint2(a3, b3);
+    };
+    // forward pre-activations: small terms (D_h) + exact main term (Dm), added in round-to-nearest; releases Dm
+    auto load_fwd = [&](int h, float (&zq)[C][4]) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) umma::tmem_ld4(tD(h) + lane_off + c * TS + pb, zq[c]);
+      // the main term in two rounds: keeps the live registers of this stage at 1.5 accumulator sets instead of 2
+      constexpr int C0 = (C + 1) / 2;
+      {
+        float sm[C0][4];
+#pragma unroll
+        for (int c = 0; c < C0; ++c) umma::tmem_ld4(tDW + lane_off + c * TS + pb, sm[c]);
+        umma::wait_ld();
+#pragma unroll
+        for (int c = 0; c < C0; ++c)
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) zq[c][pp] += sm[c][pp];
+      }
+      {
+        float sm[C - C0][4];
+#pragma unroll
+        for (int c = C0; c < C; ++c) umma::tmem_ld4(tDW + lane_off + c * TS + pb, sm[c - C0]);
+        umma::wait_ld();
+        umma::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(dsfree)) : "memory");
+#pragma unroll
+        for (int c = C0; c < C; ++c)
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) zq[c][pp] += sm[c - C0][pp];
+      }
     };
     auto signal_ready = [&](int h) {
       umma::fence_async_smem();
@@ -582,7 +686,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       // The stash keeps t0 = tanh(z_0) in channel 0 instead of z_0: nothing downstream needs z_0 itself (tanh_jet_*_t0),
       // and the reverse sweep then recomputes a^{l-1} and the adjoint without a transcendental.
 #pragma unroll
-      for (int pp = 0; pp < 4; ++pp) a[0][pp] = tanh_tc(a[0][pp]);
+      for (int pp = 0; pp < 4; ++pp) a[0][pp] = tanh_tcx<SIG::kAccTanh>(a[0][pp]);
       if constexpr (BWD) {
 #pragma unroll
         for (int c = 0; c < C; ++c) *stash_at(1, h, c) = make_float4(a[c][0], a[c][1], a[c][2], a[c][3]);
@@ -597,17 +701,15 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         for (int c = 0; c < C; ++c) a[c][pp] = av[c];
       }
 #pragma unroll
-      for (int c = 0; c < C; ++c) store_quad(arr_ptr(h, 0), c * TS + pb, a[c][0], a[c][1], a[c][2], a[c][3]);
+      for (int c = 0; c < C; ++c) store_quad_fwd(arr_ptr(h, 0), c, c * TS + pb, a[c][0], a[c][1], a[c][2], a[c][3]);
     };
     auto epi_hidden = [&](int h, int l) {
       float zq[C][4];
-#pragma unroll
-      for (int c = 0; c < C; ++c) umma::tmem_ld4(tD(h) + lane_off + c * TS + pb, zq[c]);
-      umma::wait_ld();
+      load_fwd(h, zq);
       if (!act) return;
       const float b = bs[(l - 1) * H + j];
 #pragma unroll
-      for (int pp = 0; pp < 4; ++pp) zq[0][pp] = tanh_tc(zq[0][pp] + b);      // channel 0 holds t0 from here on (see epi_layer1)
+      for (int pp = 0; pp < 4; ++pp) zq[0][pp] = tanh_tcx<SIG::kAccTanh>(zq[0][pp] + b);      // channel 0 holds t0 from here on (see epi_layer1)
       if constexpr (BWD) {
 #pragma unroll
         for (int c = 0; c < C; ++c) *stash_at(l, h, c) = make_float4(zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
@@ -622,13 +724,11 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
       }
 #pragma unroll
-      for (int c = 0; c < C; ++c) store_quad(arr_ptr(h, 0), c * TS + pb, zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
+      for (int c = 0; c < C; ++c) store_quad_fwd(arr_ptr(h, 0), c, c * TS + pb, zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
     };
     auto epi_output = [&](int h) {
       float uq[C][4];
-#pragma unroll
-      for (int c = 0; c < C; ++c) umma::tmem_ld4(tD(h) + lane_off + c * TS + pb, uq[c]);
-      umma::wait_ld();
+      load_fwd(h, uq);
       if (j < M) {
 #pragma unroll
         for (int c = 0; c < C; ++c)

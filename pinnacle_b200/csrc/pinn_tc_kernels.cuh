@@ -119,6 +119,46 @@ __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& p1, ui
   p3 = pack_bf16x2(r0, r1);
 }
 
+// (x0, x1) -> two packed bf16 pairs p2 + p3 ~= x (16 significant bits: the remainder of a value whose leading 8 bits went elsewhere)
+__device__ __forceinline__ void split2_pair(float x0, float x1, uint32_t& p2, uint32_t& p3) {
+  p2 = pack_bf16x2(x0, x1);
+  const float r0 = x0 - __uint_as_float(p2 << 16);
+  const float r1 = x1 - __uint_as_float(p2 & 0xFFFF0000u);
+  p3 = pack_bf16x2(r0, r1);
+}
+
+// Accurate tanh for the pipelined kernel's forward sweep: evaluated in double and rounded once, so the error is at most half an
+// ulp and carries no bias.  tanhf is within 2 ulp but slightly biased, and a bias that is coherent over all points acts like
+// a weight perturbation -- 1.3e-5 of gradient error on the nearly converged Laplace problem, with the FFMA kernel
+// as with the exact-main-term tensor path.  The double-precision pipe issues one warp instruction per clock per SM (measured:
+// 500 tanh per point are ~1 ms per 1 Mi points at 17 instructions), so the count matters: 16 + 1 MUFU instead of libdevice's ~70.
+//   |x| >= 2^-6:  tanh x = 1 - 2 / (1 + E), E = e^(2x) = 2^n * exp(y), y = 2x - n ln2, |y| <= 0.36, degree-8 polynomial
+//                 (remainder y^9/9! < 1e-9 * y / 2: what half an ulp of tanh tolerates through dE/E), reciprocal by rcp.approx
+//                 (2^-20) + one Newton step (2^-40: < 6e-11 of tanh >= 2^-6)
+//   |x| <  2^-6:  x (1 - x^2 (1/3 - x^2 (2/15 - 17 x^2 / 315))) in fp32: the bracket's rounding errors are scaled by x^2 < 2^-12
+__device__ __forceinline__ float tanh_dp(float z) {
+  const float az = fminf(fabsf(z), 10.0f);                          // tanh(10) rounds to 1 in fp32
+  const float z2 = z * z;
+  const float small = fmaf(z, -z2 * fmaf(-z2, fmaf(-z2, 0.053968254f, 0.13333334f), 0.33333334f), z);
+  const float nf = rintf(az * 2.8853900817779268f);                 // any integer within ~0.52 of 2x log2(e) will do
+  const double y = fma((double)nf, -0.6931471805599453, (double)(az + az));
+  double p = 2.48015873015873e-05;
+  p = fma(p, y, 1.984126984126984e-04);
+  p = fma(p, y, 1.388888888888889e-03);
+  p = fma(p, y, 8.333333333333333e-03);
+  p = fma(p, y, 4.1666666666666664e-02);
+  p = fma(p, y, 1.6666666666666666e-01);
+  p = fma(p, y, 0.5);
+  p = fma(p, y, 1.0);
+  p = fma(p, y, 1.0);
+  const double s = __hiloint2double(__double2hiint(p) + ((int)nf << 20), __double2loint(p)) + 1.0;     // 1 + e^(2x)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+  r = fma(r, fma(-s, r, 1.0), r);
+  const float big = copysignf((float)fma(-2.0, r, 1.0), z);
+  return az < 0.015625f ? small : big;
+}
+
 // tanh for the tensor-core kernels' element-wise stages.
 __device__ __forceinline__ float tanh_tc(float z) {
 #ifdef PINN_TC_FAST_TANH
@@ -129,6 +169,16 @@ __device__ __forceinline__ float tanh_tc(float z) {
   return fmaf(-2.0f, r, 1.0f);
 #else
   return tanhf(z);
+#endif
+}
+// ACC: residual signatures of the pipelined kernel (see tanh_dp); boundary-term signatures keep tanhf
+template <bool ACC>
+__device__ __forceinline__ float tanh_tcx(float z) {
+#if defined(PINN_TC_FAST_TANH) || defined(PINN_TC_TANHF)
+  return tanh_tc(z);
+#else
+  if constexpr (ACC) return tanh_dp(z);
+  else return tanh_tc(z);
 #endif
 }
 

@@ -9,6 +9,7 @@
 
 #include "../../include/pinn_b200.h"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "umma.cuh"
 
@@ -137,8 +138,15 @@ __global__ void __launch_bounds__(128, 1) umma_gemm_test_kernel(int mode, int va
 //   mode 11: A = X16(r=k, j=m) K-major,  B = X16(r=n, j=k) MN-major (N contiguous inside 16 bytes)
 //   mode 12: A in TMEM (two bf16 per 32-bit column), B = X16(r=k, j=n) K-major
 //   mode 13: A in TMEM, B MN-major
+//   modes 20..23: the same four with fp16 operands (kind::f16, a_format = b_format = F16)
+__device__ __forceinline__ uint16_t to16(float v, bool fp16) {
+  if (fp16) return __half_as_ushort(__float2half_rn(v));
+  return __bfloat16_as_ushort(__float2bfloat16(v));
+}
 __global__ void __launch_bounds__(128, 1) umma_gemm_test_bf16_kernel(int mode, int variant, int K, int N, const float* __restrict__ A,
                                                                      const float* __restrict__ B, float* __restrict__ D) {
+  const bool fp16 = mode >= 20;
+  if (fp16) mode -= 10;
   extern __shared__ __align__(1024) unsigned char sm[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t bar;
@@ -147,9 +155,9 @@ __global__ void __launch_bounds__(128, 1) umma_gemm_test_bf16_kernel(int mode, i
   const bool b_mn = (mode == 11 || mode == 13);
   const int JBk = (K / 8) * 128;     // r = k
   const int JBn = (N / 8) * 128;     // r = n
-  __nv_bfloat16* bufA = reinterpret_cast<__nv_bfloat16*>(sm);
+  uint16_t* bufA = reinterpret_cast<uint16_t*>(sm);
   const int bytesA = 16 * JBk;
-  __nv_bfloat16* bufB = reinterpret_cast<__nv_bfloat16*>(sm + bytesA);
+  uint16_t* bufB = reinterpret_cast<uint16_t*>(sm + bytesA);
   const int bytesB = b_mn ? (K / 8) * JBn : (N / 8) * JBk;
 
   if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
@@ -164,7 +172,7 @@ __global__ void __launch_bounds__(128, 1) umma_gemm_test_bf16_kernel(int mode, i
   for (int i = tid; i < K * N; i += 128) {
     const int k = i / N, n = i % N;
     const int off = b_mn ? ((k / 8) * JBn + (n / 8) * 128 + (k % 8) * 16 + (n % 8) * 2) : ((n / 8) * JBk + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2);
-    bufB[off / 2] = __float2bfloat16(B[i]);
+    bufB[off / 2] = to16(B[i], fp16);
   }
   if (a_tmem) {
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
@@ -172,8 +180,8 @@ __global__ void __launch_bounds__(128, 1) umma_gemm_test_bf16_kernel(int mode, i
       float v[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const __nv_bfloat162 pr = __floats2bfloat162_rn(A[tid * K + k0 + 2 * q], A[tid * K + k0 + 2 * q + 1]);   // .x = low half
-        v[q] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&pr));
+        const uint32_t pr = (uint32_t)to16(A[tid * K + k0 + 2 * q], fp16) | ((uint32_t)to16(A[tid * K + k0 + 2 * q + 1], fp16) << 16);   // low half first
+        v[q] = __uint_as_float(pr);
       }
       umma::tmem_st8(tA + lane_base + k0 / 2, v);
     }
@@ -181,7 +189,7 @@ __global__ void __launch_bounds__(128, 1) umma_gemm_test_bf16_kernel(int mode, i
   } else {
     for (int i = tid; i < 128 * K; i += 128) {
       const int m = i / K, k = i % K;
-      bufA[((m / 8) * JBk + (k / 8) * 128 + (m % 8) * 16 + (k % 8) * 2) / 2] = __float2bfloat16(A[i]);
+      bufA[((m / 8) * JBk + (k / 8) * 128 + (m % 8) * 16 + (k % 8) * 2) / 2] = to16(A[i], fp16);
     }
   }
   umma::fence_async_smem();
@@ -190,7 +198,8 @@ __global__ void __launch_bounds__(128, 1) umma_gemm_test_bf16_kernel(int mode, i
   umma::fence_after_sync();
 
   if (tid == 0) {
-    const uint32_t idesc = umma::make_idesc_bf16(128, N, 0, b_mn ? 1 : 0);
+    uint32_t idesc = umma::make_idesc_bf16(128, N, 0, b_mn ? 1 : 0);
+    if (fp16) idesc &= ~((1u << 7) | (1u << 10));       // a_format = b_format = 0 (F16)
     for (int ks = 0; ks < K / 16; ++ks) {
       uint64_t bd;
       if (b_mn) {
@@ -229,7 +238,7 @@ __global__ void __launch_bounds__(128, 1) umma_gemm_test_bf16_kernel(int mode, i
 }  // namespace pinn
 
 extern "C" int pinn_debug_umma_gemm(int mode, int variant, int K, int N, const float* A, const float* B, float* D, void* stream) {
-  if (mode >= 10 && mode <= 13) {
+  if ((mode >= 10 && mode <= 13) || (mode >= 20 && mode <= 23)) {
     if (K % 16 != 0 || N % 16 != 0 || N > 256 || K > 256) return 1;
     const size_t smem16 = (size_t)16 * (K / 8) * 128 + (size_t)(K / 8) * (N / 8) * 128 + 1024;
     if (cudaFuncSetAttribute(pinn::umma_gemm_test_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16) != cudaSuccess) return 2;

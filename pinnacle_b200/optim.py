@@ -34,7 +34,10 @@ class FlatAdam(torch.optim.Optimizer):
         params = list(params)
         if not params:
             raise ValueError("FlatAdam got an empty parameter list")
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        # the group carries torch.optim.Adam's remaining keys at their defaults so that a FlatAdam checkpoint loads into the
+        # reference's stock Adam (its step() reads them from the restored group)
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False, foreach=None,
+                                      capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False))
         if len(self.param_groups) != 1:
             raise ValueError("FlatAdam supports one parameter group")
         dev = params[0].device
@@ -97,19 +100,52 @@ class FlatAdam(torch.optim.Optimizer):
 
     # ---- checkpointing (deepxde/model.py:945-948 saves opt.state_dict(); restore() loads it back) -------------------
     def state_dict(self):
+        """torch.optim.Adam's own layout -- ``state[i] = {step, exp_avg, exp_avg_sq}`` per parameter, as copies shaped like
+        the parameter -- so a checkpoint written here loads into the reference's ``torch.optim.Adam`` (benchmark.py:107) and
+        back; ``flat_state`` carries the same moments as flat vectors (the fast path of ``load_state_dict``)."""
         sd = super().state_dict()
+        step = self.step_dev[:1].detach().clone().cpu().reshape(())
+        sd["state"] = {i: {"step": step.clone(), "exp_avg": self.exp_avg[off:off + k].detach().clone().view(p.shape),
+                           "exp_avg_sq": self.exp_avg_sq[off:off + k].detach().clone().view(p.shape)}
+                       for i, (p, (off, k)) in enumerate(zip(self._params, self._slices))}
         sd["flat_state"] = {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step_dev[:1].clone()}
         return sd
 
     def load_state_dict(self, state_dict):
+        """Accepts a FlatAdam checkpoint (``flat_state``) or one written by ``torch.optim.Adam`` for the same parameters
+        (per-parameter ``exp_avg`` / ``exp_avg_sq`` / ``step`` are scattered into the flat buffers).  A checkpoint with
+        optimizer state in neither form raises: resuming with silently reset moments is not an option."""
         state_dict = dict(state_dict)
         flat_state = state_dict.pop("flat_state", None)
+        per_param = state_dict.get("state", {}) or {}
+        state_dict["state"] = {}                        # the flat buffers are the state; nothing lives in self.state
         super().load_state_dict(state_dict)
         if flat_state is not None:
             self.exp_avg.copy_(flat_state["exp_avg"])
             self.exp_avg_sq.copy_(flat_state["exp_avg_sq"])
             self.step_dev.zero_()
             self.step_dev[:1].copy_(flat_state["step"])
+            return
+        if not per_param:                               # an optimizer that has never stepped
+            self.exp_avg.zero_(); self.exp_avg_sq.zero_(); self.step_dev.zero_()
+            return
+        ids = sorted(per_param)
+        if len(ids) != len(self._params):
+            raise capi.FusedOpError(f"FlatAdam.load_state_dict: checkpoint has state for {len(ids)} parameters, optimizer has {len(self._params)}")
+        steps = set()
+        for i, (p, (off, k)) in zip(ids, zip(self._params, self._slices)):
+            st = per_param[i]
+            if not all(key in st for key in ("exp_avg", "exp_avg_sq", "step")):
+                raise capi.FusedOpError("FlatAdam.load_state_dict: per-parameter state is not torch.optim.Adam's (exp_avg, exp_avg_sq, step)")
+            if st["exp_avg"].numel() != k:
+                raise capi.FusedOpError("FlatAdam.load_state_dict: parameter shapes differ from the checkpoint's")
+            self.exp_avg[off:off + k].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(float(st["step"]))
+        if len(steps) != 1:
+            raise capi.FusedOpError(f"FlatAdam.load_state_dict: parameters carry different step counts {sorted(steps)}")
+        self.step_dev.zero_()
+        self.step_dev[:1].fill_(steps.pop())
 
     def fused_step(self, solver, w_dev: Optional[torch.Tensor] = None):
         """One training step of a ``FusedPDESolver`` whose loss terms are all fused, without autograd: every term's fused

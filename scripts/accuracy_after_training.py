@@ -23,6 +23,9 @@ for name in sys.argv[1:] or ["Poisson2D_Classic", "Burgers1D", "Heat2D_Multiscal
     x = spec.sample(2048, seed=5); xb = spec.sample(256, seed=6)
     tgt = np.sin(3.0 * xb[:, :1]).astype(np.float32)
     wfile = os.path.join(ROOT, "gpurun_out", f"trained_{name}.pt")
+    fixed = os.path.join(ROOT, "tests", "golden", "trained", f"trained_{name}.pt")   # committed weights of one such run (the GPU test's)
+    if os.environ.get("PINN_LOAD_TRAINED") and not os.path.exists(wfile) and os.path.exists(fixed):
+        wfile = fixed
     if os.environ.get("PINN_LOAD_TRAINED") and os.path.exists(wfile):      # evaluate a what-if build at the SAME trained weights
         flat = torch.load(wfile).to(dev)
     else:

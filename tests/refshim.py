@@ -1,6 +1,8 @@
-"""Import the UNMODIFIED reference (/root/reference) in-process for oracle pinning.
+"""Import the UNMODIFIED reference in-process: for oracle pinning (CPU, build container) and as the comparator of the
+drop-in tests on the GPU box.
 
-Only usable where the reference tree is mounted (the build container).  Two optional
+Root = /root/reference where it is mounted (the build container), else the byte-for-byte copy that
+``scripts/install_reference.py`` placed under ``baseline/_ref`` (git-ignored; it travels to the GPU box).  Two optional
 dependencies of the reference are absent from this image and cannot be installed, so they
 are stubbed before ``import deepxde``:
 
@@ -8,7 +10,8 @@ are stubbed before ``import deepxde``:
 * ``skopt``      -> a stand-in quasi-random sampler built on scipy.stats.qmc (affects which
   training points ``dde.data.PDE`` draws, not the residual/gradient arithmetic).
 
-Nothing in the ``-m gpu`` tests, ``smoke()`` or ``bench.py`` imports this module.
+Nothing in ``pinnacle_b200/`` imports this module; ``smoke()`` does not either.  GPU tests and ``bench.py --impl
+reference`` use it through ``baseline/_ref`` only (never /root/reference, which does not exist on the GPU box).
 """
 from __future__ import annotations
 
@@ -20,7 +23,11 @@ from unittest import mock
 
 import numpy as np
 
-REFERENCE_ROOT = "/root/reference"
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = ["/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+if os.environ.get("PINN_REFERENCE_ROOT"):
+    _CANDIDATES.insert(0, os.environ["PINN_REFERENCE_ROOT"])
+REFERENCE_ROOT = next((c for c in _CANDIDATES if os.path.isdir(os.path.join(c, "deepxde"))), _CANDIDATES[0])
 
 
 def available() -> bool:

@@ -329,3 +329,100 @@ def test_flat_optimizer_checkpoint_round_trip(kind, tmp_path):
         sb.train_step()
     np.testing.assert_allclose(sb.opt.losses.detach().cpu().numpy(), sa.opt.losses.detach().cpu().numpy(), rtol=1e-6)
     assert float((_flat(net_a) - _flat(net_b)).norm() / _flat(net_a).norm()) < 1e-7
+
+
+def test_flat_adam_checkpoint_interchanges_with_torch_adam():
+    """A checkpoint written by the reference's torch.optim.Adam (benchmark.py:107) resumes under FlatAdam with its moments and
+    step count, and a FlatAdam checkpoint resumes under torch.optim.Adam: in both directions the continued run matches the
+    uninterrupted stock-Adam run (deepxde/model.py:945-948, 979-987 store / load opt.state_dict())."""
+    from pinnacle_b200 import capi
+    from pinnacle_b200.optim import FlatAdam
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    tgt = torch.randn(64, 3, device=dev)
+    xin = torch.randn(64, 7, device=dev)
+
+    def net():
+        torch.manual_seed(6)
+        return torch.nn.Sequential(torch.nn.Linear(7, 16), torch.nn.Tanh(), torch.nn.Linear(16, 3)).to(dev)
+
+    def run(n, opt, steps):
+        for _ in range(steps):
+            opt.zero_grad()
+            ((n(xin) - tgt) ** 2).mean().backward()
+            opt.step()
+
+    flat = lambda n: torch.cat([p.detach().reshape(-1) for p in n.parameters()])
+    ref = net(); oref = torch.optim.Adam(ref.parameters(), lr=3e-3, weight_decay=1e-4)
+    run(ref, oref, 5)
+    sd_torch = oref.state_dict()
+    w5 = [p.detach().clone() for p in ref.parameters()]
+    run(ref, oref, 4)
+    # torch.optim.Adam -> FlatAdam
+    a = net()
+    with torch.no_grad():
+        for p, w in zip(a.parameters(), w5):
+            p.copy_(w)
+    oa = FlatAdam(a.parameters(), lr=1.0)                 # hyper-parameters come from the checkpoint's param group
+    oa.load_state_dict(sd_torch)
+    assert float(oa.step_dev[0]) == 5.0 and float(oa.exp_avg.abs().sum()) > 0
+    run(a, oa, 4)
+    assert float((flat(a) - flat(ref)).norm() / flat(ref).norm()) < 1e-6
+    # FlatAdam -> torch.optim.Adam
+    b = net(); ob = FlatAdam(b.parameters(), lr=3e-3, weight_decay=1e-4)
+    run(b, ob, 5)
+    sd_flat = ob.state_dict()
+    c = net()
+    with torch.no_grad():
+        for p, q in zip(c.parameters(), b.parameters()):
+            p.copy_(q)
+    oc = torch.optim.Adam(c.parameters(), lr=1.0)
+    oc.load_state_dict(sd_flat)
+    run(c, oc, 4)
+    assert float((flat(c) - flat(ref)).norm() / flat(ref).norm()) < 1e-6
+    # optimizer state in neither form is an error, not a silent reset
+    bad = dict(sd_torch); bad["state"] = {k: {"momentum_buffer": v["exp_avg"]} for k, v in sd_torch["state"].items()}
+    with pytest.raises(capi.FusedOpError):
+        FlatAdam(net().parameters(), lr=1e-3).load_state_dict(bad)
+
+
+def test_workspace_is_per_stream_and_survives_graph_capture():
+    """the scratch buffer a captured step baked into its CUDA graph must never be handed to the allocator again,
+    and two streams must not share stash / partial accumulators."""
+    from pinnacle_b200 import capi, problems
+    dev = torch.device("cuda:0")
+    spec = problems.make("Poisson2D_Classic")
+    desc = spec.desc.with_net(100, 5)
+    net = _net(spec.desc, dev, 3)
+    flat = _flat(net).contiguous()
+    x = torch.as_tensor(spec.sample(3000, seed=2)).to(dev)
+    seeds = torch.ones(1, 1, device=dev)
+    ref = capi.fwd_bwd(desc, flat, x, None, 1.0 / 3000, seeds).clone()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        capi.fwd_bwd(desc, flat, x, None, 1.0 / 3000, seeds)
+    torch.cuda.synchronize()
+    out = torch.empty_like(ref)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        capi.fwd_bwd(desc, flat, x, None, 1.0 / 3000, seeds, out=out)
+    n_captured = len(capi._WS._captured)
+    assert n_captured >= 1
+    # a later, larger request on the default stream (more seeds => bigger workspace) must not disturb the captured buffer
+    big = capi.fwd_bwd(desc, flat, x, None, 1.0 / 3000, torch.ones(3, 1, device=dev))
+    junk = [torch.full((1 << 22,), float("nan"), device=dev) for _ in range(8)]      # would land in a freed workspace
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref) and torch.equal(big[:desc.n_params], ref[:desc.n_params])
+    # concurrent calls on two streams
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s1):
+        o1 = [capi.fwd_bwd(desc, flat, x, None, 1.0 / 3000, seeds) for _ in range(4)]
+    with torch.cuda.stream(s2):
+        o2 = [capi.fwd_bwd(desc, flat, x, None, 1.0 / 3000, seeds) for _ in range(4)]
+    torch.cuda.synchronize()
+    assert all(torch.equal(o, ref) for o in o1 + o2)
+    del junk

@@ -1,0 +1,60 @@
+"""The REAL reference on the GPU box: a ``dde.Model`` built the way benchmark.py:84-122 builds it (``pde.create_model(net)``,
+``model.compile(opt, loss_weights)``, every tensor on CUDA as trainer.py:39-41 arranges), ``enable_fused(model)`` and
+``model.train(iterations=50)`` -- against the same model left unpatched (the stock PyTorch GPU path a PINNacle user runs
+today).  Optimizers: Adam, the reference's LR_Adaptor (BASELINE configs[2]), MultiAdam and Adam_LBFGS (Kuramoto-Sivashinsky,
+configs[3]: 25 Adam then 25 L-BFGS iterations), and the flat-buffer swaps of ``fuse_optimizer=True``.
+
+The reference is the byte-for-byte copy under baseline/_ref (scripts/install_reference.py; git-ignored, ships with gpurun).
+Each case runs in a subprocess (tests/ref_gpu_driver.py): importing the reference on a CUDA box changes the process-wide
+default tensor type."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import refshim
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _drive(*args):
+    if not refshim.available():
+        pytest.skip("reference tree not installed (scripts/install_reference.py)")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "ref_gpu_driver.py"), *[str(a) for a in args]], capture_output=True, text=True, timeout=1200)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")]
+    assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-4000:]
+    return json.loads(lines[-1][7:])
+
+
+# (class, --method, iterations, fuse_optimizer, tolerance on the logged per-term losses, tolerance on the final weights)
+CASES = [
+    ("Burgers1D", "adam", 50, False, 2e-2, 2e-3),                       # configs[0] on the GPU
+    ("Poisson2D_Classic", "adam", 50, True, 2e-2, 2e-3),                # torch Adam swapped for FlatAdam
+    ("Heat2D_Multiscale", "adam", 50, False, 2e-2, 2e-3),
+    ("NS2D_LidDriven", "lra", 50, False, 5e-2, 5e-3),                   # configs[2]: the reference's LR_Adaptor on the fused losses
+    ("NS2D_LidDriven", "lra", 50, True, 5e-2, 5e-3),                    # ... swapped for FusedLRA
+    ("Burgers1D", "multiadam", 50, False, 5e-2, 5e-3),
+    ("KuramotoSivashinskyEquation", "lbfgs", 50, False, 1e-1, 2e-2),    # configs[3]: Adam -> L-BFGS through the fused closure
+]
+
+
+@pytest.mark.parametrize("name,method,steps,fuse_opt,tol_loss,tol_w", CASES)
+def test_real_reference_model_trains_alike_on_the_fused_path(name, method, steps, fuse_opt, tol_loss, tol_w):
+    res = _drive("train", name, method, steps, *(["--fuse-optimizer"] if fuse_opt else []))
+    print(f"{name} {method} fuse_optimizer={fuse_opt}: optimizer {res['optimizer']} impl {res['impl']} step-0 losses rel {res['first_rel']:.2e} "
+          f"history rel {res['hist_rel']:.2e} final weights rel {res['weights_rel']:.2e} fused calls {res['fused_calls']}")
+    assert res["finite"] and res["same_points"]
+    assert res["fused_calls"] >= steps                          # the CUDA kernels really ran underneath model.train
+    assert res["first_rel"] < 5e-5                              # identical weights at step 0: per-term losses to parity tolerance
+    assert res["hist_rel"] < tol_loss, (res["hist_reference"], res["hist_fused"])
+    assert res["weights_rel"] < tol_w
+    if fuse_opt:
+        assert res["optimizer"] in ("FlatAdam", "FusedLRA")
+    if method == "lra":
+        wr, wf = np.asarray(res["loss_weights_reference"]), np.asarray(res["loss_weights_fused"])
+        assert not np.allclose(wr, 1.0)
+        np.testing.assert_allclose(wf, wr, rtol=5e-2)

@@ -10,7 +10,8 @@ import torch
 from golden import common
 from pinnacle_b200 import kinds as K
 
-GOLDEN_NAMES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(common.GOLDEN_DIR, "*.npz")))
+GOLDEN_NAMES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(common.GOLDEN_DIR, "*.npz"))
+                      if not os.path.basename(f).startswith("l2re_"))        # l2re_*.npz: training-run fixtures (test_cuda_l2re.py)
 
 # Parity tolerances (BASELINE.json north_star: residuals, losses and gradients within 1e-5 relative in fp32)
 RTOL = 1e-5
