@@ -13,9 +13,16 @@ flat [grads | losses] buffer per problem per step.
 `value`   device-resident inputs, CUDA-event time of the K steps, max over ranks.
 `e2e`     the same metric through the public API (FusedPDESolver.train_step: H2D of the step's
           points from pinned host memory, fused op, autograd backward, Adam update, D2H of the losses).
-`--impl reference` times the reference algorithm (nested reverse-mode autograd, oracle/autograd_ref.py --
-the reference is pure Python/PyTorch, so there is nothing to compile into oracle/_ref) on the host cores
-with every thread torch can use, on a bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference on the host cores: the real `dde.Model` of each workload class built
+the way benchmark.py:84-122 builds it (baseline/_ref, the byte-for-byte copy scripts/install_reference.py places; imported
+through baseline/loader.py) and stepped through its own `model._train_step` (deepxde/model.py:501-509), every thread torch can
+use, on a bounded sample (`--ref-points` domain points per class).  It runs in a child process with CUDA hidden, because
+importing the reference on a CUDA box makes CUDA the default tensor type.  Where baseline/_ref is absent the port of the same
+algorithm (oracle/autograd_ref.py) is timed instead and the line says `kind: "port"`.
+
+The default line also carries `config.extra_workloads`: BASELINE configs[4] (Poisson3D_ComplexGeometry + Heat2D_LongTime, 16 Mi
+points per problem IN TOTAL, strong scaling) and configs[2] (NS2D_LidDriven + learning-rate annealing, 1 Mi residual rows in
+total, strong scaling), 5 steps each with their own clock samples.
 """
 from __future__ import annotations
 
@@ -188,20 +195,86 @@ def gpu_autograd_run(points_per_problem: int, steps: int, warmup: int, dev):
     return points_per_problem * len(specs) / (ms * 1e-3), ms
 
 
+def _reference_worker(args):
+    """Child process of reference_cpu_measure(): the unmodified reference, CPU only.  Prints one `REFWORKER {json}` line."""
+    from baseline import loader
+    dde, _ = loader.load()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.set_flush_denormal(True)         # the setting most favourable to the CPU baseline (see cpu_reference_run)
+    models, pts = [], 0
+    for i, name in enumerate(WORKLOAD_PROBLEMS):
+        dde.config.set_random_seed(i)
+        pde = loader.construct(name)
+        pde.training_points(domain=args.ref_points)                 # boundary / initial points stay at the class defaults
+        net = dde.nn.FNN([pde.input_dim] + [100] * 5 + [pde.output_dim], "tanh", "Glorot normal").float()      # benchmark.py:94
+        with torch.no_grad():
+            for lin in net.linears:
+                lin.bias.normal_(0, 0.1)
+        with loader._in_reference_dir():
+            model = pde.create_model(net)
+        model.compile(torch.optim.Adam(net.parameters(), 1e-3), loss_weights=np.ones(pde.num_loss))             # benchmark.py:107,117
+        net.auxiliary_vars = None
+        models.append(model)
+        pts += int(model.data.train_x_all.shape[0])
+
+    def step():
+        for m in models:
+            m._train_step(m.data.train_x, None, None)               # deepxde/model.py:501-509
+
+    for _ in range(max(1, args.warmup)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        step()
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    print("REFWORKER " + json.dumps({"value": pts / dt, "ms": dt * 1e3, "cores": cores, "pts": pts,
+                                     "rows": [int(m.data.train_x.shape[0]) for m in models]}), flush=True)
+
+
+def reference_cpu_measure(args, steps: int, warmup: int):
+    """The reference's CPU implementation of the step on the host cores: dict(value, ms, cores, pts, kind, sample)."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref_root, "deepxde")) and not args.port_baseline:
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="", PINN_REFERENCE_ROOT=ref_root)
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        cmd = [sys.executable, os.path.abspath(__file__), "--reference-worker", "--ref-points", str(args.ref_points), "--steps", str(steps),
+               "--warmup", str(warmup), "--workload", args.workload]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1500)
+            rows = [ln for ln in r.stdout.splitlines() if ln.startswith("REFWORKER ")]
+            if r.returncode == 0 and rows:
+                d = json.loads(rows[-1][10:])
+                d["kind"] = "reference"
+                d["sample"] = (f"unmodified reference (baseline/_ref): dde.Model of {' + '.join(WORKLOAD_PROBLEMS)} built as benchmark.py:84-122, "
+                               f"{args.ref_points} domain points per class + the classes' default boundary/initial points = {d['pts']} residual rows per step, "
+                               f"model._train_step (losses, backward, Adam) x {warmup} warm-up + {steps} timed, {d['cores']} torch threads, denormals flushed")
+                return d
+            sys.stderr.write("reference worker failed, timing the port instead:\n" + r.stdout[-1000:] + r.stderr[-2000:] + "\n")
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"reference worker failed ({e!r}), timing the port instead\n")
+    n = args.cpu_points
+    value, ms, cores, pts = cpu_reference_run(n, steps, warmup)
+    return {"value": value, "ms": ms, "cores": cores, "pts": pts, "kind": "port",
+            "sample": f"port of the reference algorithm (oracle/autograd_ref.py, nested torch.autograd): {n} points of each of {'+'.join(WORKLOAD_PROBLEMS)} "
+                      f"per step, {warmup} warm-up + {steps} timed steps, {cores} torch threads, denormals flushed"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.cpu_points
-    value, ms, cores, pts = cpu_reference_run(n, max(1, args.steps), max(1, args.warmup))
-    sample = f"{n} points of each of {'+'.join(WORKLOAD_PROBLEMS)} per step (reference holds the whole autograd graph in RAM; pts/s is flat in N); denormals flushed"
+    m = reference_cpu_measure(args, max(1, args.steps), max(1, args.warmup))
+    value, ms, cores = m["value"], m["ms"], m["cores"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "+".join(WORKLOAD_PROBLEMS) + f" x{n} pts (bounded CPU sample of the 1Mi-point config), 5x100 tanh MLP",
+        "config": {"workload": "+".join(WORKLOAD_PROBLEMS) + f", {m['pts']} residual rows per step (bounded CPU sample of the 1Mi-point config: the reference "
+                                                             "holds the whole autograd graph in RAM; its pts/s is flat in N), 5x100 tanh MLP",
                    "device": "host CPU", "threads": cores},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": m["kind"], "sample": m["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -338,6 +411,18 @@ def run_fused(args):
     e2e = {"value": pts_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "api": "FusedPDESolver.train_step (Adam update included), points from pinned host memory"}
 
+    # ---------------- BASELINE configs[4] and configs[2], strong scaling, 5 steps each (every rank takes part) ----------------
+    extra = None
+    if not args.no_extra and args.workload == "c2" and args.scaling == "weak":
+        del solvers
+        torch.cuda.empty_cache()
+        extra = {}
+        for key, fn, n_tot in (("configs[4] strong", measure_c5, 1 << 24), ("configs[2] strong", measure_c3, 1 << 20)):
+            try:
+                extra[key] = fn(n_tot, 5, 3, dev, world, rank, local_rank)
+            except Exception as e:  # noqa: BLE001
+                extra[key] = {"error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -404,9 +489,8 @@ def run_fused(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, ms, cores, pts = cpu_reference_run(args.cpu_points, 2, 1)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
-               "sample": f"{args.cpu_points} points of each of {'+'.join(WORKLOAD_PROBLEMS)} per step, 1 warm-up + 2 timed steps, torch autograd (reference algorithm) on the host cores, denormals flushed"}
+        m = reference_cpu_measure(args, 3, 1)
+        cpu = {"value": m["value"], "unit": UNIT, "cores": m["cores"], "kind": m["kind"], "ms_per_step": m["ms"], "sample": m["sample"]}
 
     gpu_ref = None
     if world == 1 and not args.no_cpu_baseline:
@@ -425,7 +509,8 @@ def run_fused(args):
         "config": {"workload": f"{' + '.join(WORKLOAD_PROBLEMS)}, {n_per} synthetic collocation points each per GPU, 5x100 tanh MLP, "
                                "losses + flat parameter gradient (+ NCCL all-reduce when N>1)",
                    "points_per_step": pts_step, "l2": "flushed between timed iterations (256 MiB write outside the event pair)",
-                   "parallelism": f"dp{world} over collocation points", "wall_s_timed_region": t_wall, "kernel": args.kernel},
+                   "parallelism": f"dp{world} over collocation points", "wall_s_timed_region": t_wall, "kernel": args.kernel,
+                   "extra_workloads": extra},
         "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
         "gpu_autograd_baseline": gpu_ref,
     }
@@ -434,28 +519,20 @@ def run_fused(args):
         dist.destroy_process_group()
 
 
-def run_c3(args):
+def measure_c3(N, steps, warmup, dev, world, rank, local_rank):
     """BASELINE.json configs[2]: NS2D_LidDriven (u, v, p; 3 coupled residuals + 5 boundary terms incl. a one-point pressure pin)
-    with learning-rate-annealing loss re-weighting, `--points` residual rows IN TOTAL sharded over the ranks (strong scaling),
+    with learning-rate-annealing loss re-weighting, `N` residual rows IN TOTAL sharded over the ranks (strong scaling),
     through the public API: FusedPDESolver + optim.FusedLRA(FlatAdam).  One step = per-term gradient rows (one NCCL
-    all-reduce of the PDE rows), the LRA statistics / re-weighting kernel, the Adam kernel.  Not the driver's default line."""
+    all-reduce of the PDE rows), the LRA statistics / re-weighting kernel, the Adam kernel.  Needs an initialised process
+    group when world > 1.  Returns the record on rank 0, None elsewhere."""
     import torch.distributed as dist
-    from pinnacle_b200 import capi, problems
+    from pinnacle_b200 import problems
     from pinnacle_b200.fused import shard_bounds
     from pinnacle_b200.nn import FNN
     from pinnacle_b200.optim import FlatAdam, FusedLRA
     from pinnacle_b200.solver import FusedPDESolver, ValueBC
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
-    capi.load()
     spec = problems.make("NS2D_LidDriven")
-    N, nb = args.points, 1024
+    nb = 1024
     beg, end = shard_bounds(N, rank, world)
     x_local = spec.sample(N, seed=7)[beg:end]                     # every rank draws the same set and keeps its block
     rs = np.random.RandomState(11)
@@ -479,13 +556,13 @@ def run_c3(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         solver.train_step()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    K = args.steps
+    K = steps
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
@@ -498,14 +575,90 @@ def run_c3(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / K
     losses = solver.opt.losses.detach().cpu().tolist()
+    if rank != 0:
+        return None
+    return {
+        "metric": METRIC, "value": N / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(warmup, 3),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"NS2D_LidDriven + learning-rate annealing (FusedLRA over FlatAdam), {N} residual rows in total + {4 * nb} boundary "
+                               "rows (replicated), 3 PDE + 5 boundary terms, 5x100 tanh MLP; optimizer update included",
+                   "parallelism": f"dp{world} over collocation points", "l2": "inputs larger than L2 at 1 GPU; no flush between steps"},
+        "clocks": clocks, "loss_weights_after": solver.opt.sync_loss_weight().tolist(), "losses_after": losses}
+
+
+def measure_c5(total_points, steps, warmup, dev, world, rank, local_rank):
+    """BASELINE.json configs[4]: Poisson3D_ComplexGeometry + Heat2D_LongTime, `total_points` collocation points per problem IN
+    TOTAL split over the ranks (strong scaling): losses + flat gradient per problem (+ the all-reduce), device-resident points."""
+    import torch.distributed as dist
+    from pinnacle_b200 import capi, problems
+    from pinnacle_b200.fused import FusedPDEResidual
+    names = WORKLOADS["c5"]
+    n_per = total_points // world
+    work = []
+    for i, name in enumerate(names):
+        spec = problems.make(name)
+        op = FusedPDEResidual(spec, 100, 5, device=dev)
+        op.set_points(torch.as_tensor(spec.sample(n_per, seed=300 + i + 1000 * rank)), shard=False)
+        op.n_global = n_per * world
+        op.inv_n_global = 1.0 / op.n_global
+        work.append((op, _seeded_params(spec.desc, seed=i).to(dev), torch.ones(1, spec.desc.n_pde, device=dev),
+                     torch.empty(spec.desc.n_params + spec.desc.n_pde, device=dev)))
+
+    def step():
+        for op, prm, sd, out in work:
+            capi.fwd_bwd(op.desc, prm, op.x, op.aux, op.inv_n_global, sd, out=out)
+            if world > 1:
+                dist.all_reduce(out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
     if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": N / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"NS2D_LidDriven + learning-rate annealing (FusedLRA over FlatAdam), {N} residual rows in total + {4 * nb} boundary "
-                                   "rows (replicated), 3 PDE + 5 boundary terms, 5x100 tanh MLP; optimizer update included",
-                       "parallelism": f"dp{world} over collocation points", "l2": "inputs larger than L2 at 1 GPU; no flush between steps"},
-            "clocks": clocks, "loss_weights_after": solver.opt.sync_loss_weight().tolist(), "losses_after": losses}), flush=True)
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    del work
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {"metric": METRIC, "value": n_per * world * len(names) / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(warmup, 3), "ms_per_step": ms, "scaling": "strong",
+            "config": {"workload": f"{' + '.join(names)}, {n_per * world} synthetic collocation points each in total ({n_per} per GPU), 5x100 tanh MLP, losses + "
+                                   "flat parameter gradient (+ NCCL all-reduce when N>1)", "l2": "inputs (2 x 200 MB in total) larger than L2; no flush between steps"},
+            "clocks": clocks}
+
+
+def run_c3(args):
+    """`--workload c3` as a line of its own (not the driver's default line)."""
+    import torch.distributed as dist
+    from pinnacle_b200 import capi
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    capi.load()
+    rec = measure_c3(args.points, args.steps, args.warmup, dev, world, rank, local_rank)
+    if rank == 0:
+        print(json.dumps(rec), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -516,7 +669,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--points", type=int, default=1 << 20, help="collocation points per problem per GPU")
-    ap.add_argument("--cpu-points", type=int, default=16384, help="points per problem of the bounded CPU sample")
+    ap.add_argument("--cpu-points", type=int, default=16384, help="points per problem of the bounded CPU sample (port of the reference algorithm)")
+    ap.add_argument("--ref-points", type=int, default=65536, help="domain points per class of the bounded CPU sample (unmodified reference)")
+    ap.add_argument("--port-baseline", action="store_true", help="time the port of the reference algorithm even where baseline/_ref is installed")
+    ap.add_argument("--reference-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-extra", action="store_true", help="skip config.extra_workloads (configs[4] at 16 Mi points and configs[2], strong scaling)")
     ap.add_argument("--impl", choices=["fused", "reference"], default="fused")
     ap.add_argument("--kernel", choices=["auto", "ffma", "tc", "tc2"], default="auto",
                     help="fused arm only: tcgen05 tensor-core kernel (auto/tc) or the FP32 FFMA kernel")
@@ -527,7 +684,9 @@ def main():
     args = ap.parse_args()
     global WORKLOAD_PROBLEMS
     WORKLOAD_PROBLEMS = WORKLOADS[args.workload]
-    if args.impl == "reference":
+    if args.reference_worker:
+        _reference_worker(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.workload == "c3":
         run_c3(args)

@@ -15,8 +15,10 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-BUILD = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libpinn_b200.so")
+# what-if builds (scripts/kernel_time.py --lib ...): PINN_BUILD_DIR / PINN_LIB_OUT redirect the objects and the library,
+# PINN_EXTRA_NVCC_FLAGS adds -D switches; the product build uses none of them
+BUILD = os.environ.get("PINN_BUILD_DIR") or os.path.join(HERE, "build")
+LIB = os.environ.get("PINN_LIB_OUT") or os.path.join(HERE, "libpinn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("PINN_EXTRA_NVCC_FLAGS", "").split()
@@ -61,8 +63,8 @@ def build(force=False, jobs=None, verbose=False):
     for cfg in parse_configs():
         cid = cfg[0]
         src = os.path.join(BUILD, f"inst_{cid}.cu")
-        body = ('#include "../pinn_inst.inl"\nnamespace pinn {\ntemplate <>\nconst ConfigInfo* get_config<%d>() { return Inst<%s>::info(); }\n}\n'
-                % (cid, ", ".join(str(a) for a in cfg)))
+        body = ('#include "%s"\nnamespace pinn {\ntemplate <>\nconst ConfigInfo* get_config<%d>() { return Inst<%s>::info(); }\n}\n'
+                % (os.path.join(HERE, "pinn_inst.inl"), cid, ", ".join(str(a) for a in cfg)))
         if not os.path.exists(src) or open(src).read() != body:
             with open(src, "w") as f:
                 f.write(body)

@@ -81,8 +81,13 @@ struct TC2fg {
   // batches, so the wait moves into the middle of the stage and grows (event trace: profiles/r1_lap_summary.md).
   static constexpr bool SPLIT_REV = false;
   static constexpr int NARR = 3 * NSUB + (BWD ? (SHZ ? 3 : 3 * NSUB) : 0);
-  // TMEM columns: D_A | D_B | dW (112) | stub (4) | four weight-split slots at a 52-column stride (the last one 48 wide)
-  static constexpr int tcD = 0, tcDstride = R, tcDW = 2 * R, tcStub = 2 * R + 112, tcW = tcStub + 4, tcWStride = 52, tcTotal = 512;
+  // TMEM columns: D_A | D_B | dW (112) | stub (4) | four weight-split slots at a 52-column stride (the last one 48 wide).
+  // The forward sweep's exact main-term accumulator Dm lives in the dW columns (idle then): one per sub-tile where 2R columns
+  // fit (DM2: R <= 64, i.e. C <= 4), else one shared by both sub-tiles (R <= 112) and handed over through `dsfree`.
+  static constexpr bool DM2 = (2 * R + 2 * R + 4 + 3 * 52 + 48 <= 512);
+  static constexpr int tcDmStride = DM2 ? R : 0;
+  static constexpr int tcDWWidth = (DM2 && 2 * R > 112) ? 2 * R : 112;
+  static constexpr int tcD = 0, tcDstride = R, tcDW = 2 * R, tcStub = 2 * R + tcDWWidth, tcW = tcStub + 4, tcWStride = 52, tcTotal = 512;
   static constexpr int tcWEnd = tcW + 3 * tcWStride + 48;
   static constexpr int oSmall = NARR * ARR;
   static constexpr int oW1 = oSmall;
@@ -417,23 +422,38 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
           wrp[wb] ^= 1;
           umma::fence_after_sync();
         }
+#ifndef PINN_EXP_NO_DM
         if (fwd && t == 5) {
           // Dm: the element-wise warps must have read the previous forward batch's main term out of it, and the last
           // reverse step's dW (same columns) must have been flushed
-          if (dm_used) {
-            mbar_wait(dsfree, dsph);
-            dsph ^= 1;
+          PINN_TR(70 + h);
+#ifndef PINN_EXP_DM_NOWAIT
+          if constexpr (!CFG::DM2) {
+            if (dm_used) {
+              mbar_wait(dsfree, dsph);
+              dsph ^= 1;
+            }
           }
+#endif
+          PINN_TR(74 + h);
           dm_used = true;
           if (flush_pending) {
             mbar_wait(dwfree, fph);
             fph ^= 1;
             flush_pending = false;
           }
+#ifndef PINN_EXP_DM_NOFENCE
           umma::fence_after_sync();
+#endif
+          PINN_TR(72 + h);
           accum = 0;
         }
-        const uint32_t dst = (fwd && t == 5) ? tDW : d;
+#endif
+#ifdef PINN_EXP_NO_DM             // what-if timing experiment only: one accumulator as in round 1
+        const uint32_t dst = d;
+#else
+        const uint32_t dst = (fwd && t == 5) ? tDW + (uint32_t)(h * CFG::tcDmStride) : d;
+#endif
 #pragma unroll
         for (int ks = 0; ks < kTcHP / 16; ++ks) {
           const uint32_t wad = (wa[t] == 0) ? (ks == 6 ? s0last : tW + s0 + (uint32_t)(ks * 8)) : tW + (uint32_t)(wa[t] * CFG::tcWStride + ks * 8);
@@ -577,20 +597,24 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
     // Forward operand of the next layer's rows contraction (see the header): a1 on the column's grid, a2 + a3 the remainder.
     // `mg` = 1.5 * 2^23 * grid per point: (v + mg) - mg rounds v to a multiple of the grid (|v| < 2^22 grids always holds).
     const unsigned wmask = (q == 3) ? ((1u << (H - 96)) - 1u) : 0xffffffffu;     // lanes of this warp that own a neuron
-    auto grid_magic = [&](float v) -> float {
-      // leading bit of max |v| over the warp's neurons -> grid 2^(e - 7) -> magic constant 1.5 * 2^(e + 16)
-      const unsigned mx = __reduce_max_sync(wmask, __float_as_uint(v) & 0x7fffffffu);
+    auto grid_magic = [&](float v0, float v1, float v2, float v3) -> float {
+      // leading bit of max |v| over the warp's neurons and the quad's four points -> grid 2^(e - 7) -> magic constant
+      // 1.5 * 2^(e + 16).  One grid per (channel, quad, warp): a point whose values are smaller than the quad's largest keeps
+      // fewer bits in a1 and more in a2 + a3 -- the sums stay exact, which is all the main term needs.
+      const unsigned b0 = __float_as_uint(v0) & 0x7fffffffu, b1 = __float_as_uint(v1) & 0x7fffffffu;
+      const unsigned b2 = __float_as_uint(v2) & 0x7fffffffu, b3 = __float_as_uint(v3) & 0x7fffffffu;
+      const unsigned mx = __reduce_max_sync(wmask, max(max(b0, b1), max(b2, b3)));
       unsigned e = mx >> 23;
       e = e > 230u ? 230u : e;
       return __uint_as_float(((e + 17u) << 23) | 0x00400000u);
     };
     auto store_quad_fwd = [&](unsigned char* base, int c, int r0, float v0, float v1, float v2, float v3) {
-      float m0, m1, m2, m3;
-      if (c == 0) {
-        m0 = m1 = m2 = m3 = 1.5f * 65536.0f;                                    // tanh values: |v| < 1, grid 2^-7
-      } else {
-        m0 = grid_magic(v0); m1 = grid_magic(v1); m2 = grid_magic(v2); m3 = grid_magic(v3);
-      }
+#ifdef PINN_EXP_STATIC_GRID      // what-if timing experiment only (results wrong)
+      const float m0 = 1.5f * 65536.0f;
+#else
+      const float m0 = (c == 0) ? 1.5f * 65536.0f : grid_magic(v0, v1, v2, v3);          // tanh values: |v| < 1, grid 2^-7
+#endif
+      const float m1 = m0, m2 = m0, m3 = m0;
       const float h0 = __fsub_rn(__fadd_rn(v0, m0), m0), h1 = __fsub_rn(__fadd_rn(v1, m1), m1);
       const float h2 = __fsub_rn(__fadd_rn(v2, m2), m2), h3 = __fsub_rn(__fadd_rn(v3, m3), m3);
       const uint32_t a1 = pack_bf16x2(h0, h1), b1 = pack_bf16x2(h2, h3);        // exact: at most 8 significant bits
@@ -606,12 +630,17 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
     auto load_fwd = [&](int h, float (&zq)[C][4]) {
 #pragma unroll
       for (int c = 0; c < C; ++c) umma::tmem_ld4(tD(h) + lane_off + c * TS + pb, zq[c]);
+#ifdef PINN_EXP_NO_DM
+      umma::wait_ld();
+      return;
+#endif
+      const uint32_t tDm = tDW + (uint32_t)(h * CFG::tcDmStride) + lane_off + pb;
       // the main term in two rounds: keeps the live registers of this stage at 1.5 accumulator sets instead of 2
       constexpr int C0 = (C + 1) / 2;
       {
         float sm[C0][4];
 #pragma unroll
-        for (int c = 0; c < C0; ++c) umma::tmem_ld4(tDW + lane_off + c * TS + pb, sm[c]);
+        for (int c = 0; c < C0; ++c) umma::tmem_ld4(tDm + c * TS, sm[c]);
         umma::wait_ld();
 #pragma unroll
         for (int c = 0; c < C0; ++c)
@@ -621,11 +650,14 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       {
         float sm[C - C0][4];
 #pragma unroll
-        for (int c = C0; c < C; ++c) umma::tmem_ld4(tDW + lane_off + c * TS + pb, sm[c - C0]);
+        for (int c = C0; c < C; ++c) umma::tmem_ld4(tDm + c * TS, sm[c - C0]);
         umma::wait_ld();
-        umma::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(dsfree)) : "memory");
+        if constexpr (!CFG::DM2) {
+          umma::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(dsfree)) : "memory");
+        }
+        PINN_TR(16 + h);
 #pragma unroll
         for (int c = C0; c < C; ++c)
 #pragma unroll

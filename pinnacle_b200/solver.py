@@ -556,6 +556,10 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
         return outputs_, losses
 
     def outputs_losses_train(inputs, targets):
+        # _test() evaluates the TRAIN losses with the net frozen first (deepxde/model.py:757-770): the logged loss_train must be
+        # weighted with the live weights too, not with the host copy of one display interval ago
+        if hasattr(model.opt, "sync_loss_weight") and not any(p.requires_grad for p in net.parameters()):
+            model.opt.sync_loss_weight()
         return outputs_losses(True, inputs, targets)
 
     def outputs_losses_test(inputs, targets):

@@ -13,7 +13,7 @@ NAMES = {1: "L1 A start", 2: "L1 B start", 3: "L1 A done", 4: "L1 B done", 10: "
          24: "rev part1 done A", 25: "rev part1 done B", 26: "rev got A", 27: "rev got B", 28: "rev done A", 29: "rev done B",
          40: "P prefetch issued", 41: "P operand free", 42: "P operand staged", 43: "P flush start", 44: "P flush done",
          58: "I step begin", 59: "I operand ready", 60: "I wait rdy A", 61: "I wait rdy B", 62: "I rdy A", 63: "I rdy B",
-         64: "I rows issued A", 65: "I rows issued B", 66: "I dW begin A", 67: "I dW begin B", 68: "I dW issued A", 69: "I dW issued B"}
+         64: "I rows issued A", 65: "I rows issued B", 16: "fwd Dm read A", 17: "fwd Dm read B", 74: "I Dm barrier passed A", 75: "I Dm barrier passed B", 70: "I Dm wait A", 71: "I Dm wait B", 72: "I Dm free A", 73: "I Dm free B", 66: "I dW begin A", 67: "I dW begin B", 68: "I dW issued A", 69: "I dW issued B"}
 path = sys.argv[1]
 nrun = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 mhz = float(sys.argv[3]) if len(sys.argv) > 3 else 1965.0

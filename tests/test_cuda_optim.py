@@ -1,6 +1,8 @@
 """Optimizer-side kernels over the flat buffers on the GPU: FlatAdam against torch.optim.Adam,
 FusedLRA against a line-by-line restatement of the reference's LR_Adaptor driven through autograd, the statistics kernel
 against torch reductions, and CUDA-graph replay of the autograd-free step."""
+import copy
+
 import numpy as np
 import pytest
 import torch
@@ -355,7 +357,7 @@ def test_flat_adam_checkpoint_interchanges_with_torch_adam():
     flat = lambda n: torch.cat([p.detach().reshape(-1) for p in n.parameters()])
     ref = net(); oref = torch.optim.Adam(ref.parameters(), lr=3e-3, weight_decay=1e-4)
     run(ref, oref, 5)
-    sd_torch = oref.state_dict()
+    sd_torch = copy.deepcopy(oref.state_dict())          # state_dict() hands out the live state tensors
     w5 = [p.detach().clone() for p in ref.parameters()]
     run(ref, oref, 4)
     # torch.optim.Adam -> FlatAdam
@@ -371,7 +373,7 @@ def test_flat_adam_checkpoint_interchanges_with_torch_adam():
     # FlatAdam -> torch.optim.Adam
     b = net(); ob = FlatAdam(b.parameters(), lr=3e-3, weight_decay=1e-4)
     run(b, ob, 5)
-    sd_flat = ob.state_dict()
+    sd_flat = copy.deepcopy(ob.state_dict())
     c = net()
     with torch.no_grad():
         for p, q in zip(c.parameters(), b.parameters()):
