@@ -20,9 +20,11 @@ from typing import Callable, List, Optional, Sequence
 import numpy as np
 import torch
 
+import collections
 from collections import namedtuple
 
 from . import capi
+from .evaluate import LazyOutputs, topk_residual
 from .fused import FusedPDEResidual, net_linear_params, net_param_provider, net_shape
 from .kinds import flux_desc, value_desc
 from .problems import ProblemSpec, describe_reference
@@ -145,8 +147,10 @@ class _StepCore:
         self._x_bc = None
         self._shape = (d, H, L, m)
         self._policy = policy
-        self._value_ops = {}            # (term index) -> FusedPDEResidual of kind VALUE
-        self.generation = 0             # bumped whenever new rows are staged
+        self._value_ops = {}            # (generation, term index) -> FusedPDEResidual of the boundary term on that point set
+        self.generation = 0             # identifies the staged point set the ops currently hold
+        self._gen_counter = 0
+        self._staged = collections.OrderedDict()    # host-array key -> device-resident point set (LRU, MAX_STAGED entries)
 
     def fused_term_loss(self, idx: int, beg: int, end: int, desc, aux_fn):
         """Mean-square of one boundary / initial / point-set term over the staged BC rows [beg, end) through the fused
@@ -157,10 +161,9 @@ class _StepCore:
     def term_op(self, idx: int, beg: int, end: int, desc, aux_fn) -> FusedPDEResidual:
         """The fused op (rows + term data device-resident) of boundary term `idx`; rebuilt when new rows were staged."""
         d, H, L, m = self._shape
-        ent = self._value_ops.get(idx)
-        if ent is None or ent[1] != self.generation:
-            op = ent[0] if ent is not None else FusedPDEResidual(
-                ProblemSpec(f"bc_term_{idx}", desc, [0, 1] * d), H, L, policy="eager", device=self.op.device)
+        ent = self._value_ops.get((self.generation, idx))
+        if ent is None:
+            op = FusedPDEResidual(ProblemSpec(f"bc_term_{idx}", desc, [0, 1] * d), H, L, policy="eager", device=self.op.device)
             op.world, op.rank = 1, 0              # BC rows are replicated on every rank (SURVEY.md §8e)
             n = end - beg
             aux = torch.as_tensor(aux_fn(), dtype=torch.float32).to(self.op.device).reshape(-1, desc.n_aux) if n > 0 else torch.zeros(0, desc.n_aux)
@@ -169,8 +172,7 @@ class _StepCore:
             if aux.shape[0] != n:
                 raise capi.FusedOpError(f"boundary term {idx}: {aux.shape[0]} rows of term data for {n} boundary rows")
             op.set_rows(self._x_bc[beg:end], aux.contiguous(), n)
-            self._value_ops[idx] = (op, self.generation)
-            ent = self._value_ops[idx]
+            ent = self._value_ops[(self.generation, idx)] = (op, self.generation)
         return ent[0]
 
     def refresh_params(self):
@@ -255,10 +257,14 @@ class _StepCore:
             _fused._backend_fwd_bwd_linear(bop.desc, flat, bop.x, bop.aux, self._lin_one, out=buf[(S + i) * P:(S + i) * P + P + 1])
         return buf[:T * P].view(T, P), None
 
+    MAX_STAGED = 3      # training set, test set, one spare (a resampled / anchor-extended set replaces the oldest)
+
     def stage(self, inputs, n_bc: int):
         """Make the rows of ``inputs`` device-resident: BC rows -> self._x_bc, residual rows -> fused op.
         Keyed on the identity of the host array, as the reference keeps one array per (re)sample
-        (data/pde.py:160-171); a new array (PDEPointResampler, add_anchors) re-uploads."""
+        (data/pde.py:160-171); a new array (PDEPointResampler, add_anchors) uploads.  The last MAX_STAGED point sets stay
+        on the device, so that ``_test()`` (train rows, then test rows, deepxde/model.py:765-781) and the training step
+        after it switch between resident sets instead of re-uploading them."""
         if isinstance(inputs, torch.Tensor):
             key = (inputs.data_ptr(), tuple(inputs.shape), n_bc)
         else:
@@ -266,16 +272,32 @@ class _StepCore:
             key = (inputs.__array_interface__["data"][0], inputs.shape, n_bc)
         if self.cache_points and key == self._key:
             return
+        op = self.op
+        ent = self._staged.get(key) if self.cache_points else None
+        if ent is not None:
+            self._staged.move_to_end(key)
+            op.x, op.aux, op.n_global, op.inv_n_global = ent["x"], ent["aux"], ent["n_global"], ent["inv_n_global"]
+            self._x_bc, self._key, self._key_ref, self.generation = ent["x_bc"], key, ent["ref"], ent["generation"]
+            return
         xt = torch.as_tensor(inputs)
-        self.op.set_points(xt[n_bc:], n_global=self.n_global)
-        self._x_bc = xt[:n_bc].to(torch.float32).to(self.op.device) if n_bc > 0 else None
-        if n_bc > 0 and xt.device != self.op.device:
-            self.op.stats["h2d_bytes"] += n_bc * xt.shape[1] * 4
+        op.set_points(xt[n_bc:], n_global=self.n_global)
+        self._x_bc = xt[:n_bc].to(torch.float32).to(op.device) if n_bc > 0 else None
+        if n_bc > 0 and xt.device != op.device:
+            op.stats["h2d_bytes"] += n_bc * xt.shape[1] * 4
         self._key = key
         # keep the staged host buffer alive: its address is the cache key, and a resampled array of the same shape
         # (PDEPointResampler, deepxde/callbacks.py:563-568) could otherwise be allocated at the address of a freed one
         self._key_ref = inputs if self.cache_points else None
-        self.generation += 1
+        self._gen_counter += 1
+        self.generation = self._gen_counter
+        if not self.cache_points:
+            self._value_ops = {k: v for k, v in self._value_ops.items() if k[0] == self.generation}
+            return
+        self._staged[key] = dict(x=op.x, aux=op.aux, n_global=op.n_global, inv_n_global=op.inv_n_global, x_bc=self._x_bc,
+                                 ref=inputs, generation=self.generation)
+        while len(self._staged) > self.MAX_STAGED:
+            _, old = self._staged.popitem(last=False)
+            self._value_ops = {k: v for k, v in self._value_ops.items() if k[0] != old["generation"]}
 
 
 class FusedPDESolver:
@@ -471,8 +493,57 @@ class FusedPDESolver:
         return loss
 
 
+def _self_check(spec: ProblemSpec, core: "_StepCore", data, net, n_rows: int, tol: float):
+    """Patch-time guard of the class-name mapping (``problems.describe_reference`` picks the residual kind from
+    ``type(pde_obj).__name__`` and the closure's constants): evaluate the LIVE ``data.pde`` closure the reference would run
+    (deepxde/data/pde.py:125-135: ``pde(inputs, outputs)`` through ``dde.grad``) on the first ``n_rows`` staged residual rows
+    and compare with the fused forward-only residual on the same rows and weights.  A subclass or an edited ``pde()`` under a
+    known class name then raises here instead of silently training on the canonical formula.  Returns the measured
+    relative L2 distance (None when there is nothing to compare: no rows yet, or a data object without a pde closure)."""
+    pde_fn = getattr(data, "pde", None)
+    train_x = getattr(data, "train_x", None)
+    if pde_fn is None or train_x is None or n_rows <= 0:
+        return None
+    n_bc = int(np.sum(data.num_bcs))
+    rows = np.ascontiguousarray(np.asarray(train_x)[n_bc:n_bc + n_rows], dtype=np.float32)
+    if rows.shape[0] == 0:
+        return None
+    dev = core.op.device
+    was_training = net.training
+    net.eval()
+    try:
+        xt = torch.as_tensor(rows).to(dev).requires_grad_(True)
+        ref = pde_fn(xt, net(xt))
+    finally:
+        net.train(was_training)
+        _clear_dde_grad_cache()
+    if ref is None:
+        return None
+    if not isinstance(ref, (list, tuple)):
+        ref = [ref]
+    ref = torch.cat([r.detach().reshape(rows.shape[0], -1) for r in ref], dim=1).to(torch.float64).cpu()
+    d, H, L, m = core._shape
+    op = FusedPDEResidual(spec, H, L, policy="lazy", device=dev, group=None)
+    op.world, op.rank = 1, 0
+    op.set_points(rows, shard=False)
+    core.refresh_params()
+    got = op.residual(core.params).to(torch.float64).cpu()
+    if tuple(got.shape) != tuple(ref.shape):
+        raise capi.FusedOpError(f"enable_fused self-check: the reference pde() returns {ref.shape[1]} residual terms, the fused kind "
+                                f"{spec.name!r} has {got.shape[1]}")
+    err = float((got - ref).norm() / max(float(ref.norm()), 1e-30))
+    if not np.isfinite(err) or err > tol:
+        raise capi.FusedOpError(
+            f"enable_fused self-check: the fused residual of kind {spec.name!r} differs from this model's own pde() closure on "
+            f"{rows.shape[0]} training rows (relative L2 {err:.3e} > {tol:g}). The problem class was mapped by its name; "
+            f"a subclass or an edited pde() needs its own descriptor (spec=...) -- "
+            f"or pass self_check=0 to skip this guard.")
+    return err
+
+
 def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto", cache_points: bool = True, group=None,
-                 fuse_bcs: bool = True, fuse_optimizer: bool = False):
+                 fuse_bcs: bool = True, fuse_optimizer: bool = False, self_check: int = 64, self_check_tol: float = 1e-4,
+                 lazy_outputs: bool = True):
     """Swap a COMPILED reference ``dde.Model`` onto the fused path (call after ``model.compile``).
 
     Raises (never falls back) when the problem class, the net or the data object is outside what
@@ -483,7 +554,12 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
     loss term is fused: ``torch.optim.Adam`` -> ``optim.FlatAdam``, the reference's ``LR_Adaptor`` (around Adam) ->
     ``optim.FusedLRA``, ``MultiAdam`` -> ``optim.FlatMultiAdam`` (same hyper-parameters; see ``_swap_optimizer``).  The
     training step then needs no autograd graph at all.  Any other optimizer (L-BFGS, NTK, a scheduler attached) is left
-    alone and keeps driving the fused losses through autograd."""
+    alone and keeps driving the fused losses through autograd.
+
+    ``self_check`` rows of the training set are evaluated through the model's own ``pde()`` closure and through the fused
+    kernel at patch time; a mismatch beyond ``self_check_tol`` (relative L2; the two fp32 evaluations agree to <= 1e-5 at
+    initial weights, the default leaves room for trained weights where the residual is a small difference of large terms)
+    raises.  The measured distance is kept as ``model.fused_self_check``."""
     if getattr(model, "opt", None) is None or not hasattr(model, "train_step"):
         raise capi.FusedOpError("enable_fused() must be called after model.compile()")
     data, net = model.data, model.net
@@ -500,6 +576,7 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
     if getattr(model, "external_trainable_variables", None):
         raise capi.FusedOpError("external trainable variables (inverse problems) are not supported by the fused path")
     core = _StepCore(spec, net, policy, None, group, cache_points)
+    model.fused_self_check = _self_check(spec, core, data, net, int(self_check), float(self_check_tol))
     n_pde = spec.desc.n_pde
     loss_weights = model.losshistory.loss_weights       # the live array compile() closed over (model.py:117,275)
 
@@ -547,9 +624,14 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
                 else:
                     terms.append(_mse(bc.error(data.train_x, x_bc, y_bc, beg, end)).reshape(1))   # data/pde.py:153-157
         if not training_graph:
-            # _test()/predict bookkeeping wants outputs for every row (model.py:767-780): plain forward
-            with torch.no_grad():
-                outputs_ = net(torch.as_tensor(inputs, dtype=torch.float32).to(core.op.device))
+            # _test() bookkeeping wants outputs for every row (model.py:767-780) but, without metrics, never reads them: hand
+            # back a stand-in that remembers the weights of this evaluation and runs the forward only if it is consumed
+            if lazy_outputs:
+                snap = torch.cat([p.detach().reshape(-1) for p in core.params])
+                outputs_ = LazyOutputs(snap, core._shape, inputs, core.op.device)
+            else:
+                with torch.no_grad():
+                    outputs_ = net(torch.as_tensor(inputs, dtype=torch.float32).to(core.op.device))
         losses = torch.cat(terms)
         losses = _apply_loss_weights(losses, loss_weights)
         _clear_dde_grad_cache()
@@ -636,6 +718,29 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
     pde_fn = getattr(data, "pde", None)
     predict_state = {"op": None, "as_list": None}
 
+    def _residual_op(x):
+        """The forward-only fused op holding the rows ``x`` (uploaded per query: a prediction must see the array's current contents)."""
+        if predict_state["op"] is None:
+            d, H, L, m = core._shape
+            op = FusedPDEResidual(spec, H, L, policy="lazy", device=core.op.device, group=None)
+            op.world, op.rank = 1, 0                                # every rank evaluates the rows it was handed
+            predict_state["op"] = op
+        op = predict_state["op"]
+        op.set_points(x if isinstance(x, torch.Tensor) else np.asarray(x, dtype=np.float32), shard=False)
+        net.eval()
+        core.refresh_params()
+        return op
+
+    def fused_residual(x):
+        """PDE residual matrix [N, n_pde] of the rows ``x`` as a DEVICE tensor (``model.predict(x, operator=pde)`` without the
+        copy to the host)."""
+        return _residual_op(x).residual(core.params)
+
+    def fused_topk_residual(x, k):
+        """(row indices of the k largest sum_terms |r|, ascending as ``np.argsort(err)[-k:]``; mean of that error) -- the
+        selection of src/utils/rar.py:21-30 reduced on the device: k indices and one scalar cross PCIe."""
+        return topk_residual(_residual_op(x), core.params, k)
+
     def predict(x, operator=None, callbacks=None):
         """deepxde/model.py:801-885.  With ``operator`` = the problem's own pde function the residual comes from the fused
         forward-only kernel (same return structure: an array, or a list of [N,1] arrays when pde() returns a list); any
@@ -646,11 +751,6 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
         if predict_state["as_list"] is None:
             probe = orig_predict(x[:2], operator=operator)          # learn the return structure from the reference itself
             predict_state["as_list"] = isinstance(probe, (list, tuple))
-        if predict_state["op"] is None:
-            d, H, L, m = core._shape
-            op = FusedPDEResidual(spec, H, L, policy="lazy", device=core.op.device, group=None)
-            op.world, op.rank = 1, 0                                # every rank evaluates the rows it was handed
-            predict_state["op"] = op
         cbs = None
         if callbacks is not None:
             import sys
@@ -658,11 +758,7 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
             cbs = dde.callbacks.CallbackList(callbacks=callbacks)
             cbs.set_model(model)
             cbs.on_predict_begin()
-        net.eval()
-        op = predict_state["op"]
-        op.set_points(x, shard=False)
-        core.refresh_params()
-        res = op.residual(core.params).cpu().numpy()                # [N, n_pde]
+        res = fused_residual(x).cpu().numpy()                       # [N, n_pde]
         if cbs is not None:
             cbs.on_predict_end()
         if predict_state["as_list"]:
@@ -673,6 +769,8 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
     model.outputs_losses_test = outputs_losses_test
     model.train_step = train_step
     model.predict = predict
+    model.fused_residual = fused_residual
+    model.fused_topk_residual = fused_topk_residual
     model.fused_core = core
     if fuse_optimizer:
         all_fused = fuse_bcs and not core.dynamic_params and all(

@@ -7,7 +7,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > $OUT/gpu.txt 2>&1
 if [ -z "$SKIP_TESTS" ]; then
-  timeout 1500 python -m pytest tests -m gpu -x -q --durations=15 > $OUT/pytest_gpu.log 2>&1
+  timeout 1500 python -m pytest tests -m gpu ${PYTEST_X--x} -q --durations=15 > $OUT/pytest_gpu.log 2>&1
   echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
   tail -5 $OUT/pytest_gpu.log
 fi

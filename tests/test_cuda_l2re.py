@@ -11,8 +11,11 @@ own sensitivity band.  Two replays on the GPU:
   ``enable_fused(model)``, ``model.train(..., callbacks=[TesterCallback])`` -- trajectory read from the errors.txt the reference's
   callback writes.
 
-Tolerance per logged epoch: 5 % of the reference value, or twice the spread of the reference's own runs where that is wider
-(fp32 training is chaotic: the reference's 1e-6-perturbed twins end up to 7 % apart on Burgers1D after 1000 steps).
+Tolerance: the FINAL L2RE (the north star's bar) within 5 % of the reference value, or twice the spread of the reference's own
+runs where that is wider (fp32 training is chaotic: the reference's 1e-6-perturbed twins end up to 7 % apart on Burgers1D
+after 1000 steps); the first logged epoch, before trajectories can diverge, at the plain 5 %; the epochs in between at 10 % /
+twice the spread -- a trajectory sanity check (mid-run the NS2D_LidDriven L2RE shows +10 % spikes that land on different logged
+epochs in the reference's own three runs, so the late-stage epochs share the widest late-stage spread).
 """
 import os
 import sys
@@ -37,7 +40,14 @@ def _fixture(name):
 def _tolerance(g):
     runs = np.vstack([g["l2re"][None, :], g["l2re_twins"]])
     spread = runs.max(axis=0) - runs.min(axis=0)
-    return np.maximum(0.05 * g["l2re"], 2.0 * spread)
+    frac = np.full(runs.shape[1], 0.10)
+    frac[0] = frac[-1] = 0.05
+    tol = np.maximum(frac * g["l2re"], 2.0 * spread)
+    # second half of the run, final epoch excluded: transient spikes of the loss (+10 % of L2RE on NS2D_LidDriven) land on
+    # different logged epochs in different runs of the reference itself -- use the widest late-stage spread for all of them
+    half = runs.shape[1] // 2
+    tol[half:-1] = np.maximum(tol[half:-1], 2.0 * spread[half:].max())
+    return tol
 
 
 def _check(name, l2, g, what):

@@ -134,6 +134,8 @@ def test_patched_dde_model_matches_unpatched_reference_step(name):
         fused.FusedPDEResidual.__init__ = init_cpu
         try:
             enable_fused(model)
+            # patch-time self-check: the live pde() closure vs the fused residual on 64 training rows
+            assert model.fused_self_check is not None and model.fused_self_check < 1e-5, model.fused_self_check
             _, new_losses = model.outputs_losses_train(x, None)
             net.zero_grad()
             new_losses.sum().backward()
@@ -151,6 +153,41 @@ def test_patched_dde_model_matches_unpatched_reference_step(name):
             assert model.opt.losses.shape[0] == pde.num_loss
         finally:
             fused.FusedPDEResidual.__init__ = orig
+
+
+@needs_ref
+def test_edited_pde_under_a_known_class_name_is_caught_at_patch_time():
+    """describe_reference maps a problem by its class name; a model whose live pde() closure computes something else (a
+    subclass, an edited residual) must not silently train on the canonical formula: enable_fused compares the two on a few
+    training rows and raises."""
+    dde, _ = refshim.load()
+    from pinnacle_b200 import capi, fused
+    from pinnacle_b200.solver import enable_fused
+    torch.manual_seed(0)
+    pde = refshim.construct("Burgers1D")
+    pde.training_points(domain=96, boundary=32, initial=32)
+    net = dde.nn.FNN([2] + [100] * 5 + [1], "tanh", "Glorot normal").float()
+    with torch.no_grad():
+        for lin in net.linears:
+            lin.bias.normal_(0, 0.1)
+    model = pde.create_model(net)
+    model.compile(torch.optim.Adam(net.parameters(), 1e-3), loss_weights=np.ones(pde.num_loss))
+    canonical = model.data.pde
+    model.data.pde = lambda x, u: canonical(x, u) + 1e-2 * u           # "the same" Burgers1D with an extra reaction term
+    orig = fused.FusedPDEResidual.__init__
+
+    def init_cpu(self, spec, H=100, L=5, policy="auto", device=None, group=None, check_library=True):
+        orig(self, spec, H, L, policy, "cpu", group, False)
+
+    fused.FusedPDEResidual.__init__ = init_cpu
+    try:
+        with oracle_backend():
+            with pytest.raises(capi.FusedOpError, match="self-check"):
+                enable_fused(model)
+            enable_fused(model, self_check=0)                           # explicit opt-out
+            assert model.fused_self_check is None
+    finally:
+        fused.FusedPDEResidual.__init__ = orig
 
 
 @needs_ref
@@ -266,6 +303,8 @@ def test_every_boundary_term_of_burgers2d_and_heatnd_is_fused():
             net.forward = lambda x, fwd=fwd: (calls.append(x.shape), fwd(x))[1]
             with oracle_backend():
                 enable_fused(model)
+                assert calls == [torch.Size([64, pde.input_dim])]      # the patch-time self-check's reference evaluation, once
+                calls.clear()
                 _, losses = model.outputs_losses_train(model.data.train_x, None)
                 losses.sum().backward()
             assert calls == [], (name, calls)
