@@ -67,7 +67,18 @@ enum pinn_kind {
   /* inverse problems with an unknown diffusion field (src/pde/inverse.py:19-24 PoissonInv, 129-136 HeatInv), outputs (u, a):
    *   r = c0 u_t + c1 div(a grad u) + c2 aux[aux_sel[0]],   div(a grad u) = a (u_xx + u_yy) + a_x u_x + a_y u_y
    * (the reference differentiates the products a u_x, a u_y).  d = 2 (c0 = 0) or 3 (x, y, t); m = 2; orders (2,2[,1]). */
-  PINN_KIND_DIV_AGRAD = 10
+  PINN_KIND_DIV_AGRAD = 10,
+  /* gPINN (src/pde/baseclass.py:151-180 use_gepinn, benchmark.py:91-92 --method gepinn): the residual of a one-output problem
+   * in two inputs AND its gradient with respect to the inputs as loss terms -- r_0 = r, r_1 = dr/dx_0, r_2 = dr/dx_1 (the order
+   * pde_wrapper appends them in).  dr/dx_j needs the mixed partials u_01, u_001, u_011: they come from order-3 Taylor jets along
+   * the FOUR directions e0, e1, e0+e1, e0-e1 (polarisation: D^3_{e0+-e1} u = u_000 +- 3 u_001 + 3 u_011 +- u_111).  The caller
+   * presents the 2-input network as a 4-"input" one: rows (x0, x1, 0, 0) and first-layer weights W1 [e0 e1 e0+e1 e0-e1], so
+   * d = 4, orders (3,3,3,3); the gradient with respect to the embedded first layer maps back by the transposed direction matrix.
+   *   GP_LINEAR2:   r = cu u + sum_{j<2} (c1_j u_j + c2_j u_jj) + src   (consts as LINEAR, constant coefficients;
+   *                 aux_sel[0..2] = columns of src, dsrc/dx0, dsrc/dx1, -1 = none)
+   *   GP_BURGERS1D: r = u_t + u u_x - c0 u_xx,  inputs (x, t)                                   (burgers.py:21-25) */
+  PINN_KIND_GP_LINEAR2 = 11,
+  PINN_KIND_GP_BURGERS1D = 12
 };
 
 typedef struct pinn_kind_desc {

@@ -332,7 +332,49 @@ struct Residual {
       case PINN_KIND_VALUE: return C == 1;
       case PINN_KIND_FLUX: return C == 1 + D && SIG::order(0) == 1;
       case PINN_KIND_DIV_AGRAD: return M == 2 && sig22() && (D == 2 || (D == 3 && SIG::order(D - 1) >= 1));
+      case PINN_KIND_GP_LINEAR2:
+      case PINN_KIND_GP_BURGERS1D: return gp4();
       default: return false;
+    }
+  }
+
+  // gPINN kinds: order-3 jets along e0, e1, e0+e1, e0-e1 of a one-output net (see include/pinn_b200.h)
+  PINN_HD static constexpr bool gp4() {
+    if constexpr (SIG::kLap) return false;
+    else return M == 1 && D == 4 && SIG::order(0) >= 3 && SIG::order(1) >= 3 && SIG::order(2) >= 3 && SIG::order(3) >= 3;
+  }
+  // the partial derivatives a gPINN residual in two inputs (x, y) can use, from the four directional jets:
+  //   2 c(2,2) = u_xx + 2 u_xy + u_yy;  6 c(2,3) = u_xxx + 3 u_xxy + 3 u_xyy + u_yyy;  6 c(3,3) = u_xxx - 3 u_xxy + 3 u_xyy - u_yyy
+  struct Gp {
+    float u, ux, uy, uxx, uyy, uxy, uxxx, uyyy, uxxy, uxyy;
+  };
+  PINN_HD static Gp gp_derivs(const float (&Uo)[C]) {
+    Gp g{};
+    if constexpr (gp4()) {
+      const float c01 = Uo[SIG::chan(0, 1)], c02 = Uo[SIG::chan(0, 2)], c03 = Uo[SIG::chan(0, 3)];
+      const float c11 = Uo[SIG::chan(1, 1)], c12 = Uo[SIG::chan(1, 2)], c13 = Uo[SIG::chan(1, 3)];
+      const float c22 = Uo[SIG::chan(2, 2)], c23 = Uo[SIG::chan(2, 3)], c33 = Uo[SIG::chan(3, 3)];
+      g.u = Uo[0]; g.ux = c01; g.uy = c11;
+      g.uxx = 2.0f * c02; g.uyy = 2.0f * c12; g.uxy = c22 - c02 - c12;
+      g.uxxx = 6.0f * c03; g.uyyy = 6.0f * c13;
+      g.uxxy = (c23 - c33) - 2.0f * c13;
+      g.uxyy = (c23 + c33) - 2.0f * c03;
+    }
+    return g;
+  }
+  // transpose of gp_derivs: adjoints of the partial derivatives -> adjoints of the jet channels
+  PINN_HD static void gp_derivs_adj(const Gp& b, float (&Ubo)[C]) {
+    if constexpr (gp4()) {
+      Ubo[0] = b.u;
+      Ubo[SIG::chan(0, 1)] = b.ux;
+      Ubo[SIG::chan(1, 1)] = b.uy;
+      Ubo[SIG::chan(0, 2)] = 2.0f * b.uxx - b.uxy;
+      Ubo[SIG::chan(1, 2)] = 2.0f * b.uyy - b.uxy;
+      Ubo[SIG::chan(2, 2)] = b.uxy;
+      Ubo[SIG::chan(0, 3)] = 6.0f * b.uxxx - 2.0f * b.uxyy;
+      Ubo[SIG::chan(1, 3)] = 6.0f * b.uyyy - 2.0f * b.uxxy;
+      Ubo[SIG::chan(2, 3)] = b.uxxy + b.uxyy;
+      Ubo[SIG::chan(3, 3)] = b.uxyy - b.uxxy;
     }
   }
 
@@ -452,6 +494,24 @@ struct Residual {
             const float u = U[0][0], ux = U[0][SIG::chan(0, 1)];
             r[0] = U[0][SIG::chan(1, 1)] + c[0] * u * ux + c[1] * 2.0f * U[0][SIG::chan(0, 2)] + c[2] * 24.0f * U[0][SIG::chan(0, 4)];
           }
+        }
+      } break;
+      case PINN_KIND_GP_LINEAR2: {
+        if constexpr (gp4()) {
+          const Gp g = gp_derivs(U[0]);
+          const float cu = c[LIN_CU], c1x = c[LIN_C1], c1y = c[LIN_C1 + 1], c2x = c[LIN_C2], c2y = c[LIN_C2 + 1];
+          r[0] = cu * g.u + c1x * g.ux + c1y * g.uy + c2x * g.uxx + c2y * g.uyy + (kp.aux_sel[0] >= 0 ? aux[kp.aux_sel[0]] : 0.f);
+          r[1] = cu * g.ux + c1x * g.uxx + c1y * g.uxy + c2x * g.uxxx + c2y * g.uxyy + (kp.aux_sel[1] >= 0 ? aux[kp.aux_sel[1]] : 0.f);
+          r[2] = cu * g.uy + c1x * g.uxy + c1y * g.uyy + c2x * g.uxxy + c2y * g.uyyy + (kp.aux_sel[2] >= 0 ? aux[kp.aux_sel[2]] : 0.f);
+        }
+      } break;
+      case PINN_KIND_GP_BURGERS1D: {
+        if constexpr (gp4()) {
+          // inputs (x, t): uy = u_t, uxy = u_xt, uyy = u_tt, uxxy = u_xxt
+          const Gp g = gp_derivs(U[0]);
+          r[0] = g.uy + g.u * g.ux - c[0] * g.uxx;
+          r[1] = g.uxy + g.ux * g.ux + g.u * g.uxx - c[0] * g.uxxx;
+          r[2] = g.uyy + g.uy * g.ux + g.u * g.uxy - c[0] * g.uxxy;
         }
       } break;
       case PINN_KIND_VALUE: {
@@ -621,6 +681,40 @@ struct Residual {
             Ub[0][SIG::chan(0, 4)] = 24.0f * c[2] * g;
             Ub[0][SIG::chan(1, 1)] = g;
           }
+        }
+      } break;
+      case PINN_KIND_GP_LINEAR2: {
+        if constexpr (gp4()) {
+          const float cu = c[LIN_CU], c1x = c[LIN_C1], c1y = c[LIN_C1 + 1], c2x = c[LIN_C2], c2y = c[LIN_C2 + 1];
+          const float g0 = rb[0], g1 = rb[1], g2 = rb[2];
+          Gp b{};
+          b.u = cu * g0;
+          b.ux = c1x * g0 + cu * g1;
+          b.uy = c1y * g0 + cu * g2;
+          b.uxx = c2x * g0 + c1x * g1;
+          b.uyy = c2y * g0 + c1y * g2;
+          b.uxy = c1y * g1 + c1x * g2;
+          b.uxxx = c2x * g1;
+          b.uyyy = c2y * g2;
+          b.uxxy = c2x * g2;
+          b.uxyy = c2y * g1;
+          gp_derivs_adj(b, Ub[0]);
+        }
+      } break;
+      case PINN_KIND_GP_BURGERS1D: {
+        if constexpr (gp4()) {
+          const Gp g = gp_derivs(U[0]);
+          const float g0 = rb[0], g1 = rb[1], g2 = rb[2], nu = c[0];
+          Gp b{};
+          b.u = g0 * g.ux + g1 * g.uxx + g2 * g.uxy;
+          b.ux = g0 * g.u + 2.0f * g1 * g.ux + g2 * g.uy;
+          b.uy = g0 + g2 * g.ux;
+          b.uxx = -nu * g0 + g1 * g.u;
+          b.uyy = g2;
+          b.uxy = g1 + g2 * g.u;
+          b.uxxx = -nu * g1;
+          b.uxxy = -nu * g2;
+          gp_derivs_adj(b, Ub[0]);
         }
       } break;
       case PINN_KIND_VALUE: {

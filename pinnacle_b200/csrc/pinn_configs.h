@@ -22,6 +22,7 @@
 // 19-20 flux-type boundary terms (PINN_KIND_FLUX: Neumann / affine Robin): first-order signatures (1,1), (1,1,1), m = 1
 // 29-30 PoissonInv (inverse.py:19-24; outputs u, a): (2,2) m=2 and its forward-Laplacian form LapSig<2> m=2 (HeatInv uses 5 / 26)
 // 31    LapSig<3> with per-point direction weights (orders entry -(10+d)): Wave2D_Heterogeneous, u_xx + u_yy - u_tt / c(x,y)
+// 32    gPINN kinds (GP_LINEAR2, GP_BURGERS1D: residual + its input gradient, two inputs embedded along e0, e1, e0+e1, e0-e1): (3,3,3,3)
 // 28    the same for the 6-dimensional Neumann term of HeatND (heat.py:296-301): (1,1,1,1,1,1)
 #pragma once
 
@@ -57,6 +58,7 @@
   X(28, 100, 1, 16, 2, 0, 1, 1, 1, 1, 1, 1) \
   X(29, 100, 2, 32, 4, 32, 2, 2)           \
   X(30, 100, 2, 32, 4, 32, -2)             \
-  X(31, 100, 1, 32, 4, 32, -13)
+  X(31, 100, 1, 32, 4, 32, -13)           \
+  X(32, 100, 1, 16, 2, 0, 3, 3, 3, 3)
 
-#define PINN_NUM_CONFIGS 32
+#define PINN_NUM_CONFIGS 33

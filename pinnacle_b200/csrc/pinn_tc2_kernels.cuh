@@ -309,35 +309,65 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       for (int c = 0; c < CFG::tcWEnd - CFG::tcStub; c += 16) tmem_st16(tStub + lane_off + c, z);
       umma::wait_st();
     }
-    // dW_l (TMEM, 100 x 100 used) -> this CTA's private partial [k/4][n][k%4], plain read-modify-write (single writer).
-    // Two rounds of 52 / 48 columns; the global loads of a round are all in flight together.
+    // dW_l (TMEM, 100 x 100 used) -> this CTA's private partial [k/4][n][k%4] in L2, read-modify-write through registers (single
+    // writer per address, so the partial is deterministic).  Rounds of 32 columns: the round's 8 global loads and its two
+    // 16-column TMEM loads are all in flight together -- one L2 and one TMEM round trip per round (round 1 of this kernel
+    // waited for each of 25 4-column TMEM loads separately).
+    // Tried: 128-bit `red.global.add` instead of the read-modify-write (-DPINN_FLUSH_RED): halves the L2 bytes and needs no
+    // load, but the kernel got SLOWER (Poisson2D 9.85 -> 10.32 ms, Heat2D_Multiscale 12.32 -> 12.64 ms per 1 Mi points): the L2
+    // atomic units serialise the 4 lanes of every vector reduction and delay the stash / weight traffic behind them.
+    auto red_add4 = [&](float4* dst, float a, float b, float c, float d) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+    };
     auto flush_dw = [&](int s, int l) {
 #ifdef PINN_EXP_NO_FLUSH
       return;
 #endif
       float4* gt = reinterpret_cast<float4*>(p.gwt) + ((size_t)(blockIdx.x * S + s) * (L - 1) + (l - 2)) * kTcGwtLayer4 + j;
+#ifdef PINN_FLUSH_RED
 #pragma unroll
-      for (int rd = 0; rd < 2; ++rd) {
-        constexpr int NV = 13;
-        const int c0 = 52 * rd;
-        const int nv = (rd == 0) ? 13 : 12;
-        float4 acc[NV];
+      for (int rd = 0; rd < 3; ++rd) {
+        float v0[16], v1[16];
+        tmem_ld16(tDW + lane_off + 32 * rd, v0);
+        tmem_ld16(tDW + lane_off + 32 * rd + 16, v1);
+        umma::wait_ld();
 #pragma unroll
-        for (int i = 0; i < NV; ++i)
-          if (i < nv) acc[i] = gt[(size_t)(c0 / 4 + i) * 128];
+        for (int i = 0; i < 4; ++i) red_add4(gt + (size_t)(8 * rd + i) * 128, v0[4 * i], v0[4 * i + 1], v0[4 * i + 2], v0[4 * i + 3]);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          if (i < nv) {
-            float v[4];
-            umma::tmem_ld4(tDW + lane_off + c0 + 4 * i, v);
-            umma::wait_ld();
-            acc[i].x += v[0]; acc[i].y += v[1]; acc[i].z += v[2]; acc[i].w += v[3];
-          }
+        for (int i = 0; i < 4; ++i) red_add4(gt + (size_t)(8 * rd + 4 + i) * 128, v1[4 * i], v1[4 * i + 1], v1[4 * i + 2], v1[4 * i + 3]);
+      }
+      {
+        float v3[4];
+        umma::tmem_ld4(tDW + lane_off + 96, v3);
+        umma::wait_ld();
+        red_add4(gt + (size_t)24 * 128, v3[0], v3[1], v3[2], v3[3]);
+      }
+#else
+      float4 tail = gt[(size_t)24 * 128];                      // columns 96..99 ride along with the first round
+#pragma unroll
+      for (int rd = 0; rd < 3; ++rd) {
+        float4 acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = gt[(size_t)(8 * rd + i) * 128];
+        float v0[16], v1[16];
+        tmem_ld16(tDW + lane_off + 32 * rd, v0);
+        tmem_ld16(tDW + lane_off + 32 * rd + 16, v1);
+        float v3[4];
+        if (rd == 0) umma::tmem_ld4(tDW + lane_off + 96, v3);
+        umma::wait_ld();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[i].x += v0[4 * i]; acc[i].y += v0[4 * i + 1]; acc[i].z += v0[4 * i + 2]; acc[i].w += v0[4 * i + 3];
+          acc[4 + i].x += v1[4 * i]; acc[4 + i].y += v1[4 * i + 1]; acc[4 + i].z += v1[4 * i + 2]; acc[4 + i].w += v1[4 * i + 3];
         }
 #pragma unroll
-        for (int i = 0; i < NV; ++i)
-          if (i < nv) gt[(size_t)(c0 / 4 + i) * 128] = acc[i];
+        for (int i = 0; i < 8; ++i) gt[(size_t)(8 * rd + i) * 128] = acc[i];
+        if (rd == 0) {
+          tail.x += v3[0]; tail.y += v3[1]; tail.z += v3[2]; tail.w += v3[3];
+          gt[(size_t)24 * 128] = tail;
+        }
       }
+#endif
     };
     long long nstep = 0;                   // pipeline steps so far (forward and reverse, all tiles)
     int pend_s = -1, pend_l = -1;          // dW of the previous reverse step, still in TMEM

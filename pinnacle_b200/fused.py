@@ -29,7 +29,7 @@ import numpy as np
 import torch
 
 from . import capi
-from .kinds import KindDesc
+from .kinds import KIND_FLUX, KindDesc
 from .problems import ProblemSpec
 
 # The compute backend: always the C ABI.  Kept as module attributes so the gloo/CPU tests of the
@@ -109,6 +109,10 @@ class _FusedLossFn(torch.autograd.Function):
             n = int(np.prod(shp))
             grads.append(flat_grad[off:off + n].view(shp) if ctx.needs_input_grad[1 + i] else None)
             off += n
+        if desc.kind == KIND_FLUX and desc.aux_sel[1] < 0:
+            # n.grad u does not depend on the output-layer bias: autograd reports None for that tensor in the reference, and
+            # its LRA wrapper counts only the entries of non-None gradients (src/optimizer/lr_adaptor.py:50-54)
+            grads[-1] = None
         return (None,) + tuple(grads)
 
 
@@ -151,6 +155,10 @@ class FusedPDEResidual:
         same GLOBAL array and keeps its contiguous shard.  With ``n_global`` given the rows are already
         this rank's own share of ``n_global`` rows in total (no slicing)."""
         xt = torch.as_tensor(x)
+        embed = getattr(self.spec, "embed", None)
+        if embed is not None and xt.dim() == 2 and xt.shape[1] == embed.shape[0]:
+            # embedded problem (gPINN): the kernels' extra "inputs" are jet directions, their coordinates are zero
+            xt = torch.cat([xt, xt.new_zeros(xt.shape[0], self.desc.d - xt.shape[1])], dim=1)
         if xt.dim() != 2 or xt.shape[1] != self.desc.d:
             raise ValueError(f"points must be [N,{self.desc.d}], got {tuple(xt.shape)}")
         if n_global is not None:
@@ -266,6 +274,22 @@ def pfnn_params(net) -> List[torch.Tensor]:
         rows.append(torch.nn.functional.pad(f.weight, (left, right)))
     out += [torch.cat(rows, dim=0), torch.cat([f.bias for f in last])]
     return out
+
+
+def embedded_param_provider(base_fn, embed: np.ndarray):
+    """Parameters of the embedded network of a gPINN problem: the first-layer weight times the direction matrix V (so that the
+    kernels' input directions are the columns of V); autograd carries the gradient back to the real W1 through the product."""
+    state = {}
+
+    def fn():
+        params = list(base_fn())
+        w1 = params[0]
+        V = state.get("V")
+        if V is None or V.device != w1.device:
+            V = state["V"] = torch.as_tensor(embed, dtype=w1.dtype).to(w1.device)
+        return [w1 @ V] + params[1:]
+
+    return fn
 
 
 def net_param_provider(net):

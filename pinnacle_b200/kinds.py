@@ -34,6 +34,9 @@ KIND_VALUE = 8           # value-type BC/IC/point-set term: u_c - g(x)  (icbc/bo
 KIND_FLUX = 9            # flux-type BC term: n(x).grad u_c + beta(x) u_c - g(x)  (icbc/boundary_conditions.py:44-57,83-105)
 KIND_DIV_AGRAD = 10      # inverse problems, outputs (u, a): c0 u_t + c1 div(a grad u) + c2 src   (inverse.py:19-24, 129-136)
 
+KIND_GP_LINEAR2 = 11     # gPINN: LINEAR residual in two inputs + its input gradient (baseclass.py:151-180); 4 jet directions, order 3
+KIND_GP_BURGERS1D = 12   # gPINN: Burgers1D residual + its input gradient
+
 KIND_NAMES = {
     KIND_LINEAR: "linear",
     KIND_BURGERS1D: "burgers1d",
@@ -46,6 +49,8 @@ KIND_NAMES = {
     KIND_VALUE: "value",
     KIND_FLUX: "flux",
     KIND_DIV_AGRAD: "div_agrad",
+    KIND_GP_LINEAR2: "gpinn_linear2",
+    KIND_GP_BURGERS1D: "gpinn_burgers1d",
 }
 
 # LINEAR kind constant layout

@@ -248,6 +248,12 @@ class FusedLRA(torch.optim.Optimizer):
                 self._rows_w_next = torch.empty_like(self._rows_w)
                 self._rows_counts = self.counts
         G, losses = self.solver.term_gradient_rows(opt.flat, self._seeds)
+        tc = getattr(getattr(self.solver, "core", None), "term_counts", None)
+        if tc is not None and tuple(tc) != getattr(self, "_counts_key", None):
+            # per boundary term: the number of parameters its gradient reaches (P - m for Neumann terms, see gradient_rows)
+            self._counts_key = tuple(tc)
+            self._rows_counts = self._rows_counts.clone()
+            self._rows_counts[self._rows_counts.numel() - len(tc):] = torch.as_tensor(tc, dtype=torch.float32, device=w.device)
         if self._pde_equal:
             self._rows_w[:1] = pde_w[:1]
             self._rows_w[1:] = w[n_pde:]

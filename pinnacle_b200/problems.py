@@ -37,6 +37,14 @@ class ProblemSpec:
     desc: KindDesc
     bbox: Sequence[float]                      # [lo0, hi0, lo1, hi1, ...] in input order
     aux_fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None   # x[N,d] -> aux[N,n_aux] (same dtype/device)
+    # gPINN: direction matrix V [d_net, desc.d].  The kernels see a desc.d-"input" network whose rows are (x, 0, .., 0) and
+    # whose first layer is W1 @ V, so that their per-direction jets are directional derivatives along the columns of V.
+    embed: Optional[np.ndarray] = None
+
+    @property
+    def net_d(self) -> int:
+        """Input dimension of the network the user trains (desc.d unless the problem is embedded)."""
+        return int(self.embed.shape[0]) if self.embed is not None else self.desc.d
 
     def aux(self, x: torch.Tensor) -> Optional[torch.Tensor]:
         if self.aux_fn is None:
@@ -50,7 +58,7 @@ class ProblemSpec:
         rng = np.random.default_rng(seed)
         lo = np.asarray(self.bbox[0::2], dtype=np.float64)
         hi = np.asarray(self.bbox[1::2], dtype=np.float64)
-        return rng.uniform(lo, hi, size=(n, self.desc.d)).astype(dtype)
+        return rng.uniform(lo, hi, size=(n, self.net_d)).astype(dtype)
 
 
 def _col(x, j):
@@ -354,6 +362,30 @@ def make(name: str, **kwargs) -> ProblemSpec:
 # live reference objects
 # ----------------------------------------------------------------------------------------
 
+GP_DIRECTIONS = np.array([[1.0, 0.0, 1.0, 1.0], [0.0, 1.0, 1.0, -1.0]])     # e0, e1, e0+e1, e0-e1 (include/pinn_b200.h, gPINN kinds)
+
+
+def gpinn(spec: ProblemSpec) -> ProblemSpec:
+    """The gPINN form of a problem (src/pde/baseclass.py:151-180 ``use_gepinn``; benchmark.py:91-92 ``--method gepinn``): loss
+    terms [r, dr/dx_0, dr/dx_1].  Covered: one-output problems in two inputs whose residual is Burgers1D's or a LINEAR one with
+    constant coefficients and no per-point source (Poisson2D_Classic, Wave1D): the mixed third-order partials come from
+    order-3 jets along four directions.  Anything else raises."""
+    d = spec.desc
+    if d.d != 2 or d.m != 1 or d.n_pde != 1:
+        raise UnsupportedProblem(f"gPINN: {spec.name} has d={d.d}, m={d.m}, n_pde={d.n_pde}; the fused gPINN kinds cover one-output, "
+                                 "one-residual problems in two inputs (three inputs need 9 jet directions of order 3)")
+    if d.kind == K.KIND_BURGERS1D:
+        g = KindDesc(K.KIND_GP_BURGERS1D, 4, 1, (3, 3, 3, 3), n_pde=3, consts=[d.consts[0]], name=spec.name + "_gepinn")
+    elif d.kind == K.KIND_LINEAR:
+        if d.n_aux or any(a >= 0 for a in d.aux_sel):
+            raise UnsupportedProblem(f"gPINN: {spec.name} has per-point coefficients or a per-point source; its input gradient "
+                                     "needs their derivatives as extra columns (not wired up)")
+        g = KindDesc(K.KIND_GP_LINEAR2, 4, 1, (3, 3, 3, 3), n_pde=3, consts=list(d.consts), name=spec.name + "_gepinn")
+    else:
+        raise UnsupportedProblem(f"gPINN: no fused residual-gradient kind for {spec.name} (kind {K.KIND_NAMES.get(d.kind, d.kind)})")
+    return ProblemSpec(spec.name + "_gepinn", g, list(spec.bbox), None, GP_DIRECTIONS.copy())
+
+
 def _closure_vars(fn) -> dict:
     """Names -> values captured by a Python closure."""
     out = {}
@@ -375,9 +407,13 @@ def describe_reference(pde_obj) -> ProblemSpec:
     name = type(pde_obj).__name__
     if name not in BUILDERS:
         raise UnsupportedProblem(f"no fused residual kind for reference class {name!r}; supported: {sorted(BUILDERS)}")
-    if getattr(pde_obj, "num_gepinn", 0):
-        raise UnsupportedProblem("gPINN residual-gradient terms (baseclass.py:151-180) are not supported by the fused path")
     cv = _closure_vars(pde_obj.pde)
+    gepinn = bool(getattr(pde_obj, "num_gepinn", 0))
+    if gepinn:
+        # use_gepinn() replaced pde by pde_wrapper, which closes over the original closure (baseclass.py:152-153)
+        if "pde_original" not in cv:
+            raise UnsupportedProblem("gPINN: cannot find the wrapped residual closure (baseclass.py:152)")
+        cv = _closure_vars(cv["pde_original"])
     bbox = list(pde_obj.bbox)
     if name == "Burgers1D":
         spec = burgers1d(bbox[0:2], bbox[2:4], cv["nu"])
@@ -431,6 +467,13 @@ def describe_reference(pde_obj) -> ProblemSpec:
         spec = heat_inv(bbox)
     else:  # pragma: no cover
         raise UnsupportedProblem(name)
+    if gepinn:
+        if pde_obj.num_gepinn != pde_obj.input_dim * pde_obj.num_pde:
+            raise UnsupportedProblem("gPINN: unexpected number of residual-gradient terms")
+        g = gpinn(spec)
+        if g.net_d != pde_obj.input_dim or g.desc.n_pde != pde_obj.num_pde + pde_obj.num_gepinn:
+            raise UnsupportedProblem(f"{name}: gPINN descriptor does not match the reference object")
+        return g
     if spec.desc.d != pde_obj.input_dim or spec.desc.m != pde_obj.output_dim or spec.desc.n_pde != pde_obj.num_pde:
         raise UnsupportedProblem(
             f"{name}: descriptor (d={spec.desc.d}, m={spec.desc.m}, n_pde={spec.desc.n_pde}) does not match the reference "

@@ -25,8 +25,8 @@ from collections import namedtuple
 
 from . import capi
 from .evaluate import LazyOutputs, topk_residual
-from .fused import FusedPDEResidual, net_linear_params, net_param_provider, net_shape
-from .kinds import flux_desc, value_desc
+from .fused import FusedPDEResidual, embedded_param_provider, net_linear_params, net_param_provider, net_shape
+from .kinds import KIND_FLUX, flux_desc, value_desc
 from .problems import ProblemSpec, describe_reference
 
 # A value-type boundary / initial / point-set term on BC rows [beg, end):  u[:, component] - values
@@ -134,10 +134,15 @@ class _StepCore:
 
     def __init__(self, spec: ProblemSpec, net, policy="auto", device=None, group=None, cache_points=True, n_global=None):
         d, H, L, m = net_shape(net)
-        if d != spec.desc.d or m != spec.desc.m:
-            raise capi.FusedOpError(f"net maps {d}->{m} but problem {spec.name} needs {spec.desc.d}->{spec.desc.m}")
-        self._param_fn, self.dynamic_params = net_param_provider(net)
-        self.params = self._param_fn()
+        if d != spec.net_d or m != spec.desc.m:
+            raise capi.FusedOpError(f"net maps {d}->{m} but problem {spec.name} needs {spec.net_d}->{spec.desc.m}")
+        self._net_param_fn, self.dynamic_params = net_param_provider(net)
+        self._param_fn = self._net_param_fn
+        if spec.embed is not None:
+            # gPINN: the PDE op sees the embedded first layer W1 @ V; boundary terms and plain outputs keep the real one
+            self._param_fn, self.dynamic_params = embedded_param_provider(self._net_param_fn, spec.embed), True
+        self.params = self._param_fn()              # what the PDE op differentiates with respect to
+        self.net_params = self._net_param_fn()      # the net's own (effective FNN) parameters: boundary terms, outputs
         self.net = net
         dev = self.params[0].device if device is None else torch.device(device)
         self.op = FusedPDEResidual(spec, H, L, policy=policy, device=dev, group=group)
@@ -156,7 +161,7 @@ class _StepCore:
         """Mean-square of one boundary / initial / point-set term over the staged BC rows [beg, end) through the fused
         op.  `desc` is the term's kind descriptor (VALUE or FLUX); `aux_fn()` is called once per staged point set and
         returns its aux columns, broadcastable to [n, desc.n_aux]."""
-        return self.term_op(idx, beg, end, desc, aux_fn).losses(self.params)
+        return self.term_op(idx, beg, end, desc, aux_fn).losses(self.net_params)
 
     def term_op(self, idx: int, beg: int, end: int, desc, aux_fn) -> FusedPDEResidual:
         """The fused op (rows + term data device-resident) of boundary term `idx`; rebuilt when new rows were staged."""
@@ -179,6 +184,7 @@ class _StepCore:
         """Adaptive-activation nets: rebuild the effective (W', b') from the live W, b, a (once per loss evaluation)."""
         if self.dynamic_params:
             self.params = self._param_fn()
+            self.net_params = self._net_param_fn()
 
     def periodic_op(self, idx: int, beg: int, end: int, component: int) -> FusedPDEResidual:
         if (end - beg) % 2:
@@ -188,7 +194,7 @@ class _StepCore:
 
     def periodic_term_loss(self, idx: int, beg: int, end: int, component: int):
         """mean (u[beg:mid, c] - u[mid:end, c])^2 (PeriodicBC, derivative_order 0) through the fused VALUE kernels."""
-        return _PeriodicLossFn.apply(self.periodic_op(idx, beg, end, component), *self.params)
+        return _PeriodicLossFn.apply(self.periodic_op(idx, beg, end, component), *self.net_params)
 
     def value_term_loss(self, idx: int, beg: int, end: int, component: int, values_fn):
         """u[beg:end, component] - values (DirichletBC / IC / PointSetBC)."""
@@ -201,7 +207,7 @@ class _StepCore:
         Returns (G [S + len(terms), P], unweighted losses [n_pde + len(terms)]); buffers are reused by the next call.
 
         ``linear``: rows are gradients of the residual SUMS sum_rows r (``pinn_fwd_bwd_linear``; the statistics of
-        src/optimizer/ntk.py:24-58) into a second buffer; the loss vector is then meaningless.  Single process only."""
+        src/optimizer/ntk.py:24-58) into a second buffer; the loss vector is then meaningless."""
         from . import fused as _fused
         if linear:
             return self._linear_rows(flat, pde_seeds, terms)
@@ -223,6 +229,10 @@ class _StepCore:
             _fused._all_reduce(out, op.group)
             op.stats["allreduce_calls"] += 1
         losses[:n_pde].copy_(out[S * P:])
+        # parameters a term's gradient actually reaches: a Neumann term n.grad u never sees the output-layer bias, autograd
+        # leaves that tensor's grad at None and the reference's LRA averages |grad| over the OTHER entries only
+        # (lr_adaptor.py:50-54: count += numel of the non-None grads)
+        self.term_counts = [float(P - desc.m) if (t[0] == "op" and t[4].kind == KIND_FLUX and t[4].aux_sel[1] < 0) else float(P) for t in terms]
         for i, t in enumerate(terms):
             o = buf[(S + i) * P:(S + i) * P + P + 1]
             if t[3] - t[2] == 0:
@@ -239,8 +249,6 @@ class _StepCore:
     def _linear_rows(self, flat, pde_seeds, terms):
         from . import fused as _fused
         op = self.op
-        if op.world > 1:
-            raise capi.FusedOpError("linear gradient rows are not sharded yet (NTK statistics): run single-process")
         desc = op.desc
         P, S = desc.n_params, int(pde_seeds.shape[0])
         T = S + len(terms)
@@ -250,6 +258,12 @@ class _StepCore:
             buf = self._lin_buf = torch.empty(need, dtype=torch.float32, device=flat.device)
             self._lin_one = torch.ones(1, 1, dtype=torch.float32, device=flat.device)
         _fused._backend_fwd_bwd_linear(desc, flat, op.x, op.aux, pde_seeds, out=buf[:S * P + desc.n_pde])
+        if op.world > 1:
+            # the residual rows are sharded: a linear row is a plain sum over rows (seed 1 per row, no 1/N), so one SUM
+            # all-reduce of the PDE block makes it global before the non-linear statistics (ntk.py:38-63) are taken; the
+            # boundary rows are replicated and every rank computes their (identical) linear rows itself
+            _fused._all_reduce(buf[:S * P + desc.n_pde], op.group)
+            op.stats["allreduce_calls"] += 1
         for i, t in enumerate(terms):
             if t[0] == "periodic":
                 raise capi.FusedOpError("periodic terms have no linear gradient row (NTK statistics): use the autograd optimizer")
@@ -591,9 +605,10 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
         outputs_ = None
         if n_bc > 0:
             bcs_start = np.cumsum([0] + list(data.num_bcs))
-            flux = [(_flux_bc_info(bc, core) if fuse_bcs else None) for bc in data.bcs]
-            periodic = [fuse_bcs and _periodic_bc_component(bc) is not None for bc in data.bcs]
-            fused_ok = [fuse_bcs and (_value_bc_info(bc) is not None or flux[i] is not None or periodic[i]) for i, bc in enumerate(data.bcs)]
+            infos = [_bc_info(bc) for bc in data.bcs]
+            flux = [(inf[1] if fuse_bcs else None) for inf in infos]
+            periodic = [fuse_bcs and inf[0] is not None for inf in infos]
+            fused_ok = [fuse_bcs and (inf[2] is not None or flux[i] is not None or periodic[i]) for i, inf in enumerate(infos)]
             x_bc = y_bc = None
             if not all(fused_ok):
                 x_bc = core._x_bc.detach().requires_grad_(True)
@@ -606,7 +621,7 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
                     if end == beg:
                         terms.append(torch.full((1,), float("nan"), device=pde_losses.device))
                     else:
-                        terms.append(core.periodic_term_loss(i, beg, end, _periodic_bc_component(bc)))
+                        terms.append(core.periodic_term_loss(i, beg, end, infos[i][0]))
                 elif fused_ok[i] and flux[i] is not None:
                     # NeumannBC / affine RobinBC: n.grad u_c + beta u_c - g, term data evaluated once per point set
                     fdesc, aux_fn = flux[i]
@@ -616,7 +631,7 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
                         terms.append(core.fused_term_loss(i, beg, end, fdesc, lambda af=aux_fn, b=beg, e=end: af(data.train_x, b, e)))
                 elif fused_ok[i]:
                     # DirichletBC / IC / PointSetBC: u[beg:end, c] - values, values evaluated once per point set
-                    comp, values_fn = _value_bc_info(bc)
+                    comp, values_fn = infos[i][2]
                     if end == beg:
                         terms.append(torch.full((1,), float("nan"), device=pde_losses.device))   # mean over no rows, as the reference
                     else:
@@ -627,7 +642,7 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
             # _test() bookkeeping wants outputs for every row (model.py:767-780) but, without metrics, never reads them: hand
             # back a stand-in that remembers the weights of this evaluation and runs the forward only if it is consumed
             if lazy_outputs:
-                snap = torch.cat([p.detach().reshape(-1) for p in core.params])
+                snap = torch.cat([p.detach().reshape(-1) for p in core.net_params])
                 outputs_ = LazyOutputs(snap, core._shape, inputs, core.op.device)
             else:
                 with torch.no_grad():
@@ -649,11 +664,49 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
             model.opt.sync_loss_weight()         # FusedLRA keeps the live weights on the device; refresh the host array for logging
         return outputs_losses(False, inputs, targets)
 
+    bc_info = {}            # id(bc) -> (periodic component, flux info, value info): resolved once, not per step
+
+    def _bc_info(bc):
+        ent = bc_info.get(id(bc))
+        if ent is None:
+            ent = bc_info[id(bc)] = (_periodic_bc_component(bc), _flux_bc_info(bc, core), _value_bc_info(bc))
+        return ent
+
+    resolved = {"key": None, "terms": None}
+
+    def resolved_terms():
+        """Boundary terms of the staged point set as ``core.gradient_rows`` wants them, or None when one of them is not on
+        the fused path or has no rows (the autograd-free step then does not apply).  Cached per staged point set."""
+        key = (core.generation, tuple(int(v) for v in data.num_bcs))
+        if resolved["key"] == key:
+            return resolved["terms"]
+        bcs_start = np.cumsum([0] + list(data.num_bcs))
+        d, H, L, m = core._shape
+        terms = []
+        for i, bc in enumerate(data.bcs):
+            beg, end = int(bcs_start[i]), int(bcs_start[i + 1])
+            comp, flux, val = _bc_info(bc)
+            if end <= beg or not fuse_bcs:
+                terms = None
+                break
+            if comp is not None:
+                terms.append(("periodic", i, beg, end, comp))
+            elif flux is not None:
+                terms.append(("op", i, beg, end, flux[0], lambda af=flux[1], b=beg, e=end: af(data.train_x, b, e)))
+            elif val is not None:
+                terms.append(("op", i, beg, end, value_desc(d, m, val[0]), lambda vf=val[1], b=beg, e=end: vf(data.train_x, b, e)))
+            else:
+                terms = None
+                break
+        resolved["key"], resolved["terms"] = key, terms
+        return terms
+
     class _Rows:
         """What the flat-buffer optimizers need from a solver (see FusedPDESolver): the loss-term layout and gradient rows."""
 
         def __init__(self):
             self.spec = spec
+            self.core = core
             self.loss_weights = loss_weights
             self.inputs = None
 
@@ -663,24 +716,11 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
 
         def term_gradient_rows(self, flat, pde_seeds, linear=False):
             inputs = data.train_x if self.inputs is None else self.inputs
-            n_bc = int(np.sum(data.num_bcs))
-            core.stage(inputs, n_bc)
-            bcs_start = np.cumsum([0] + list(data.num_bcs))
-            d, H, L, m = core._shape
-            terms = []
-            for i, bc in enumerate(data.bcs):
-                beg, end = int(bcs_start[i]), int(bcs_start[i + 1])
-                comp = _periodic_bc_component(bc)
-                flux = _flux_bc_info(bc, core)
-                val = _value_bc_info(bc)
-                if comp is not None:
-                    terms.append(("periodic", i, beg, end, comp))
-                elif flux is not None:
-                    terms.append(("op", i, beg, end, flux[0], lambda af=flux[1], b=beg, e=end: af(data.train_x, b, e)))
-                elif val is not None:
-                    terms.append(("op", i, beg, end, value_desc(d, m, val[0]), lambda vf=val[1], b=beg, e=end: vf(data.train_x, b, e)))
-                else:
-                    raise capi.FusedOpError(f"boundary term {i} ({type(bc).__name__}) is not on the fused path")
+            core.stage(inputs, int(np.sum(data.num_bcs)))
+            terms = resolved_terms()
+            if terms is None:
+                raise capi.FusedOpError("a boundary term of this model is not on the fused path (or has no rows): the flat-buffer "
+                                        "optimizers need every loss term fused")
             return core.gradient_rows(flat, pde_seeds, terms, linear)
 
     rows = _Rows()
@@ -689,13 +729,19 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
         from .optim import FlatAdam, FlatMultiAdam, FusedLRA, FusedNTK
         if isinstance(model.opt, (FlatAdam, FlatMultiAdam, FusedLRA, FusedNTK)) and model.lr_scheduler is None and not core.dynamic_params:
             rows.inputs = inputs
+            core.stage(inputs, int(np.sum(data.num_bcs)))
+            all_rows = resolved_terms() is not None
             if isinstance(model.opt, FlatAdam):
-                model.opt.fused_step(rows)
+                if all_rows:                            # else: an Operator term, a batched PointSetBC, an empty term -> closure path below
+                    model.opt.fused_step(rows)
+                    return
             else:
+                if not all_rows:
+                    raise capi.FusedOpError(f"{type(model.opt).__name__} needs every loss term on the fused path with at least one row")
                 if model.opt.solver is None:
                     model.opt.attach(rows)
                 model.opt.step()
-            return
+                return
 
         def closure(*, skip_backward=False):
             losses = outputs_losses_train(inputs, targets)[1]
@@ -773,8 +819,7 @@ def enable_fused(model, spec: Optional[ProblemSpec] = None, policy: str = "auto"
     model.fused_topk_residual = fused_topk_residual
     model.fused_core = core
     if fuse_optimizer:
-        all_fused = fuse_bcs and not core.dynamic_params and all(
-            _periodic_bc_component(bc) is not None or _flux_bc_info(bc, core) is not None or _value_bc_info(bc) is not None for bc in data.bcs)
+        all_fused = fuse_bcs and not core.dynamic_params and all(any(v is not None for v in _bc_info(bc)) for bc in data.bcs)
         if all_fused and model.lr_scheduler is None:
             new_opt = _swap_optimizer(model.opt, net, loss_weights, n_pde)
             if new_opt is not None:

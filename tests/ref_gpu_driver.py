@@ -34,6 +34,8 @@ def build(name, method, seed=0, points=None):
     pde = refshim.construct(name)
     if points is not None:
         pde.training_points(**points)
+    if method == "gepinn":                     # benchmark.py:91-92
+        pde.use_gepinn()
     net = dde.nn.FNN([pde.input_dim] + [100] * 5 + [pde.output_dim], "tanh", "Glorot normal").float()
     g = torch.Generator(device="cpu").manual_seed(seed + 1)
     with torch.no_grad():

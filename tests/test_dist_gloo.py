@@ -150,7 +150,10 @@ def _rows_worker(rank, world, port, n, q):
             s = FusedPDESolver(spec, net, x[beg:end], xb, terms, device="cpu", n_global=n).compile(torch.optim.Adam(net.parameters(), 1e-3))
             flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
             G, L = s.term_gradient_rows(flat, torch.eye(3))
-            q.put((rank, G.clone().numpy(), L.clone().numpy(), dict(s.core.op.stats)))
+            G, L = G.clone().numpy(), L.clone().numpy()
+            # linear rows (NTK statistics, src/optimizer/ntk.py:24-58): gradient of the residual SUMS, sharded the same way
+            Glin, _ = s.term_gradient_rows(flat, torch.ones(1, 3), linear=True)
+            q.put((rank, G, L, dict(s.core.op.stats), Glin.clone().numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -192,11 +195,17 @@ def test_two_rank_gradient_rows_match_single_process():
             s = FusedPDESolver(spec, net, x, xb, terms, device="cpu").compile(torch.optim.Adam(net.parameters(), 1e-3))
             flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
             G, L = s.term_gradient_rows(flat, torch.eye(3))
+            G, L = G.clone(), L.clone()
+            Glin, _ = s.term_gradient_rows(flat, torch.ones(1, 3), linear=True)
     finally:
         fused.FusedPDEResidual.__init__ = orig
-    for rank, Gr, Lr, stats in res:
+    for rank, Gr, Lr, stats, Glr in res:
         np.testing.assert_allclose(Lr, L.numpy(), rtol=2e-5)
         for t in range(5):
             assert np.linalg.norm(Gr[t] - G[t].numpy()) <= 2e-5 * np.linalg.norm(G[t].numpy()), t
-        assert stats["allreduce_calls"] == 1
+        assert Glr.shape == (3, G.shape[1])                     # one PDE row (seed of ones) + two boundary rows
+        for t in range(3):
+            assert np.linalg.norm(Glr[t] - Glin[t].numpy()) <= 2e-5 * np.linalg.norm(Glin[t].numpy()), ("linear", t)
+        assert stats["allreduce_calls"] == 2                    # one for the loss rows, one for the linear rows
+    assert np.array_equal(res[0][4], res[1][4])                 # ranks agree bit for bit => replicated NTK weights stay in lock-step
     assert np.array_equal(res[0][1], res[1][1])

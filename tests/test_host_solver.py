@@ -194,7 +194,7 @@ def test_edited_pde_under_a_known_class_name_is_caught_at_patch_time():
 def test_unsupported_problems_raise():
     from pinnacle_b200 import problems
     dde, _ = refshim.load()
-    pde = refshim.construct("Burgers1D")
+    pde = refshim.construct("Heat2D_Multiscale")      # gPINN in three inputs: not covered (tests/test_gpinn.py has the covered cases)
     pde.use_gepinn()
     with pytest.raises(problems.UnsupportedProblem):
         problems.describe_reference(pde)

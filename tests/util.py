@@ -11,7 +11,7 @@ from golden import common
 from pinnacle_b200 import kinds as K
 
 GOLDEN_NAMES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(common.GOLDEN_DIR, "*.npz"))
-                      if not os.path.basename(f).startswith("l2re_"))        # l2re_*.npz: training-run fixtures (test_cuda_l2re.py)
+                      if not os.path.basename(f).startswith(("l2re_", "gepinn_")))   # l2re_*: training runs (test_cuda_l2re.py); gepinn_*: test_gpinn*.py
 
 # Parity tolerances (BASELINE.json north_star: residuals, losses and gradients within 1e-5 relative in fp32)
 RTOL = 1e-5
@@ -36,6 +36,42 @@ class Golden:
         x = torch.as_tensor(self.g["x"].astype(nd))
         aux = torch.as_tensor(self.g[f"aux{tag}"].astype(nd)) if self.desc.n_aux else None
         return flat, x, aux
+
+
+class GpinnGolden:
+    """tests/golden/gepinn_<Class>.npz (make_gpinn_golden.py): the reference with use_gepinn() on the REAL two-input network.
+    ``embedded(dtype)`` is what the kernels are handed -- first layer times the direction matrix, rows padded with zeros --
+    and ``back(g)`` maps a gradient with respect to the embedded parameters to the real ones (chain rule through W1 @ V)."""
+
+    def __init__(self, name):
+        from pinnacle_b200 import problems
+        self.name = name
+        self.g = g = np.load(common.fixture_path("gepinn_" + name))
+        self.spec = problems.gpinn(problems.make(name))
+        self.desc = self.spec.desc
+        assert int(g["kind"]) == self.desc.kind and np.allclose(g["embed"], self.spec.embed)
+        np.testing.assert_allclose(np.asarray(self.desc.consts, dtype=np.float64), g["consts"], rtol=1e-6)
+        self.base = problems.make(name).desc
+        self.seed = int(g["seed"])
+        self.flat64 = common.golden_params(self.base.layer_shapes(), self.seed)
+        self.idx = g["idx"]
+        self.probes = common.probe_vectors(self.base.n_params, self.seed)
+
+    def embedded(self, dtype):
+        nd = np.float32 if dtype == torch.float32 else np.float64
+        H = self.base.H
+        flat = self.flat64.astype(nd)
+        w1 = flat[:2 * H].reshape(H, 2)
+        flat_e = np.concatenate([(w1 @ self.spec.embed.astype(nd)).reshape(-1), flat[2 * H:]]).astype(nd)
+        x = self.g["x"].astype(nd)
+        x_e = np.concatenate([x, np.zeros((x.shape[0], self.desc.d - 2), nd)], axis=1)
+        return torch.as_tensor(flat_e), torch.as_tensor(np.ascontiguousarray(x_e))
+
+    def back(self, grad_e):
+        grad_e = np.asarray(grad_e, dtype=np.float64)
+        H, de = self.base.H, self.desc.d
+        w1 = grad_e[..., :de * H].reshape(grad_e.shape[:-1] + (H, de)) @ self.spec.embed.T
+        return np.concatenate([w1.reshape(grad_e.shape[:-1] + (2 * H,)), grad_e[..., de * H:]], axis=-1)
 
 
 def rel_l2(a, b):
@@ -78,15 +114,26 @@ def oracle_fwd_bwd(desc, params, x, aux, inv_n_global, seeds, out=None):
     return res
 
 
+def oracle_fwd_bwd_linear(desc, params, x, aux, seeds, out=None):
+    from oracle import autograd_ref as O
+    with torch.enable_grad():
+        rows, sq = O.linear_rows(desc, params.detach(), x, aux, seeds)
+    res = torch.cat([rows.reshape(-1), sq]).to(torch.float32)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
 class oracle_backend:
     """Context manager swapping pinnacle_b200.fused's backend for the oracle (CPU tests only)."""
 
     def __enter__(self):
         from pinnacle_b200 import fused
-        self._saved = (fused._backend_fwd, fused._backend_fwd_bwd)
-        fused._backend_fwd, fused._backend_fwd_bwd = oracle_fwd, oracle_fwd_bwd
+        self._saved = (fused._backend_fwd, fused._backend_fwd_bwd, fused._backend_fwd_bwd_linear)
+        fused._backend_fwd, fused._backend_fwd_bwd, fused._backend_fwd_bwd_linear = oracle_fwd, oracle_fwd_bwd, oracle_fwd_bwd_linear
         return self
 
     def __exit__(self, *a):
         from pinnacle_b200 import fused
-        fused._backend_fwd, fused._backend_fwd_bwd = self._saved
+        fused._backend_fwd, fused._backend_fwd_bwd, fused._backend_fwd_bwd_linear = self._saved
