@@ -32,6 +32,7 @@ import os
 import statistics
 import subprocess
 import sys
+import math
 import threading
 import time
 
@@ -110,6 +111,11 @@ class ClockSampler:
 
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
+        # nvidia-smi needs ~0.1-0.3 s before its first line: wait for it, so that even a short timed region is sampled
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < 3.0:
+            time.sleep(0.01)
+        self.rows.clear()                           # samples taken before the timed region started do not count
 
     def stop(self):
         if self.proc is None:
@@ -558,12 +564,31 @@ def measure_c3(N, steps, warmup, dev, world, rank, local_rank):
 
     for _ in range(max(warmup, 3)):
         solver.train_step()
+    # The whole step -- fused passes, the NCCL all-reduce of the PDE rows, the LRA statistics and the Adam update: ~30 launches
+    # around 1.3 ms of kernels at 8 GPUs -- replayed as ONE CUDA graph (FusedPDESolver.capture_step; PINN_C3_GRAPH=0: eager)
+    graphed = False
+    if os.environ.get("PINN_C3_GRAPH", "1") != "0":
+        try:
+            solver.capture_step(warmup=2)
+            graphed = True
+        except Exception as e:  # noqa: BLE001
+            graphed = repr(e)[:200]
     barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        solver.train_step()
+    e1.record()
+    barrier()
+    est = torch.tensor([e0.elapsed_time(e1) / 3.0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    # long enough for the clock sampler (20 ms period) to see the run under load: >= 1.2 s of steps, every rank the same count
+    K = int(min(max(steps, math.ceil(1200.0 / max(float(est.item()), 1e-3))), 4000))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    K = steps
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     e0.record()
     for _ in range(K):
         solver.train_step()
@@ -582,7 +607,8 @@ def measure_c3(N, steps, warmup, dev, world, rank, local_rank):
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"NS2D_LidDriven + learning-rate annealing (FusedLRA over FlatAdam), {N} residual rows in total + {4 * nb} boundary "
                                "rows (replicated), 3 PDE + 5 boundary terms, 5x100 tanh MLP; optimizer update included",
-                   "parallelism": f"dp{world} over collocation points", "l2": "inputs larger than L2 at 1 GPU; no flush between steps"},
+                   "parallelism": f"dp{world} over collocation points", "l2": "inputs larger than L2 at 1 GPU; no flush between steps",
+                   "cuda_graph": graphed},
         "clocks": clocks, "loss_weights_after": solver.opt.sync_loss_weight().tolist(), "losses_after": losses}
 
 

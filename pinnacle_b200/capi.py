@@ -15,7 +15,8 @@ import torch
 from .kinds import CKindDesc, KindDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpinn_b200.so")
+# PINN_B200_LIB: an alternative build of the same library (what-if builds under variants/, see scripts/whatif_times.sh)
+LIB_PATH = os.environ.get("PINN_B200_LIB") or os.path.join(_HERE, "csrc", "libpinn_b200.so")
 
 EXPORTS = (
     "pinn_param_count", "pinn_supported", "pinn_workspace_bytes", "pinn_fwd", "pinn_fwd_bwd", "pinn_fwd_bwd_linear",

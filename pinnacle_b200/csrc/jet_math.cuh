@@ -22,6 +22,18 @@
 
 namespace pinn {
 
+// Multiply / add / subtract that the compiler may not contract into an fma: the error-free transformations below rely on the
+// rounding of each step (nvcc fuses a * b + c by default).  The host build has no fma contraction to begin with.
+#if defined(__CUDA_ARCH__)
+#define PINN_MUL(a, b) __fmul_rn((a), (b))
+#define PINN_ADD(a, b) __fadd_rn((a), (b))
+#define PINN_SUB(a, b) __fsub_rn((a), (b))
+#else
+#define PINN_MUL(a, b) ((a) * (b))
+#define PINN_ADD(a, b) ((a) + (b))
+#define PINN_SUB(a, b) ((a) - (b))
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // compile-time jet signature
 // ---------------------------------------------------------------------------------------------
@@ -109,7 +121,8 @@ PINN_HD void tanh_series(const float (&zz)[K + 1], float t0, float w0, float (&t
 
 // t0 = tanh(z[0]) supplied by the caller (a[0] of the forward pass, stashed by the tensor-core kernel)
 // `lw`: the D direction weights of a forward-Laplacian signature (LapSig); ignored by JetSig signatures.
-template <class SIG>
+// PRECISE (forward-Laplacian signatures only): carry q = sum_j w_j z_j^2 as an unevaluated fp32 pair into a_s, see the definition.
+template <class SIG, bool PRECISE = false>
 PINN_HD void tanh_jet_fwd_t0(const float (&z)[SIG::C], float t0, float (&a)[SIG::C], const float* lw = nullptr);
 template <class SIG>
 PINN_HD void tanh_jet_bwd_t0(const float (&z)[SIG::C], float t0, const float (&abar)[SIG::C], float (&zbar)[SIG::C], const float* lw = nullptr);
@@ -136,16 +149,16 @@ PINN_HD float pinn_tanh(float z) {
 #endif
 }
 
-template <class SIG>
+template <class SIG, bool PRECISE = false>
 PINN_HD void tanh_jet_fwd(const float (&z)[SIG::C], float (&a)[SIG::C], const float* lw = nullptr) {
 #ifdef PINN_EXP_NO_JET
-  tanh_jet_fwd_t0<SIG>(z, z[0], a, lw);
+  tanh_jet_fwd_t0<SIG, PRECISE>(z, z[0], a, lw);
 #else
-  tanh_jet_fwd_t0<SIG>(z, SIG::kAccTanh ? pinn_tanh(z[0]) : tanhf(z[0]), a, lw);
+  tanh_jet_fwd_t0<SIG, PRECISE>(z, SIG::kAccTanh ? pinn_tanh(z[0]) : tanhf(z[0]), a, lw);
 #endif
 }
 
-template <class SIG>
+template <class SIG, bool PRECISE>
 PINN_HD void tanh_jet_fwd_t0(const float (&z)[SIG::C], float t0, float (&a)[SIG::C], const float* lw) {
 #ifdef PINN_EXP_NO_JET      // what-if timing experiment only
   for (int c = 0; c < SIG::C; ++c) a[c] = z[c] * 0.5f;
@@ -153,7 +166,44 @@ PINN_HD void tanh_jet_fwd_t0(const float (&z)[SIG::C], float t0, float (&a)[SIG:
 #endif
   const float w0 = fmaf(-t0, t0, 1.0f);
   a[0] = t0;
-  if constexpr (SIG::kLap) {
+#ifdef PINN_LAP_CHEAP_FWD       // A/B builds: the plain rule everywhere
+  constexpr bool kPrecise = false;
+#else
+  constexpr bool kPrecise = PRECISE;
+#endif
+  if constexpr (SIG::kLap && kPrecise) {
+    // The FORWARD sweep's version of the rule below.  a_s = t' (z_s - 2 t q) cancels (z_s against 2 t q), so the half-ulp
+    // rounding of q alone costs a_s an error of 2^-25 |2 t q| -- a smooth function of the point, hence correlated over the
+    // points with dr/dtheta.  Near a minimum the gradient error is (2/N) sum_i delta r_i dr_i/dtheta to leading order (the
+    // error of the residual VALUES, which seed the reverse sweep; derivative errors enter multiplied by the small r_i): on the
+    // nearly converged Laplace problem the plain rule put the FP32 kernel at 1.1e-5 of the fp64 gradient where per-direction
+    // second-order jets stay at 1.4e-6 (host build of this header, tests/host_harness; seeding the reverse sweep with the
+    // fp64 residuals instead gives 1.2e-7 for both).  Carrying q as an unevaluated pair (error-free squares, two-sum) into
+    // the combination brings the Laplacian form to 2.5e-6.  The reverse sweep's recomputation of a^{l-1} keeps the cheap rule.
+    float qh = 0.f, ql = 0.f;
+#pragma unroll
+    for (int j = 0; j < SIG::D; ++j) {
+      const float zj = z[1 + j];
+      a[1 + j] = w0 * zj;
+      if (lw[j] == 0.f) continue;                       // a direction the Laplacian channel does not use (time, in the heat kinds)
+      const float tj = PINN_MUL(lw[j], zj);
+      const float p = PINN_MUL(tj, zj);
+      const float ep = fmaf(fmaf(lw[j], zj, -tj), zj, fmaf(tj, zj, -p));    // exact error of p (both roundings), to first order
+      if (j == 0) {
+        qh = p;
+        ql = ep;
+      } else {
+        const float s = PINN_ADD(qh, p);                // two-sum: s + e == qh + p exactly
+        const float bb = PINN_SUB(s, qh);
+        ql += PINN_ADD(PINN_ADD(PINN_SUB(qh, PINN_SUB(s, bb)), PINN_SUB(p, bb)), ep);
+        qh = s;
+      }
+    }
+    // z_s - 2 t qh in ONE rounding (an fma's product is exact), relative to the cancelled result; then the tail of q
+    const float m2 = -2.0f * t0;
+    a[SIG::lap] = w0 * fmaf(m2, ql, fmaf(m2, qh, z[SIG::lap]));
+    return;
+  } else if constexpr (SIG::kLap) {
     float q = 0.f;
 #pragma unroll
     for (int j = 0; j < SIG::D; ++j) {

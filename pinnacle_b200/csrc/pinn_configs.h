@@ -22,6 +22,9 @@
 // 19-20 flux-type boundary terms (PINN_KIND_FLUX: Neumann / affine Robin): first-order signatures (1,1), (1,1,1), m = 1
 // 29-30 PoissonInv (inverse.py:19-24; outputs u, a): (2,2) m=2 and its forward-Laplacian form LapSig<2> m=2 (HeatInv uses 5 / 26)
 // 31    LapSig<3> with per-point direction weights (orders entry -(10+d)): Wave2D_Heterogeneous, u_xx + u_yy - u_tt / c(x,y)
+// 33-42 / 43-52  hidden widths 64 and 128 (benchmark.py:65 --hidden-layers, src/utils/args.py:4-12), FP32 FFMA kernel only: Burgers1D (2,1);
+//       the forward-Laplacian signatures of the Poisson2D / Heat2D / NS2D families (-2, -3, -2 with m = 3); Kuramoto-Sivashinsky (4,1);
+//       value-type boundary terms 2x1, 2x3, 3x1; flux-type boundary terms (1,1), (1,1,1)
 // 32    gPINN kinds (GP_LINEAR2, GP_BURGERS1D: residual + its input gradient, two inputs embedded along e0, e1, e0+e1, e0-e1): (3,3,3,3)
 // 28    the same for the 6-dimensional Neumann term of HeatND (heat.py:296-301): (1,1,1,1,1,1)
 #pragma once
@@ -59,6 +62,26 @@
   X(29, 100, 2, 32, 4, 32, 2, 2)           \
   X(30, 100, 2, 32, 4, 32, -2)             \
   X(31, 100, 1, 32, 4, 32, -13)           \
-  X(32, 100, 1, 16, 2, 0, 3, 3, 3, 3)
+  X(32, 100, 1, 16, 2, 0, 3, 3, 3, 3)     \
+  X(33, 64, 1, 32, 4, 0, 2, 1)            \
+  X(34, 64, 1, 32, 4, 0, -2)              \
+  X(35, 64, 1, 32, 4, 0, -3)              \
+  X(36, 64, 3, 32, 4, 0, -2)              \
+  X(37, 64, 1, 32, 4, 0, 4, 1)            \
+  X(38, 64, 1, 32, 4, 0, 0, 0)            \
+  X(39, 64, 3, 32, 4, 0, 0, 0)            \
+  X(40, 64, 1, 32, 4, 0, 0, 0, 0)         \
+  X(41, 64, 1, 32, 4, 0, 1, 1)            \
+  X(42, 64, 1, 32, 4, 0, 1, 1, 1)         \
+  X(43, 128, 1, 16, 2, 0, 2, 1)           \
+  X(44, 128, 1, 16, 2, 0, -2)             \
+  X(45, 128, 1, 16, 2, 0, -3)             \
+  X(46, 128, 3, 16, 2, 0, -2)             \
+  X(47, 128, 1, 16, 2, 0, 4, 1)           \
+  X(48, 128, 1, 16, 2, 0, 0, 0)           \
+  X(49, 128, 3, 16, 2, 0, 0, 0)           \
+  X(50, 128, 1, 16, 2, 0, 0, 0, 0)        \
+  X(51, 128, 1, 16, 2, 0, 1, 1)           \
+  X(52, 128, 1, 16, 2, 0, 1, 1, 1)
 
-#define PINN_NUM_CONFIGS 33
+#define PINN_NUM_CONFIGS 53

@@ -92,7 +92,7 @@ struct KCfg {
   static constexpr int LD = CT + ((4 - CT % 32 + 32) % 32);
   static constexpr int E4 = C * TN;  // float4 (= 4 points) per thread per layer
   // outer-product (dW) thread tiling
-  static constexpr int OTK = 10, OTN = NT / OTK, ON = H / OTN, OK = H / OTK;
+  static constexpr int OTK = (H % 10 == 0) ? 10 : 8, OTN = NT / OTK, ON = H / OTN, OK = H / OTK;     // H = 100: 10 x 20 threads; H = 64, 128: 8 x 16 / 8 x 32
   // shared memory carve-up, in floats
   static constexpr int oWs = 0;
   static constexpr int oA = oWs + H * H;
@@ -227,7 +227,7 @@ __device__ __forceinline__ void frag_tanh_fwd(float (&acc)[CFG::C][4][CFG::TN], 
       float z[CFG::C], a[CFG::C];
 #pragma unroll
       for (int c = 0; c < CFG::C; ++c) z[c] = acc[c][p][n];
-      tanh_jet_fwd<typename CFG::SIG>(z, a, lw);
+      tanh_jet_fwd<typename CFG::SIG, true>(z, a, lw);
 #pragma unroll
       for (int c = 0; c < CFG::C; ++c) acc[c][p][n] = a[c];
     }

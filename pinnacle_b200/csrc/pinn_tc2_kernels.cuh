@@ -310,12 +310,14 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       umma::wait_st();
     }
     // dW_l (TMEM, 100 x 100 used) -> this CTA's private partial [k/4][n][k%4] in L2, read-modify-write through registers (single
-    // writer per address, so the partial is deterministic).  Rounds of 32 columns: the round's 8 global loads and its two
-    // 16-column TMEM loads are all in flight together -- one L2 and one TMEM round trip per round (round 1 of this kernel
-    // waited for each of 25 4-column TMEM loads separately).
-    // Tried: 128-bit `red.global.add` instead of the read-modify-write (-DPINN_FLUSH_RED): halves the L2 bytes and needs no
-    // load, but the kernel got SLOWER (Poisson2D 9.85 -> 10.32 ms, Heat2D_Multiscale 12.32 -> 12.64 ms per 1 Mi points): the L2
-    // atomic units serialise the 4 lanes of every vector reduction and delay the stash / weight traffic behind them.
+    // writer per address, so the partial is deterministic).  Two rounds of 52 / 48 columns; the global loads of a round are all
+    // in flight together, the TMEM loads go 4 columns at a time.
+    // Tried in round 2, same box, 1 Mi points (profiles/r2_whatif.md): 128-bit `red.global.add` instead of the read-modify-write
+    // (-DPINN_FLUSH_RED: half the L2 bytes, no load) -- SLOWER, Poisson2D 9.85 -> 10.32 ms, Heat2D_Multiscale 12.32 -> 12.64 ms
+    // (the L2 atomic units serialise the lanes of a vector reduction and hold up the stash / weight traffic behind them);
+    // rounds of 32 columns with all TMEM loads of a round in flight (-DPINN_FLUSH_BATCHED: 4 TMEM round trips instead of 25) --
+    // SLOWER too, 9.84 -> 10.11 ms and 12.35 -> 12.70 ms: the flush is not latency-bound, and its burst of TMEM reads then
+    // collides with the rows MMAs of the next step.
     auto red_add4 = [&](float4* dst, float a, float b, float c, float d) {
       asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
     };
@@ -341,6 +343,29 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         umma::tmem_ld4(tDW + lane_off + 96, v3);
         umma::wait_ld();
         red_add4(gt + (size_t)24 * 128, v3[0], v3[1], v3[2], v3[3]);
+      }
+#elif !defined(PINN_FLUSH_BATCHED)
+#pragma unroll
+      for (int rd = 0; rd < 2; ++rd) {
+        constexpr int NV = 13;
+        const int c0 = 52 * rd;
+        const int nv = (rd == 0) ? 13 : 12;
+        float4 acc[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (i < nv) acc[i] = gt[(size_t)(c0 / 4 + i) * 128];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          if (i < nv) {
+            float v[4];
+            umma::tmem_ld4(tDW + lane_off + c0 + 4 * i, v);
+            umma::wait_ld();
+            acc[i].x += v[0]; acc[i].y += v[1]; acc[i].z += v[2]; acc[i].w += v[3];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (i < nv) gt[(size_t)(c0 / 4 + i) * 128] = acc[i];
       }
 #else
       float4 tail = gt[(size_t)24 * 128];                      // columns 96..99 ride along with the first round
@@ -612,6 +637,25 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
     float4* stash = reinterpret_cast<float4*>(p.stash) + (size_t)blockIdx.x * L * NSUB * C * NEW;
     auto stash_at = [&](int l, int h, int c) -> float4* { return stash + ((size_t)((l - 1) * NSUB + h) * C + c) * NEW + tid; };
     const bool stash_discard = (reinterpret_cast<uintptr_t>(p.stash) & 127) == 0;
+    // Stash stores / loads carry an L2 evict_last policy: the scratch lines are the last candidates for replacement (and
+    // write-back) between their write in the forward sweep and their last read in the reverse sweep, after which they are
+    // discarded.  Measured (ncu, Poisson2D_Classic, 1 Mi points): DRAM writes 3.25 GB -> 0.56 GB per launch, same duration.
+    // -DPINN_NO_STASH_EVICT_LAST restores plain accesses.
+#ifndef PINN_NO_STASH_EVICT_LAST
+    uint64_t stash_pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(stash_pol));
+    auto stash_st = [&](float4* ptr, float a, float b, float c, float d) {
+      asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(a), "f"(b), "f"(c), "f"(d), "l"(stash_pol) : "memory");
+    };
+    auto stash_ld = [&](const float4* ptr) -> float4 {
+      float4 v;
+      asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(stash_pol) : "memory");
+      return v;
+    };
+#else
+    auto stash_st = [&](float4* ptr, float a, float b, float c, float d) { *ptr = make_float4(a, b, c, d); };
+    auto stash_ld = [&](const float4* ptr) -> float4 { return *ptr; };
+#endif
     uint32_t ph[2] = {0, 0}, dph[2] = {0, 0};
     bool dwp[2] = {false, false};          // a dW contraction that reads sub-tile h's arrays may still be running
 
@@ -751,14 +795,14 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       for (int pp = 0; pp < 4; ++pp) a[0][pp] = tanh_tcx<SIG::kAccTanh>(a[0][pp]);
       if constexpr (BWD) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) *stash_at(1, h, c) = make_float4(a[c][0], a[c][1], a[c][2], a[c][3]);
+        for (int c = 0; c < C; ++c) stash_st(stash_at(1, h, c), a[c][0], a[c][1], a[c][2], a[c][3]);
       }
 #pragma unroll
       for (int pp = 0; pp < 4; ++pp) {
         float z[C], av[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) z[c] = a[c][pp];
-        tanh_jet_fwd_t0<SIG>(z, z[0], av, lw_at(h * TS + pb + pp));
+        tanh_jet_fwd_t0<SIG, true>(z, z[0], av, lw_at(h * TS + pb + pp));
 #pragma unroll
         for (int c = 0; c < C; ++c) a[c][pp] = av[c];
       }
@@ -774,14 +818,14 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
       for (int pp = 0; pp < 4; ++pp) zq[0][pp] = tanh_tcx<SIG::kAccTanh>(zq[0][pp] + b);      // channel 0 holds t0 from here on (see epi_layer1)
       if constexpr (BWD) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) *stash_at(l, h, c) = make_float4(zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
+        for (int c = 0; c < C; ++c) stash_st(stash_at(l, h, c), zq[c][0], zq[c][1], zq[c][2], zq[c][3]);
       }
 #pragma unroll
       for (int pp = 0; pp < 4; ++pp) {
         float z[C], av[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-        tanh_jet_fwd_t0<SIG>(z, z[0], av, lw_at(h * TS + pb + pp));
+        tanh_jet_fwd_t0<SIG, true>(z, z[0], av, lw_at(h * TS + pb + pp));
 #pragma unroll
         for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
       }
@@ -918,7 +962,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                   float zq[C][4];
 #pragma unroll
                   for (int c = 0; c < C; ++c) {
-                    const float4 v = *stash_at(l - 1, h, c);
+                    const float4 v = stash_ld(stash_at(l - 1, h, c));
                     zq[c][0] = v.x; zq[c][1] = v.y; zq[c][2] = v.z; zq[c][3] = v.w;
                   }
 #pragma unroll
@@ -950,7 +994,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                 float zq[C][4];
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                  const float4 v = *stash_at(l, h, c);
+                  const float4 v = stash_ld(stash_at(l, h, c));
                   zq[c][0] = v.x; zq[c][1] = v.y; zq[c][2] = v.z; zq[c][3] = v.w;
                 }
                 if (IS_TOP) {

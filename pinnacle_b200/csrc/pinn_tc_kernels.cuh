@@ -131,7 +131,7 @@ __device__ __forceinline__ void split2_pair(float x0, float x1, uint32_t& p2, ui
 // ulp and carries no bias.  tanhf is within 2 ulp but slightly biased, and a bias that is coherent over all points acts like
 // a weight perturbation -- 1.3e-5 of gradient error on the nearly converged Laplace problem, with the FFMA kernel
 // as with the exact-main-term tensor path.  The double-precision pipe issues one warp instruction per clock per SM (measured:
-// 500 tanh per point are ~1 ms per 1 Mi points at 17 instructions), so the count matters: 12 + 1 MUFU instead of libdevice's ~70.
+// 500 tanh per point are ~1 ms per 1 Mi points at 17 instructions), so the count matters: 16 + 1 MUFU instead of libdevice's ~70.
 //   |x| >= 2^-6:  tanh x = 1 - 2 / (1 + E), E = e^(2x) = 2^n * exp(y), y = 2x - n ln2, |y| <= 0.36, degree-8 polynomial
 //                 (remainder y^9/9! < 1e-9 * y / 2: what half an ulp of tanh tolerates through dE/E), reciprocal by rcp.approx
 //                 (2^-20) + one Newton step (2^-40: < 6e-11 of tanh >= 2^-6)
@@ -143,7 +143,7 @@ __device__ __forceinline__ float tanh_dp(float z) {
   const float nf = rintf(az * 2.8853900817779268f);                 // any integer within ~0.52 of 2x log2(e) will do
   const float a2 = az + az;
   const double y = fma((double)nf, -0.6931471805599453, (double)a2);
-#ifdef PINN_TANH_DP_FULL   // the whole degree-8 polynomial in double (round 2's first version: 16 DP instructions + 1 MUFU)
+#ifndef PINN_TANH_TAIL32   // the whole degree-8 polynomial in double: 16 DP instructions + 1 MUFU
   double p = 2.48015873015873e-05;
   p = fma(p, y, 1.984126984126984e-04);
   p = fma(p, y, 1.388888888888889e-03);
@@ -154,11 +154,10 @@ __device__ __forceinline__ float tanh_dp(float z) {
   p = fma(p, y, 1.0);
   p = fma(p, y, 1.0);
 #else
-  // exp(y) = 1 + y + y^2/2 in double + the tail y^3 (1/6 + y/24 + .. + y^5/40320) in fp32: the tail is < 0.008, so its fp32
-  // rounding (1.2e-9 of E at |y| = 0.36, shrinking like y^3) stays under what half an ulp of tanh tolerates (3e-8 * y).  12 DP
-  // instructions + 1 MUFU; the element-wise forward stage is bound by the DP pipe (one warp instruction per clock per SM).
-  // Host check over 11 M inputs in [2^-6, 10] (same arithmetic in C): max error 0.536 ulp (0.509 with the full double
-  // polynomial), 0.13 % of the results differ from the correctly rounded value by one ulp, mean signed error 3e-4 ulp.
+  // -DPINN_TANH_TAIL32 (tried, not adopted): exp(y) = 1 + y + y^2/2 in double + the tail y^3 (1/6 + y/24 + .. + y^5/40320) in fp32
+  // -- 12 DP instructions + 1 MUFU.  Host check over 11 M inputs in [2^-6, 10]: max error 0.536 ulp (0.509 with the full double
+  // polynomial), 0.13 % of the results one ulp off the correctly rounded value (0.025 %).  On the GPU the kernels were no faster
+  // (same box: 9.84 / 12.35 ms against 9.82 / 12.32 ms) and the gradient error at trained weights rose by 2-10 %.
   const float yf = fmaf(nf, -0.69314718f, a2);
   float tq = 2.48015873e-05f;
   tq = fmaf(tq, yf, 1.98412698e-04f);
@@ -498,7 +497,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
           float z[C], av[C];
 #pragma unroll
           for (int c = 0; c < C; ++c) z[c] = a[c][pp];
-          tanh_jet_fwd_t0<SIG>(z, z[0], av, lw_at(pb + pp));
+          tanh_jet_fwd_t0<SIG, true>(z, z[0], av, lw_at(pb + pp));
 #pragma unroll
           for (int c = 0; c < C; ++c) a[c][pp] = av[c];
         }
@@ -547,7 +546,7 @@ __global__ void __launch_bounds__(CFG::NTH, 1) pinn_tc_kernel(const TcLaunchPara
               float z[C], av[C];
 #pragma unroll
               for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-              tanh_jet_fwd_t0<SIG>(z, z[0], av, lw_at(pb + pp));
+              tanh_jet_fwd_t0<SIG, true>(z, z[0], av, lw_at(pb + pp));
 #pragma unroll
               for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
             }

@@ -16,14 +16,18 @@ for name in sys.argv[1:] or ["Poisson2D_Classic", "Burgers1D", "Heat2D_Multiscal
     spec = problems.make(name)
     d = spec.desc
     torch.manual_seed(41)
-    net = FNN([d.d] + [100] * 5 + [d.m]).to(dev)
+    net = FNN([d.d] + [100] * 5 + [d.m])
     with torch.no_grad():
         for lin in net.linears:
-            lin.bias.normal_(0, 0.1)
+            lin.bias.normal_(0, 0.1)           # on the CPU generator, like tests/test_cuda_solver.py::_net: the test's own end state
+    net = net.to(dev)
     x = spec.sample(2048, seed=5); xb = spec.sample(256, seed=6)
     tgt = np.sin(3.0 * xb[:, :1]).astype(np.float32)
     wfile = os.path.join(ROOT, "gpurun_out", f"trained_{name}.pt")
-    fixed = os.path.join(ROOT, "tests", "golden", "trained", f"trained_{name}.pt")   # committed weights of one such run (the GPU test's)
+    # committed weights of such runs: tests/golden/trained (round 2, first kernel) and tests/golden/trained_b (the end state of
+    # tests/test_cuda_solver.py::test_parity_holds_after_a_thousand_adam_steps with the plain Laplacian tanh rule -- the state on
+    # which that rule cost 1e-5); PINN_TRAINED_DIR selects
+    fixed = os.path.join(ROOT, "tests", "golden", os.environ.get("PINN_TRAINED_DIR", "trained"), f"trained_{name}.pt")
     if os.environ.get("PINN_LOAD_TRAINED") and not os.path.exists(wfile) and os.path.exists(fixed):
         wfile = fixed
     if os.environ.get("PINN_LOAD_TRAINED") and os.path.exists(wfile):      # evaluate a what-if build at the SAME trained weights

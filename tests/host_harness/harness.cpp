@@ -171,6 +171,11 @@ static float tc_dot(const float* w, const float* a, int n, int astride, int mode
   return acc + acc2;
 }
 
+// diagnostic (scripts/lap_error_study.py): seed the reverse sweep with externally supplied residual values (e.g. the fp64
+// reference's) instead of the ones this forward pass computed -- separates the two error terms of the gradient near a minimum
+static const double* g_resid_override = nullptr;
+extern "C" void harness_set_resid_override(const double* r) { g_resid_override = r; }
+
 template <class SIG, int M>
 static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x, const float* aux, long long n, double inv_n,
                     const float* seeds, int S, double* grad, double* loss, float* resid) {
@@ -206,7 +211,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
         if constexpr (SIG::order(j) >= 1) zz[SIG::base(j)] = params[offW[1] + nn * D + j];
       });
       float aa[C];
-      tanh_jet_fwd<SIG>(zz, aa, lwp);
+      tanh_jet_fwd<SIG, true>(zz, aa, lwp);
       for (int c = 0; c < C; ++c) { z[((size_t)1 * H + nn) * C + c] = zz[c]; a[((size_t)1 * H + nn) * C + c] = aa[c]; }
     }
     for (int l = 2; l <= L; ++l) {
@@ -222,7 +227,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
         }
         zz[0] += params[offB[l] + nn];
         float aa[C];
-        tanh_jet_fwd<SIG>(zz, aa, lwp);
+        tanh_jet_fwd<SIG, true>(zz, aa, lwp);
         for (int c = 0; c < C; ++c) { z[((size_t)l * H + nn) * C + c] = zz[c]; a[((size_t)l * H + nn) * C + c] = aa[c]; }
       }
     }
@@ -243,7 +248,8 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
     for (int s = 0; s < S; ++s) {
       double* g = grad + (size_t)s * P;
       float rb[PINN_MAX_PDE] = {0, 0, 0};
-      for (int k = 0; k < d->n_pde; ++k) rb[k] = seeds[s * d->n_pde + k] * 2.0f * r[k] * (float)inv_n;
+      for (int k = 0; k < d->n_pde; ++k)
+        rb[k] = seeds[s * d->n_pde + k] * 2.0f * (g_resid_override ? (float)g_resid_override[pt * d->n_pde + k] : r[k]) * (float)inv_n;
       float Ub[M][C];
       Residual<SIG, M>::adjoint(kp, auxv, U, rb, Ub);
       for (int o = 0; o < M; ++o) {

@@ -233,8 +233,8 @@ def test_errors_are_loud():
     flat, x, _ = G.inputs(torch.float32)
     with pytest.raises(capi.FusedOpError):                       # CPU tensors: no fallback
         capi.fwd(G.desc, flat, x, None, 1.0)
-    with pytest.raises(capi.FusedOpError):                       # wrong H
-        capi.check_supported(G.desc.with_net(64, 5))
+    with pytest.raises(capi.FusedOpError):                       # a hidden width no kernel is instantiated for (100, 64, 128 are)
+        capi.check_supported(G.desc.with_net(80, 5))
     with pytest.raises(capi.FusedOpError):
         capi.fwd(G.desc, flat.to(dev)[:-1].contiguous(), x.to(dev), None, 1.0)
 

@@ -2,7 +2,7 @@
 ``model.compile(opt, loss_weights)``, every tensor on CUDA as trainer.py:39-41 arranges), ``enable_fused(model)`` and
 ``model.train(iterations=50)`` -- against the same model left unpatched (the stock PyTorch GPU path a PINNacle user runs
 today).  Optimizers: Adam, the reference's LR_Adaptor (BASELINE configs[2]), MultiAdam and Adam_LBFGS (Kuramoto-Sivashinsky,
-configs[3]: 25 Adam then 25 L-BFGS iterations), and the flat-buffer swaps of ``fuse_optimizer=True``.
+configs[3]: 25 Adam then 10 L-BFGS iterations), and the flat-buffer swaps of ``fuse_optimizer=True``.
 
 The reference is the byte-for-byte copy under baseline/_ref (scripts/install_reference.py; git-ignored, ships with gpurun).
 Each case runs in a subprocess (tests/ref_gpu_driver.py): importing the reference on a CUDA box changes the process-wide
@@ -38,10 +38,12 @@ CASES = [
     ("NS2D_LidDriven", "lra", 50, False, 5e-2, 5e-3),                   # configs[2]: the reference's LR_Adaptor on the fused losses
     ("NS2D_LidDriven", "lra", 50, True, 5e-2, 5e-3),                    # ... swapped for FusedLRA
     ("Burgers1D", "multiadam", 50, False, 5e-2, 5e-3),
-    # configs[3]: Adam -> L-BFGS through the fused closure.  25 L-BFGS iterations (strong-Wolfe line search, up to 25 closure calls
-    # each) amplify 1e-7-level gradient differences far more than Adam does: 3.5e-2 on the logged losses / 5.8e-2 on the weights
-    # measured, against 1e-6 / 1e-7 for the Adam cases above
-    ("KuramotoSivashinskyEquation", "lbfgs", 50, False, 1e-1, 1.5e-1),
+    # configs[3]: Adam -> L-BFGS through the fused closure: 25 Adam iterations, then 10 of the reference's L-BFGS (benchmark.py:114-115:
+    # torch.optim.LBFGS, lr 1, max_iter 20, NO line search).  Without a line search the iteration is violently sensitive: the two
+    # runs, 1e-6 apart when L-BFGS takes over, are 0.7 % apart 5 iterations later and 9 % apart after 15 (measured: the logged loss
+    # of the momentum term, 0.0651 / 0.0655 at iteration 30 and 0.0579 / 0.0530 at 40), and either of them can leave the basin
+    # altogether a few iterations further on -- so the comparison stops at iteration 35
+    ("KuramotoSivashinskyEquation", "lbfgs", 35, False, 1e-1, 1.5e-1),
 ]
 
 
@@ -50,7 +52,7 @@ def test_real_reference_model_trains_alike_on_the_fused_path(name, method, steps
     res = _drive("train", name, method, steps, *(["--fuse-optimizer"] if fuse_opt else []))
     print(f"{name} {method} fuse_optimizer={fuse_opt}: optimizer {res['optimizer']} impl {res['impl']} step-0 losses rel {res['first_rel']:.2e} "
           f"history rel {res['hist_rel']:.2e} final weights rel {res['weights_rel']:.2e} fused calls {res['fused_calls']}")
-    assert res["finite"] and res["same_points"]
+    assert res["finite"] and res["same_points"], (res["hist_reference"], res["hist_fused"])
     assert res["fused_calls"] >= steps                          # the CUDA kernels really ran underneath model.train
     assert res["first_rel"] < 5e-5                              # identical weights at step 0: per-term losses to parity tolerance
     assert res["hist_rel"] < tol_loss, (res["hist_reference"], res["hist_fused"])
