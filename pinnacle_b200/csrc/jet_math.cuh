@@ -121,7 +121,7 @@ PINN_HD void tanh_series(const float (&zz)[K + 1], float t0, float w0, float (&t
 
 // t0 = tanh(z[0]) supplied by the caller (a[0] of the forward pass, stashed by the tensor-core kernel)
 // `lw`: the D direction weights of a forward-Laplacian signature (LapSig); ignored by JetSig signatures.
-// PRECISE (forward-Laplacian signatures only): carry q = sum_j w_j z_j^2 as an unevaluated fp32 pair into a_s, see the definition.
+// PRECISE (forward-Laplacian signatures, layer 1 of the forward sweep): q = sum_j w_j z_j^2 enters a_s as an unevaluated fp32 pair.
 template <class SIG, bool PRECISE = false>
 PINN_HD void tanh_jet_fwd_t0(const float (&z)[SIG::C], float t0, float (&a)[SIG::C], const float* lw = nullptr);
 template <class SIG>
@@ -172,14 +172,16 @@ PINN_HD void tanh_jet_fwd_t0(const float (&z)[SIG::C], float t0, float (&a)[SIG:
   constexpr bool kPrecise = PRECISE;
 #endif
   if constexpr (SIG::kLap && kPrecise) {
-    // The FORWARD sweep's version of the rule below.  a_s = t' (z_s - 2 t q) cancels (z_s against 2 t q), so the half-ulp
-    // rounding of q alone costs a_s an error of 2^-25 |2 t q| -- a smooth function of the point, hence correlated over the
-    // points with dr/dtheta.  Near a minimum the gradient error is (2/N) sum_i delta r_i dr_i/dtheta to leading order (the
-    // error of the residual VALUES, which seed the reverse sweep; derivative errors enter multiplied by the small r_i): on the
-    // nearly converged Laplace problem the plain rule put the FP32 kernel at 1.1e-5 of the fp64 gradient where per-direction
-    // second-order jets stay at 1.4e-6 (host build of this header, tests/host_harness; seeding the reverse sweep with the
-    // fp64 residuals instead gives 1.2e-7 for both).  Carrying q as an unevaluated pair (error-free squares, two-sum) into
-    // the combination brings the Laplacian form to 2.5e-6.  The reverse sweep's recomputation of a^{l-1} keeps the cheap rule.
+    // LAYER 1's version of the rule below (forward sweep).  In layer 1 the derivative channels are the weight columns,
+    // z_j = W1[n][j], and z_s = 0: q = sum_j w_j W1[n][j]^2 is a per-neuron CONSTANT, so its half-ulp rounding is the same
+    // relative perturbation of a_s = -2 t t' q at every point -- coherent over the points like a weight perturbation.  Near a
+    // minimum the gradient error is (2/N) sum_i delta r_i dr_i/dtheta to leading order (the error of the residual VALUES, which
+    // seed the reverse sweep; derivative errors enter multiplied by the small r_i), and a coherent delta r is not averaged out:
+    // on the nearly converged Laplace problem the plain rule put the FP32 kernel at 1.1e-5 of the fp64 gradient where
+    // per-direction second-order jets stay at 1.4e-6 (host build of this header, tests/host_harness; seeding the reverse sweep
+    // with the fp64 residuals gives 1.2e-7 for both).  Carrying q as an unevaluated fp32 pair (error-free squares, two-sum)
+    // into the combination brings the Laplacian form to 2.1e-6; applying it to the hidden layers as well adds nothing (1.7e-6)
+    // and cost 3-5 % of the kernel, so they and the reverse sweep's recomputation of a^{l-1} keep the plain rule.
     float qh = 0.f, ql = 0.f;
 #pragma unroll
     for (int j = 0; j < SIG::D; ++j) {

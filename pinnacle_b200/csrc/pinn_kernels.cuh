@@ -218,7 +218,8 @@ __device__ __forceinline__ void frag_store_stash(float4* st, const float (&acc)[
       st[(size_t)(n * CFG::C + c) * CFG::NT + tid] = make_float4(acc[c][0][n], acc[c][1][n], acc[c][2][n], acc[c][3][n]);
 }
 
-template <class CFG>
+// PRECISE: layer 1 (its derivative channels are the weight columns, the same for every point: see tanh_jet_fwd_t0)
+template <class CFG, bool PRECISE = false>
 __device__ __forceinline__ void frag_tanh_fwd(float (&acc)[CFG::C][4][CFG::TN], const float* lw) {
 #pragma unroll
   for (int n = 0; n < CFG::TN; ++n)
@@ -227,7 +228,7 @@ __device__ __forceinline__ void frag_tanh_fwd(float (&acc)[CFG::C][4][CFG::TN], 
       float z[CFG::C], a[CFG::C];
 #pragma unroll
       for (int c = 0; c < CFG::C; ++c) z[c] = acc[c][p][n];
-      tanh_jet_fwd<typename CFG::SIG, true>(z, a, lw);
+      tanh_jet_fwd<typename CFG::SIG, PRECISE>(z, a, lw);
 #pragma unroll
       for (int c = 0; c < CFG::C; ++c) acc[c][p][n] = a[c];
     }
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(CFG::NTP, 1) pinn_fused_kernel(const LaunchPar
         }
       }
       if constexpr (BWD) frag_store_stash<CFG>(stash, acc, tid);
-      frag_tanh_fwd<CFG>(acc, kps->lapw);
+      frag_tanh_fwd<CFG, true>(acc, kps->lapw);
       frag_store_smem<CFG>(bufA, acc, pg, ng);
     }
     __syncthreads();

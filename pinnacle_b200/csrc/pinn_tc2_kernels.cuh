@@ -825,7 +825,7 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
         float z[C], av[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) z[c] = zq[c][pp];
-        tanh_jet_fwd_t0<SIG, true>(z, z[0], av, lw_at(h * TS + pb + pp));
+        tanh_jet_fwd_t0<SIG>(z, z[0], av, lw_at(h * TS + pb + pp));
 #pragma unroll
         for (int c = 0; c < C; ++c) zq[c][pp] = av[c];
       }

@@ -211,7 +211,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
         if constexpr (SIG::order(j) >= 1) zz[SIG::base(j)] = params[offW[1] + nn * D + j];
       });
       float aa[C];
-      tanh_jet_fwd<SIG, true>(zz, aa, lwp);
+      tanh_jet_fwd<SIG, true>(zz, aa, lwp);      // layer 1: the pair rule (jet_math.cuh)
       for (int c = 0; c < C; ++c) { z[((size_t)1 * H + nn) * C + c] = zz[c]; a[((size_t)1 * H + nn) * C + c] = aa[c]; }
     }
     for (int l = 2; l <= L; ++l) {
@@ -227,7 +227,7 @@ static void run_cfg(const pinn_kind_desc* d, const float* params, const float* x
         }
         zz[0] += params[offB[l] + nn];
         float aa[C];
-        tanh_jet_fwd<SIG, true>(zz, aa, lwp);
+        tanh_jet_fwd<SIG>(zz, aa, lwp);
         for (int c = 0; c < C; ++c) { z[((size_t)l * H + nn) * C + c] = zz[c]; a[((size_t)l * H + nn) * C + c] = aa[c]; }
       }
     }
