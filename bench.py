@@ -566,8 +566,12 @@ def measure_c3(N, steps, warmup, dev, world, rank, local_rank):
         solver.train_step()
     # The whole step -- fused passes, the NCCL all-reduce of the PDE rows, the LRA statistics and the Adam update: ~30 launches
     # around 1.3 ms of kernels at 8 GPUs -- replayed as ONE CUDA graph (FusedPDESolver.capture_step; PINN_C3_GRAPH=0: eager)
+    # Single process only by default: with NCCL kernels captured in the graph the measurement itself ran (2 GPUs: same step time as
+    # eager), but the processes then hung in teardown (ProcessGroupNCCL watchdog against the graph's event destruction) until killed
+    # -- PINN_C3_GRAPH=force captures under torchrun anyway.
     graphed = False
-    if os.environ.get("PINN_C3_GRAPH", "1") != "0":
+    want_graph = os.environ.get("PINN_C3_GRAPH", "1")
+    if want_graph == "force" or (want_graph != "0" and world == 1):
         try:
             solver.capture_step(warmup=2)
             graphed = True
@@ -600,6 +604,10 @@ def measure_c3(N, steps, warmup, dev, world, rank, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / K
     losses = solver.opt.losses.detach().cpu().tolist()
+    weights_after = solver.opt.sync_loss_weight().tolist()
+    if graphed is True:                                   # release the graph before anything else of the process goes away
+        solver._graph = None
+        torch.cuda.synchronize()
     if rank != 0:
         return None
     return {
@@ -609,7 +617,7 @@ def measure_c3(N, steps, warmup, dev, world, rank, local_rank):
                                "rows (replicated), 3 PDE + 5 boundary terms, 5x100 tanh MLP; optimizer update included",
                    "parallelism": f"dp{world} over collocation points", "l2": "inputs larger than L2 at 1 GPU; no flush between steps",
                    "cuda_graph": graphed},
-        "clocks": clocks, "loss_weights_after": solver.opt.sync_loss_weight().tolist(), "losses_after": losses}
+        "clocks": clocks, "loss_weights_after": weights_after, "losses_after": losses}
 
 
 def measure_c5(total_points, steps, warmup, dev, world, rank, local_rank):

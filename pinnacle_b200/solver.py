@@ -426,7 +426,12 @@ class FusedPDESolver:
         loss assembly and the foreach Adam around a 0.3 ms fused kernel.  Replaying a graph removes that overhead.
         Requirements: a capturable optimizer (``torch.optim.Adam(..., capturable=True)``), no lr scheduler, static
         points (``cache_points=True``) and loss weights that do not change between replays.  After capture
-        ``train_step()`` replays the graph; ``self.opt.losses`` is the static tensor the graph writes."""
+        ``train_step()`` replays the graph; ``self.opt.losses`` is the static tensor the graph writes.
+
+        Under torchrun the NCCL all-reduce of the PDE rows is captured with the rest and replays correctly (measured on 2 GPUs),
+        but the processes then hung in teardown (ProcessGroupNCCL's watchdog against the destruction of the graph's events):
+        drop the graph (``solver._graph = None``) and synchronize before ``destroy_process_group()``, or keep multi-process
+        steps eager -- at >= 128 k rows per GPU the launches are hidden behind the kernels anyway."""
         if self.opt is None:
             raise capi.FusedOpError("compile() first")
         if self.lr_scheduler is not None:
