@@ -352,6 +352,7 @@ def run_fused(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    one_step()                                # back under load after the sampler's start-up wait (untimed)
     K = args.steps
     step_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     kern_ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ops] for _ in range(K)]
@@ -592,6 +593,7 @@ def measure_c3(N, steps, warmup, dev, world, rank, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    solver.train_step()                       # back under load after the sampler's start-up wait (untimed)
     barrier()
     e0.record()
     for _ in range(K):
@@ -654,7 +656,9 @@ def measure_c5(total_points, steps, warmup, dev, world, rank, local_rank):
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()                       # blocks until nvidia-smi delivers its first line: the other ranks must not start timing yet
+    step()                                    # back under load after that wait (untimed)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):

@@ -149,11 +149,13 @@ int pinn_set_laplacian_collapse(int enable);
 /* Number of kernel launches the last pinn_fwd / pinn_fwd_bwd call of this thread enqueued. */
 int pinn_last_launch_count(void);
 
-/* FP32 FFMA micro-benchmark used for the compute roofline denominator: runs `iters` dependent-free
- * FFMA per thread on every SM and returns achieved TFLOP/s (negative on error). Synchronous. */
+/* ---- diagnostics (not part of the hot path; unlike the calls above these two manage their own resources) ----
+ * FP32 FFMA micro-benchmark used for the compute roofline denominator: runs `iters` dependent-free
+ * FFMA per thread on every SM and returns achieved TFLOP/s (negative on error).  Allocates and frees 4 bytes of device
+ * memory, launches on the default stream and synchronises the device: call it outside timed regions and CUDA graphs. */
 double pinn_ffma_peak_tflops(int iters);
 
-/* Hardware self-test of the tcgen05 descriptor conventions the fused kernels rely on: one CTA computes
+/* Hardware self-test of the tcgen05 descriptor conventions the fused kernels rely on (caller-owned buffers, no allocation): one CTA computes
  * D[128][N] = A[128][K] * B[K][N] (tf32 x tf32 -> fp32, row-major device arrays) with the operands staged exactly
  * as the fused kernels stage them.  mode 0: A in TMEM, B in shared memory MN-major; mode 1: A and B in shared
  * memory, K-major.  variant bit 0 swaps the descriptor LBO/SBO fields (diagnostic).  K % 8 == 0, N % 16 == 0. */

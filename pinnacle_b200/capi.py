@@ -169,6 +169,24 @@ class Workspace:
 _WS = Workspace()
 
 
+# PINN_NVTX=1: every C-ABI call below is bracketed by an NVTX range named after it and its residual kind, so that a timeline
+# (ncu --nvtx, nsys where available) shows which loss term a kernel belongs to (tracing)
+_NVTX = os.environ.get("PINN_NVTX", "0") == "1"
+
+
+class _nvtx:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+
+
 def _stream_ptr(device) -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -188,7 +206,7 @@ def fwd(desc: KindDesc, params: torch.Tensor, x: torch.Tensor, aux: Optional[tor
     if desc.n_aux and (aux is None or tuple(aux.shape) != (n, desc.n_aux)):
         raise FusedOpError(f"aux must be [N,{desc.n_aux}]")
     c = desc.to_c()
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _nvtx(f"pinn_fwd:{desc.name or desc.kind}"):
         ws = _WS.get(x.device, workspace_bytes(desc, 0))
         loss = torch.empty(desc.n_pde, dtype=torch.float32, device=x.device)
         resid = torch.empty((n, desc.n_pde), dtype=torch.float32, device=x.device) if want_residual else None
@@ -216,7 +234,7 @@ def fwd_bwd(desc: KindDesc, params: torch.Tensor, x: torch.Tensor, aux: Optional
         raise FusedOpError(f"seeds must be [S,{desc.n_pde}]")
     S = seeds.shape[0]
     c = desc.to_c()
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _nvtx(f"pinn_fwd_bwd:{desc.name or desc.kind}"):
         ws = _WS.get(x.device, workspace_bytes(desc, S))
         if out is None:
             out = torch.empty(S * desc.n_params + desc.n_pde, dtype=torch.float32, device=x.device)
@@ -368,7 +386,7 @@ def fwd_bwd_linear(desc: KindDesc, params: torch.Tensor, x: torch.Tensor, aux: O
         raise FusedOpError(f"seeds must be [S,{desc.n_pde}]")
     S = seeds.shape[0]
     c = desc.to_c()
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _nvtx(f"pinn_fwd_bwd_linear:{desc.name or desc.kind}"):
         ws = _WS.get(x.device, workspace_bytes(desc, S))
         if out is None:
             out = torch.empty(S * desc.n_params + desc.n_pde, dtype=torch.float32, device=x.device)
