@@ -69,9 +69,17 @@ struct TC2fg {
   static constexpr bool SHZ = (C > 5);
   // separate instantiations of the top / bottom reverse stages: measured -14 % (NS2D, m = 3), -1 % (C <= 5, m = 1),
   // +5 % (C = 6, m = 1: more spills)
+#ifdef PINN_EXP_PEEL_C5          // what-if builds
+  static constexpr bool PEEL = (M > 1) || (C <= 4) || (C == 5 && PINN_EXP_PEEL_C5);
+#else
   static constexpr bool PEEL = (M > 1) || (C <= 5);
+#endif
   // sub-tile loop of a reverse stage: unrolled for C <= 5, rolled for C = 6 (measured: Poisson2D 11.4 vs 11.8 ms, Burgers2D 16.4 vs 15.7 ms)
+#ifdef PINN_EXP_REVUNROLL_C5
+  static constexpr int REV_UNROLL = (C <= 4) ? NSUB : (C == 5 ? PINN_EXP_REVUNROLL_C5 : 1);
+#else
   static constexpr int REV_UNROLL = (C <= 5) ? NSUB : 1;
+#endif
   // Reverse-sweep schedule.  Joint (default): per sub-tile a^{l-1}, zbar^l, then the issuer runs rows(h) + dW(h).
   // Split (what-if, private zbar arrays only): the element-wise warps first turn BOTH sub-tiles' abar^l into zbar^l (the
   // operand of the rows MMAs), then rebuild both a^{l-1} (second operand of the dW contraction); the issuer runs

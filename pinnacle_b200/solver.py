@@ -21,6 +21,8 @@ import numpy as np
 import torch
 
 import collections
+import contextlib
+import os
 from collections import namedtuple
 
 from . import capi
@@ -28,6 +30,8 @@ from .evaluate import LazyOutputs, topk_residual
 from .fused import FusedPDEResidual, embedded_param_provider, net_linear_params, net_param_provider, net_shape
 from .kinds import KIND_FLUX, flux_desc, value_desc
 from .problems import ProblemSpec, describe_reference
+
+_TERM_STREAMS = os.environ.get("PINN_TERM_STREAMS", "1") != "0"     # boundary-term launches of the autograd-free step on side streams
 
 # A value-type boundary / initial / point-set term on BC rows [beg, end):  u[:, component] - values
 # (DirichletBC / IC / PointSetBC of deepxde/icbc).  Evaluated by the fused op (kind VALUE) instead of stock autograd.
@@ -223,6 +227,18 @@ class _StepCore:
             self._one_seed = torch.ones(1, 1, dtype=torch.float32, device=flat.device)
         losses = self._rows_losses
         out = buf[:S * P + n_pde]
+        # Boundary terms are small launches (32 .. 96 CTAs of a 40 us kernel each): they go to side streams, forked BEFORE the
+        # residual launch, so that they run next to each other and into the tail of the residual kernel instead of one after the
+        # other behind it (5 terms of NS2D_LidDriven: ~0.2 ms of a 1.9 ms step at 8 GPUs).  Every term writes its own slice of
+        # `buf`; scratch is per stream (capi.Workspace).  PINN_TERM_STREAMS=0: everything on the current stream.
+        side = None
+        if n_bc >= 2 and flat.is_cuda and _TERM_STREAMS:
+            side = getattr(self, "_term_streams", None)
+            if side is None or len(side) < n_bc:
+                side = self._term_streams = [torch.cuda.Stream(device=flat.device) for _ in range(n_bc)]
+            main = torch.cuda.current_stream(flat.device)
+            fork = torch.cuda.Event()
+            fork.record(main)
         _fused._backend_fwd_bwd(desc, flat, op.x, op.aux, op.inv_n_global, pde_seeds, out=out)
         op.stats["fwd_bwd_calls"] += 1
         if op.world > 1:
@@ -233,17 +249,34 @@ class _StepCore:
         # leaves that tensor's grad at None and the reference's LRA averages |grad| over the OTHER entries only
         # (lr_adaptor.py:50-54: count += numel of the non-None grads)
         self.term_counts = [float(P - desc.m) if (t[0] == "op" and t[4].kind == KIND_FLUX and t[4].aux_sel[1] < 0) else float(P) for t in terms]
+        if side is not None:
+            # the kernels append a term's loss behind its gradient row, i.e. ON the first entry of the next row: harmless one
+            # after the other (the next term overwrites it), a race side by side -- concurrent terms write private staging rows
+            scr = getattr(self, "_term_scr", None)
+            if scr is None or scr.shape != (n_bc, P + PINN_ROW_SLACK) or scr.device != flat.device:
+                scr = self._term_scr = torch.empty((n_bc, P + PINN_ROW_SLACK), dtype=torch.float32, device=flat.device)
         for i, t in enumerate(terms):
-            o = buf[(S + i) * P:(S + i) * P + P + 1]
+            o = buf[(S + i) * P:(S + i) * P + P + 1] if side is None else scr[i, :P + 1]
             if t[3] - t[2] == 0:
                 raise capi.FusedOpError("gradient rows: boundary term without rows")
-            if t[0] == "periodic":
-                _periodic_eval(self.periodic_op(t[1], t[2], t[3], t[4]), flat, True, o)
-            else:
-                bop = self.term_op(t[1], t[2], t[3], t[4], t[5])
-                _fused._backend_fwd_bwd(bop.desc, flat, bop.x, bop.aux, bop.inv_n_global, self._one_seed, out=o)
-                bop.stats["fwd_bwd_calls"] += 1
-            losses[n_pde + i:n_pde + i + 1].copy_(o[P:])
+            if side is not None:
+                side[i].wait_event(fork)
+            with (torch.cuda.stream(side[i]) if side is not None else contextlib.nullcontext()):
+                if t[0] == "periodic":
+                    _periodic_eval(self.periodic_op(t[1], t[2], t[3], t[4]), flat, True, o)
+                else:
+                    bop = self.term_op(t[1], t[2], t[3], t[4], t[5])
+                    _fused._backend_fwd_bwd(bop.desc, flat, bop.x, bop.aux, bop.inv_n_global, self._one_seed, out=o)
+                    bop.stats["fwd_bwd_calls"] += 1
+                if side is None:
+                    losses[n_pde + i:n_pde + i + 1].copy_(o[P:])
+        if side is not None:
+            for i in range(n_bc):
+                main.wait_stream(side[i])
+            # joined: move the staged rows and losses into place on the main stream (behind the copy of the residual losses,
+            # which the residual kernel parked on the head of the first boundary row)
+            buf[S * P:(S + n_bc) * P].view(n_bc, P).copy_(scr[:, :P])
+            losses[n_pde:].copy_(scr[:, P])
         return buf[:T * P].view(T, P), losses
 
     def _linear_rows(self, flat, pde_seeds, terms):
