@@ -11,7 +11,7 @@ if [ -z "$SKIP_TESTS" ]; then
   echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
   tail -5 $OUT/pytest_gpu.log
   # the numbers DESIGN.md section 5 quotes: L2RE of the replays, gradient error at the test's own trained states
-  timeout 600 python -m pytest tests/test_cuda_l2re.py -m gpu -q -s 2>&1 | grep "L2RE fused" > $OUT/l2re.txt
+  timeout 600 python -m pytest tests/test_cuda_l2re.py -m gpu -q -s 2>&1 | grep "L2RE" > $OUT/l2re.txt
   timeout 600 python -m pytest tests/test_cuda_solver.py -m gpu -q -s -k thousand 2>&1 | grep "fused-vs-fp64" > $OUT/trained_states.txt
 fi
 timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err
