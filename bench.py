@@ -394,11 +394,9 @@ def run_fused(args):
         solvers.append(s)
 
     def e2e_step2():
-        tot = 0.0
         for s in solvers:
-            s.train_step()                                        # H2D (pinned) + fused op + backward + Adam
-            tot += float(s.opt.losses.detach().cpu().sum())       # D2H read of the step's result
-        return tot
+            s.train_step()                                        # H2D (pinned, on the op's upload stream) + fused op + Adam
+        return sum(float(s.opt.losses.detach().cpu().sum()) for s in solvers)      # D2H read of the step's results
 
     for _ in range(2):
         e2e_step2()

@@ -175,7 +175,19 @@ class FusedPDEResidual:
         if xt.device != self.device:
             self.stats["h2d_bytes"] += xt.numel() * 4
             self.stats["uploads"] += 1
-            xt = xt.contiguous().to(self.device, non_blocking=True)
+            if self.device.type == "cuda":
+                # the host -> device copy runs on a stream of its own: it does not queue behind whatever the compute stream is
+                # still doing (another problem's kernels, the previous step's update), only the consumer waits for it
+                up = getattr(self, "_upload_stream", None)
+                if up is None:
+                    up = self._upload_stream = torch.cuda.Stream(device=self.device)
+                cur = torch.cuda.current_stream(self.device)
+                with torch.cuda.stream(up):
+                    xt = xt.contiguous().to(self.device, non_blocking=True)
+                cur.wait_stream(up)
+                xt.record_stream(cur)
+            else:
+                xt = xt.contiguous().to(self.device, non_blocking=True)
         self.x = xt.contiguous()
         self.aux = None
         if self.desc.n_aux:
