@@ -154,6 +154,11 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
                 ARR = CFG::ARR, NEW = CFG::NEW, NTHALL = CFG::NTHALL;
   constexpr bool BWD = CFG::BWD;
 
+#ifdef PINN_EXP_WARP_ARRIVE       // what-if, measured: one mbarrier arrival per warp instead of per thread -- no gain (see below)
+  constexpr int kArr = 32;
+#else
+  constexpr int kArr = 1;
+#endif
   extern __shared__ __align__(1024) unsigned char smraw[];
   float* W1s = reinterpret_cast<float*>(smraw + CFG::oW1);
   float* bs = reinterpret_cast<float*>(smraw + CFG::oBias);
@@ -227,18 +232,21 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
   if (tid == 0) {
     mbar_init_n(&bars[0], 1);
     mbar_init_n(&bars[1], 1);
-    mbar_init_n(&rdy[0], NEW);
-    mbar_init_n(&rdy[1], NEW);
-    mbar_init_n(&rdy2[0], NEW);
-    mbar_init_n(&rdy2[1], NEW);
-    for (int i = 0; i < 4; ++i) mbar_init_n(&wr[i], CFG::NPR);
+    // one arrival per thread.  -DPINN_EXP_WARP_ARRIVE (every thread fences its own writes, the warp synchronises, lane 0 arrives:
+    // 16 / 4 arrivals on a barrier word instead of 512 / 128) was measured at 10.16 ms against 9.84 ms (Poisson2D_Classic, same
+    // box; Heat2D_Multiscale unchanged): the arrivals do not queue noticeably, the extra warp synchronisation costs
+    mbar_init_n(&rdy[0], NEW / kArr);
+    mbar_init_n(&rdy[1], NEW / kArr);
+    mbar_init_n(&rdy2[0], NEW / kArr);
+    mbar_init_n(&rdy2[1], NEW / kArr);
+    for (int i = 0; i < 4; ++i) mbar_init_n(&wr[i], CFG::NPR / kArr);
     mbar_init_n(&wfree[0], 1);
     mbar_init_n(&wfree[1], 1);
     mbar_init_n(wf1, 1);
     mbar_init_n(wf2, 1);
     mbar_init_n(&dwd[0], 1);
     mbar_init_n(&dwd[1], 1);
-    mbar_init_n(dwfree, CFG::NPR);
+    mbar_init_n(dwfree, CFG::NPR / kArr);
     mbar_init_n(dsfree, NEW / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     *kps = p.kp;
@@ -306,6 +314,10 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
     };
     auto arrive = [&](uint64_t* bar) {
       umma::fence_before_sync();
+      if constexpr (kArr == 32) {
+        __syncwarp();
+        if (lane != 0) return;
+      }
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(bar)) : "memory");
     };
     if (do_prod) {
@@ -749,11 +761,19 @@ __global__ void __launch_bounds__(CFG::NTHALL, 1) pinn_tc2_kernel(const TcLaunch
     auto signal_ready = [&](int h) {
       umma::fence_async_smem();
       umma::fence_before_sync();
+      if constexpr (kArr == 32) {
+        __syncwarp();
+        if (lane != 0) return;
+      }
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(&rdy[h])) : "memory");
     };
     auto signal_ready2 = [&](int h) {
       umma::fence_async_smem();
       umma::fence_before_sync();
+      if constexpr (kArr == 32) {
+        __syncwarp();
+        if (lane != 0) return;
+      }
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(&rdy2[h])) : "memory");
     };
     auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NEW) : "memory"); };
