@@ -423,7 +423,8 @@ def run_fused(args):
         del solvers
         torch.cuda.empty_cache()
         extra = {}
-        for key, fn, n_tot in (("configs[4] strong", measure_c5, 1 << 24), ("configs[2] strong", measure_c3, 1 << 20)):
+        for key, fn, n_tot in (("configs[4] strong", measure_c5, 1 << 24), ("configs[2] strong", measure_c3, 1 << 20),
+                               ("configs[3] strong", measure_c4, 1 << 20)):
             try:
                 extra[key] = fn(n_tot, 5, 3, dev, world, rank, local_rank)
             except Exception as e:  # noqa: BLE001
@@ -619,6 +620,89 @@ def measure_c3(N, steps, warmup, dev, world, rank, local_rank):
                    "parallelism": f"dp{world} over collocation points", "l2": "inputs larger than L2 at 1 GPU; no flush between steps",
                    "cuda_graph": graphed},
         "clocks": clocks, "loss_weights_after": weights_after, "losses_after": losses}
+
+
+def measure_c4(total_points, steps, warmup, dev, world, rank, local_rank):
+    """BASELINE.json configs[3]: Kuramoto-Sivashinsky (fourth-order jets in x), `total_points` synthetic collocation points IN
+    TOTAL split over the ranks, Adam then L-BFGS through the public API: FusedPDESolver + optim.FlatAdam for the Adam phase, then
+    torch.optim.LBFGS (lr 1, max_iter 20, no line search: what benchmark.py:114-115 / src/optimizer/adam_lbfgs.py hand to the
+    reference) driving the fused closure.  Reported: ms per Adam step (the line's ms_per_step / value) and ms per L-BFGS closure
+    evaluation (one fused forward + reverse + all-reduce, the two-loop recursion and the update of torch's own L-BFGS)."""
+    import torch.distributed as dist
+    from pinnacle_b200 import problems
+    from pinnacle_b200.fused import shard_bounds
+    from pinnacle_b200.nn import FNN
+    from pinnacle_b200.optim import FlatAdam
+    from pinnacle_b200.solver import FusedPDESolver
+    spec = problems.make("KuramotoSivashinskyEquation")
+    beg, end = shard_bounds(total_points, rank, world)
+    x_local = spec.sample(total_points, seed=9)[beg:end]
+    torch.manual_seed(0)
+    net = FNN([2] + [100] * 5 + [1]).to(dev)
+    with torch.no_grad():
+        for lin in net.linears:
+            lin.bias.normal_(0, 0.1)
+    solver = FusedPDESolver(spec, net, x_local, n_global=total_points).compile(FlatAdam(net.parameters(), 1e-3))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 3)):
+        solver.train_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    solver.train_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    K = max(steps, 20)
+    e0.record()
+    for _ in range(K):
+        solver.train_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    # L-BFGS phase: same solver, the reference's optimizer settings, the fused losses through autograd (closure protocol)
+    solver.compile(torch.optim.LBFGS(net.parameters(), lr=1, max_iter=20))
+    evals = [0]
+    orig = solver.outputs_losses_train
+
+    def counted(*a, **k):
+        evals[0] += 1
+        return orig(*a, **k)
+
+    solver.outputs_losses_train = counted
+    solver.train_step()                       # untimed first iteration (history empty)
+    evals[0] = 0
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(3):
+        solver.train_step()                   # one L-BFGS step = up to 20 closure evaluations
+    e3.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t2 = torch.tensor([e2.elapsed_time(e3)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / K
+    n_ev = max(evals[0], 1)
+    loss = float(solver.opt.losses.detach().sum().cpu()) if hasattr(solver.opt, "losses") else None
+    if loss is not None and not math.isfinite(loss):
+        loss = None                           # (an L-BFGS without line search may leave the basin; the timing stands)
+    if rank != 0:
+        return None
+    return {"metric": METRIC, "value": total_points / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(warmup, 3),
+            "ms_per_step": ms, "scaling": "strong",
+            "config": {"workload": f"KuramotoSivashinskyEquation (jet orders (4,1)), {total_points} synthetic collocation points in total, 5x100 tanh MLP, "
+                                   "Adam (FlatAdam, update included) then L-BFGS (torch.optim.LBFGS lr 1 max_iter 20, fused closure)",
+                       "parallelism": f"dp{world} over collocation points"},
+            "lbfgs": {"closure_evaluations": n_ev, "ms_per_closure_evaluation": float(t2.item()) / n_ev, "loss_after": loss},
+            "clocks": clocks}
 
 
 def measure_c5(total_points, steps, warmup, dev, world, rank, local_rank):
