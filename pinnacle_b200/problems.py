@@ -368,8 +368,8 @@ GP_DIRECTIONS = np.array([[1.0, 0.0, 1.0, 1.0], [0.0, 1.0, 1.0, -1.0]])     # e0
 def gpinn(spec: ProblemSpec) -> ProblemSpec:
     """The gPINN form of a problem (src/pde/baseclass.py:151-180 ``use_gepinn``; benchmark.py:91-92 ``--method gepinn``): loss
     terms [r, dr/dx_0, dr/dx_1].  Covered: one-output problems in two inputs whose residual is Burgers1D's or a LINEAR one with
-    constant coefficients and no per-point source (Poisson2D_Classic, Wave1D): the mixed third-order partials come from
-    order-3 jets along four directions.  Anything else raises."""
+    constant coefficients, with or without an additive source (Poisson2D_Classic, Wave1D, Helmholtz2D, PoissonBoltzmann2D): the mixed
+    third-order partials come from order-3 jets along four directions.  Anything else raises."""
     d = spec.desc
     if d.d != 2 or d.m != 1 or d.n_pde != 1:
         raise UnsupportedProblem(f"gPINN: {spec.name} has d={d.d}, m={d.m}, n_pde={d.n_pde}; the fused gPINN kinds cover one-output, "
@@ -377,9 +377,24 @@ def gpinn(spec: ProblemSpec) -> ProblemSpec:
     if d.kind == K.KIND_BURGERS1D:
         g = KindDesc(K.KIND_GP_BURGERS1D, 4, 1, (3, 3, 3, 3), n_pde=3, consts=[d.consts[0]], name=spec.name + "_gepinn")
     elif d.kind == K.KIND_LINEAR:
-        if d.n_aux or any(a >= 0 for a in d.aux_sel):
-            raise UnsupportedProblem(f"gPINN: {spec.name} has per-point coefficients or a per-point source; its input gradient "
-                                     "needs their derivatives as extra columns (not wired up)")
+        sel = list(d.aux_sel)
+        if any(a >= 0 for i, a in enumerate(sel) if i != K.LIN_SEL_SRC):
+            raise UnsupportedProblem(f"gPINN: {spec.name} has per-point coefficients; the input gradient of its residual needs "
+                                     "their derivatives too (not wired up)")
+        if sel[K.LIN_SEL_SRC] >= 0:
+            # additive per-point source f(x) (Helmholtz2D, PoissonBoltzmann2D): dr/dx_j gains df/dx_j.  The source closures are
+            # torch formulas, so their gradient comes from autograd, evaluated in float64 once per point set like the source
+            src_col, base_aux = sel[K.LIN_SEL_SRC], spec.aux_fn
+
+            def aux_fn(x):
+                with torch.enable_grad():
+                    xr = x[:, :2].detach().to(torch.float64).clone().requires_grad_(True)
+                    f = base_aux(xr)[:, src_col:src_col + 1]
+                    (gf,) = torch.autograd.grad(f.sum(), xr)
+                return torch.cat([f.detach(), gf], dim=1).to(dtype=x.dtype, device=x.device)
+
+            g = KindDesc(K.KIND_GP_LINEAR2, 4, 1, (3, 3, 3, 3), n_pde=3, n_aux=3, consts=list(d.consts), aux_sel=[0, 1, 2], name=spec.name + "_gepinn")
+            return ProblemSpec(spec.name + "_gepinn", g, list(spec.bbox), aux_fn, GP_DIRECTIONS.copy())
         g = KindDesc(K.KIND_GP_LINEAR2, 4, 1, (3, 3, 3, 3), n_pde=3, consts=list(d.consts), name=spec.name + "_gepinn")
     else:
         raise UnsupportedProblem(f"gPINN: no fused residual-gradient kind for {spec.name} (kind {K.KIND_NAMES.get(d.kind, d.kind)})")

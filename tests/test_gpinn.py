@@ -53,7 +53,7 @@ def test_device_math_matches_reference_gepinn(harness_lib, name):
 
 
 @needs_ref
-@pytest.mark.parametrize("name", CASES + ["Wave1D"])
+@pytest.mark.parametrize("name", CASES + ["Wave1D", "Helmholtz2D", "PoissonBoltzmann2D"])
 def test_patched_gepinn_model_matches_unpatched_reference_step(name):
     """benchmark.py:84-122 with --method gepinn: pde.use_gepinn(), create_model, compile, enable_fused -- same losses (three PDE
     terms + the boundary terms), same parameter gradients, one optimizer step through the patched train_step."""
