@@ -23,9 +23,16 @@ dev = torch.device("cuda:0")
 IM = {"auto": 0, "ffma": 1, "tc": 2, "tc2": 3}
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for name in args.problems.split(","):
-    spec = problems.make(name, **({"darcy_2d_coef": np.random.RandomState(0).rand(64, 3)} if name == "Wave2D_Heterogeneous" else {}))
+    gep = name.endswith("_gepinn")            # e.g. Poisson2D_Classic_gepinn: the gPINN form (problems.gpinn), embedded rows (x0, x1, 0, 0)
+    base = name[:-7] if gep else name
+    spec = problems.make(base, **({"darcy_2d_coef": np.random.RandomState(0).rand(64, 3)} if base == "Wave2D_Heterogeneous" else {}))
+    if gep:
+        spec = problems.gpinn(spec)
     d = spec.desc
-    x = torch.as_tensor(spec.sample(args.points, seed=1)).to(dev)
+    x = torch.as_tensor(spec.sample(args.points, seed=1))
+    if gep:
+        x = torch.cat([x, torch.zeros(x.shape[0], d.d - x.shape[1])], dim=1)
+    x = x.to(dev).contiguous()
     aux = spec.aux(x)
     g = torch.Generator().manual_seed(0)
     params = (torch.randn(d.n_params, generator=g) * 0.1).to(dev)
