@@ -24,7 +24,7 @@ import refshim  # noqa: E402
 from golden import common  # noqa: E402
 from pinnacle_b200 import problems  # noqa: E402
 
-CASES = ["Poisson2D_Classic", "Burgers1D"]
+CASES = ["Poisson2D_Classic", "Burgers1D", "Wave1D", "Helmholtz2D", "PoissonBoltzmann2D"]
 
 
 def run(name):

@@ -11,16 +11,17 @@ import refshim
 from util import GpinnGolden, assert_parity, oracle_backend
 
 CASES = ["Poisson2D_Classic", "Burgers1D"]
+GOLDEN_CASES = CASES + ["Wave1D", "Helmholtz2D", "PoissonBoltzmann2D"]      # tests/golden/gepinn_<Class>.npz
 needs_ref = pytest.mark.skipif(not refshim.available(), reason="reference tree not available")
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_oracle_matches_reference_gepinn(name):
     from oracle import autograd_ref as O
     G = GpinnGolden(name)
     for dtype, tag, tol in ((torch.float64, "64", 1e-9), (torch.float32, "32", 2e-5)):
         flat, x = G.embedded(dtype)
-        losses, grads, res = O.losses_and_grads(G.desc, flat, x, None, seeds=np.eye(3))
+        losses, grads, res = O.losses_and_grads(G.desc, flat, x, G.aux(x), seeds=np.eye(3))
         grads = G.back(grads.numpy())
         assert_parity(res.numpy(), G.g[f"resid{tag}"], "residual", tol)
         assert_parity(losses.numpy(), G.g[f"loss{tag}"], "loss", tol)
@@ -28,12 +29,14 @@ def test_oracle_matches_reference_gepinn(name):
         assert_parity(grads @ G.probes.T, G.g[f"gproj{tag}"], "grad projections", tol)
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_device_math_matches_reference_gepinn(harness_lib, name):
     """Order-3 jets along e0, e1, e0+e1, e0-e1, the polarisation formulas for u_xy, u_xxy, u_xyy and their hand adjoints."""
     G = GpinnGolden(name)
     desc = G.desc
     flat, x = G.embedded(torch.float32)
+    aux = G.aux(x)
+    auxn = None if aux is None else np.ascontiguousarray(aux.numpy())
     flat, x = flat.numpy(), x.numpy()
     n, P = x.shape[0], desc.n_params
     seeds = np.eye(3, dtype=np.float32)
@@ -41,8 +44,8 @@ def test_device_math_matches_reference_gepinn(harness_lib, name):
     loss = np.zeros(3)
     resid = np.zeros((n, 3), np.float32)
     cd = desc.to_c()
-    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    rc = harness_lib.harness_run(ctypes.byref(cd), vp(flat), vp(x), None, ctypes.c_longlong(n), ctypes.c_double(1.0 / n), vp(seeds), 3,
+    vp = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+    rc = harness_lib.harness_run(ctypes.byref(cd), vp(flat), vp(x), vp(auxn), ctypes.c_longlong(n), ctypes.c_double(1.0 / n), vp(seeds), 3,
                                  vp(grad), vp(loss), vp(resid))
     assert rc == 0
     grad = G.back(grad)
@@ -53,7 +56,7 @@ def test_device_math_matches_reference_gepinn(harness_lib, name):
 
 
 @needs_ref
-@pytest.mark.parametrize("name", CASES + ["Wave1D", "Helmholtz2D", "PoissonBoltzmann2D"])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_patched_gepinn_model_matches_unpatched_reference_step(name):
     """benchmark.py:84-122 with --method gepinn: pde.use_gepinn(), create_model, compile, enable_fused -- same losses (three PDE
     terms + the boundary terms), same parameter gradients, one optimizer step through the patched train_step."""

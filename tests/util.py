@@ -67,6 +67,10 @@ class GpinnGolden:
         x_e = np.concatenate([x, np.zeros((x.shape[0], self.desc.d - 2), nd)], axis=1)
         return torch.as_tensor(flat_e), torch.as_tensor(np.ascontiguousarray(x_e))
 
+    def aux(self, x_e):
+        """Aux columns of the embedded rows (source and its input gradient for the sourced LINEAR kinds), or None."""
+        return self.spec.aux(x_e).contiguous() if self.desc.n_aux else None
+
     def back(self, grad_e):
         grad_e = np.asarray(grad_e, dtype=np.float64)
         H, de = self.base.H, self.desc.d
