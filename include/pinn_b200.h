@@ -75,7 +75,8 @@ enum pinn_kind {
    * presents the 2-input network as a 4-"input" one: rows (x0, x1, 0, 0) and first-layer weights W1 [e0 e1 e0+e1 e0-e1], so
    * d = 4, orders (3,3,3,3); the gradient with respect to the embedded first layer maps back by the transposed direction matrix.
    *   GP_LINEAR2:   r = cu u + sum_{j<2} (c1_j u_j + c2_j u_jj) + src   (consts as LINEAR, constant coefficients;
-   *                 aux_sel[0..2] = columns of src, dsrc/dx0, dsrc/dx1, -1 = none)
+   *                 aux_sel[0..2] = columns of src, dsrc/dx0, dsrc/dx1, -1 = none; aux_sel[3], aux_sel[4] = per-point multipliers of
+   *                 the c2 terms / the cu term that the reference treats as constants under autograd (table look-ups), -1 = none)
    *   GP_BURGERS1D: r = u_t + u u_x - c0 u_xx,  inputs (x, t)                                   (burgers.py:21-25) */
   PINN_KIND_GP_LINEAR2 = 11,
   PINN_KIND_GP_BURGERS1D = 12

@@ -551,7 +551,9 @@ struct Residual {
       case PINN_KIND_GP_LINEAR2: {
         if constexpr (gp4()) {
           const Gp g = gp_derivs(U[0]);
-          const float cu = c[LIN_CU], c1x = c[LIN_C1], c1y = c[LIN_C1 + 1], c2x = c[LIN_C2], c2y = c[LIN_C2 + 1];
+          // per-point multipliers the reference treats as constants under autograd (table look-ups: Poisson2D_ManyArea's a(x))
+          const float m2 = aux_or_one(aux, kp.aux_sel[3]), mu = aux_or_one(aux, kp.aux_sel[4]);
+          const float cu = c[LIN_CU] * mu, c1x = c[LIN_C1], c1y = c[LIN_C1 + 1], c2x = c[LIN_C2] * m2, c2y = c[LIN_C2 + 1] * m2;
           r[0] = cu * g.u + c1x * g.ux + c1y * g.uy + c2x * g.uxx + c2y * g.uyy + (kp.aux_sel[0] >= 0 ? aux[kp.aux_sel[0]] : 0.f);
           r[1] = cu * g.ux + c1x * g.uxx + c1y * g.uxy + c2x * g.uxxx + c2y * g.uxyy + (kp.aux_sel[1] >= 0 ? aux[kp.aux_sel[1]] : 0.f);
           r[2] = cu * g.uy + c1x * g.uxy + c1y * g.uyy + c2x * g.uxxy + c2y * g.uyyy + (kp.aux_sel[2] >= 0 ? aux[kp.aux_sel[2]] : 0.f);
@@ -737,7 +739,8 @@ struct Residual {
       } break;
       case PINN_KIND_GP_LINEAR2: {
         if constexpr (gp4()) {
-          const float cu = c[LIN_CU], c1x = c[LIN_C1], c1y = c[LIN_C1 + 1], c2x = c[LIN_C2], c2y = c[LIN_C2 + 1];
+          const float m2 = aux_or_one(aux, kp.aux_sel[3]), mu = aux_or_one(aux, kp.aux_sel[4]);
+          const float cu = c[LIN_CU] * mu, c1x = c[LIN_C1], c1y = c[LIN_C1 + 1], c2x = c[LIN_C2] * m2, c2y = c[LIN_C2 + 1] * m2;
           const float g0 = rb[0], g1 = rb[1], g2 = rb[2];
           Gp b{};
           b.u = cu * g0;

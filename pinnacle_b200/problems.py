@@ -40,6 +40,8 @@ class ProblemSpec:
     # gPINN: direction matrix V [d_net, desc.d].  The kernels see a desc.d-"input" network whose rows are (x, 0, .., 0) and
     # whose first layer is W1 @ V, so that their per-direction jets are directional derivatives along the columns of V.
     embed: Optional[np.ndarray] = None
+    # True: the aux columns are table look-ups the reference computes outside autograd (constants when a residual is differentiated)
+    aux_constant: bool = False
 
     @property
     def net_d(self) -> int:
@@ -145,7 +147,7 @@ def poisson2d_manyarea(a_cof: np.ndarray, f_cof: np.ndarray, bbox=(-10, 10, -10,
         return torch.as_tensor(out).to(dtype=xy.dtype, device=xy.device)
 
     d = linear_desc(2, (2, 2), c2=(1.0, 1.0), n_aux=2, src_col=1, c2_cols=(0, 0), name="Poisson2D_ManyArea")
-    return ProblemSpec("Poisson2D_ManyArea", d, list(bbox), aux)
+    return ProblemSpec("Poisson2D_ManyArea", d, list(bbox), aux, aux_constant=True)
 
 
 def poisson_nd(dim=5, len=1) -> ProblemSpec:
@@ -368,7 +370,8 @@ GP_DIRECTIONS = np.array([[1.0, 0.0, 1.0, 1.0], [0.0, 1.0, 1.0, -1.0]])     # e0
 def gpinn(spec: ProblemSpec) -> ProblemSpec:
     """The gPINN form of a problem (src/pde/baseclass.py:151-180 ``use_gepinn``; benchmark.py:91-92 ``--method gepinn``): loss
     terms [r, dr/dx_0, dr/dx_1].  Covered: one-output problems in two inputs whose residual is Burgers1D's or a LINEAR one with
-    constant coefficients, with or without an additive source (Poisson2D_Classic, Wave1D, Helmholtz2D, PoissonBoltzmann2D): the mixed
+    constant coefficients, with or without an additive source (Poisson2D_Classic, Wave1D, Helmholtz2D, PoissonBoltzmann2D), or with
+    table-look-up coefficients that are constants to the reference's autograd (Poisson2D_ManyArea): the mixed
     third-order partials come from order-3 jets along four directions.  Anything else raises."""
     d = spec.desc
     if d.d != 2 or d.m != 1 or d.n_pde != 1:
@@ -378,9 +381,20 @@ def gpinn(spec: ProblemSpec) -> ProblemSpec:
         g = KindDesc(K.KIND_GP_BURGERS1D, 4, 1, (3, 3, 3, 3), n_pde=3, consts=[d.consts[0]], name=spec.name + "_gepinn")
     elif d.kind == K.KIND_LINEAR:
         sel = list(d.aux_sel)
-        if any(a >= 0 for i, a in enumerate(sel) if i != K.LIN_SEL_SRC):
-            raise UnsupportedProblem(f"gPINN: {spec.name} has per-point coefficients; the input gradient of its residual needs "
-                                     "their derivatives too (not wired up)")
+        c2_sels = {sel[K.LIN_SEL_C2 + j] for j in range(2) if d.consts[K.LIN_C2 + j] != 0.0}
+        table_aux = getattr(spec, "aux_constant", False)
+        if (sel[K.LIN_SEL_CU] >= 0 or c2_sels != {-1}) and not table_aux:
+            raise UnsupportedProblem(f"gPINN: {spec.name} has per-point coefficients that autograd differentiates; the input gradient "
+                                     "of its residual needs their derivatives too (not wired up)")
+        if table_aux:
+            # coefficients AND source come from table look-ups on the host (Poisson2D_ManyArea, poisson.py:228-252): constants to
+            # the reference's autograd, so dr/dx_j carries the multipliers and no source gradient
+            if len(c2_sels) != 1:
+                raise UnsupportedProblem(f"gPINN: {spec.name}: the second-order terms do not share one per-point multiplier")
+            g = KindDesc(K.KIND_GP_LINEAR2, 4, 1, (3, 3, 3, 3), n_pde=3, n_aux=d.n_aux, consts=list(d.consts),
+                         aux_sel=[sel[K.LIN_SEL_SRC], -1, -1, c2_sels.pop(), sel[K.LIN_SEL_CU]], name=spec.name + "_gepinn")
+            base_aux = spec.aux_fn
+            return ProblemSpec(spec.name + "_gepinn", g, list(spec.bbox), (lambda x: base_aux(x[:, :2])), GP_DIRECTIONS.copy())
         if sel[K.LIN_SEL_SRC] >= 0:
             # additive per-point source f(x) (Helmholtz2D, PoissonBoltzmann2D): dr/dx_j gains df/dx_j.  The source closures are
             # torch formulas, so their gradient comes from autograd, evaluated in float64 once per point set like the source

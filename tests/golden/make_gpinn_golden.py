@@ -24,7 +24,7 @@ import refshim  # noqa: E402
 from golden import common  # noqa: E402
 from pinnacle_b200 import problems  # noqa: E402
 
-CASES = ["Poisson2D_Classic", "Burgers1D", "Wave1D", "Helmholtz2D", "PoissonBoltzmann2D"]
+CASES = ["Poisson2D_Classic", "Burgers1D", "Wave1D", "Helmholtz2D", "PoissonBoltzmann2D", "Poisson2D_ManyArea"]
 
 
 def run(name):
@@ -41,8 +41,11 @@ def run(name):
     idx = common.golden_index_set(shapes, seed)
     probes = common.probe_vectors(base.n_params, seed)
     x64 = spec.sample(common.N_POINTS, seed=seed, dtype=np.float64).astype(np.float32).astype(np.float64)
+    x_e = np.concatenate([x64, np.zeros((x64.shape[0], desc.d - 2))], axis=1)
+    aux64 = spec.aux(torch.as_tensor(x_e)).numpy() if desc.n_aux else np.zeros((x64.shape[0], 0))
     out = dict(x=x64, seed=np.int64(seed), idx=idx, kind=np.int64(desc.kind), consts=np.asarray(desc.consts, dtype=np.float64),
-               embed=np.asarray(spec.embed, dtype=np.float64))
+               embed=np.asarray(spec.embed, dtype=np.float64), n_aux=np.int64(desc.n_aux), aux_sel=np.asarray(desc.aux_sel),
+               aux64=aux64, base_d=np.int64(base.d), H=np.int64(base.H), L=np.int64(base.L))
     for tag, tdt, ndt in (("64", torch.float64, np.float64), ("32", torch.float32, np.float32)):
         torch.set_default_dtype(tdt)
         dde.config.set_default_float("float64" if tag == "64" else "float32")

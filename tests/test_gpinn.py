@@ -11,7 +11,7 @@ import refshim
 from util import GpinnGolden, assert_parity, oracle_backend
 
 CASES = ["Poisson2D_Classic", "Burgers1D"]
-GOLDEN_CASES = CASES + ["Wave1D", "Helmholtz2D", "PoissonBoltzmann2D"]      # tests/golden/gepinn_<Class>.npz
+GOLDEN_CASES = CASES + ["Wave1D", "Helmholtz2D", "PoissonBoltzmann2D", "Poisson2D_ManyArea"]      # tests/golden/gepinn_<Class>.npz
 needs_ref = pytest.mark.skipif(not refshim.available(), reason="reference tree not available")
 
 
@@ -19,7 +19,10 @@ needs_ref = pytest.mark.skipif(not refshim.available(), reason="reference tree n
 def test_oracle_matches_reference_gepinn(name):
     from oracle import autograd_ref as O
     G = GpinnGolden(name)
-    for dtype, tag, tol in ((torch.float64, "64", 1e-9), (torch.float32, "32", 2e-5)):
+    # (Poisson2D_ManyArea: the fused path keeps the coefficient columns in float32 as the reference's float32 run does,
+    # poisson.py:251; the reference's float64 run holds them in double: 2e-8)
+    tol64 = 2e-7 if name == "Poisson2D_ManyArea" else 1e-9
+    for dtype, tag, tol in ((torch.float64, "64", tol64), (torch.float32, "32", 2e-5)):
         flat, x = G.embedded(dtype)
         losses, grads, res = O.losses_and_grads(G.desc, flat, x, G.aux(x), seeds=np.eye(3))
         grads = G.back(grads.numpy())

@@ -44,14 +44,14 @@ class GpinnGolden:
     and ``back(g)`` maps a gradient with respect to the embedded parameters to the real ones (chain rule through W1 @ V)."""
 
     def __init__(self, name):
-        from pinnacle_b200 import problems
         self.name = name
         self.g = g = np.load(common.fixture_path("gepinn_" + name))
-        self.spec = problems.gpinn(problems.make(name))
-        self.desc = self.spec.desc
-        assert int(g["kind"]) == self.desc.kind and np.allclose(g["embed"], self.spec.embed)
-        np.testing.assert_allclose(np.asarray(self.desc.consts, dtype=np.float64), g["consts"], rtol=1e-6)
-        self.base = problems.make(name).desc
+        self.embed = np.asarray(g["embed"], dtype=np.float64)
+        # the descriptor as the generator recorded it (problems.gpinn of the live reference object); the fixture carries the aux
+        # columns of its points, so no coefficient tables are needed here
+        self.desc = K.KindDesc(int(g["kind"]), self.embed.shape[1], 1, (3,) * self.embed.shape[1], 3, int(g["n_aux"]),
+                               [float(c) for c in g["consts"]], [int(a) for a in g["aux_sel"]], name=name + "_gepinn")
+        self.base = K.KindDesc(K.KIND_LINEAR, 2, 1, (2, 2), name=name)           # only the layer shapes of the real 2-input net matter
         self.seed = int(g["seed"])
         self.flat64 = common.golden_params(self.base.layer_shapes(), self.seed)
         self.idx = g["idx"]
@@ -62,19 +62,21 @@ class GpinnGolden:
         H = self.base.H
         flat = self.flat64.astype(nd)
         w1 = flat[:2 * H].reshape(H, 2)
-        flat_e = np.concatenate([(w1 @ self.spec.embed.astype(nd)).reshape(-1), flat[2 * H:]]).astype(nd)
+        flat_e = np.concatenate([(w1 @ self.embed.astype(nd)).reshape(-1), flat[2 * H:]]).astype(nd)
         x = self.g["x"].astype(nd)
         x_e = np.concatenate([x, np.zeros((x.shape[0], self.desc.d - 2), nd)], axis=1)
         return torch.as_tensor(flat_e), torch.as_tensor(np.ascontiguousarray(x_e))
 
     def aux(self, x_e):
-        """Aux columns of the embedded rows (source and its input gradient for the sourced LINEAR kinds), or None."""
-        return self.spec.aux(x_e).contiguous() if self.desc.n_aux else None
+        """Aux columns of the fixture's (embedded) rows -- source and its input gradient, or table coefficients -- or None."""
+        if not self.desc.n_aux:
+            return None
+        return torch.as_tensor(np.ascontiguousarray(self.g["aux64"])).to(x_e.dtype)
 
     def back(self, grad_e):
         grad_e = np.asarray(grad_e, dtype=np.float64)
         H, de = self.base.H, self.desc.d
-        w1 = grad_e[..., :de * H].reshape(grad_e.shape[:-1] + (H, de)) @ self.spec.embed.T
+        w1 = grad_e[..., :de * H].reshape(grad_e.shape[:-1] + (H, de)) @ self.embed.T
         return np.concatenate([w1.reshape(grad_e.shape[:-1] + (2 * H,)), grad_e[..., de * H:]], axis=-1)
 
 
