@@ -367,6 +367,33 @@ def make(name: str, **kwargs) -> ProblemSpec:
 GP_DIRECTIONS = np.array([[1.0, 0.0, 1.0, 1.0], [0.0, 1.0, 1.0, -1.0]])     # e0, e1, e0+e1, e0-e1 (include/pinn_b200.h, gPINN kinds)
 
 
+def _gpinn_1d(spec: ProblemSpec) -> ProblemSpec:
+    """One input (Poisson1D): loss terms [r, dr/dx].  The same kind and kernel as the two-input case with the single input
+    direction repeated -- V = [e0, 0, e0, e0] makes every "y" partial vanish identically (u_xy = c22 - c02 - c12 = 0, ...) -- and
+    n_pde = 2, so the third residual the kernel forms is never seeded nor reported."""
+    d = spec.desc
+    sel = list(d.aux_sel)
+    if sel[K.LIN_SEL_CU] >= 0 or sel[K.LIN_SEL_C2] >= 0:
+        raise UnsupportedProblem(f"gPINN: {spec.name} has per-point coefficients (not wired up)")
+    consts = [0.0] * K.PINN_MAX_CONSTS
+    consts[K.LIN_CU], consts[K.LIN_C1], consts[K.LIN_C2] = d.consts[K.LIN_CU], d.consts[K.LIN_C1], d.consts[K.LIN_C2]
+    embed = np.array([[1.0, 0.0, 1.0, 1.0]])
+    if sel[K.LIN_SEL_SRC] < 0:
+        g = KindDesc(K.KIND_GP_LINEAR2, 4, 1, (3, 3, 3, 3), n_pde=2, consts=consts, name=spec.name + "_gepinn")
+        return ProblemSpec(spec.name + "_gepinn", g, list(spec.bbox), None, embed)
+    src_col, base_aux = sel[K.LIN_SEL_SRC], spec.aux_fn
+
+    def aux_fn(x):
+        with torch.enable_grad():
+            xr = x[:, :1].detach().to(torch.float64).clone().requires_grad_(True)
+            f = base_aux(xr)[:, src_col:src_col + 1]
+            (gf,) = torch.autograd.grad(f.sum(), xr)
+        return torch.cat([f.detach(), gf], dim=1).to(dtype=x.dtype, device=x.device)
+
+    g = KindDesc(K.KIND_GP_LINEAR2, 4, 1, (3, 3, 3, 3), n_pde=2, n_aux=2, consts=consts, aux_sel=[0, 1, -1], name=spec.name + "_gepinn")
+    return ProblemSpec(spec.name + "_gepinn", g, list(spec.bbox), aux_fn, embed)
+
+
 def gpinn(spec: ProblemSpec) -> ProblemSpec:
     """The gPINN form of a problem (src/pde/baseclass.py:151-180 ``use_gepinn``; benchmark.py:91-92 ``--method gepinn``): loss
     terms [r, dr/dx_0, dr/dx_1].  Covered: one-output problems in two inputs whose residual is Burgers1D's or a LINEAR one with
@@ -374,9 +401,11 @@ def gpinn(spec: ProblemSpec) -> ProblemSpec:
     table-look-up coefficients that are constants to the reference's autograd (Poisson2D_ManyArea): the mixed
     third-order partials come from order-3 jets along four directions.  Anything else raises."""
     d = spec.desc
+    if d.d == 1 and d.m == 1 and d.n_pde == 1 and d.kind == K.KIND_LINEAR:
+        return _gpinn_1d(spec)
     if d.d != 2 or d.m != 1 or d.n_pde != 1:
         raise UnsupportedProblem(f"gPINN: {spec.name} has d={d.d}, m={d.m}, n_pde={d.n_pde}; the fused gPINN kinds cover one-output, "
-                                 "one-residual problems in two inputs (three inputs need 9 jet directions of order 3)")
+                                 "one-residual problems in one or two inputs (three inputs need 9 jet directions of order 3)")
     if d.kind == K.KIND_BURGERS1D:
         g = KindDesc(K.KIND_GP_BURGERS1D, 4, 1, (3, 3, 3, 3), n_pde=3, consts=[d.consts[0]], name=spec.name + "_gepinn")
     elif d.kind == K.KIND_LINEAR:

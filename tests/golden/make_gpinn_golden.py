@@ -24,7 +24,7 @@ import refshim  # noqa: E402
 from golden import common  # noqa: E402
 from pinnacle_b200 import problems  # noqa: E402
 
-CASES = ["Poisson2D_Classic", "Burgers1D", "Wave1D", "Helmholtz2D", "PoissonBoltzmann2D", "Poisson2D_ManyArea"]
+CASES = ["Poisson2D_Classic", "Burgers1D", "Wave1D", "Helmholtz2D", "PoissonBoltzmann2D", "Poisson2D_ManyArea", "Poisson1D"]
 
 
 def run(name):
@@ -34,14 +34,14 @@ def run(name):
     pde.use_gepinn()
     spec = problems.describe_reference(pde)               # kind GP_*, d = 4 directions, embed = direction matrix
     desc = spec.desc
-    assert spec.embed is not None and desc.n_pde == 3
+    assert spec.embed is not None and desc.n_pde == 1 + base.d
     seed = common.class_seed("gepinn_" + name)
     shapes = base.layer_shapes()
     flat64 = common.golden_params(shapes, seed)
     idx = common.golden_index_set(shapes, seed)
     probes = common.probe_vectors(base.n_params, seed)
     x64 = spec.sample(common.N_POINTS, seed=seed, dtype=np.float64).astype(np.float32).astype(np.float64)
-    x_e = np.concatenate([x64, np.zeros((x64.shape[0], desc.d - 2))], axis=1)
+    x_e = np.concatenate([x64, np.zeros((x64.shape[0], desc.d - base.d))], axis=1)
     aux64 = spec.aux(torch.as_tensor(x_e)).numpy() if desc.n_aux else np.zeros((x64.shape[0], 0))
     out = dict(x=x64, seed=np.int64(seed), idx=idx, kind=np.int64(desc.kind), consts=np.asarray(desc.consts, dtype=np.float64),
                embed=np.asarray(spec.embed, dtype=np.float64), n_aux=np.int64(desc.n_aux), aux_sel=np.asarray(desc.aux_sel),
@@ -49,7 +49,7 @@ def run(name):
     for tag, tdt, ndt in (("64", torch.float64, np.float64), ("32", torch.float32, np.float32)):
         torch.set_default_dtype(tdt)
         dde.config.set_default_float("float64" if tag == "64" else "float32")
-        net = dde.nn.FNN([2] + [base.H] * base.L + [1], "tanh", "Glorot normal")
+        net = dde.nn.FNN([base.d] + [base.H] * base.L + [1], "tanh", "Glorot normal")
         flat = torch.as_tensor(flat64.astype(ndt))
         off = 0
         with torch.no_grad():
@@ -57,7 +57,7 @@ def run(name):
                 p.copy_(flat[off:off + p.numel()].view_as(p))
                 off += p.numel()
         losses, grads, res = refshim.reference_losses_and_grads(pde, net, x64.astype(ndt))
-        assert res.shape[1] == 3
+        assert res.shape[1] == desc.n_pde
         out[f"loss{tag}"] = losses.numpy()
         out[f"resid{tag}"] = res.numpy()
         out[f"grad{tag}"] = grads.numpy()[:, idx]

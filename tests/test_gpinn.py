@@ -11,7 +11,7 @@ import refshim
 from util import GpinnGolden, assert_parity, oracle_backend
 
 CASES = ["Poisson2D_Classic", "Burgers1D"]
-GOLDEN_CASES = CASES + ["Wave1D", "Helmholtz2D", "PoissonBoltzmann2D", "Poisson2D_ManyArea"]      # tests/golden/gepinn_<Class>.npz
+GOLDEN_CASES = CASES + ["Wave1D", "Helmholtz2D", "PoissonBoltzmann2D", "Poisson2D_ManyArea", "Poisson1D"]      # tests/golden/gepinn_<Class>.npz
 needs_ref = pytest.mark.skipif(not refshim.available(), reason="reference tree not available")
 
 
@@ -24,7 +24,7 @@ def test_oracle_matches_reference_gepinn(name):
     tol64 = 2e-7 if name == "Poisson2D_ManyArea" else 1e-9
     for dtype, tag, tol in ((torch.float64, "64", tol64), (torch.float32, "32", 2e-5)):
         flat, x = G.embedded(dtype)
-        losses, grads, res = O.losses_and_grads(G.desc, flat, x, G.aux(x), seeds=np.eye(3))
+        losses, grads, res = O.losses_and_grads(G.desc, flat, x, G.aux(x), seeds=np.eye(G.desc.n_pde))
         grads = G.back(grads.numpy())
         assert_parity(res.numpy(), G.g[f"resid{tag}"], "residual", tol)
         assert_parity(losses.numpy(), G.g[f"loss{tag}"], "loss", tol)
@@ -41,19 +41,19 @@ def test_device_math_matches_reference_gepinn(harness_lib, name):
     aux = G.aux(x)
     auxn = None if aux is None else np.ascontiguousarray(aux.numpy())
     flat, x = flat.numpy(), x.numpy()
-    n, P = x.shape[0], desc.n_params
-    seeds = np.eye(3, dtype=np.float32)
-    grad = np.zeros((3, P))
+    n, P, S = x.shape[0], desc.n_params, desc.n_pde
+    seeds = np.eye(S, dtype=np.float32)
+    grad = np.zeros((S, P))
     loss = np.zeros(3)
-    resid = np.zeros((n, 3), np.float32)
+    resid = np.zeros((n, S), np.float32)
     cd = desc.to_c()
     vp = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
-    rc = harness_lib.harness_run(ctypes.byref(cd), vp(flat), vp(x), vp(auxn), ctypes.c_longlong(n), ctypes.c_double(1.0 / n), vp(seeds), 3,
+    rc = harness_lib.harness_run(ctypes.byref(cd), vp(flat), vp(x), vp(auxn), ctypes.c_longlong(n), ctypes.c_double(1.0 / n), vp(seeds), S,
                                  vp(grad), vp(loss), vp(resid))
     assert rc == 0
     grad = G.back(grad)
     assert_parity(resid, G.g["resid64"], "residual")
-    assert_parity(loss, G.g["loss64"], "loss")
+    assert_parity(loss[:S], G.g["loss64"], "loss")
     assert_parity(grad[:, G.idx], G.g["grad64"], "grad")
     assert_parity(grad @ G.probes.T, G.g["gproj64"], "grad projections")
 
@@ -71,7 +71,7 @@ def test_patched_gepinn_model_matches_unpatched_reference_step(name):
     pde = refshim.construct(name)
     pde.use_gepinn()
     pde.training_points(domain=96, boundary=32, **({"initial": 32} if hasattr(pde, "num_initial_points") else {}))
-    net = dde.nn.FNN([2] + [100] * 5 + [1], "tanh", "Glorot normal").float()
+    net = dde.nn.FNN([pde.input_dim] + [100] * 5 + [1], "tanh", "Glorot normal").float()
     with torch.no_grad():
         for lin in net.linears:
             lin.bias.normal_(0, 0.1)
@@ -81,7 +81,8 @@ def test_patched_gepinn_model_matches_unpatched_reference_step(name):
     net.auxiliary_vars = None
     x = model.data.train_x
     _, ref_losses = model.outputs_losses_train(x, None)
-    assert ref_losses.shape[0] == 3 + len(model.data.bcs)
+    n_terms = 1 + pde.input_dim
+    assert ref_losses.shape[0] == n_terms + len(model.data.bcs)
     net.zero_grad()
     ref_losses.sum().backward()
     ref_grads = [p.grad.clone() for p in net.parameters()]
@@ -94,7 +95,7 @@ def test_patched_gepinn_model_matches_unpatched_reference_step(name):
     try:
         with oracle_backend():
             enable_fused(model)
-            assert model.fused_core.op.desc.n_pde == 3 and model.fused_self_check < 1e-5
+            assert model.fused_core.op.desc.n_pde == n_terms and model.fused_self_check < 1e-5
             _, new_losses = model.outputs_losses_train(x, None)
             net.zero_grad()
             new_losses.sum().backward()
@@ -102,7 +103,7 @@ def test_patched_gepinn_model_matches_unpatched_reference_step(name):
             for p, rg in zip(net.parameters(), ref_grads):
                 assert (p.grad - rg).norm() <= 2e-5 * max(float(rg.norm()), 1e-12), (name, float((p.grad - rg).norm()), float(rg.norm()))
             model._train_step(x, None, None)
-            assert model.opt.losses.shape[0] == pde.num_loss and torch.isfinite(model.opt.losses[:3]).all()   # (a boundary term without rows is nan in the reference too)
+            assert model.opt.losses.shape[0] == pde.num_loss and torch.isfinite(model.opt.losses[:n_terms]).all()   # (a boundary term without rows is nan in the reference too)
     finally:
         fused.FusedPDEResidual.__init__ = orig
 

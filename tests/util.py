@@ -49,9 +49,10 @@ class GpinnGolden:
         self.embed = np.asarray(g["embed"], dtype=np.float64)
         # the descriptor as the generator recorded it (problems.gpinn of the live reference object); the fixture carries the aux
         # columns of its points, so no coefficient tables are needed here
-        self.desc = K.KindDesc(int(g["kind"]), self.embed.shape[1], 1, (3,) * self.embed.shape[1], 3, int(g["n_aux"]),
+        self.desc = K.KindDesc(int(g["kind"]), self.embed.shape[1], 1, (3,) * self.embed.shape[1], int(g["loss64"].shape[0]), int(g["n_aux"]),
                                [float(c) for c in g["consts"]], [int(a) for a in g["aux_sel"]], name=name + "_gepinn")
-        self.base = K.KindDesc(K.KIND_LINEAR, 2, 1, (2, 2), name=name)           # only the layer shapes of the real 2-input net matter
+        self.base_d = int(g["base_d"])
+        self.base = K.KindDesc(K.KIND_LINEAR, self.base_d, 1, (2,) * self.base_d, name=name)   # only the layer shapes of the real net matter
         self.seed = int(g["seed"])
         self.flat64 = common.golden_params(self.base.layer_shapes(), self.seed)
         self.idx = g["idx"]
@@ -61,10 +62,11 @@ class GpinnGolden:
         nd = np.float32 if dtype == torch.float32 else np.float64
         H = self.base.H
         flat = self.flat64.astype(nd)
-        w1 = flat[:2 * H].reshape(H, 2)
-        flat_e = np.concatenate([(w1 @ self.embed.astype(nd)).reshape(-1), flat[2 * H:]]).astype(nd)
+        bd = self.base_d
+        w1 = flat[:bd * H].reshape(H, bd)
+        flat_e = np.concatenate([(w1 @ self.embed.astype(nd)).reshape(-1), flat[bd * H:]]).astype(nd)
         x = self.g["x"].astype(nd)
-        x_e = np.concatenate([x, np.zeros((x.shape[0], self.desc.d - 2), nd)], axis=1)
+        x_e = np.concatenate([x, np.zeros((x.shape[0], self.desc.d - bd), nd)], axis=1)
         return torch.as_tensor(flat_e), torch.as_tensor(np.ascontiguousarray(x_e))
 
     def aux(self, x_e):
@@ -77,7 +79,7 @@ class GpinnGolden:
         grad_e = np.asarray(grad_e, dtype=np.float64)
         H, de = self.base.H, self.desc.d
         w1 = grad_e[..., :de * H].reshape(grad_e.shape[:-1] + (H, de)) @ self.embed.T
-        return np.concatenate([w1.reshape(grad_e.shape[:-1] + (2 * H,)), grad_e[..., de * H:]], axis=-1)
+        return np.concatenate([w1.reshape(grad_e.shape[:-1] + (self.base_d * H,)), grad_e[..., de * H:]], axis=-1)
 
 
 def rel_l2(a, b):
