@@ -75,6 +75,15 @@ class _LazyArray:
     def materialized(self) -> bool:
         return self._val is not None
 
+    def __getattr__(self, name):
+        # anything else an ndarray offers (.T, .astype, .reshape, .mean, ...): compute the outputs and delegate
+        if name.startswith("__") or name in ("_owner", "_val"):
+            raise AttributeError(name)
+        return getattr(self._get(), name)
+
+    def __iter__(self):
+        return iter(self._get())
+
 
 class LazyOutputs:
     """Network outputs for every row of ``inputs`` at the CURRENT weights, computed only on demand.

@@ -34,6 +34,7 @@ def test_lazy_outputs_keep_the_weights_of_the_evaluation_and_cost_nothing_unread
     assert arr.materialized and evaluate.D2H_BYTES["outputs"] == before + 257 * 2 * 4
     np.testing.assert_allclose(want - arr, np.zeros_like(want), atol=1e-6)      # ndarray arithmetic (deepxde metrics)
     np.testing.assert_allclose(arr[3:5], want[3:5], rtol=1e-5, atol=1e-6)
+    assert arr.T.shape == (2, 257) and arr.astype(np.float64).dtype == np.float64 and abs(float(arr.mean()) - float(want.mean())) < 1e-6
 
 
 def test_topk_residual_selects_like_the_reference_rar_loop():
