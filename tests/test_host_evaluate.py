@@ -174,3 +174,40 @@ def test_fused_rar_wrapper_adds_the_same_anchor_as_the_reference_loop():
     a, b = ref_model.data.anchors, model.data.anchors
     assert a.shape == b.shape == (3, 2)
     np.testing.assert_array_equal(np.sort(a, axis=0), np.sort(b, axis=0))
+
+
+def test_staged_point_sets_are_an_lru_of_three_and_drop_their_term_ops():
+    """_StepCore.stage keeps the last three host arrays resident; a fourth evicts the oldest together with the boundary-term
+    ops built on it; re-staging a resident array is a switch (no new generation)."""
+    from pinnacle_b200 import fused, problems
+    from pinnacle_b200.solver import FusedPDESolver, ValueBC
+    spec = problems.make("Burgers1D")
+    torch.manual_seed(0)
+    net = FNN([2] + [100] * 5 + [1])
+    xb = spec.sample(16, seed=1)
+    terms = [ValueBC(0, 16, 0, np.zeros((16, 1), np.float32))]
+    orig = fused.FusedPDEResidual.__init__
+
+    def init_cpu(self, spec, H=100, L=5, policy="auto", device=None, group=None, check_library=True):
+        orig(self, spec, H, L, policy, "cpu", group, False)
+
+    fused.FusedPDEResidual.__init__ = init_cpu
+    try:
+        with oracle_backend():
+            s = FusedPDESolver(spec, net, spec.sample(40, seed=2), xb, terms, device="cpu").compile(torch.optim.Adam(net.parameters(), 1e-3))
+            arrays = [np.vstack([xb, spec.sample(40, seed=10 + i)]).astype(np.float32) for i in range(4)]
+            gens = []
+            for a in arrays[:3]:
+                s.outputs_losses_train(a)
+                gens.append(s.core.generation)
+            assert len(set(gens)) == 3 and len(s.core._staged) == 3
+            assert {k[0] for k in s.core._value_ops} == set(gens)
+            s.outputs_losses_train(arrays[1])                       # resident: switched, not re-staged
+            assert s.core.generation == gens[1] and len(s.core._staged) == 3
+            s.outputs_losses_train(arrays[3])                       # evicts the least recently used (arrays[0])
+            assert len(s.core._staged) == 3 and gens[0] not in {k[0] for k in s.core._value_ops}
+            l_a = s.outputs_losses_train(arrays[0])[1]              # comes back as a new generation with the same losses
+            s2 = FusedPDESolver(spec, net, arrays[0][16:], xb, terms, device="cpu").compile(torch.optim.Adam(net.parameters(), 1e-3))
+            np.testing.assert_allclose(l_a.detach().numpy(), s2.outputs_losses_train()[1].detach().numpy(), rtol=1e-6)
+    finally:
+        fused.FusedPDEResidual.__init__ = orig
