@@ -12,7 +12,7 @@ from typing import Optional
 
 import torch
 
-from .kinds import CKindDesc, KindDesc
+from .kinds import CKindDesc, CRegion, KindDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # PINN_B200_LIB: an alternative build of the same library (what-if builds under variants/, see scripts/whatif_times.sh)
@@ -23,6 +23,7 @@ EXPORTS = (
     "pinn_last_launch_count", "pinn_ffma_peak_tflops", "pinn_last_error", "pinn_build_info", "pinn_debug_umma_gemm", "pinn_set_impl", "pinn_has_tensor_core_kernel",
     "pinn_selected_impl", "pinn_effective_channels", "pinn_set_laplacian_collapse",
     "pinn_adam_step", "pinn_optim_scratch_floats", "pinn_grad_stats", "pinn_lra_combine", "pinn_multiadam_step",
+    "pinn_sample_points",
 )
 
 
@@ -87,6 +88,8 @@ def load() -> ctypes.CDLL:
     lib.pinn_lra_combine.restype = ctypes.c_int
     lib.pinn_selected_impl.argtypes = [P]
     lib.pinn_selected_impl.restype = ctypes.c_int
+    lib.pinn_sample_points.argtypes = [V, I64, I64, ctypes.POINTER(CRegion), ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, V]
+    lib.pinn_sample_points.restype = ctypes.c_int
     lib.pinn_last_error.argtypes = []
     lib.pinn_last_error.restype = ctypes.c_char_p
     lib.pinn_build_info.argtypes = []
@@ -398,3 +401,16 @@ def fwd_bwd_linear(desc: KindDesc, params: torch.Tensor, x: torch.Tensor, aux: O
                                      _stream_ptr(x.device))
     _check(rc, "pinn_fwd_bwd_linear")
     return out
+
+
+def sample_points(x: torch.Tensor, region: CRegion, key: int, draw: int, first_row: int = 0):
+    """pinn_sample_points: fill the rows of the device array ``x`` [n, ld] (its first ``region.d`` columns) with points
+    first_row .. first_row + n of the uniform stream (key, draw) over ``region`` -- one launch, nothing crosses PCIe."""
+    _req(x, "x")
+    if x.dim() != 2 or x.shape[1] < region.d:
+        raise FusedOpError(f"sample_points: x must be [n, >= {region.d}], got {tuple(x.shape)}")
+    with torch.cuda.device(x.device):
+        rc = load().pinn_sample_points(_ptr(x), x.shape[1], x.shape[0], ctypes.byref(region), int(key) & 0xFFFFFFFFFFFFFFFF, int(draw),
+                                       int(first_row), _stream_ptr(x.device))
+    _check(rc, "pinn_sample_points")
+    return x

@@ -72,6 +72,7 @@ def build(force=False, jobs=None, verbose=False):
     units.append((os.path.join(HERE, "pinn_api.cu"), os.path.join(BUILD, "pinn_api.o")))
     units.append((os.path.join(HERE, "pinn_umma_test.cu"), os.path.join(BUILD, "pinn_umma_test.o")))
     units.append((os.path.join(HERE, "pinn_optim.cu"), os.path.join(BUILD, "pinn_optim.o")))
+    units.append((os.path.join(HERE, "pinn_sample.cu"), os.path.join(BUILD, "pinn_sample.o")))
     todo = [(s, o) for s, o in units if force or _newer(o, deps + [s])]
     if todo:
         with cf.ThreadPoolExecutor(max_workers=jobs or os.cpu_count()) as ex:

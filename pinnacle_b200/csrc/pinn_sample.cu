@@ -1,0 +1,184 @@
+// pinn_sample.cu -- collocation points drawn on the device (`PDEPointResampler` on device).
+//
+// The reference redraws its residual points on the host: dde.callbacks.PDEPointResampler (deepxde/callbacks.py:540-575) calls
+// PDE.resample_train_points (deepxde/data/pde.py:186-193), which re-runs geom.random_points(num_domain, "pseudo") --
+// np.random.rand scaled into the bounding box (geometry_nd.py Hypercube.random_points) with rejection of the points that fall
+// into a subtracted shape (csg.py CSGDifference.random_points) -- and the new float32 array is then uploaded by the next
+// train step.  At 16 Mi rows that is a few hundred ms of numpy and a 200 MB copy per resample.  Here one launch writes the new
+// rows straight into the staged device array.
+//
+// Every row is a pure function of (key, draw, global row index): Philox4x32-10 on the counter (row_lo, row_hi, attempt,
+// block | draw << 8) gives four 32-bit words = four coordinates of block `block` (coordinates 4*block .. 4*block+3); a point
+// that falls into a hole is redrawn with attempt + 1.  No generator state and no global atomics: the rows a rank draws do not
+// depend on how the set is sharded, and the oracle (oracle/sample_ref.py) restates the same integer and float32 arithmetic bit
+// for bit.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "../../include/pinn_b200.h"
+
+namespace pinn {
+void set_error_string(const std::string& s);   // pinn_api.cu
+}
+
+namespace {
+
+constexpr int kRows = 256;          // rows per CTA = threads per CTA
+constexpr int kMaxAttempts = 64;    // a row still inside a hole after this many draws keeps its last draw (p < hole_fraction^64)
+
+struct U4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = U4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+__device__ __forceinline__ uint32_t word(const U4& v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
+
+// One draw: coordinates p[0..d) of global row g, attempt `attempt`, and whether the point lies in a hole.
+__device__ __forceinline__ bool draw_point(const pinn_region& R, uint64_t g, uint32_t attempt, uint32_t draw, uint32_t k0, uint32_t k1,
+                                           float (&p)[PINN_MAX_DIM]) {
+  const int d = R.d;
+#pragma unroll
+  for (int b = 0; b < (PINN_MAX_DIM + 3) / 4; ++b) {
+    if (4 * b >= d) break;
+    const U4 v = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), attempt, (uint32_t)b | (draw << 8)}, k0, k1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = 4 * b + j;
+      if (c < PINN_MAX_DIM && c < d) {
+        const float u = __fmul_rn((float)(word(v, j) >> 8), 5.9604644775390625e-08f);   // 24 bits -> [0, 1), exact
+        p[c] = __fadd_rn(__fmul_rn(u, __fsub_rn(R.hi[c], R.lo[c])), R.lo[c]);
+      }
+    }
+  }
+  bool in_hole = false;
+  for (int h = 0; h < R.n_holes && !in_hole; ++h) {
+    const pinn_hole& H = R.holes[h];
+    const int k = H.n_dims;                                  // 1..3, validated on the host
+    if (H.shape == PINN_HOLE_BALL) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (j < k) {
+          const float dj = __fsub_rn(p[j], H.a[j]);
+          s = __fadd_rn(s, __fmul_rn(dj, dj));
+        }
+      in_hole = s <= __fmul_rn(H.b[0], H.b[0]);
+    } else {
+      bool all = true;
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (j < k) all = all && p[j] >= H.a[j] && p[j] <= H.b[j];
+      in_hole = all;
+    }
+  }
+  return in_hole;
+}
+
+// x[row][0..d) for rows [0, n_rows).  A CTA owns kRows consecutive rows and stages them in shared memory.  Round 0: every
+// thread draws its own row.  The rows that fell into a hole are collected in a shared list and redrawn by the FIRST threads
+// of the CTA in the next round (attempt + 1), and so on: a warp never waits for its slowest lane's rejections, the cost of a
+// redraw round is proportional to the rows still pending (13 % of the rows need a second attempt on the reference's
+// 17-disk domain; done lane by lane that kept every warp busy for its unluckiest row, 3-4 full attempts).  The tile goes
+// out with unit-stride stores when rows are contiguous (ld == d), otherwise only the first d of every ld columns are touched.
+__global__ void __launch_bounds__(kRows) sample_kernel(float* __restrict__ x, int64_t ld, int64_t n_rows, pinn_region R, uint32_t k0, uint32_t k1,
+                                                      uint32_t draw, uint64_t first_row) {
+  __shared__ float tile[kRows * PINN_MAX_DIM];
+  __shared__ int pending[2][kRows];
+  __shared__ int n_pending[2];
+  const int d = R.d;
+  const int t = threadIdx.x;
+  const int64_t row0 = (int64_t)blockIdx.x * kRows;
+  const int64_t left = n_rows - row0;
+  const int rows_here = (int)(left < kRows ? left : kRows);
+  if (t < 2) n_pending[t] = 0;
+  __syncthreads();
+  float p[PINN_MAX_DIM];
+  if (t < rows_here) {
+    const bool rejected = draw_point(R, first_row + (uint64_t)(row0 + t), 0u, draw, k0, k1, p);
+#pragma unroll
+    for (int c = 0; c < PINN_MAX_DIM; ++c)
+      if (c < d) tile[t * d + c] = p[c];
+    if (rejected) pending[0][atomicAdd(&n_pending[0], 1)] = t;
+  }
+  if (R.n_holes > 0) {
+    for (uint32_t attempt = 1; attempt < (uint32_t)kMaxAttempts; ++attempt) {
+      const int cur = (attempt - 1) & 1, nxt = cur ^ 1;
+      __syncthreads();
+      const int n = n_pending[cur];
+      if (n == 0) break;                                     // uniform: read after the barrier
+      if (t < n) {
+        const int r = pending[cur][t];
+        const bool rejected = draw_point(R, first_row + (uint64_t)(row0 + r), attempt, draw, k0, k1, p);
+#pragma unroll
+        for (int c = 0; c < PINN_MAX_DIM; ++c)
+          if (c < d) tile[r * d + c] = p[c];                 // the last draw stays if every attempt is rejected
+        if (rejected) pending[nxt][atomicAdd(&n_pending[nxt], 1)] = r;
+      }
+      __syncthreads();
+      if (t == 0) n_pending[cur] = 0;                        // consumed; it is the next round's output list
+    }
+  }
+  __syncthreads();
+  const int count = rows_here * d;
+  if (ld == d) {
+    float* base = x + row0 * d;
+    for (int i = t; i < count; i += kRows) base[i] = tile[i];
+  } else {
+    for (int i = t; i < count; i += kRows) x[(row0 + i / d) * ld + i % d] = tile[i];
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int pinn_sample_points(float* x, int64_t ld, int64_t n_rows, const pinn_region* region, uint64_t key, uint32_t draw, uint64_t first_row,
+                       void* stream) {
+  if (!x || !region || n_rows < 0 || ld < 1) {
+    pinn::set_error_string("pinn_sample_points: null buffer, negative row count or ld < 1");
+    return 1;
+  }
+  const pinn_region& R = *region;
+  if (R.d < 1 || R.d > PINN_MAX_DIM || ld < R.d || R.n_holes < 0 || R.n_holes > PINN_MAX_HOLES || draw >= (1u << 24)) {
+    pinn::set_error_string("pinn_sample_points: need 1 <= d <= PINN_MAX_DIM <= ld, at most PINN_MAX_HOLES holes and draw < 2^24");
+    return 1;
+  }
+  for (int c = 0; c < R.d; ++c)
+    if (!(R.hi[c] >= R.lo[c])) {
+      pinn::set_error_string("pinn_sample_points: empty bounding box (hi < lo or NaN)");
+      return 1;
+    }
+  for (int h = 0; h < R.n_holes; ++h) {
+    const pinn_hole& H = R.holes[h];
+    if ((H.shape != PINN_HOLE_BALL && H.shape != PINN_HOLE_BOX) || H.n_dims < 1 || H.n_dims > 3 || H.n_dims > R.d) {
+      pinn::set_error_string("pinn_sample_points: a hole is a ball or a box over the first 1..3 coordinates");
+      return 1;
+    }
+  }
+  if (n_rows == 0) return 0;
+  const int64_t blocks = (n_rows + kRows - 1) / kRows;
+  if (blocks > 0x7fffffffLL) {
+    pinn::set_error_string("pinn_sample_points: more than 2^31 * 256 rows in one call");
+    return 1;
+  }
+  sample_kernel<<<(unsigned)blocks, kRows, 0, (cudaStream_t)stream>>>(x, ld, n_rows, R, (uint32_t)key, (uint32_t)(key >> 32), draw, first_row);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    pinn::set_error_string(std::string("pinn_sample_points: ") + cudaGetErrorString(e));
+    return 2;
+  }
+  return 0;
+}
+
+}  // extern "C"

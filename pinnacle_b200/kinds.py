@@ -80,6 +80,23 @@ class CKindDesc(ctypes.Structure):
     ]
 
 
+PINN_MAX_HOLES = 32
+HOLE_BALL, HOLE_BOX = 0, 1
+
+
+class CHole(ctypes.Structure):
+    """ctypes mirror of ``struct pinn_hole``."""
+
+    _fields_ = [("shape", ctypes.c_int32), ("n_dims", ctypes.c_int32), ("a", ctypes.c_float * 3), ("b", ctypes.c_float * 3)]
+
+
+class CRegion(ctypes.Structure):
+    """ctypes mirror of ``struct pinn_region``: the sampling region of ``pinn_sample_points``."""
+
+    _fields_ = [("d", ctypes.c_int32), ("n_holes", ctypes.c_int32), ("lo", ctypes.c_float * PINN_MAX_DIM), ("hi", ctypes.c_float * PINN_MAX_DIM),
+                ("holes", CHole * PINN_MAX_HOLES)]
+
+
 @dataclass
 class KindDesc:
     kind: int

@@ -347,6 +347,38 @@ class _StepCore:
             self._value_ops = {k: v for k, v in self._value_ops.items() if k[0] != old["generation"]}
 
 
+    def redraw_domain_rows(self, inputs, n_bc: int, n_domain: int, region, key: int, draw: int):
+        """Overwrite the LAST ``n_domain`` residual rows of the staged point set ``inputs`` (deepxde keeps the interior points
+        at the end of ``train_x_all``: data/pde.py:228-243, :312-321) with rows 0..n_domain of the uniform stream (key, draw)
+        over ``region``, on the device, and re-evaluate the per-point aux columns.  Tensors are updated in place: captured
+        CUDA graphs and the boundary-term ops of the set stay valid.  Sharded sets: every rank draws the rows of its own shard
+        (a row is a function of its global index, not of the rank count)."""
+        from .fused import shard_bounds
+        inputs = inputs if isinstance(inputs, torch.Tensor) else np.asarray(inputs)
+        self.stage(inputs, n_bc)
+        if not self.cache_points:
+            raise capi.FusedOpError("redraw_domain_rows: needs cache_points=True (the rows live in the staged set)")
+        ent = self._staged[self._key]
+        op = self.op
+        x, n_global = ent["x"], int(ent["n_global"])
+        if not 0 < n_domain <= n_global:
+            raise capi.FusedOpError(f"redraw_domain_rows: {n_domain} domain rows of {n_global} residual rows")
+        beg, end = (0, n_global)
+        if self.n_global is not None:
+            if op.world > 1:
+                raise capi.FusedOpError("redraw_domain_rows: rows handed over per rank (n_global=...) carry no global index")
+        elif op.world > 1:
+            beg, end = shard_bounds(n_global, op.rank, op.world)
+        if x.shape[0] != end - beg:
+            raise capi.FusedOpError("redraw_domain_rows: staged rows do not match the shard bounds")
+        g0 = max(beg, n_global - n_domain)
+        if g0 < end:
+            capi.sample_points(x[g0 - beg:end - beg], region.to_c(), key, draw, g0 - (n_global - n_domain))
+        if ent["aux"] is not None:
+            ent["aux"].copy_(op.spec.aux(x).to(torch.float32))
+        op.stats["device_redraws"] = op.stats.get("device_redraws", 0) + 1
+
+
 class FusedPDESolver:
     """Reference-free front end with the reference's step semantics (model.py:258-323).
 

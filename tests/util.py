@@ -133,15 +133,35 @@ def oracle_fwd_bwd_linear(desc, params, x, aux, seeds, out=None):
     return res
 
 
+def region_holes(region_c):
+    """(shape, a, b) tuples of a ctypes pinn_region, as oracle/sample_ref.py takes them."""
+    out = []
+    for i in range(region_c.n_holes):
+        h = region_c.holes[i]
+        out.append((int(h.shape), [h.a[j] for j in range(h.n_dims)], [h.b[j] for j in range(h.n_dims if h.shape == 1 else 1)]))
+    return out
+
+
+def oracle_sample_points(x, region_c, key, draw, first_row=0):
+    """Stand-in for capi.sample_points on CPU tensors: the rows the kernel would write, from oracle/sample_ref.py."""
+    from oracle import sample_ref as S
+    d = region_c.d
+    rows = S.sample_points(x.shape[0], [region_c.lo[j] for j in range(d)], [region_c.hi[j] for j in range(d)], region_holes(region_c),
+                           key=int(key), draw=int(draw), first_row=int(first_row))
+    x[:, :d] = torch.from_numpy(rows)
+    return x
+
+
 class oracle_backend:
-    """Context manager swapping pinnacle_b200.fused's backend for the oracle (CPU tests only)."""
+    """Context manager swapping pinnacle_b200.fused's backend (and the device point sampler) for the oracle (CPU tests only)."""
 
     def __enter__(self):
-        from pinnacle_b200 import fused
-        self._saved = (fused._backend_fwd, fused._backend_fwd_bwd, fused._backend_fwd_bwd_linear)
+        from pinnacle_b200 import capi, fused
+        self._saved = (fused._backend_fwd, fused._backend_fwd_bwd, fused._backend_fwd_bwd_linear, capi.sample_points)
         fused._backend_fwd, fused._backend_fwd_bwd, fused._backend_fwd_bwd_linear = oracle_fwd, oracle_fwd_bwd, oracle_fwd_bwd_linear
+        capi.sample_points = oracle_sample_points
         return self
 
     def __exit__(self, *a):
-        from pinnacle_b200 import fused
-        fused._backend_fwd, fused._backend_fwd_bwd, fused._backend_fwd_bwd_linear = self._saved
+        from pinnacle_b200 import capi, fused
+        fused._backend_fwd, fused._backend_fwd_bwd, fused._backend_fwd_bwd_linear, capi.sample_points = self._saved
