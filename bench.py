@@ -424,7 +424,7 @@ def run_fused(args):
         torch.cuda.empty_cache()
         extra = {}
         for key, fn, n_tot in (("configs[4] strong", measure_c5, 1 << 24), ("configs[2] strong", measure_c3, 1 << 20),
-                               ("configs[3] strong", measure_c4, 1 << 20)):
+                               ("configs[3] strong", measure_c4, 1 << 20), ("redraw of the residual points", measure_redraw, 1 << 24)):
             try:
                 extra[key] = fn(n_tot, 5, 3, dev, world, rank, local_rank)
             except Exception as e:  # noqa: BLE001
@@ -620,6 +620,43 @@ def measure_c3(N, steps, warmup, dev, world, rank, local_rank):
                    "parallelism": f"dp{world} over collocation points", "l2": "inputs larger than L2 at 1 GPU; no flush between steps",
                    "cuda_graph": graphed},
         "clocks": clocks, "loss_weights_after": weights_after, "losses_after": losses}
+
+
+def measure_redraw(total_points, steps, warmup, dev, world, rank, local_rank):
+    """PDEPointResampler's redraw (deepxde/callbacks.py:563-568) on the device: `total_points` rows x 3 of Heat2D_ComplexGeometry's
+    domain (rectangle minus 17 disks, times the time interval) and of its plain bounding box, split over the ranks by row range (a
+    row is a function of its global index: no exchange), one pinn_sample_points launch per rank, in place.  CUDA events, max over
+    ranks."""
+    import torch.distributed as dist
+    from pinnacle_b200 import capi
+    from pinnacle_b200.fused import shard_bounds
+    from pinnacle_b200.resample import Region
+    lo, hi = (-8.0, -12.0, 0.0), (8.0, 12.0, 3.0)
+    disks = [(0, (cx, cy), (1.0,)) for cx, cy in ((-4, -3), (4, -3), (-4, 3), (4, 3), (-4, -9), (4, -9), (-4, 9), (4, 9), (0, 0), (0, 6), (0, -6))]
+    disks += [(0, (cx, cy), (0.4,)) for cx, cy in ((-3.2, -6), (-3.2, 6), (3.2, -6), (3.2, 6), (-3.2, 0), (3.2, 0))]
+    beg, end = shard_bounds(total_points, rank, world)
+    x = torch.empty((end - beg, 3), dtype=torch.float32, device=dev)
+    out = {"rows": total_points, "bytes_written": total_points * 12}
+    for tag, reg in (("box_minus_17_disks_ms", Region(lo, hi, disks)), ("plain_box_ms", Region(lo, hi))):
+        c = reg.to_c()
+        for i in range(max(warmup, 3)):
+            capi.sample_points(x, c, 7, i, beg)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev[0].record()
+        for i in range(steps):
+            capi.sample_points(x, c, 7, 100 + i, beg)
+        ev[1].record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ev[0].elapsed_time(ev[1]) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[tag] = float(t.item())
+    out["plain_box_gbs_written"] = out["bytes_written"] / (out["plain_box_ms"] * 1e-3) / 1e9
+    out["note"] = "the reference's host redraw of the same 16 Mi rows: 0.69 s (box) / 17.9 s (17 disks) of numpy + a 201 MB upload (profiles/r2_resample.md)"
+    return out
 
 
 def measure_c4(total_points, steps, warmup, dev, world, rank, local_rank):

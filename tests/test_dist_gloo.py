@@ -209,3 +209,68 @@ def test_two_rank_gradient_rows_match_single_process():
         assert stats["allreduce_calls"] == 2                    # one for the loss rows, one for the linear rows
     assert np.array_equal(res[0][4], res[1][4])                 # ranks agree bit for bit => replicated NTK weights stay in lock-step
     assert np.array_equal(res[0][1], res[1][1])
+
+
+def _redraw_worker(rank, world, port, n, n_bc, n_dom, q):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pinnacle_b200 import fused, problems
+        from pinnacle_b200.nn import FNN
+        from pinnacle_b200.resample import Region
+        from pinnacle_b200.solver import _StepCore
+        from util import oracle_backend
+        torch.manual_seed(0)
+        torch.set_num_threads(2)
+        spec = problems.make("PoissonBoltzmann2D")
+        net = FNN([2] + [100] * 5 + [1])
+        orig = fused.FusedPDEResidual.__init__
+
+        def init_cpu(self, spec, H=100, L=5, policy="auto", device=None, group=None, check_library=True):
+            orig(self, spec, H, L, policy, "cpu", group, False)
+
+        fused.FusedPDEResidual.__init__ = init_cpu
+        with oracle_backend():
+            core = _StepCore(spec, net, "auto", "cpu", None, True)
+            X = spec.sample(n_bc + n, seed=6).astype(np.float32).copy()
+            core.stage(X, n_bc)
+            region = Region(spec.bbox[0::2], spec.bbox[1::2], [(0, (0.0, 0.0), (0.4,))])
+            core.redraw_domain_rows(X, n_bc, n_dom, region, key=21, draw=3)
+            params = [t for lin in net.linears for t in (lin.weight, lin.bias)]
+            losses = core.op.losses(params)
+            q.put((rank, core.op.x.numpy().copy(), core.op.aux.numpy().copy(), losses.detach().numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_redraw_draws_the_rows_one_rank_would():
+    """Sharded residual rows, device redraw (oracle standing in for the kernel): the two shards put together are the rows a
+    single process draws -- a row is a function of its global index -- and the all-reduced loss is the single-process loss."""
+    from oracle.sample_ref import sample_points
+    from pinnacle_b200 import problems
+    from pinnacle_b200.fused import shard_bounds
+    n, n_bc, n_dom, world = 301, 17, 250, 2             # rank 0's shard holds kept rows AND redrawn rows
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_redraw_worker, args=(r, world, port, n, n_bc, n_dom, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    spec = problems.make("PoissonBoltzmann2D")
+    X = spec.sample(n_bc + n, seed=6).astype(np.float32)
+    want = X[n_bc:].copy()
+    want[n - n_dom:] = sample_points(n_dom, spec.bbox[0::2], spec.bbox[1::2], [(0, (0.0, 0.0), (0.4,))], key=21, draw=3)
+    got = np.vstack([r[1] for r in res])
+    assert np.array_equal(got, want)
+    for r in res:
+        beg, end = shard_bounds(n, r[0], world)
+        np.testing.assert_allclose(r[2], spec.aux(torch.from_numpy(want[beg:end])).numpy(), rtol=1e-6)
+    np.testing.assert_allclose(res[0][3], res[1][3], rtol=0, atol=0)
