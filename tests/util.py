@@ -11,7 +11,7 @@ from golden import common
 from pinnacle_b200 import kinds as K
 
 GOLDEN_NAMES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(common.GOLDEN_DIR, "*.npz"))
-                      if not os.path.basename(f).startswith(("l2re_", "gepinn_")))   # l2re_*: training runs (test_cuda_l2re.py); gepinn_*: test_gpinn*.py
+                      if not os.path.basename(f).startswith(("l2re_", "gepinn_", "regions")))   # l2re_*: training runs (test_cuda_l2re.py); gepinn_*: test_gpinn*.py; regions: test_resample.py
 
 # Parity tolerances (BASELINE.json north_star: residuals, losses and gradients within 1e-5 relative in fp32)
 RTOL = 1e-5
