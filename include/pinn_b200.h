@@ -194,9 +194,10 @@ int pinn_lra_combine(const float* G, int n_terms, int n_pde, int64_t P, int64_t 
 /* ---- collocation points drawn on the device (replaces the host resampling of dde.callbacks.PDEPointResampler,
  * deepxde/callbacks.py:563-568 -> PDE.resample_train_points, deepxde/data/pde.py:186-193 -> geom.random_points(n, "pseudo")) ----
  *
- * Region = axis-aligned box [lo, hi) in d coordinates minus up to PINN_MAX_HOLES closed holes, each a ball (a = centre,
- * b[0] = radius) or a box (a = low corner, b = high corner) over the FIRST n_dims coordinates: the shapes src/pde builds its
- * domains from (Rectangle / Cuboid / Hypercube minus Disk / Sphere / Rectangle, times a TimeDomain). */
+ * Region = axis-aligned box [lo, hi) in d coordinates, optionally intersected with one closed ball over the first keep_dims
+ * coordinates (keep_dims = 0: none), minus up to PINN_MAX_HOLES closed holes, each a ball (a = centre, b[0] = radius) or a box
+ * (a = low corner, b = high corner) over the FIRST n_dims coordinates: the shapes src/pde builds its domains from (Rectangle /
+ * Cuboid / Hypercube minus Disk / Sphere / Rectangle; HeatND's Hypersphere; times a TimeDomain). */
 #define PINN_MAX_HOLES 32
 enum pinn_hole_shape { PINN_HOLE_BALL = 0, PINN_HOLE_BOX = 1 };
 typedef struct pinn_hole {
@@ -210,13 +211,16 @@ typedef struct pinn_region {
   int32_t n_holes;
   float lo[PINN_MAX_DIM];
   float hi[PINN_MAX_DIM];
+  int32_t keep_dims;                /* 0, or 1..d: points outside the ball below are redrawn */
+  float keep_radius;
+  float keep_center[PINN_MAX_DIM];
   pinn_hole holes[PINN_MAX_HOLES];
 } pinn_region;
 /* x[r][0..d) <- uniform point number first_row + r of the stream (key, draw), r in [0, n_rows); x is a device array with row
  * stride ld >= d floats (columns d..ld are left alone); `region` is a HOST struct, copied into the launch.  Row g of a stream
  * is a pure function of (key, draw, g) -- Philox4x32-10 on the counter (g_lo, g_hi, attempt, block | draw << 8), coordinate
- * 4*block + j = lo + (word_j >> 8) * 2^-24 * (hi - lo) in float32, a point inside a hole redrawn with attempt + 1 (at most 64
- * attempts) -- so ranks that draw disjoint row ranges of the same stream produce the rows one rank would.  draw < 2^24. */
+ * 4*block + j = lo + (word_j >> 8) * 2^-24 * (hi - lo) in float32, a point outside the kept ball or inside a hole redrawn with
+ * attempt + 1 (at most 256 attempts) -- so ranks that draw disjoint row ranges of the same stream produce the rows one rank would.  draw < 2^24. */
 int pinn_sample_points(float* x, int64_t ld, int64_t n_rows, const pinn_region* region, uint64_t key, uint32_t draw,
                        uint64_t first_row, void* stream);
 

@@ -7,7 +7,9 @@ What it follows.  The reference redraws residual points with ``geom.random_point
 (deepxde/data/pde.py:232-234 under ``PDE.resample_train_points`` :186-193): ``np.random.rand(n, dim)`` scaled into the
 bounding box (deepxde/geometry/geometry_nd.py Hypercube.random_points; geometry_2d.py Rectangle inherits it), times a uniform
 ``t`` for ``GeometryXTime`` (timedomain.py:86-98 with "pseudo"), with rejection of the points inside a subtracted shape
-(deepxde/geometry/csg.py CSGDifference.random_points: draw from geom1, keep ``~geom2.inside``, repeat until n points).  The
+(deepxde/geometry/csg.py CSGDifference.random_points: draw from geom1, keep ``~geom2.inside``, repeat until n points); a
+``Hypersphere`` domain (HeatND, src/pde/heat.py:257) is sampled by the reference as Gaussian direction x radius**(1/d)
+(geometry_nd.py:138-150), here by rejection from its bounding cube -- the same uniform law on the ball.  The
 distribution is the same; the random stream is not numpy's MT19937 but a counter-based one (Philox4x32-10, Salmon et al.,
 "Parallel random numbers: as easy as 1, 2, 3", SC'11 -- the generator is pinned below by the known-answer vectors of that
 paper's Random123 distribution), so that every row is a pure function of (key, draw, row index) and the device can produce
@@ -21,7 +23,7 @@ import numpy as np
 M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 W0, W1 = 0x9E3779B9, 0xBB67AE85
 MASK = np.uint64(0xFFFFFFFF)
-MAX_ATTEMPTS = 64
+MAX_ATTEMPTS = 256
 HOLE_BALL, HOLE_BOX = 0, 1
 
 
@@ -71,9 +73,22 @@ def in_holes(p: np.ndarray, holes) -> np.ndarray:
     return bad
 
 
-def sample_points(n_rows: int, lo, hi, holes=(), key: int = 0, draw: int = 0, first_row: int = 0) -> np.ndarray:
+def outside_ball(p: np.ndarray, keep) -> np.ndarray:
+    """keep = (centre over the first k coordinates, radius) or None: True where the point lies outside the closed ball
+    (deepxde/geometry/geometry_nd.py Hypersphere.inside: ``norm(x - center) <= radius``)."""
+    if keep is None:
+        return np.zeros(p.shape[0], dtype=bool)
+    c, r = np.asarray(keep[0], dtype=np.float32), np.float32(keep[1])
+    s = np.zeros(p.shape[0], dtype=np.float32)
+    for j in range(c.shape[0]):
+        dj = p[:, j] - c[j]
+        s = s + dj * dj
+    return s > r * r
+
+
+def sample_points(n_rows: int, lo, hi, holes=(), key: int = 0, draw: int = 0, first_row: int = 0, keep=None) -> np.ndarray:
     """Rows first_row .. first_row + n_rows of the stream (key, draw): float32 [n_rows, d].  ``holes``: sequence of
-    (shape, a, b) as in ``pinn_hole``."""
+    (shape, a, b) as in ``pinn_hole``; ``keep``: (centre, radius) of the ball the points must lie in, or None."""
     lo = np.asarray(lo, dtype=np.float32)
     hi = np.asarray(hi, dtype=np.float32)
     rows = np.arange(n_rows, dtype=np.uint64) + np.uint64(first_row)
@@ -84,5 +99,5 @@ def sample_points(n_rows: int, lo, hi, holes=(), key: int = 0, draw: int = 0, fi
             break
         p = _draw(rows[todo], np.uint64(attempt), lo, hi, key, draw)
         out[todo] = p                                   # the last draw stays if every attempt is rejected
-        todo = todo[in_holes(p, holes)]
+        todo = todo[outside_ball(p, keep) | in_holes(p, holes)]
     return out

@@ -26,7 +26,7 @@ void set_error_string(const std::string& s);   // pinn_api.cu
 namespace {
 
 constexpr int kRows = 256;          // rows per CTA = threads per CTA
-constexpr int kMaxAttempts = 64;    // a row still inside a hole after this many draws keeps its last draw (p < hole_fraction^64)
+constexpr int kMaxAttempts = 256;   // a row still rejected after this many draws keeps its last draw (5-ball in its cube: 0.836^256 = 1e-20)
 
 struct U4 { uint32_t x, y, z, w; };
 
@@ -44,7 +44,8 @@ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
 
 __device__ __forceinline__ uint32_t word(const U4& v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
 
-// One draw: coordinates p[0..d) of global row g, attempt `attempt`, and whether the point lies in a hole.
+// One draw: coordinates p[0..d) of global row g, attempt `attempt`, and whether the point is rejected (outside the kept ball or
+// inside a hole).
 __device__ __forceinline__ bool draw_point(const pinn_region& R, uint64_t g, uint32_t attempt, uint32_t draw, uint32_t k0, uint32_t k1,
                                            float (&p)[PINN_MAX_DIM]) {
   const int d = R.d;
@@ -62,6 +63,16 @@ __device__ __forceinline__ bool draw_point(const pinn_region& R, uint64_t g, uin
     }
   }
   bool in_hole = false;
+  if (R.keep_dims > 0) {                                     // the domain is a ball (HeatND's Hypersphere): outside counts as a hole
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < PINN_MAX_DIM; ++j)
+      if (j < R.keep_dims) {
+        const float dj = __fsub_rn(p[j], R.keep_center[j]);
+        s = __fadd_rn(s, __fmul_rn(dj, dj));
+      }
+    in_hole = s > __fmul_rn(R.keep_radius, R.keep_radius);
+  }
   for (int h = 0; h < R.n_holes && !in_hole; ++h) {
     const pinn_hole& H = R.holes[h];
     const int k = H.n_dims;                                  // 1..3, validated on the host
@@ -111,7 +122,7 @@ __global__ void __launch_bounds__(kRows) sample_kernel(float* __restrict__ x, in
       if (c < d) tile[t * d + c] = p[c];
     if (rejected) pending[0][atomicAdd(&n_pending[0], 1)] = t;
   }
-  if (R.n_holes > 0) {
+  if (R.n_holes > 0 || R.keep_dims > 0) {
     for (uint32_t attempt = 1; attempt < (uint32_t)kMaxAttempts; ++attempt) {
       const int cur = (attempt - 1) & 1, nxt = cur ^ 1;
       __syncthreads();
@@ -159,6 +170,10 @@ int pinn_sample_points(float* x, int64_t ld, int64_t n_rows, const pinn_region* 
       pinn::set_error_string("pinn_sample_points: empty bounding box (hi < lo or NaN)");
       return 1;
     }
+  if (R.keep_dims < 0 || R.keep_dims > R.d || (R.keep_dims > 0 && !(R.keep_radius > 0.f))) {
+    pinn::set_error_string("pinn_sample_points: keep_dims must be 0..d and the kept ball needs a positive radius");
+    return 1;
+  }
   for (int h = 0; h < R.n_holes; ++h) {
     const pinn_hole& H = R.holes[h];
     if ((H.shape != PINN_HOLE_BALL && H.shape != PINN_HOLE_BOX) || H.n_dims < 1 || H.n_dims > 3 || H.n_dims > R.d) {

@@ -94,6 +94,7 @@ class CRegion(ctypes.Structure):
     """ctypes mirror of ``struct pinn_region``: the sampling region of ``pinn_sample_points``."""
 
     _fields_ = [("d", ctypes.c_int32), ("n_holes", ctypes.c_int32), ("lo", ctypes.c_float * PINN_MAX_DIM), ("hi", ctypes.c_float * PINN_MAX_DIM),
+                ("keep_dims", ctypes.c_int32), ("keep_radius", ctypes.c_float), ("keep_center", ctypes.c_float * PINN_MAX_DIM),
                 ("holes", CHole * PINN_MAX_HOLES)]
 
 

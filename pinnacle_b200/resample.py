@@ -15,7 +15,9 @@ Differences from the reference's callback, all deliberate:
 * only the ``num_domain`` interior rows are redrawn; the boundary / initial rows that deepxde also keeps in the residual
   set (``train_points()``, data/pde.py:236-243, :312-319) stay (``bc_points`` resampling is not offered: it would change
   the boundary terms' targets, which are evaluated once per point set);
-* geometries outside the box-minus-holes family (``Hypersphere`` domains, polygons) are refused at ``on_train_begin``.
+* geometries outside the (box or ball)-minus-holes family (polygons, unions as domains) are refused at ``on_train_begin``;
+  a ``Hypersphere`` domain (HeatND) is drawn by rejection from its bounding cube (the reference: Gaussian direction times
+  radius**(1/d), deepxde/geometry/geometry_nd.py:138-150 -- the same uniform law).
 """
 from __future__ import annotations
 
@@ -33,10 +35,12 @@ Hole = Tuple[int, Tuple[float, ...], Tuple[float, ...]]      # (shape, a, b) as 
 
 @dataclass
 class Region:
-    """Axis-aligned box [lo, hi) minus closed holes over the leading coordinates (``struct pinn_region``)."""
+    """Axis-aligned box [lo, hi), optionally intersected with one closed ball over the leading coordinates (``keep`` =
+    (centre, radius): a ``Hypersphere`` domain inside its bounding cube), minus closed holes (``struct pinn_region``)."""
     lo: Sequence[float]
     hi: Sequence[float]
     holes: List[Hole] = field(default_factory=list)
+    keep: Optional[Tuple[Tuple[float, ...], float]] = None
 
     def __post_init__(self):
         self.lo = tuple(float(v) for v in self.lo)
@@ -47,6 +51,10 @@ class Region:
             raise ValueError("region: hi < lo")
         if len(self.holes) > PINN_MAX_HOLES:
             raise ValueError(f"region: more than {PINN_MAX_HOLES} holes")
+        if self.keep is not None:
+            self.keep = (tuple(float(v) for v in self.keep[0]), float(self.keep[1]))
+            if not 1 <= len(self.keep[0]) <= self.d or not self.keep[1] > 0:
+                raise ValueError("region: the kept ball spans 1..d coordinates and has a positive radius")
         self.holes = [(int(s), tuple(float(v) for v in a), tuple(float(v) for v in b)) for s, a, b in self.holes]
         for s, a, b in self.holes:
             if s not in (HOLE_BALL, HOLE_BOX) or not 1 <= len(a) <= min(3, self.d) or (s == HOLE_BOX and len(b) != len(a)) or len(b) < 1:
@@ -61,6 +69,10 @@ class Region:
         r.d, r.n_holes = self.d, len(self.holes)
         for j in range(self.d):
             r.lo[j], r.hi[j] = self.lo[j], self.hi[j]
+        if self.keep is not None:
+            r.keep_dims, r.keep_radius = len(self.keep[0]), self.keep[1]
+            for j, v in enumerate(self.keep[0]):
+                r.keep_center[j] = v
         for i, (s, a, b) in enumerate(self.holes):
             r.holes[i].shape, r.holes[i].n_dims = s, len(a)
             for j, v in enumerate(a):
@@ -70,9 +82,15 @@ class Region:
         return r
 
     def volume_fraction_bound(self) -> float:
-        """Upper bound of the fraction of the box the holes cover (sum of their volumes inside the spatial box, ignoring
-        overlaps and clipping) -- a redraw takes ``attempts ~ 1 / (1 - fraction)`` Philox blocks per row."""
+        """Upper bound of the fraction of the box that is rejected (outside the kept ball + the holes' volumes inside the
+        spatial box, ignoring overlaps and clipping) -- a redraw takes ``attempts ~ 1 / (1 - fraction)`` Philox blocks per row."""
         tot = 0.0
+        if self.keep is not None:
+            import math
+            k, r = len(self.keep[0]), self.keep[1]
+            ball = math.pi ** (k / 2) / math.gamma(k / 2 + 1) * r ** k
+            box = float(np.prod([self.hi[j] - self.lo[j] for j in range(k)]))
+            tot += max(1.0 - ball / box, 0.0) if box > 0 else 0.0
         for s, a, b in self.holes:
             k = len(a)
             box = float(np.prod([self.hi[j] - self.lo[j] for j in range(k)]))
@@ -115,21 +133,25 @@ def geometry_region(geom) -> Region:
     n = _cls(geom)
     if n == "GeometryXTime":
         r = geometry_region(geom.geometry)
-        return Region(r.lo + (float(geom.timedomain.t0),), r.hi + (float(geom.timedomain.t1),), r.holes)
+        return Region(r.lo + (float(geom.timedomain.t0),), r.hi + (float(geom.timedomain.t1),), r.holes, r.keep)
+    if n in ("Disk", "Sphere", "Hypersphere"):          # a ball as the DOMAIN (HeatND, src/pde/heat.py:257): its bounding cube, outside rejected
+        c = np.asarray(geom.center, dtype=np.float64).reshape(-1)
+        rad = float(geom.radius)
+        return Region(c - rad, c + rad, [], (tuple(c), rad))
     if n in ("Interval", "TimeDomain"):
         return Region((float(geom.l),), (float(geom.r),))
     if n in ("Rectangle", "Cuboid", "Hypercube"):
         return Region(np.asarray(geom.xmin).reshape(-1), np.asarray(geom.xmax).reshape(-1))
     if n == "CSGDifference":
         r = geometry_region(geom.geom1)
-        return Region(r.lo, r.hi, r.holes + _holes_of(geom.geom2))
+        return Region(r.lo, r.hi, r.holes + _holes_of(geom.geom2), r.keep)
     if n == "CSGMultiDifference":                       # src/utils/geom.py:7-43
         r = geometry_region(geom.geom1)
         holes = list(r.holes)
         for g2 in geom.geom2_list:
             holes += _holes_of(g2)
-        return Region(r.lo, r.hi, holes)
-    raise capi.FusedOpError(f"device resampler: geometry {n} is not a box minus disks / spheres / boxes (times a time interval); "
+        return Region(r.lo, r.hi, holes, r.keep)
+    raise capi.FusedOpError(f"device resampler: geometry {n} is not a box or ball minus disks / spheres / boxes (times a time interval); "
                             "use dde.callbacks.PDEPointResampler for it")
 
 

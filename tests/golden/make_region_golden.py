@@ -24,7 +24,7 @@ import refshim  # noqa: E402
 from pinnacle_b200.resample import geometry_region  # noqa: E402
 
 CASES = ["Burgers1D", "Poisson2D_Classic", "Heat2D_ComplexGeometry", "Heat2D_Multiscale", "NS2D_Classic", "NS2D_LidDriven", "NS2D_BackStep",
-         "Poisson3D_ComplexGeometry", "KuramotoSivashinskyEquation", "Wave1D", "PoissonBoltzmann2D", "GrayScottEquation"]
+         "Poisson3D_ComplexGeometry", "KuramotoSivashinskyEquation", "Wave1D", "PoissonBoltzmann2D", "GrayScottEquation", "HeatND", "PoissonND"]
 
 
 def main():
@@ -50,12 +50,19 @@ def main():
             inside = np.asarray(geom.geometry.inside(probe[:, :-1])).astype(bool)
         else:
             inside = np.asarray(geom.inside(probe)).astype(bool)
+        if reg.keep is not None:                          # pull 64 probes onto the sphere that bounds the domain
+            k = len(reg.keep[0])
+            ang = rng.normal(size=(64, k))
+            ang /= np.linalg.norm(ang, axis=1, keepdims=True)
+            probe[-64:, :k] = (np.asarray(reg.keep[0]) + ang * reg.keep[1] * (1 + rng.uniform(-0.02, 0.02, (64, 1)))).astype(np.float32)
+            inside = np.asarray(geom.geometry.inside(probe[:, :-1]) if type(geom).__name__ == "GeometryXTime" else geom.inside(probe)).astype(bool)
         np.random.seed(sum(map(ord, name)))
         own = np.asarray(geom.random_points(256, random="pseudo"), dtype=np.float32)
         out[name + "_probe"] = probe
         out[name + "_inside"] = inside
         out[name + "_refdraw"] = own
-        meta[name] = dict(lo=list(reg.lo), hi=list(reg.hi), holes=[[s, list(a), list(b)] for s, a, b in reg.holes], geometry=type(geom).__name__)
+        meta[name] = dict(lo=list(reg.lo), hi=list(reg.hi), holes=[[s, list(a), list(b)] for s, a, b in reg.holes], geometry=type(geom).__name__,
+                          keep=None if reg.keep is None else [list(reg.keep[0]), reg.keep[1]])
         print(f"{name:32s} d={reg.d} holes={len(reg.holes):2d} inside fraction {inside.mean():.3f}")
     out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     np.savez_compressed(os.path.join(HERE, "regions.npz"), **out)

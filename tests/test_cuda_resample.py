@@ -20,18 +20,18 @@ def _regions():
 
 
 @pytest.mark.parametrize("name", ["Poisson2D_Classic", "Heat2D_ComplexGeometry", "NS2D_Classic", "NS2D_BackStep", "Poisson3D_ComplexGeometry",
-                                  "PoissonBoltzmann2D", "Burgers1D", "GrayScottEquation"])
+                                  "PoissonBoltzmann2D", "Burgers1D", "GrayScottEquation", "HeatND", "PoissonND"])
 def test_kernel_is_bit_identical_to_the_oracle_on_reference_geometries(name):
-    from oracle.sample_ref import in_holes, sample_points
+    from oracle.sample_ref import in_holes, outside_ball, sample_points
     from pinnacle_b200.resample import Region, sample_region
     _, meta = _regions()
     m = meta[name]
-    region = Region(m["lo"], m["hi"], [tuple(h) for h in m["holes"]])
+    region = Region(m["lo"], m["hi"], [tuple(h) for h in m["holes"]], None if m["keep"] is None else (m["keep"][0], m["keep"][1]))
     for n, key, draw, first in ((10007, 5, 0, 0), (777, (1 << 63) + 12345, (1 << 24) - 1, (1 << 32) - 300), (1, 0, 3, 1 << 40), (256, 1, 1, 0)):
         got = sample_region(region, n, key, draw, first, device="cuda:0").cpu().numpy()
-        want = sample_points(n, region.lo, region.hi, region.holes, key=key, draw=draw, first_row=first)
+        want = sample_points(n, region.lo, region.hi, region.holes, key=key, draw=draw, first_row=first, keep=region.keep)
         assert np.array_equal(got, want), (name, n, key, draw, first, np.flatnonzero((got != want).any(1))[:5])
-        assert not in_holes(got, region.holes).any()
+        assert not in_holes(got, region.holes).any() and not outside_ball(got, region.keep).any()
     assert sample_region(region, 0, device="cuda:0").shape == (0, region.d)
 
 

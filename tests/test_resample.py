@@ -65,31 +65,53 @@ def test_distribution_is_uniform_on_box_minus_holes():
     assert np.abs(c - np.eye(6)).max() < 0.03 and np.abs(q.mean(0) - 0.5).max() < 0.01
 
 
+def test_ball_domain_is_uniform():
+    """HeatND's domain: the unit 5-ball times [0, 1], drawn by rejection from the bounding cube (16 % accepted per attempt,
+    so rows need up to dozens of attempts).  Uniform on the ball: E|x|^2 = d/(d+2), P(|x| < r) = r^d; t untouched."""
+    from oracle.sample_ref import outside_ball, sample_points
+    n = 100_000
+    keep = ((0.0,) * 5, 1.0)
+    p = sample_points(n, (-1,) * 5 + (0,), (1,) * 5 + (1,), key=2, keep=keep)
+    assert not outside_ball(p, keep).any()
+    r2 = (p[:, :5].astype(np.float64) ** 2).sum(1)
+    assert abs(r2.mean() - 5 / 7) < 5 * np.sqrt(np.var(r2) / n)
+    assert abs((r2 < 0.8 ** 2).mean() - 0.8 ** 5) < 5 * np.sqrt(0.8 ** 5 * (1 - 0.8 ** 5) / n)
+    assert np.abs(p[:, :5].mean(0)).max() < 5 * np.sqrt(1 / 7 / n) and abs(p[:, 5].mean() - 0.5) < 5 / np.sqrt(12 * n)
+
+
 @pytest.mark.parametrize("name", ["Poisson2D_Classic", "Heat2D_ComplexGeometry", "NS2D_Classic", "NS2D_BackStep", "Poisson3D_ComplexGeometry",
-                                  "PoissonBoltzmann2D", "Burgers1D"])
+                                  "PoissonBoltzmann2D", "Burgers1D", "HeatND", "PoissonND"])
 def test_hole_rule_equals_the_reference_geometry_inside(name):
     """4096 probe points per class (some pulled onto the hole boundaries) with the verdicts of the reference's own
     ``geom.inside`` (tests/golden/make_region_golden.py): the region's point-in-hole rule must agree, the reference's own draw
     must be accepted, and our draw must be accepted by the stored verdict rule."""
-    from oracle.sample_ref import in_holes, sample_points
+    from oracle.sample_ref import in_holes, outside_ball, sample_points
     z, meta = regions()
     m = meta[name]
     holes = [(s, a, b) for s, a, b in m["holes"]]
+    keep = None if m["keep"] is None else (m["keep"][0], m["keep"][1])
+    rejected = lambda p: in_holes(p, holes) | outside_ball(p, keep)     # noqa: E731
     probe, inside = z[name + "_probe"], z[name + "_inside"]
-    ours = ~in_holes(probe, holes)
-    # float32 (ours) against float64 norms (numpy's) can differ on points within rounding of a hole boundary
+    ours = ~rejected(probe)
+    # float32 (ours) against float64 norms (numpy's) can differ on points within rounding of a ball's boundary
+    balls = [(a, b[0]) for s, a, b in holes if s == 0] + ([keep] if keep else [])
     disagree = np.flatnonzero(ours != inside)
     for i in disagree:
-        dist = min(abs(np.linalg.norm(probe[i, :len(a)].astype(np.float64) - np.asarray(a)) - b[0]) for s, a, b in holes if s == 0)
+        dist = min(abs(np.linalg.norm(probe[i, :len(a)].astype(np.float64) - np.asarray(a)) - r) for a, r in balls)
         assert dist < 1e-6, (name, i, probe[i], dist)
     assert len(disagree) <= 2
-    assert not in_holes(z[name + "_refdraw"], holes).any()
-    own = sample_points(5000, m["lo"], m["hi"], holes, key=5)
-    assert not in_holes(own, holes).any()
+    refdraw = z[name + "_refdraw"]
+    bad = np.flatnonzero(rejected(refdraw))                               # the reference's own draw; radius**(1/d) can land ON the sphere
+    for i in bad:
+        assert keep and abs(np.linalg.norm(refdraw[i, :len(keep[0])].astype(np.float64) - np.asarray(keep[0])) - keep[1]) < 1e-6
+    own = sample_points(5000, m["lo"], m["hi"], holes, key=5, keep=keep)
+    assert not rejected(own).any()
     assert (own >= np.asarray(m["lo"], np.float32)).all() and (own <= np.asarray(m["hi"], np.float32)).all()
     # acceptance: the share of box-uniform probes the reference keeps = the share of first attempts we keep
     first = sample_points(4096, m["lo"], m["hi"], [], key=5)
-    assert abs((~in_holes(first, holes)).mean() - inside[24 * len(holes):].mean()) < 0.04
+    n_pulled = 24 * len(holes)
+    body = slice(n_pulled, 4096 - (64 if keep else 0))
+    assert abs((~rejected(first)).mean() - inside[body].mean()) < 0.04
 
 
 class Interval:
@@ -152,7 +174,13 @@ def test_geometry_to_region_mapping():
     c = r.to_c()
     assert (c.d, c.n_holes, c.holes[0].n_dims) == (3, 2, 3) and abs(c.holes[0].b[0] - 0.2) < 1e-7 and c.hi[2] == 1.0
     assert 0.03 < r.volume_fraction_bound() < 0.04
-    for bad in (GeometryXTime(Hypersphere([0] * 5, 1), TimeDomain(0, 1)), Polygon(), CSGDifference(Rectangle([0, 0], [1, 1]), Polygon()),
+    r = geometry_region(GeometryXTime(Hypersphere([0] * 5, 1), TimeDomain(0, 2)))          # HeatND: the ball inside its bounding cube
+    assert r.d == 6 and r.lo == (-1.0,) * 5 + (0.0,) and r.hi == (1.0,) * 5 + (2.0,) and r.keep == ((0.0,) * 5, 1.0) and r.holes == []
+    c = r.to_c()
+    assert (c.keep_dims, c.keep_radius, c.n_holes) == (5, 1.0, 0) and 0.83 < r.volume_fraction_bound() < 0.84
+    r = geometry_region(CSGDifference(Disk([1, 2], 3), Rectangle([0, 0], [1, 1])))
+    assert r.lo == (-2.0, -1.0) and r.keep == ((1.0, 2.0), 3.0) and len(r.holes) == 1
+    for bad in (Polygon(), CSGDifference(Rectangle([0, 0], [1, 1]), Polygon()), CSGUnion(Rectangle([0, 0], [1, 1]), Disk([0, 0], 1)),
                 CSGDifference(Cuboid([0] * 4, [1] * 4), Hypersphere([0] * 4, 0.1))):
         with pytest.raises(capi.FusedOpError):
             geometry_region(bad)
@@ -167,7 +195,8 @@ def test_region_struct_layout_matches_header():
     txt = open(os.path.join(ROOT, "include", "pinn_b200.h")).read()
     assert int(re.search(r"#define PINN_MAX_HOLES (\d+)", txt).group(1)) == kinds.PINN_MAX_HOLES
     assert ctypes.sizeof(kinds.CHole) == 8 + 4 * 3 + 4 * 3
-    assert ctypes.sizeof(kinds.CRegion) == 8 + 2 * 4 * kinds.PINN_MAX_DIM + kinds.PINN_MAX_HOLES * ctypes.sizeof(kinds.CHole)
+    assert ctypes.sizeof(kinds.CRegion) == 8 + 2 * 4 * kinds.PINN_MAX_DIM + 8 + 4 * kinds.PINN_MAX_DIM + kinds.PINN_MAX_HOLES * ctypes.sizeof(kinds.CHole)
+    assert kinds.CRegion.holes.offset == 8 + 3 * 4 * kinds.PINN_MAX_DIM + 8 and kinds.CRegion.keep_center.offset == 8 + 2 * 4 * kinds.PINN_MAX_DIM + 8
     assert re.search(r"PINN_HOLE_BALL = (\d+), PINN_HOLE_BOX = (\d+)", txt).groups() == (str(kinds.HOLE_BALL), str(kinds.HOLE_BOX))
 
 
@@ -272,10 +301,10 @@ def test_callback_schedule_and_host_sync():
         with pytest.raises(capi.FusedOpError, match="exclusions"):
             cb.on_train_begin()
         model.data.exclusions = None
-        model.data.geom = GeometryXTime(Hypersphere([0] * 2, 1), TimeDomain(0, 5))
+        model.data.geom = GeometryXTime(Polygon(), TimeDomain(0, 5))
         cb2 = DevicePointResampler(period=3)
         cb2.set_model(model)
-        with pytest.raises(capi.FusedOpError, match="Hypersphere"):
+        with pytest.raises(capi.FusedOpError, match="Polygon"):
             cb2.on_train_begin()
         model.data.geom = Rectangle([0, 0], [1, 1])
         with pytest.raises(capi.FusedOpError, match="coordinates"):
@@ -286,7 +315,7 @@ def test_callback_schedule_and_host_sync():
 
 
 @needs_ref
-@pytest.mark.parametrize("name", ["Poisson2D_Classic", "Burgers1D", "Heat2D_ComplexGeometry"])
+@pytest.mark.parametrize("name", ["Poisson2D_Classic", "Burgers1D", "Heat2D_ComplexGeometry", "HeatND"])
 def test_resampler_on_the_reference_model(name):
     """The real dde.Model, patched, trains with the device resampler as a callback: every redraw lands inside the
     reference geometry, the number of rows and the boundary rows never change, host arrays are current after train()."""

@@ -146,8 +146,9 @@ def oracle_sample_points(x, region_c, key, draw, first_row=0):
     """Stand-in for capi.sample_points on CPU tensors: the rows the kernel would write, from oracle/sample_ref.py."""
     from oracle import sample_ref as S
     d = region_c.d
+    keep = ([region_c.keep_center[j] for j in range(region_c.keep_dims)], region_c.keep_radius) if region_c.keep_dims > 0 else None
     rows = S.sample_points(x.shape[0], [region_c.lo[j] for j in range(d)], [region_c.hi[j] for j in range(d)], region_holes(region_c),
-                           key=int(key), draw=int(draw), first_row=int(first_row))
+                           key=int(key), draw=int(draw), first_row=int(first_row), keep=keep)
     x[:, :d] = torch.from_numpy(rows)
     return x
 
