@@ -30,99 +30,105 @@ constexpr int kMaxAttempts = 256;   // a row still rejected after this many draw
 
 struct U4 { uint32_t x, y, z, w; };
 
-__device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+// What the host precomputes once per launch (all of it exact, so the float32 result is the one the header describes):
+// the ten round keys of Philox (key + r * Weyl constant), lo, and (hi - lo) * 2^-24 -- a power-of-two scaling commutes with
+// the rounding of the product, fl(fl(u * 2^-24) * span) == fl(u * (span * 2^-24)) for the 24-bit integer u.
+struct SampleParams {
+  uint32_t rk[10][2];
+  float lo[PINN_MAX_DIM];
+  float span24[PINN_MAX_DIM];
+};
+
+__device__ __forceinline__ U4 philox4x32_10(U4 c, const SampleParams& P) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = U4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
+    c = U4{hi1 ^ c.y ^ P.rk[r][0], lo1, hi0 ^ c.w ^ P.rk[r][1], lo0};
   }
   return c;
 }
 
 __device__ __forceinline__ uint32_t word(const U4& v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
 
-// One draw: coordinates p[0..d) of global row g, attempt `attempt`, and whether the point is rejected (outside the kept ball or
-// inside a hole).
-__device__ __forceinline__ bool draw_point(const pinn_region& R, uint64_t g, uint32_t attempt, uint32_t draw, uint32_t k0, uint32_t k1,
-                                           float (&p)[PINN_MAX_DIM]) {
-  const int d = R.d;
+// One draw: coordinates p[0..D) of global row g, attempt `attempt`, and (REJECT) whether the point is rejected: outside the kept
+// ball or inside a hole.
+template <int D, bool REJECT>
+__device__ __forceinline__ bool draw_point(const pinn_region& R, const SampleParams& P, uint64_t g, uint32_t attempt, uint32_t draw,
+                                           float (&p)[D]) {
 #pragma unroll
-  for (int b = 0; b < (PINN_MAX_DIM + 3) / 4; ++b) {
-    if (4 * b >= d) break;
-    const U4 v = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), attempt, (uint32_t)b | (draw << 8)}, k0, k1);
+  for (int b = 0; b < (D + 3) / 4; ++b) {
+    const U4 v = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), attempt, (uint32_t)b | (draw << 8)}, P);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = 4 * b + j;
-      if (c < PINN_MAX_DIM && c < d) {
-        const float u = __fmul_rn((float)(word(v, j) >> 8), 5.9604644775390625e-08f);   // 24 bits -> [0, 1), exact
-        p[c] = __fadd_rn(__fmul_rn(u, __fsub_rn(R.hi[c], R.lo[c])), R.lo[c]);
-      }
+      if (c < D) p[c] = __fadd_rn(__fmul_rn((float)(word(v, j) >> 8), P.span24[c]), P.lo[c]);
     }
   }
-  bool in_hole = false;
-  if (R.keep_dims > 0) {                                     // the domain is a ball (HeatND's Hypersphere): outside counts as a hole
+  if constexpr (!REJECT) return false;
+  bool rejected = false;
+  if (R.keep_dims > 0) {                                     // the domain is a ball (HeatND's Hypersphere): outside is redrawn
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < PINN_MAX_DIM; ++j)
+    for (int j = 0; j < D; ++j)
       if (j < R.keep_dims) {
         const float dj = __fsub_rn(p[j], R.keep_center[j]);
         s = __fadd_rn(s, __fmul_rn(dj, dj));
       }
-    in_hole = s > __fmul_rn(R.keep_radius, R.keep_radius);
+    rejected = s > __fmul_rn(R.keep_radius, R.keep_radius);
   }
-  for (int h = 0; h < R.n_holes && !in_hole; ++h) {
+  for (int h = 0; h < R.n_holes && !rejected; ++h) {
     const pinn_hole& H = R.holes[h];
-    const int k = H.n_dims;                                  // 1..3, validated on the host
+    const int k = H.n_dims;                                  // 1..min(3, D), validated on the host
     if (H.shape == PINN_HOLE_BALL) {
       float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 3; ++j)
+      for (int j = 0; j < (D < 3 ? D : 3); ++j)
         if (j < k) {
           const float dj = __fsub_rn(p[j], H.a[j]);
           s = __fadd_rn(s, __fmul_rn(dj, dj));
         }
-      in_hole = s <= __fmul_rn(H.b[0], H.b[0]);
+      rejected = s <= __fmul_rn(H.b[0], H.b[0]);
     } else {
       bool all = true;
 #pragma unroll
-      for (int j = 0; j < 3; ++j)
+      for (int j = 0; j < (D < 3 ? D : 3); ++j)
         if (j < k) all = all && p[j] >= H.a[j] && p[j] <= H.b[j];
-      in_hole = all;
+      rejected = all;
     }
   }
-  return in_hole;
+  return rejected;
 }
 
-// x[row][0..d) for rows [0, n_rows).  A CTA owns kRows consecutive rows and stages them in shared memory.  Round 0: every
-// thread draws its own row.  The rows that fell into a hole are collected in a shared list and redrawn by the FIRST threads
+// x[row][0..D) for rows [0, n_rows).  A CTA owns kRows consecutive rows and stages them in shared memory.  Round 0: every
+// thread draws its own row.  REJECT: the rows that were rejected are collected in a shared list and redrawn by the FIRST threads
 // of the CTA in the next round (attempt + 1), and so on: a warp never waits for its slowest lane's rejections, the cost of a
 // redraw round is proportional to the rows still pending (13 % of the rows need a second attempt on the reference's
 // 17-disk domain; done lane by lane that kept every warp busy for its unluckiest row, 3-4 full attempts).  The tile goes
-// out with unit-stride stores when rows are contiguous (ld == d), otherwise only the first d of every ld columns are touched.
-__global__ void __launch_bounds__(kRows) sample_kernel(float* __restrict__ x, int64_t ld, int64_t n_rows, pinn_region R, uint32_t k0, uint32_t k1,
-                                                      uint32_t draw, uint64_t first_row) {
-  __shared__ float tile[kRows * PINN_MAX_DIM];
-  __shared__ int pending[2][kRows];
+// out with unit-stride stores when rows are contiguous (ld == D), otherwise only the first D of every ld columns are touched.
+template <int D, bool REJECT>
+__global__ void __launch_bounds__(kRows) sample_kernel(float* __restrict__ x, int64_t ld, int64_t n_rows, const __grid_constant__ pinn_region R,
+                                                      const __grid_constant__ SampleParams P, uint32_t draw, uint64_t first_row) {
+  __shared__ float tile[kRows * D];
+  __shared__ int pending[REJECT ? 2 : 1][REJECT ? kRows : 1];
   __shared__ int n_pending[2];
-  const int d = R.d;
   const int t = threadIdx.x;
   const int64_t row0 = (int64_t)blockIdx.x * kRows;
   const int64_t left = n_rows - row0;
   const int rows_here = (int)(left < kRows ? left : kRows);
-  if (t < 2) n_pending[t] = 0;
-  __syncthreads();
-  float p[PINN_MAX_DIM];
-  if (t < rows_here) {
-    const bool rejected = draw_point(R, first_row + (uint64_t)(row0 + t), 0u, draw, k0, k1, p);
-#pragma unroll
-    for (int c = 0; c < PINN_MAX_DIM; ++c)
-      if (c < d) tile[t * d + c] = p[c];
-    if (rejected) pending[0][atomicAdd(&n_pending[0], 1)] = t;
+  if constexpr (REJECT) {
+    if (t < 2) n_pending[t] = 0;
+    __syncthreads();
   }
-  if (R.n_holes > 0 || R.keep_dims > 0) {
+  float p[D];
+  if (t < rows_here) {
+    const bool rejected = draw_point<D, REJECT>(R, P, first_row + (uint64_t)(row0 + t), 0u, draw, p);
+#pragma unroll
+    for (int c = 0; c < D; ++c) tile[t * D + c] = p[c];
+    if constexpr (REJECT)
+      if (rejected) pending[0][atomicAdd(&n_pending[0], 1)] = t;
+  }
+  if constexpr (REJECT) {
     for (uint32_t attempt = 1; attempt < (uint32_t)kMaxAttempts; ++attempt) {
       const int cur = (attempt - 1) & 1, nxt = cur ^ 1;
       __syncthreads();
@@ -130,10 +136,9 @@ __global__ void __launch_bounds__(kRows) sample_kernel(float* __restrict__ x, in
       if (n == 0) break;                                     // uniform: read after the barrier
       if (t < n) {
         const int r = pending[cur][t];
-        const bool rejected = draw_point(R, first_row + (uint64_t)(row0 + r), attempt, draw, k0, k1, p);
+        const bool rejected = draw_point<D, true>(R, P, first_row + (uint64_t)(row0 + r), attempt, draw, p);
 #pragma unroll
-        for (int c = 0; c < PINN_MAX_DIM; ++c)
-          if (c < d) tile[r * d + c] = p[c];                 // the last draw stays if every attempt is rejected
+        for (int c = 0; c < D; ++c) tile[r * D + c] = p[c];  // the last draw stays if every attempt is rejected
         if (rejected) pending[nxt][atomicAdd(&n_pending[nxt], 1)] = r;
       }
       __syncthreads();
@@ -141,13 +146,31 @@ __global__ void __launch_bounds__(kRows) sample_kernel(float* __restrict__ x, in
     }
   }
   __syncthreads();
-  const int count = rows_here * d;
-  if (ld == d) {
-    float* base = x + row0 * d;
-    for (int i = t; i < count; i += kRows) base[i] = tile[i];
+  const int count = rows_here * D;
+  if (ld == D) {
+    float* base = x + row0 * D;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const int i = t + k * kRows;
+      if (i < count) base[i] = tile[i];
+    }
   } else {
-    for (int i = t; i < count; i += kRows) x[(row0 + i / d) * ld + i % d] = tile[i];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const int i = t + k * kRows;
+      if (i < count) x[(row0 + i / D) * ld + i % D] = tile[i];
+    }
   }
+}
+
+template <int D>
+cudaError_t launch_sample(float* x, int64_t ld, int64_t n_rows, const pinn_region& R, const SampleParams& P, uint32_t draw, uint64_t first_row,
+                          unsigned blocks, cudaStream_t st) {
+  if (R.n_holes > 0 || R.keep_dims > 0)
+    sample_kernel<D, true><<<blocks, kRows, 0, st>>>(x, ld, n_rows, R, P, draw, first_row);
+  else
+    sample_kernel<D, false><<<blocks, kRows, 0, st>>>(x, ld, n_rows, R, P, draw, first_row);
+  return cudaGetLastError();
 }
 
 }  // namespace
@@ -187,8 +210,26 @@ int pinn_sample_points(float* x, int64_t ld, int64_t n_rows, const pinn_region* 
     pinn::set_error_string("pinn_sample_points: more than 2^31 * 256 rows in one call");
     return 1;
   }
-  sample_kernel<<<(unsigned)blocks, kRows, 0, (cudaStream_t)stream>>>(x, ld, n_rows, R, (uint32_t)key, (uint32_t)(key >> 32), draw, first_row);
-  cudaError_t e = cudaGetLastError();
+  SampleParams P;
+  for (int r = 0; r < 10; ++r) {
+    P.rk[r][0] = (uint32_t)key + (uint32_t)r * 0x9E3779B9u;
+    P.rk[r][1] = (uint32_t)(key >> 32) + (uint32_t)r * 0xBB67AE85u;
+  }
+  for (int c = 0; c < PINN_MAX_DIM; ++c) {
+    const volatile float span = c < R.d ? R.hi[c] - R.lo[c] : 0.f;      // one float32 subtraction, then an exact scaling
+    P.lo[c] = c < R.d ? R.lo[c] : 0.f;
+    P.span24[c] = span * 5.9604644775390625e-08f;
+  }
+  cudaError_t e = cudaSuccess;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (R.d) {
+    case 1: e = launch_sample<1>(x, ld, n_rows, R, P, draw, first_row, (unsigned)blocks, st); break;
+    case 2: e = launch_sample<2>(x, ld, n_rows, R, P, draw, first_row, (unsigned)blocks, st); break;
+    case 3: e = launch_sample<3>(x, ld, n_rows, R, P, draw, first_row, (unsigned)blocks, st); break;
+    case 4: e = launch_sample<4>(x, ld, n_rows, R, P, draw, first_row, (unsigned)blocks, st); break;
+    case 5: e = launch_sample<5>(x, ld, n_rows, R, P, draw, first_row, (unsigned)blocks, st); break;
+    default: e = launch_sample<6>(x, ld, n_rows, R, P, draw, first_row, (unsigned)blocks, st); break;
+  }
   if (e != cudaSuccess) {
     pinn::set_error_string(std::string("pinn_sample_points: ") + cudaGetErrorString(e));
     return 2;
