@@ -483,6 +483,15 @@ class FusedPDESolver:
                 raise capi.FusedOpError("term_gradient_rows() needs every boundary term on the fused path (ValueBC / FluxBC / PeriodicPairBC)")
         return core.gradient_rows(flat, pde_seeds, terms, linear)
 
+    def redraw_points(self, region, n_domain: Optional[int] = None, key: int = 0, draw: int = 0):
+        """Redraw the last ``n_domain`` residual rows (default: all of them) on the device, in place, from the uniform stream
+        (key, draw) over ``region`` (``resample.Region``) -- what ``resample.DevicePointResampler`` does for a patched
+        ``dde.Model``.  ``self.train_x`` on the host is NOT refreshed; a captured step graph stays valid."""
+        self.core.stage(self.train_x, self.n_bc)
+        n_rows = int(self.core.op.n_global)
+        self.core.redraw_domain_rows(self.train_x, self.n_bc, n_rows if n_domain is None else int(n_domain), region, key, draw)
+        return self
+
     # ---- whole-step CUDA graph -----------------------------------------------------------------------
     def capture_step(self, warmup: int = 3):
         """Capture one full training step (fused PDE op, BC terms, backward, optimizer update) into a CUDA graph.

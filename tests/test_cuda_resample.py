@@ -206,7 +206,7 @@ def test_redraw_under_a_captured_step_graph():
     solver.capture_step()
     solver.train_step()
     before = solver.opt.losses.detach().clone()
-    solver.core.redraw_domain_rows(solver.train_x, 0, n - 1000, region, 4, 0)
+    solver.redraw_points(region, n_domain=n - 1000, key=4, draw=0)
     solver.train_step()
     after = solver.opt.losses.detach().clone()
     assert solver._graph is not None and not torch.equal(before, after)

@@ -356,3 +356,85 @@ def test_resampler_on_the_reference_model(name):
             assert np.isfinite(model.train_state.loss_train).all()
     finally:
         fused.FusedPDEResidual.__init__ = orig
+
+
+@needs_ref
+def test_resampler_and_rar_hand_over_through_the_host_arrays():
+    """RAR (evaluate.fused_rar_wrapper, the reference's schedule) between training intervals reads ``train_state.X_train`` on the
+    host and prepends anchors with ``data.add_anchors``; the device resampler must have brought that array up to date at the
+    end of the interval (on_train_end), and keeps redrawing the -- still last -- interior rows of the extended set afterwards."""
+    dde, _ = refshim.load()
+    from oracle.sample_ref import sample_points
+    from pinnacle_b200 import fused
+    from pinnacle_b200.evaluate import fused_rar_wrapper
+    from pinnacle_b200.resample import DevicePointResampler
+    from pinnacle_b200.solver import enable_fused
+    torch.manual_seed(0)
+    dde.config.set_random_seed(0)
+    pde = refshim.construct("Burgers1D")
+    pde.training_points(domain=64, boundary=32, initial=32)
+    pde.num_test_points = 64
+    net = dde.nn.FNN([2] + [100] * 5 + [1], "tanh", "Glorot normal").float()
+    model = pde.create_model(net)
+    model.compile(torch.optim.Adam(net.parameters(), 1e-3), loss_weights=np.ones(pde.num_loss))
+    orig = fused.FusedPDEResidual.__init__
+
+    def init_cpu(self, spec, H=100, L=5, policy="auto", device=None, group=None, check_library=True):
+        orig(self, spec, H, L, policy, "cpu", group, False)
+
+    fused.FusedPDEResidual.__init__ = init_cpu
+    try:
+        with oracle_backend():
+            enable_fused(model)
+            n_all = model.data.train_x_all.shape[0]
+            cb = DevicePointResampler(period=2, seed=5)
+            train = fused_rar_wrapper(pde, model, {"interval": 4, "count": 3})
+            train(iterations=12, display_every=4, callbacks=[cb])
+            # 3 intervals of 4 steps -> 2 redraws each; 2 RAR rounds of 3 anchors in between
+            assert cb.draws == 6
+            data = model.data
+            assert data.train_x_all.shape[0] == n_all + 6 and data.anchors.shape[0] == 6
+            reg = cb.region
+            want = sample_points(64, reg.lo, reg.hi, reg.holes, key=5, draw=5)
+            assert np.array_equal(data.train_x_all[-64:], want) and np.array_equal(data.train_x[-64:], want)
+            # the anchors of the second RAR round were picked among rows that include the 4th redraw's interior points
+            prev = sample_points(64, reg.lo, reg.hi, reg.holes, key=5, draw=3)
+            pool = np.vstack([data.train_x_all[6:-64], prev])
+            for a in data.anchors[:3]:
+                assert (np.abs(pool - a).max(axis=1) == 0).any() or (np.abs(data.anchors[3:] - a).max(axis=1) == 0).any()
+            assert np.isfinite(model.train_state.loss_train).all()
+    finally:
+        fused.FusedPDEResidual.__init__ = orig
+
+
+def test_reference_free_solver_redraws_its_points():
+    from oracle.sample_ref import sample_points
+    from pinnacle_b200 import fused, problems
+    from pinnacle_b200.nn import FNN
+    from pinnacle_b200.resample import Region
+    from pinnacle_b200.solver import FusedPDESolver
+    spec = problems.make("Heat2D_Multiscale")
+    region = Region(spec.bbox[0::2], spec.bbox[1::2])
+    torch.manual_seed(0)
+    net = FNN([3] + [100] * 5 + [1])
+    orig = fused.FusedPDEResidual.__init__
+
+    def init_cpu(self, spec, H=100, L=5, policy="auto", device=None, group=None, check_library=True):
+        orig(self, spec, H, L, policy, "cpu", group, False)
+
+    fused.FusedPDEResidual.__init__ = init_cpu
+    try:
+        with oracle_backend():
+            x = spec.sample(60, seed=1).astype(np.float32).copy()
+            solver = FusedPDESolver(spec, net, x, device="cpu").compile("adam")
+            l0 = solver.outputs_losses_train()[1].detach().clone()
+            solver.redraw_points(region, key=3, draw=1)
+            assert np.array_equal(solver.core.op.x.numpy(), sample_points(60, region.lo, region.hi, key=3, draw=1))
+            l1 = solver.outputs_losses_train()[1].detach()
+            assert not torch.equal(l0, l1)
+            solver.redraw_points(region, n_domain=20, key=3, draw=2)
+            assert np.array_equal(solver.core.op.x[40:].numpy(), sample_points(20, region.lo, region.hi, key=3, draw=2))
+            assert np.array_equal(solver.core.op.x[:40].numpy(), sample_points(60, region.lo, region.hi, key=3, draw=1)[:40])
+            solver.train_step()
+    finally:
+        fused.FusedPDEResidual.__init__ = orig
