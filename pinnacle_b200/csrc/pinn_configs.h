@@ -25,6 +25,9 @@
 // 33-42 / 43-52  hidden widths 64 and 128 (benchmark.py:65 --hidden-layers, src/utils/args.py:4-12), FP32 FFMA kernel only: Burgers1D (2,1);
 //       the forward-Laplacian signatures of the Poisson2D / Heat2D / NS2D families (-2, -3, -2 with m = 3); Kuramoto-Sivashinsky (4,1);
 //       value-type boundary terms 2x1, 2x3, 3x1; flux-type boundary terms (1,1), (1,1,1)
+// 53-65 / 66-78  the remaining classes at hidden widths 64 and 128 (FFMA kernel): Burgers2D / Gray-Scott / HeatInv (-3, m = 2), Poisson1D (2),
+//       PoissonND (-5), HeatND (-6), NS2D_LongTime (-3, m = 3), Wave2D_Heterogeneous ((2,2,2): its per-point direction weights exist in the tensor-core kernels only), PoissonInv (-2, m = 2); value-type boundary
+//       terms 3x2, 3x3, 1x1, 5x1, 6x1; HeatND's 6-dimensional Neumann term
 // 32    gPINN kinds (GP_LINEAR2, GP_BURGERS1D: residual + its input gradient, two inputs embedded along e0, e1, e0+e1, e0-e1): (3,3,3,3)
 // 28    the same for the 6-dimensional Neumann term of HeatND (heat.py:296-301): (1,1,1,1,1,1)
 #pragma once
@@ -82,6 +85,32 @@
   X(49, 128, 3, 16, 2, 0, 0, 0)           \
   X(50, 128, 1, 16, 2, 0, 0, 0, 0)        \
   X(51, 128, 1, 16, 2, 0, 1, 1)           \
-  X(52, 128, 1, 16, 2, 0, 1, 1, 1)
+  X(52, 128, 1, 16, 2, 0, 1, 1, 1)        \
+  X(53, 64, 2, 32, 4, 0, -3) \
+  X(54, 64, 1, 32, 4, 0, 2) \
+  X(55, 64, 1, 16, 2, 0, -5) \
+  X(56, 64, 1, 16, 2, 0, -6) \
+  X(57, 64, 3, 32, 4, 0, -3) \
+  X(58, 64, 1, 16, 2, 0, 2, 2, 2) \
+  X(59, 64, 2, 32, 4, 0, -2) \
+  X(60, 64, 2, 32, 4, 0, 0, 0, 0) \
+  X(61, 64, 3, 32, 4, 0, 0, 0, 0) \
+  X(62, 64, 1, 32, 4, 0, 0) \
+  X(63, 64, 1, 32, 4, 0, 0, 0, 0, 0, 0) \
+  X(64, 64, 1, 32, 4, 0, 0, 0, 0, 0, 0, 0) \
+  X(65, 64, 1, 16, 2, 0, 1, 1, 1, 1, 1, 1) \
+  X(66, 128, 2, 16, 2, 0, -3) \
+  X(67, 128, 1, 16, 2, 0, 2) \
+  X(68, 128, 1, 16, 2, 0, -5) \
+  X(69, 128, 1, 16, 2, 0, -6) \
+  X(70, 128, 3, 16, 2, 0, -3) \
+  X(71, 128, 1, 16, 2, 0, 2, 2, 2) \
+  X(72, 128, 2, 16, 2, 0, -2) \
+  X(73, 128, 2, 16, 2, 0, 0, 0, 0) \
+  X(74, 128, 3, 16, 2, 0, 0, 0, 0) \
+  X(75, 128, 1, 16, 2, 0, 0) \
+  X(76, 128, 1, 16, 2, 0, 0, 0, 0, 0, 0) \
+  X(77, 128, 1, 16, 2, 0, 0, 0, 0, 0, 0, 0) \
+  X(78, 128, 1, 16, 2, 0, 1, 1, 1, 1, 1, 1)
 
-#define PINN_NUM_CONFIGS 53
+#define PINN_NUM_CONFIGS 79
