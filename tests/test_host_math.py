@@ -128,3 +128,39 @@ def test_tensor_core_arithmetic_model_keeps_parity(harness_lib, name):
         harness_lib.harness_set_tc_mode(0)
     assert err[2] < 1e-6 and err[1] < 1e-5
     assert err[1] > err[2]            # the truncating accumulate is the less accurate one
+
+
+_TABLE = np.array([[0.0, 0.0, 1.0], [1.0, 1.0, 2.0], [0.0, 1.0, 1.5], [1.0, 0.0, 1.2]])
+
+
+@pytest.mark.parametrize("H", [64, 128])
+@pytest.mark.parametrize("name", ["Burgers1D", "Burgers2D", "GrayScottEquation", "Poisson1D", "PoissonND", "HeatND", "NS2D_LongTime",
+                                  "Wave2D_Heterogeneous", "PoissonInv", "HeatInv", "Poisson3D_ComplexGeometry", "KuramotoSivashinskyEquation"])
+def test_device_math_at_other_hidden_widths(harness_lib, name, H):
+    """The jet recurrences, residual functors and adjoints are width-generic: hidden widths 64 and 128 (benchmark.py:65
+    --hidden-layers) against the fp64 reference algorithm, on the host build (the GPU side: tests/test_cuda_widths.py)."""
+    from golden import common
+    from oracle import autograd_ref as O
+    from pinnacle_b200 import problems
+    spec = problems.BUILDERS[name](*((_TABLE,) if name == "Wave2D_Heterogeneous" else ()))
+    desc = spec.desc.with_net(H, 5)
+    flat64 = common.golden_params(desc.layer_shapes(), 7 + H)
+    x = spec.sample(97, seed=H)
+    xt = torch.as_tensor(x)
+    aux = spec.aux(xt)
+    S = desc.n_pde
+    ol, og, orr = O.losses_and_grads(desc, torch.as_tensor(flat64), xt.double(), None if aux is None else aux.double(), seeds=np.eye(S))
+    flat = flat64.astype(np.float32)
+    xx = np.ascontiguousarray(x.astype(np.float32))
+    auxn = None if aux is None else np.ascontiguousarray(aux.numpy().astype(np.float32))
+    n, P = xx.shape[0], desc.n_params
+    grad = np.zeros((S, P)); loss = np.zeros(3); resid = np.zeros((n, S), np.float32)
+    seeds = np.eye(S, dtype=np.float32)
+    cd = desc.to_c()
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+    rc = harness_lib.harness_run(ctypes.byref(cd), vp(flat), vp(xx), vp(auxn), ctypes.c_longlong(n), ctypes.c_double(1.0 / n), vp(seeds), S,
+                                 vp(grad), vp(loss), vp(resid))
+    assert rc == 0
+    assert_parity(resid, orr.numpy(), "residual")
+    assert_parity(loss[:S], ol.numpy(), "loss")
+    assert_parity(grad, og.numpy(), "grad")
