@@ -223,7 +223,7 @@ class DevicePointResampler:
         """Redraw the ``num_domain`` interior rows of the staged training set in place (one launch + the aux columns)."""
         data, core = self.model.data, self.model.fused_core
         n_bc = int(np.sum(data.num_bcs))
-        core.redraw_domain_rows(data.train_x, n_bc, int(data.num_domain), self.region, self.seed, self.draws)
+        core.redraw_domain_rows(data.train_x, n_bc, int(data.num_domain), self.region, self.seed, self.draws, on_evict=self.sync_host)
         self._stale = (data.train_x, n_bc, self.draws)
         self.draws += 1
 

@@ -345,14 +345,18 @@ class _StepCore:
         while len(self._staged) > self.MAX_STAGED:
             _, old = self._staged.popitem(last=False)
             self._value_ops = {k: v for k, v in self._value_ops.items() if k[0] != old["generation"]}
+            if old.get("on_evict") is not None:         # rows redrawn on the device: let the owner refresh the host copy first
+                old["on_evict"]()
 
 
-    def redraw_domain_rows(self, inputs, n_bc: int, n_domain: int, region, key: int, draw: int):
+    def redraw_domain_rows(self, inputs, n_bc: int, n_domain: int, region, key: int, draw: int, on_evict=None):
         """Overwrite the LAST ``n_domain`` residual rows of the staged point set ``inputs`` (deepxde keeps the interior points
         at the end of ``train_x_all``: data/pde.py:228-243, :312-321) with rows 0..n_domain of the uniform stream (key, draw)
         over ``region``, on the device, and re-evaluate the per-point aux columns.  Tensors are updated in place: captured
         CUDA graphs and the boundary-term ops of the set stay valid.  Sharded sets: every rank draws the rows of its own shard
-        (a row is a function of its global index, not of the rank count)."""
+        (a row is a function of its global index, not of the rank count).  ``on_evict``: called if this point set is later
+        dropped from the resident sets (LRU) -- the host array is then the only copy, and it lags behind the device rows until
+        somebody refreshes it (``DevicePointResampler.sync_host``)."""
         from .fused import shard_bounds
         inputs = inputs if isinstance(inputs, torch.Tensor) else np.asarray(inputs)
         self.stage(inputs, n_bc)
@@ -376,6 +380,7 @@ class _StepCore:
             capi.sample_points(x[g0 - beg:end - beg], region.to_c(), key, draw, g0 - (n_global - n_domain))
         if ent["aux"] is not None:
             ent["aux"].copy_(op.spec.aux(x).to(torch.float32))
+        ent["on_evict"] = on_evict
         op.stats["device_redraws"] = op.stats.get("device_redraws", 0) + 1
 
 

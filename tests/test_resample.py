@@ -438,3 +438,36 @@ def test_reference_free_solver_redraws_its_points():
             solver.train_step()
     finally:
         fused.FusedPDEResidual.__init__ = orig
+
+
+def test_host_copy_is_refreshed_before_a_redrawn_set_leaves_the_device():
+    """The resident point sets are an LRU of three.  A training set whose interior rows were redrawn on the device must not be
+    dropped while its host array still holds the old rows -- a later re-upload would silently bring them back."""
+    from oracle.sample_ref import sample_points
+    from pinnacle_b200 import problems
+    from pinnacle_b200.resample import DevicePointResampler
+    spec = problems.make("Heat2D_Multiscale")
+    geom = GeometryXTime(Rectangle([0, 0], [1, 1]), TimeDomain(0, 5))
+    with oracle_backend():
+        core, net = _core(spec)
+        X = spec.sample(100, seed=3).astype(np.float32)
+        X0 = X.copy()
+        model = _FakeModel()
+        model.data, model.fused_core = _FakeData(X, 10, 70, geom), core
+        # on the CPU "device" the staged rows alias the host array; stage a copy so that the host array really lags
+        core.stage(X, 10)
+        ent = core._staged[core._key]
+        ent["x"] = ent["x"].clone()
+        core.op.x = ent["x"]
+        cb = DevicePointResampler(period=1, seed=8)
+        cb.set_model(model)
+        cb.on_train_begin()
+        cb.on_epoch_end()
+        assert np.array_equal(X, X0) and cb._stale is not None
+        for s in range(3):                                          # three other point sets push the training set out
+            core.stage(spec.sample(40, seed=20 + s).astype(np.float32), 5)
+        assert len(core._staged) == core.MAX_STAGED and cb._stale is None
+        want = sample_points(70, (0, 0, 0), (1, 1, 5), key=8, draw=0)
+        assert np.array_equal(X[30:], want) and np.array_equal(X[:30], X0[:30])
+        core.stage(X, 10)                                           # re-upload: the redrawn rows come back, not the old ones
+        assert np.array_equal(core.op.x[20:].numpy(), want)
